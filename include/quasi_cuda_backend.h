@@ -1,0 +1,102 @@
+/*
+ * quasi_cuda_backend.h - what the opaque handles of quasi_plugin_abi.h mean
+ * when Q_gpu_context::backend == Q_GPU_BACKEND_CUDA, plus the optional
+ * CUDA-only entry points of libquasi_cuda.so.
+ *
+ * The ten Q_plugin_* functions are the whole contract with an unmodified
+ * Quasi host. Everything here is additive: a host that knows nothing about
+ * CUDA fills the three descriptors below in its gpu/cuda context (the
+ * counterpart of Q::gpu::metal::context,
+ * /root/reference/src/quasi/gpu/metal/context.hpp:54-103) and never calls a
+ * Q_cuda_* function. The Q_cuda_* functions exist for what the reference ABI
+ * has no slot for (SURVEY.md section 0 fact 5, section 8b "out-of-band"):
+ * ray statistics for the Mrays/s metric, and device-side access to the
+ * accumulation layers so a multi-GPU host can reduce them over NVLink without
+ * a round trip through host memory.
+ *
+ * No CUDA header is needed to include this file: streams and device pointers
+ * are passed as void*.
+ */
+#ifndef QUASI_CUDA_BACKEND_H
+#define QUASI_CUDA_BACKEND_H
+
+#include "quasi_plugin_abi.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Q_gpu_context::device points at one of these, owned by the host for the
+ * lifetime of the plugin. Replaces id<MTLDevice>
+ * (/root/reference/backends/metal/plugin.mm:570). */
+typedef struct Q_cuda_device_desc {
+    uint32_t struct_size;  /* sizeof(Q_cuda_device_desc), for forward compatibility */
+    int32_t device_ordinal; /* cudaSetDevice() ordinal the plugin must use */
+    /* Sample sharding. This GPU renders RNG frame
+     * indices shard_index + i*shard_count for its i-th render call since the
+     * last restart. A single-GPU host passes {0, 1}, which is the reference's
+     * behaviour (frame index == call index, plugin.mm:677,791). */
+    uint32_t shard_index;
+    uint32_t shard_count;
+} Q_cuda_device_desc;
+
+/* Q_render_frame::drawable points at one of these, or is NULL when there is
+ * nothing to present (headless EXR rendering): the tonemap pass is skipped
+ * then. Replaces id<CAMetalDrawable> (plugin.mm:629, 777-788). */
+typedef struct Q_cuda_drawable {
+    void* pixels;         /* BGRA8 unorm, row 0 = top; device or pinned-host memory */
+    uint32_t pitch_bytes; /* bytes between rows, >= 4*width, multiple of 4 */
+    uint32_t reserved;
+} Q_cuda_drawable;
+
+/* Counters since Q_plugin_create (not reset by camera_dirty). */
+typedef struct Q_cuda_stats {
+    uint64_t rays;            /* closest-hit queries = trace_scene calls (plugin.mm:199) */
+    uint64_t paths;           /* camera rays = pixel samples */
+    uint64_t kernel_launches; /* kernels this plugin enqueued */
+    uint32_t frame_count;     /* render calls since the last restart */
+    uint32_t width;
+    uint32_t height;
+    uint32_t reserved;
+} Q_cuda_stats;
+
+/* Device-side view of the accumulated RGBA32F layers (index = Q_aov_type),
+ * each width*height*4 floats, row 0 = top, holding the mean of this GPU's
+ * frame_count samples. Valid until the next resize or Q_plugin_destroy. */
+typedef struct Q_cuda_layers {
+    float* device_ptr[Q_AOV_COUNT];
+    uint32_t width;
+    uint32_t height;
+    uint32_t frame_count;
+    uint32_t reserved;
+} Q_cuda_layers;
+
+/* Blocking: waits for enqueued renders so that the counters are final. */
+Q_PLUGIN_EXPORT int Q_cuda_plugin_stats(Q_plugin_handle* handle, Q_cuda_stats* out);
+
+/* Does not block; work already enqueued on the frame stream is ordered before
+ * anything enqueued later on `stream` (a cudaStream_t; NULL = legacy default). */
+Q_PLUGIN_EXPORT int Q_cuda_plugin_layers(Q_plugin_handle* handle, void* stream,
+                                         Q_cuda_layers* out);
+
+/* Stand-alone passes on caller-owned DEVICE buffers, enqueued on `stream`.
+ * They are the CUDA forms of the reference's accumulate and tonemap shaders
+ * (plugin.mm:313-330, 334-350) and of the post-reduce scale. */
+Q_PLUGIN_EXPORT int Q_cuda_accumulate(const float* current, const float* history, float* output,
+                                      uint64_t n_pixels, uint32_t frame_count, void* stream);
+Q_PLUGIN_EXPORT int Q_cuda_tonemap_bgra8(const float* accumulated, uint32_t width,
+                                         uint32_t height, void* bgra, uint32_t pitch_bytes,
+                                         void* stream);
+/* out = (sum over g of shards[g]) * scale, summed in order g = 0..n-1;
+ * scale == 0 means 1/n_shards. shards[] are device pointers (peer-mapped
+ * pointers are fine; n_shards <= 16); optionally also writes the tonemapped
+ * BGRA8 image of `out` (tightly packed) when bgra != NULL. After an NCCL sum
+ * the same entry point does the scale (+tonemap) with n_shards == 1. */
+Q_PLUGIN_EXPORT int Q_cuda_combine_shards(const float* const* shards, uint32_t n_shards,
+                                          uint64_t n_pixels, float scale, float* out, void* bgra,
+                                          void* stream);
+
+#ifdef __cplusplus
+} /* extern "C" */
+#endif
+#endif /* QUASI_CUDA_BACKEND_H */

@@ -1,0 +1,37 @@
+/// @file kernels.hpp
+/// @brief Launchers for the sm_100a kernels of libquasi_cuda.so.
+
+#pragma once
+
+#include "scene_params.hpp"
+
+#include <cuda_runtime_api.h>
+
+#include <cstdint>
+
+namespace Q::cuda {
+
+inline constexpr uint32_t k_max_shards = 16;
+
+/// @brief One new sample per pixel, folded into the four accumulated layers in place.
+/// @param layers Device pointers to beauty, albedo, normal, depth (RGBA32F, row 0 = top).
+/// @param ray_counter Device counter incremented by the number of closest-hit queries.
+cudaError_t launch_pathtrace_accumulate(const scene_params& scene, const frame_params& frame,
+                                        float* const layers[4], unsigned long long* ray_counter,
+                                        cudaStream_t stream);
+
+/// @brief output = mix(history, current, 1/(frame_count+1)) over n_pixels float4s.
+cudaError_t launch_accumulate(const float* current, const float* history, float* output,
+                              uint64_t n_pixels, uint32_t frame_count, cudaStream_t stream);
+
+/// @brief Reinhard + gamma 2.2 into BGRA8 unorm (row 0 = top).
+cudaError_t launch_tonemap_bgra8(const float* accumulated, uint32_t width, uint32_t height,
+                                 void* bgra, uint32_t pitch_bytes, cudaStream_t stream);
+
+/// @brief out = (shards[0] + shards[1] + ...) * scale, in that order (scale 0 = 1/n);
+/// optional fused tonemap.
+cudaError_t launch_combine_shards(const float* const* shards, uint32_t n_shards,
+                                  uint64_t n_pixels, float scale, float* out, void* bgra,
+                                  cudaStream_t stream);
+
+}  // namespace Q::cuda

@@ -1,0 +1,474 @@
+/// @file plugin.cu
+/// @brief libquasi_cuda.so: the CUDA backend behind Quasi's plugin C ABI.
+///
+/// Counterpart of the Metal backend's host half
+/// (/root/reference/backends/metal/plugin.mm:389-904). Same ten entry points, same
+/// null-tolerance, ownership and per-call semantics; the
+/// GPU work is the kernels in pathtrace.cu and post.cu. There is no CPU path: if
+/// CUDA fails, create returns NULL and render/readback do nothing.
+
+#include "kernels.hpp"
+
+#include <quasi_cuda_backend.h>
+
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+namespace {
+
+using Q::cuda::frame_params;
+using Q::cuda::scene_params;
+
+constexpr const char* k_name = "CUDA Path Tracer";
+constexpr const char* k_description = "Cornell Box path tracer using CUDA (sm_100a)";
+constexpr const char* k_author = "Quasi";
+
+/// Pinned host buffers handed out by readback. The ABI's free functions take no
+/// plugin handle (plugin_interface.hpp:140, 149), so the pool is per library
+/// image. Buffers are recycled: cudaHostAlloc of 33 MB costs milliseconds,
+/// reuse costs nothing, and pinned memory lets the D2H copy run at PCIe speed.
+class readback_pool {
+public:
+    float* acquire(size_t bytes) {
+        std::lock_guard<std::mutex> lock(mutex_);
+        for (auto& e : entries_) {
+            if (!e.in_use && e.bytes == bytes) {
+                e.in_use = true;
+                return e.ptr;
+            }
+        }
+        void* p = nullptr;
+        if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+            (void)cudaGetLastError();
+            return nullptr;
+        }
+        entries_.push_back({static_cast<float*>(p), bytes, true});
+        return static_cast<float*>(p);
+    }
+
+    void release(float* ptr) {
+        std::lock_guard<std::mutex> lock(mutex_);
+        for (auto& e : entries_) {
+            if (e.ptr == ptr) {
+                e.in_use = false;
+                return;
+            }
+        }
+    }
+
+    /// Frees idle buffers; called when the last plugin instance goes away.
+    void trim() {
+        std::lock_guard<std::mutex> lock(mutex_);
+        std::vector<entry> keep;
+        for (auto& e : entries_) {
+            if (e.in_use) {
+                keep.push_back(e);
+            } else {
+                cudaFreeHost(e.ptr);
+            }
+        }
+        entries_.swap(keep);
+    }
+
+private:
+    struct entry {
+        float* ptr;
+        size_t bytes;
+        bool in_use;
+    };
+    std::mutex mutex_;
+    std::vector<entry> entries_;
+};
+
+readback_pool g_pool;
+std::mutex g_instances_mutex;
+int g_instances = 0;
+
+struct plugin_state {
+    Q_plugin_context* context = nullptr;
+    int device = 0;
+    uint32_t shard_index = 0;
+    uint32_t shard_count = 1;
+    cudaStream_t queue = nullptr;
+
+    Q::cuda::scene_desc scene_desc;
+    scene_params scene;
+
+    float* layers[Q_AOV_COUNT] = {nullptr, nullptr, nullptr, nullptr};
+    unsigned long long* ray_counter = nullptr;
+    cudaEvent_t last_render = nullptr;
+    bool render_pending = false;
+
+    uint32_t frame_count = 0;
+    uint32_t last_width = 0;
+    uint32_t last_height = 0;
+
+    uint64_t paths = 0;
+    uint64_t kernel_launches = 0;
+};
+
+void log_msg(const plugin_state* state, const char* msg) {
+    if (state->context && state->context->log) {
+        state->context->log(state->context->host_data, msg);
+    }
+}
+
+bool check(const plugin_state* state, cudaError_t err, const char* what) {
+    if (err == cudaSuccess) return true;
+    char buf[256];
+    std::snprintf(buf, sizeof buf, "CUDA error in %s: %s", what, cudaGetErrorString(err));
+    log_msg(state, buf);
+    (void)cudaGetLastError();
+    return false;
+}
+
+void free_layers(plugin_state* state) {
+    for (auto& l : state->layers) {
+        if (l) cudaFree(l);
+        l = nullptr;
+    }
+}
+
+/// Counterpart of create_textures (plugin.mm:491-535): four RGBA32F layers,
+/// accumulated in place, so 4 allocations instead of 12.
+bool create_layers(plugin_state* state, uint32_t width, uint32_t height) {
+    if (state->render_pending) cudaEventSynchronize(state->last_render);
+    free_layers(state);
+    size_t bytes = static_cast<size_t>(width) * height * 4 * sizeof(float);
+    if (bytes != 0) {
+        for (auto& l : state->layers) {
+            if (!check(state, cudaMalloc(reinterpret_cast<void**>(&l), bytes), "cudaMalloc(layer)")) {
+                free_layers(state);
+                return false;
+            }
+        }
+    }
+    state->last_width = width;
+    state->last_height = height;
+    state->frame_count = 0;
+    return true;
+}
+
+uint32_t env_u32(const char* name, uint32_t fallback, uint32_t lo, uint32_t hi) {
+    const char* s = std::getenv(name);
+    if (!s || !*s) return fallback;
+    long v = std::strtol(s, nullptr, 10);
+    if (v < static_cast<long>(lo)) v = lo;
+    if (v > static_cast<long>(hi)) v = hi;
+    return static_cast<uint32_t>(v);
+}
+
+Q_aov_buffer download_layer(plugin_state* state, int layer) {
+    Q_aov_buffer buf{};
+    const float* src = state->layers[layer];
+    if (!src || state->frame_count == 0) return buf;
+    size_t bytes = static_cast<size_t>(state->last_width) * state->last_height * 4 * sizeof(float);
+    float* dst = g_pool.acquire(bytes);
+    if (!dst) return buf;
+    if (!check(state, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, state->queue),
+               "cudaMemcpyAsync(readback)")) {
+        g_pool.release(dst);
+        return buf;
+    }
+    buf.data = dst;
+    buf.width = state->last_width;
+    buf.height = state->last_height;
+    buf.channels = 4;
+    return buf;
+}
+
+/// Orders `stream` after the most recent render without blocking the host.
+void order_after_render(plugin_state* state, cudaStream_t stream) {
+    if (state->render_pending) cudaStreamWaitEvent(stream, state->last_render, 0);
+}
+
+}  // namespace
+
+extern "C" {
+
+/// plugin.mm:543-545
+Q_PLUGIN_EXPORT uint32_t Q_plugin_abi_version(void) { return Q_PLUGIN_ABI_VERSION; }
+
+/// plugin.mm:547-554
+Q_PLUGIN_EXPORT Q_plugin_info Q_plugin_get_info(void) {
+    Q_plugin_info info;
+    info.name = k_name;
+    info.version = {1, 0, 0};
+    info.description = k_description;
+    info.author = k_author;
+    return info;
+}
+
+/// plugin.mm:556-592
+Q_PLUGIN_EXPORT Q_plugin_handle* Q_plugin_create(Q_plugin_context* ctx) {
+    if (!ctx || !ctx->gpu) return nullptr;
+
+    if (ctx->gpu->backend != Q_GPU_BACKEND_CUDA) {
+        if (ctx->log) ctx->log(ctx->host_data, "CUDA backend requires CUDA GPU context");
+        return nullptr;
+    }
+
+    auto* state = new (std::nothrow) plugin_state{};
+    if (!state) return nullptr;
+    state->context = ctx;
+    state->queue = static_cast<cudaStream_t>(ctx->gpu->queue);
+
+    const auto* desc = static_cast<const Q_cuda_device_desc*>(ctx->gpu->device);
+    if (desc && desc->struct_size >= sizeof(Q_cuda_device_desc)) {
+        state->device = desc->device_ordinal;
+        state->shard_count = desc->shard_count ? desc->shard_count : 1u;
+        state->shard_index = desc->shard_index % state->shard_count;
+    } else if (cudaGetDevice(&state->device) != cudaSuccess) {
+        state->device = 0;
+    }
+
+    bool ok = check(state, cudaSetDevice(state->device), "cudaSetDevice");
+    ok = ok && check(state, cudaEventCreateWithFlags(&state->last_render, cudaEventDisableTiming),
+                     "cudaEventCreate");
+    ok = ok && check(state, cudaMalloc(reinterpret_cast<void**>(&state->ray_counter),
+                                       sizeof(unsigned long long)), "cudaMalloc(counter)");
+    ok = ok && check(state, cudaMemsetAsync(state->ray_counter, 0, sizeof(unsigned long long),
+                                            state->queue), "cudaMemset(counter)");
+    if (ok) {
+        // The plugin builds its own scene (plugin.mm:581-584). The ABI has no
+        // slot for options, so they come from the environment.
+        state->scene_desc = Q::cuda::make_cornell_box();
+        uint32_t bounces = env_u32("QUASI_CUDA_MAX_BOUNCES", Q::cuda::k_max_bounces, 1, 64);
+        Q::cuda::prepare_scene(state->scene_desc, bounces, state->scene);
+        ok = create_layers(state, ctx->viewport_width, ctx->viewport_height);
+    }
+    if (!ok) {
+        free_layers(state);
+        if (state->ray_counter) cudaFree(state->ray_counter);
+        if (state->last_render) cudaEventDestroy(state->last_render);
+        delete state;
+        return nullptr;
+    }
+
+    {
+        std::lock_guard<std::mutex> lock(g_instances_mutex);
+        g_instances++;
+    }
+    log_msg(state, "Cornell Box path tracer initialized (CUDA)");
+    return reinterpret_cast<Q_plugin_handle*>(state);
+}
+
+/// plugin.mm:594-617. Also drains the GPU: after this returns the library may be
+/// dlclose'd by the hot-reload manager (manager.hpp:350-360).
+Q_PLUGIN_EXPORT void Q_plugin_destroy(Q_plugin_handle* handle) {
+    if (!handle) return;
+    auto* state = reinterpret_cast<plugin_state*>(handle);
+    log_msg(state, "Path tracer destroyed");
+
+    cudaSetDevice(state->device);
+    if (state->render_pending) cudaEventSynchronize(state->last_render);
+    cudaStreamSynchronize(state->queue);
+    free_layers(state);
+    if (state->ray_counter) cudaFree(state->ray_counter);
+    if (state->last_render) cudaEventDestroy(state->last_render);
+    delete state;
+
+    bool last;
+    {
+        std::lock_guard<std::mutex> lock(g_instances_mutex);
+        last = --g_instances == 0;
+    }
+    if (last) g_pool.trim();
+}
+
+/// plugin.mm:619-622
+Q_PLUGIN_EXPORT void Q_plugin_update(Q_plugin_handle* handle, float delta_time) {
+    (void)handle;
+    (void)delta_time;
+}
+
+/// plugin.mm:624-792
+Q_PLUGIN_EXPORT void Q_plugin_render(Q_plugin_handle* handle, Q_render_frame* frame) {
+    if (!handle || !frame) return;
+    auto* state = reinterpret_cast<plugin_state*>(handle);
+
+    // The Metal backend needs a drawable and a command buffer (plugin.mm:632).
+    // Here the command buffer is the frame's stream and is required; the
+    // drawable is optional because a headless host has nothing to present.
+    auto stream = static_cast<cudaStream_t>(frame->command_buffer);
+    if (!stream) return;
+    const auto* drawable = static_cast<const Q_cuda_drawable*>(frame->drawable);
+
+    if (cudaSetDevice(state->device) != cudaSuccess) return;
+
+    const uint32_t width = frame->width;
+    const uint32_t height = frame->height;
+
+    // plugin.mm:637-640
+    if (width != state->last_width || height != state->last_height) {
+        if (!create_layers(state, width, height)) return;
+    }
+    if (width == 0 || height == 0) return;
+
+    // plugin.mm:642-646
+    if (frame->camera_dirty) state->frame_count = 0;
+
+    // plugin.mm:648-677; frame index per shard: SURVEY.md 8e.
+    frame_params fp;
+    const uint32_t frame_index = state->shard_index + state->frame_count * state->shard_count;
+    Q::cuda::prepare_frame(frame->camera.position, frame->camera.target, frame->camera.up,
+                           frame->camera.fov, width, height, frame_index, state->frame_count, fp);
+
+    // Frames may arrive on different streams (one per frame in flight); the
+    // layers are shared, so order this frame after the previous one.
+    order_after_render(state, stream);
+
+    if (!check(state, Q::cuda::launch_pathtrace_accumulate(state->scene, fp, state->layers,
+                                                          state->ray_counter, stream),
+               "pathtrace_accumulate")) {
+        return;
+    }
+    state->kernel_launches++;
+
+    // plugin.mm:776-788
+    if (drawable && drawable->pixels) {
+        uint32_t pitch = drawable->pitch_bytes ? drawable->pitch_bytes : 4u * width;
+        if (check(state, Q::cuda::launch_tonemap_bgra8(state->layers[Q_AOV_BEAUTY], width, height,
+                                                       drawable->pixels, pitch, stream),
+                  "tonemap")) {
+            state->kernel_launches++;
+        }
+    }
+
+    cudaEventRecord(state->last_render, stream);
+    state->render_pending = true;
+
+    state->paths += static_cast<uint64_t>(width) * height;
+    state->frame_count++;  // plugin.mm:791
+}
+
+/// plugin.mm:846-863
+Q_PLUGIN_EXPORT Q_readback_result Q_plugin_readback(Q_plugin_handle* handle) {
+    Q_readback_result result{};
+    if (!handle) return result;
+    auto* state = reinterpret_cast<plugin_state*>(handle);
+    if (cudaSetDevice(state->device) != cudaSuccess) return result;
+
+    order_after_render(state, state->queue);
+    Q_aov_buffer buf = download_layer(state, Q_AOV_BEAUTY);
+    if (buf.data && !check(state, cudaStreamSynchronize(state->queue), "readback sync")) {
+        g_pool.release(buf.data);
+        buf = Q_aov_buffer{};
+    }
+    result.data = buf.data;
+    result.width = buf.width;
+    result.height = buf.height;
+    result.channels = buf.channels;
+    if (buf.data) log_msg(state, "HDR readback complete");
+    return result;
+}
+
+/// plugin.mm:865-870
+Q_PLUGIN_EXPORT void Q_plugin_readback_free(Q_readback_result* result) {
+    if (result && result->data) {
+        g_pool.release(result->data);
+        result->data = nullptr;
+    }
+}
+
+/// plugin.mm:872-892. The four copies are enqueued back to back and waited for
+/// once, instead of four blit + waitUntilCompleted round trips.
+Q_PLUGIN_EXPORT Q_readback_aov_result Q_plugin_readback_aov(Q_plugin_handle* handle) {
+    Q_readback_aov_result result{};
+    if (!handle) return result;
+    auto* state = reinterpret_cast<plugin_state*>(handle);
+    if (cudaSetDevice(state->device) != cudaSuccess) return result;
+
+    order_after_render(state, state->queue);
+    for (int i = 0; i < Q_AOV_COUNT; i++) result.buffers[i] = download_layer(state, i);
+    if (!check(state, cudaStreamSynchronize(state->queue), "readback sync")) {
+        for (auto& b : result.buffers) {
+            if (b.data) g_pool.release(b.data);
+            b = Q_aov_buffer{};
+        }
+        return result;
+    }
+    log_msg(state, "AOV readback complete");
+    return result;
+}
+
+/// plugin.mm:894-902
+Q_PLUGIN_EXPORT void Q_plugin_readback_aov_free(Q_readback_aov_result* result) {
+    if (!result) return;
+    for (auto& b : result->buffers) {
+        if (b.data) {
+            g_pool.release(b.data);
+            b.data = nullptr;
+        }
+    }
+}
+
+/* ---- CUDA-only extension entry points (quasi_cuda_backend.h) ---- */
+
+Q_PLUGIN_EXPORT int Q_cuda_plugin_stats(Q_plugin_handle* handle, Q_cuda_stats* out) {
+    if (!handle || !out) return -1;
+    auto* state = reinterpret_cast<plugin_state*>(handle);
+    if (cudaSetDevice(state->device) != cudaSuccess) return -1;
+    if (state->render_pending) cudaEventSynchronize(state->last_render);
+    unsigned long long rays = 0;
+    order_after_render(state, state->queue);
+    if (!check(state, cudaMemcpyAsync(&rays, state->ray_counter, sizeof rays,
+                                      cudaMemcpyDeviceToHost, state->queue), "stats copy") ||
+        !check(state, cudaStreamSynchronize(state->queue), "stats sync")) {
+        return -1;
+    }
+    std::memset(out, 0, sizeof *out);
+    out->rays = rays;
+    out->paths = state->paths;
+    out->kernel_launches = state->kernel_launches;
+    out->frame_count = state->frame_count;
+    out->width = state->last_width;
+    out->height = state->last_height;
+    return 0;
+}
+
+Q_PLUGIN_EXPORT int Q_cuda_plugin_layers(Q_plugin_handle* handle, void* stream,
+                                         Q_cuda_layers* out) {
+    if (!handle || !out) return -1;
+    auto* state = reinterpret_cast<plugin_state*>(handle);
+    if (cudaSetDevice(state->device) != cudaSuccess) return -1;
+    order_after_render(state, static_cast<cudaStream_t>(stream));
+    std::memset(out, 0, sizeof *out);
+    for (int i = 0; i < Q_AOV_COUNT; i++) out->device_ptr[i] = state->layers[i];
+    out->width = state->last_width;
+    out->height = state->last_height;
+    out->frame_count = state->frame_count;
+    return 0;
+}
+
+Q_PLUGIN_EXPORT int Q_cuda_accumulate(const float* current, const float* history, float* output,
+                                      uint64_t n_pixels, uint32_t frame_count, void* stream) {
+    if (!current || !history || !output) return -1;
+    return Q::cuda::launch_accumulate(current, history, output, n_pixels, frame_count,
+                                      static_cast<cudaStream_t>(stream)) == cudaSuccess ? 0 : -1;
+}
+
+Q_PLUGIN_EXPORT int Q_cuda_tonemap_bgra8(const float* accumulated, uint32_t width,
+                                         uint32_t height, void* bgra, uint32_t pitch_bytes,
+                                         void* stream) {
+    if (!accumulated || !bgra) return -1;
+    if (pitch_bytes == 0) pitch_bytes = 4u * width;
+    return Q::cuda::launch_tonemap_bgra8(accumulated, width, height, bgra, pitch_bytes,
+                                         static_cast<cudaStream_t>(stream)) == cudaSuccess ? 0 : -1;
+}
+
+Q_PLUGIN_EXPORT int Q_cuda_combine_shards(const float* const* shards, uint32_t n_shards,
+                                          uint64_t n_pixels, float scale, float* out, void* bgra,
+                                          void* stream) {
+    if (!shards || !out) return -1;
+    return Q::cuda::launch_combine_shards(shards, n_shards, n_pixels, scale, out, bgra,
+                                          static_cast<cudaStream_t>(stream)) == cudaSuccess ? 0 : -1;
+}
+
+}  // extern "C"

@@ -1,0 +1,266 @@
+/// @file scene_params.hpp
+/// @brief Launch-parameter blocks of the CUDA path tracer and the host code that fills them.
+///
+/// The Metal backend rebuilds a 2 624-byte GpuSceneUniforms block on the CPU every
+/// frame and pushes it with setFragmentBytes
+/// (/root/reference/backends/metal/plugin.mm:354-387, 662-700, 735); its shader
+/// then re-derives every quad's plane, every quad's sampling frame and the
+/// camera basis once per ray or per pixel. Here the same quantities are derived
+/// ONCE on the host, with the same IEEE binary32 operations in the same order, and
+/// handed to the kernel as __grid_constant__ parameters, which live in the
+/// constant bank and are read with warp-uniform loads. Hoisting an exactly
+/// rounded operation out of a loop cannot change its result, so the images stay
+/// bit-identical to the literal shader (tests/test_cuda_parity.py).
+///
+/// This header is plain C++ (no CUDA types) so that host-only code can use it.
+
+#pragma once
+
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+
+namespace Q::cuda {
+
+inline constexpr uint32_t k_max_quads = 32;   ///< plugin.mm:21, 30
+inline constexpr uint32_t k_max_bounces = 5;  ///< plugin.mm:22, 31
+
+/// One quad, pre-digested. 40 floats (160 bytes), 16-byte aligned rows so the
+/// constant-bank loads vectorise.
+struct alignas(16) quad_params {
+    float normal[3];   ///< n * rsqrt(dot(n,n)), n = cross(u,v)   (plugin.mm:165-170)
+    float plane_d;     ///< dot(normal, origin)                   (plugin.mm:171)
+    float w[3];        ///< n / dot(n,n)                          (plugin.mm:182)
+    float valid;       ///< 0 when dot(n,n) < 1e-8                (plugin.mm:168)
+    float origin[3];
+    float pad0;
+    float u[3];
+    float pad1;
+    float v[3];
+    float pad2;
+    /// Cosine-sampling frame for a hit on the side the normal points to
+    /// (plugin.mm:119-122). The other side is exactly (frame_u, -frame_v, -frame_w).
+    float frame_u[3];
+    float pad3;
+    float frame_v[3];
+    float pad4;
+    float frame_w[3];
+    float pad5;
+    float albedo[3];
+    float is_light;    ///< max(emission) > 0.1                   (plugin.mm:255-256)
+    float emission[3];
+    float pad6;
+};
+static_assert(sizeof(quad_params) == 160);
+
+struct alignas(16) scene_params {
+    quad_params quads[k_max_quads];
+    uint32_t quad_count;
+    uint32_t max_bounces;
+    uint32_t pad[2];
+};
+
+/// Per-call camera and sample bookkeeping.
+struct alignas(16) frame_params {
+    float position[3];     ///< ray origin
+    float weight;          ///< 1 / (sample_index + 1)            (plugin.mm:326)
+    float lower_left[3];   ///< plugin.mm:145
+    uint32_t width;
+    float horizontal[3];   ///< plugin.mm:143
+    uint32_t height;
+    float vertical[3];     ///< plugin.mm:144
+    uint32_t frame_index;  ///< RNG frame index                   (plugin.mm:295)
+    uint32_t sample_index; ///< render calls since the last restart
+    uint32_t pad[3];
+};
+
+/// The scene as the host describes it: the same 12+8 floats per quad the Metal
+/// plugin uploads (GpuQuad / GpuMaterial, plugin.mm:363-377).
+struct quad_desc {
+    float origin[3];
+    float u[3];
+    float v[3];
+    float albedo[3];
+    float roughness;
+    float emission[3];
+    float metallic;
+};
+
+struct scene_desc {
+    quad_desc quads[k_max_quads];
+    uint32_t quad_count = 0;
+    uint32_t light_index = 0;
+};
+
+namespace detail {
+
+struct f3 {
+    float x, y, z;
+};
+inline f3 load3(const float* p) { return {p[0], p[1], p[2]}; }
+inline void store3(float* p, f3 a) { p[0] = a.x; p[1] = a.y; p[2] = a.z; }
+inline f3 operator+(f3 a, f3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline f3 operator-(f3 a, f3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline f3 operator-(f3 a) { return {-a.x, -a.y, -a.z}; }
+inline f3 operator*(f3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
+inline f3 operator/(f3 a, float s) { return {a.x / s, a.y / s, a.z / s}; }
+/// (a.x*b.x + a.y*b.y) + a.z*b.z, /root/reference/src/quasi/math/vec.hpp:92-94
+inline float dot(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+/// vec.hpp:100-106
+inline f3 cross(f3 a, f3 b) {
+    return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+/// v / length(v), vec.hpp:108-114
+inline f3 normalize(f3 a) { return a / std::sqrt(dot(a, a)); }
+
+/// cornell_box.hpp:32-37
+inline f3 rotate_y(f3 p, float angle_deg) {
+    float rad = angle_deg * 3.14159265359f / 180.0f;
+    float c = std::cos(rad);
+    float s = std::sin(rad);
+    return {p.x * c + p.z * s, p.y, -p.x * s + p.z * c};
+}
+
+}  // namespace detail
+
+/// @brief The demo scene: a Cornell box of 16 quads, light at index 5.
+///
+/// Same geometry, order and materials as Q::scene::make_cornell_box
+/// (/root/reference/src/quasi/scene/cornell_box.hpp:95-134, add_box :45-90);
+/// checked bit-for-bit against that function in tests/test_scene.py.
+inline scene_desc make_cornell_box() {
+    using namespace detail;
+    scene_desc s;
+
+    struct mat {
+        float albedo[3];
+        float emission[3];
+    };
+    const mat white{{0.73f, 0.73f, 0.73f}, {0, 0, 0}};
+    const mat red{{0.65f, 0.05f, 0.05f}, {0, 0, 0}};
+    const mat green{{0.12f, 0.45f, 0.15f}, {0, 0, 0}};
+    const mat light{{0, 0, 0}, {15.0f, 15.0f, 15.0f}};
+
+    auto push = [&s](f3 origin, f3 u, f3 v, const mat& m) {
+        quad_desc& q = s.quads[s.quad_count++];
+        store3(q.origin, origin);
+        store3(q.u, u);
+        store3(q.v, v);
+        std::memcpy(q.albedo, m.albedo, sizeof q.albedo);
+        std::memcpy(q.emission, m.emission, sizeof q.emission);
+        q.roughness = 1.0f;
+        q.metallic = 0.0f;
+    };
+
+    push({-1, 0, -1}, {2, 0, 0}, {0, 0, 2}, white);   // floor
+    push({-1, 2, 1}, {2, 0, 0}, {0, 0, -2}, white);   // ceiling
+    push({-1, 0, -1}, {2, 0, 0}, {0, 2, 0}, white);   // back wall
+    push({-1, 0, 1}, {0, 0, -2}, {0, 2, 0}, red);     // left wall
+    push({1, 0, -1}, {0, 0, 2}, {0, 2, 0}, green);    // right wall
+    s.light_index = s.quad_count;
+    push({-0.25f, 1.99f, -0.25f}, {0.5f, 0, 0}, {0, 0, 0.5f}, light);
+
+    auto box = [&](f3 center, f3 size, float angle, const mat& m) {
+        float hw = size.x * 0.5f, h = size.y, hd = size.z * 0.5f;
+        const f3 local[8] = {{-hw, 0, -hd}, {hw, 0, -hd}, {-hw, 0, hd}, {hw, 0, hd},
+                             {-hw, h, -hd}, {hw, h, -hd}, {-hw, h, hd}, {hw, h, hd}};
+        f3 p[8];
+        for (int i = 0; i < 8; i++) p[i] = rotate_y(local[i], angle) + center;
+        push(p[4], p[5] - p[4], p[6] - p[4], m);  // top
+        push(p[0], p[1] - p[0], p[4] - p[0], m);  // front
+        push(p[3], p[2] - p[3], p[7] - p[3], m);  // back
+        push(p[2], p[0] - p[2], p[6] - p[2], m);  // left
+        push(p[1], p[3] - p[1], p[5] - p[1], m);  // right
+    };
+    box({-0.35f, 0.0f, 0.3f}, {0.5f, 1.2f, 0.5f}, 15.0f, white);
+    box({0.35f, 0.0f, -0.3f}, {0.55f, 0.55f, 0.55f}, -18.0f, white);
+    return s;
+}
+
+/// @brief Derives the per-quad constants the shader recomputes per ray.
+inline void prepare_scene(const scene_desc& desc, uint32_t max_bounces, scene_params& out) {
+    using namespace detail;
+    std::memset(&out, 0, sizeof out);
+    out.quad_count = desc.quad_count < k_max_quads ? desc.quad_count : k_max_quads;
+    out.max_bounces = max_bounces;
+    for (uint32_t i = 0; i < out.quad_count; i++) {
+        const quad_desc& q = desc.quads[i];
+        quad_params& g = out.quads[i];
+        f3 origin = load3(q.origin), u = load3(q.u), v = load3(q.v);
+        store3(g.origin, origin);
+        store3(g.u, u);
+        store3(g.v, v);
+        std::memcpy(g.albedo, q.albedo, sizeof g.albedo);
+        std::memcpy(g.emission, q.emission, sizeof g.emission);
+        float emit = std::fmax(q.emission[0], std::fmax(q.emission[1], q.emission[2]));
+        g.is_light = emit > 0.1f ? 1.0f : 0.0f;
+
+        f3 n = cross(u, v);
+        float area_sq = dot(n, n);
+        if (area_sq < 1e-8f) {
+            g.valid = 0.0f;
+            continue;
+        }
+        g.valid = 1.0f;
+        f3 normal = n * (1.0f / std::sqrt(area_sq));
+        store3(g.normal, normal);
+        g.plane_d = dot(normal, origin);
+        store3(g.w, n / area_sq);
+
+        // cosine_sample_hemisphere's basis for hit.normal == normal.
+        f3 w = normalize(normal);
+        f3 a = (std::fabs(w.x) > 0.9f) ? f3{0, 1, 0} : f3{1, 0, 0};
+        f3 fv = normalize(cross(w, a));
+        f3 fu = cross(w, fv);
+        store3(g.frame_u, fu);
+        store3(g.frame_v, fv);
+        store3(g.frame_w, w);
+    }
+}
+
+/// @brief Camera block for one render call: plugin.mm:648-674 (host) followed by
+/// the pixel-invariant half of get_camera_ray, plugin.mm:134-145.
+///
+/// tan() is the correctly rounded binary32 tangent (binary64 libm, rounded
+/// once), the same definition the oracle uses.
+inline void prepare_frame(const float position[3], const float target[3], const float up_in[3],
+                          float fov, uint32_t width, uint32_t height, uint32_t frame_index,
+                          uint32_t sample_index, frame_params& out) {
+    using namespace detail;
+    std::memset(&out, 0, sizeof out);
+    float aspect = static_cast<float>(width) / static_cast<float>(height);
+    float dx = target[0] - position[0];
+    float dy = target[1] - position[1];
+    float dz = target[2] - position[2];
+    float len = std::sqrt(dx * dx + dy * dy + dz * dz);
+    if (len > 0.0f) {
+        dx /= len;
+        dy /= len;
+        dz /= len;
+    }
+    constexpr float pi_f = 3.14159265358979323846264338327950288f;
+    float theta = fov * pi_f / 180.0f;
+    float h = static_cast<float>(std::tan(static_cast<double>(theta / 2.0f)));
+    float viewport_height = 2.0f * h;
+    float viewport_width = aspect * viewport_height;
+
+    f3 pos = load3(position);
+    f3 w = normalize(-f3{dx, dy, dz});
+    f3 right = normalize(cross(load3(up_in), w));
+    f3 up = cross(w, right);
+    f3 horizontal = right * viewport_width;
+    f3 vertical = up * viewport_height;
+    f3 lower_left = pos - horizontal * 0.5f - vertical * 0.5f - w;
+
+    store3(out.position, pos);
+    store3(out.lower_left, lower_left);
+    store3(out.horizontal, horizontal);
+    store3(out.vertical, vertical);
+    out.width = width;
+    out.height = height;
+    out.frame_index = frame_index;
+    out.sample_index = sample_index;
+    out.weight = 1.0f / static_cast<float>(sample_index + 1u);
+}
+
+}  // namespace Q::cuda

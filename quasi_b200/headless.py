@@ -1,0 +1,63 @@
+"""Headless host loop over the plugin C ABI, in Python.
+
+Mirrors the reference host's batch mode (`--render N`,
+/root/reference/src/quasi/host/main.cpp:120-327): open the backend library,
+create the GPU context, load the plugin, then per frame update -> begin_frame ->
+fill camera -> render -> end_frame, and finally read the AOVs back. The C++
+headless host under quasi_b200/host/ is the deliverable; this twin exists so
+that pytest and bench.py can drive the same ABI without a subprocess.
+"""
+from __future__ import annotations
+
+from . import PLUGIN_PATH, abi
+from .cuda_context import cuda_context, orbit_camera
+from .loader import dynamic_library, loader
+
+
+class headless_host:
+    def __init__(self, width: int, height: int, plugin_path=PLUGIN_PATH, device_ordinal: int = 0,
+                 shard_index: int = 0, shard_count: int = 1, present: bool = False, log=None):
+        self.messages = []
+        self._user_log = log
+
+        def _log(_host_data, message):
+            text = message.decode() if message else ""
+            self.messages.append(text)
+            if self._user_log:
+                self._user_log(text)
+
+        self.context = cuda_context.create(width, height, device_ordinal, shard_index, shard_count,
+                                           present=present)
+        self.library = dynamic_library.open(plugin_path)
+        self.plugin_context = self.context.make_plugin_context(log=_log)
+        self.plugin = loader.load(self.library, self.plugin_context)
+        self.camera = orbit_camera()
+        self.camera.update_position()
+        self.frames_rendered = 0
+
+    def render_frame(self, camera_dirty=None):
+        """One iteration of the main loop, main.cpp:243-270. Enqueue only."""
+        self.plugin.update(0.0)
+        frame = self.context.begin_frame()
+        self.camera.fill_camera(frame.camera)
+        dirty = self.camera.dirty if camera_dirty is None else camera_dirty
+        frame.camera_dirty = 1 if dirty else 0
+        self.camera.dirty = False
+        self.plugin.render(frame)
+        self.context.end_frame(frame)
+        self.frames_rendered += 1
+        return frame
+
+    def render(self, frames: int):
+        for _ in range(frames):
+            self.render_frame()
+
+    def readback_aov(self):
+        return self.plugin.readback_aov_numpy()
+
+    def stats(self) -> abi.Q_cuda_stats:
+        return self.plugin.cuda_stats()
+
+    def close(self):
+        self.plugin.destroy()
+        self.library.close()
