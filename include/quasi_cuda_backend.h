@@ -62,7 +62,9 @@ typedef struct Q_cuda_stats {
 
 /* Device-side view of the accumulated RGBA32F layers (index = Q_aov_type),
  * each width*height*4 floats, row 0 = top, holding the mean of this GPU's
- * frame_count samples. Valid until the next resize or Q_plugin_destroy. */
+ * frame_count samples. The four layers are contiguous in that order, so
+ * device_ptr[0] addresses all 16*width*height floats. Valid until the next
+ * resize or Q_plugin_destroy. */
 typedef struct Q_cuda_layers {
     float* device_ptr[Q_AOV_COUNT];
     uint32_t width;

@@ -16,9 +16,10 @@ inline constexpr uint32_t k_max_shards = 16;
 /// @brief One new sample per pixel, folded into the four accumulated layers in place.
 /// @param layers Device pointers to beauty, albedo, normal, depth (RGBA32F, row 0 = top).
 /// @param ray_counter Device counter incremented by the number of closest-hit queries.
+/// @param sm_count Multiprocessors of the device; the grid is 4 resident CTAs per SM.
 cudaError_t launch_pathtrace_accumulate(const scene_params& scene, const frame_params& frame,
                                         float* const layers[4], unsigned long long* ray_counter,
-                                        cudaStream_t stream);
+                                        int sm_count, cudaStream_t stream);
 
 /// @brief output = mix(history, current, 1/(frame_count+1)) over n_pixels float4s.
 cudaError_t launch_accumulate(const float* current, const float* history, float* output,

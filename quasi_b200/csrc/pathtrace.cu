@@ -3,16 +3,31 @@
 ///
 /// One launch does what Q_plugin_render's PASS 1 (pathtrace_frag into four MRT
 /// targets) and PASS 2 (four accumulate dispatches) do in the Metal backend
-/// (/root/reference/backends/metal/plugin.mm:715-774): each thread traces one new
-/// sample of one pixel and folds it straight into the four accumulated RGBA32F
-/// layers in place. The 64 B/px MRT store, its 64 B/px re-read and the ping-pong
-/// copies never exist: 128 B/px of HBM traffic per call instead of 276.
+/// (/root/reference/backends/metal/plugin.mm:715-774): every pixel gets one new
+/// sample, folded straight into the four accumulated RGBA32F layers in place.
+/// The 64 B/px MRT store, its re-read and the ping-pong copies never exist:
+/// 128 B/px of HBM traffic per call instead of 276.
 ///
-/// Arithmetic contract (DESIGN.md "Numerics"): compiled with -fmad=false,
-/// IEEE division and square root; every expression below is written in the
-/// operation order of the shader so results are bit-identical to oracle/.
-/// sin/cos are evaluated in binary64 and rounded once (correctly rounded
-/// binary32), which is also how the oracle defines them.
+/// Execution model (DESIGN.md "Kernels"):
+///  - Persistent warps with path regeneration. The grid is resident CTAs only
+///    (4 per SM); each warp owns every n_warps-th 8x4 pixel tile. A lane whose
+///    path ended writes its pixel and immediately starts the warp's next pixel
+///    (ballot + popc compaction of the idle lanes), so every lane of the warp is
+///    always inside the same bounce step. In the thread-per-pixel form the warp
+///    ran at 18 of 32 lanes (ncu, profiles/r1_v1_*).
+///  - The 16-quad scan is fully unrolled; plane, edge and margin constants are
+///    immediate constant-bank operands. The scan DECIDES with cheap forms
+///    (MUFU.RCP instead of IEEE division, one dot product per barycentric
+///    instead of two cross products) plus explicit margins, then computes the
+///    accepted hit with the literal IEEE sequence. Anything inside a margin
+///    (an edge, a near tie between two quads, t next to t_min) goes to the
+///    literal scan, so the result is bit-identical to the shader's loop.
+///  - Shading constants of the hit quad are read from shared memory (the index
+///    diverges across lanes; constant-bank loads would serialise).
+///
+/// Arithmetic contract (DESIGN.md "Numerics"): -fmad=false, IEEE division and
+/// square root; every value that reaches a pixel is computed with the shader's
+/// operation order. sin/cos are evaluated in binary64 and rounded once.
 
 #include "kernels.hpp"
 
@@ -54,6 +69,17 @@ __device__ __forceinline__ float random_float(uint32_t& state) {
     return __uint2float_rn(state) * 2.3283064365386963e-10f;
 }
 
+/// One MUFU.RCP, relative error <= 2^-23. Only ever feeds decisions with margins.
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 struct hit_record {
     float t;
     v3 point;
@@ -61,15 +87,14 @@ struct hit_record {
     bool front;  ///< denom < 0: the stored normal faces the ray
 };
 
-/// trace_scene + intersect_quad, plugin.mm:157-212. Planes, w = n/|n|^2 and the
-/// degenerate-quad test come pre-computed in scene_params.
-__device__ __forceinline__ hit_record trace_scene(const scene_params& scene, v3 ro, v3 rd) {
-    hit_record closest;
+/// The shader's loop, literally: trace_scene + intersect_quad, plugin.mm:157-212.
+/// Used for the rare rays the fast scan cannot decide with its margins.
+__device__ __noinline__ void trace_scene_exact(const scene_params& scene, v3 ro, v3 rd,
+                                               hit_record& closest) {
     closest.t = 1e30f;
     closest.index = -1;
     closest.front = true;
     closest.point = make_v3(0.0f, 0.0f, 0.0f);
-
     const uint32_t count = scene.quad_count;
 #pragma unroll 1
     for (uint32_t i = 0; i < count; i++) {
@@ -93,80 +118,72 @@ __device__ __forceinline__ hit_record trace_scene(const scene_params& scene, v3 
         closest.index = static_cast<int>(i);
         closest.front = denom < 0.0f;
     }
-    return closest;
 }
 
-struct path_result {
-    v3 color;
-    v3 albedo;
-    v3 normal;
-    float depth;
-    uint32_t rays;
-};
+constexpr int k_shade_stride = 25;  // odd: lanes reading different quads hit different banks
 
-/// path_trace + cosine_sample_hemisphere, plugin.mm:111-125, 223-276.
-__device__ __forceinline__ path_result path_trace(const scene_params& scene, v3 ro, v3 rd,
-                                                  uint32_t& rng) {
-    path_result r;
-    r.color = make_v3(0.0f, 0.0f, 0.0f);
-    r.albedo = make_v3(0.0f, 0.0f, 0.0f);
-    r.normal = make_v3(0.0f, 0.0f, 0.0f);
-    r.depth = 0.0f;
-    r.rays = 0;
-    v3 throughput = make_v3(1.0f, 1.0f, 1.0f);
+// Offsets inside the shared-memory shading record (quad_params floats 28..51).
+constexpr int k_sh_normal = 0, k_sh_is_light = 3, k_sh_frame_u = 4, k_sh_plane_d = 7,
+              k_sh_frame_v = 8, k_sh_frame_w = 12, k_sh_albedo = 16, k_sh_emission = 20;
 
-    const uint32_t max_bounces = scene.max_bounces;
-#pragma unroll 1
-    for (uint32_t bounce = 0; bounce < max_bounces; bounce++) {
-        hit_record hit = trace_scene(scene, ro, rd);
-        r.rays++;
-        if (hit.index < 0) break;
+// Margins of the fast scan. t' = num * rcp(denom) is within 2^-21 relative of the
+// IEEE quotient t; the bands below are ten times wider than that.
+constexpr float k_inf = __builtin_huge_valf();
+constexpr float k_t_min_lo = 0.001f * (1.0f - 4e-6f);  // below: surely t < t_min
+constexpr float k_t_min_hi = 0.001f * (1.0f + 4e-6f);  // above: surely t >= t_min
+constexpr float k_tie = 1.0f + 4e-6f;                  // two hits closer than this: literal scan
 
-        const quad_params& q = scene.quads[hit.index];
-        const float side = hit.front ? 1.0f : -1.0f;
-        v3 normal = load_v3(q.normal) * side;  // exact sign flip
-        v3 emission = load_v3(q.emission);
-        v3 albedo = load_v3(q.albedo);
-        const bool is_light = q.is_light != 0.0f;
+/// Closest hit of one ray against the NQ first quads. Same result, bit for bit,
+/// as trace_scene_exact. `shade` is the shared-memory copy of the quads' shading
+/// records; the winner's plane is re-read from it for the literal finalisation.
+template <int NQ>
+__device__ __forceinline__ void trace_scene(const scene_params& scene, const float* shade, v3 ro,
+                                            v3 rd, hit_record& hit) {
+    float best_t = k_inf;        // smallest t' among quads that are surely hit
+    float challenger_t = k_inf;  // smallest t' among every other quad that may be hit
+    int best_i = -1;
 
-        if (bounce == 0) {
-            r.albedo = is_light ? emission : albedo;
-            r.normal = make_v3(normal.x * 0.5f + 0.5f, normal.y * 0.5f + 0.5f,
-                               normal.z * 0.5f + 0.5f);
-            r.depth = hit.t;
+#pragma unroll
+    for (int i = 0; i < NQ; i++) {
+        const quad_params& q = scene.quads[i];
+        if (q.valid == 0.0f) continue;  // launch-uniform
+        const v3 normal = load_v3(q.normal);
+        const float denom = dot(normal, rd);            // the shader's value
+        const float num = q.plane_d - dot(normal, ro);  // the shader's value
+        const float t_fast = num * rcp_approx(denom);
+        // plugin.mm:174 exactly; plugin.mm:177 (t < t_min) with a margin
+        if (fabsf(denom) >= 1e-8f && t_fast > k_t_min_lo) {
+            const v3 planar = (ro + rd * t_fast) - load_v3(q.origin);
+            const float alpha = dot(planar, load_v3(q.fast_a));
+            const float beta = dot(planar, load_v3(q.fast_b));
+            const float lo = fminf(alpha, beta);
+            const float hi = fmaxf(alpha, beta);
+            const bool maybe = lo >= -q.delta && hi <= q.one_plus_delta;  // else surely outside
+            const bool sure = lo > q.delta && hi < q.one_minus_delta && t_fast > k_t_min_hi;
+            const bool better = maybe && sure && t_fast < best_t;
+            // Whoever does not become the winner challenges it.
+            const float loser = better ? best_t : (maybe ? t_fast : k_inf);
+            challenger_t = fminf(challenger_t, loser);
+            best_t = better ? t_fast : best_t;
+            best_i = better ? i : best_i;
         }
-
-        r.color = r.color + throughput * emission;
-        if (is_light) break;
-
-        throughput = throughput * albedo;
-
-        if (bounce > 2) {
-            float p = fmaxf(0.05f, fmaxf(throughput.x, fmaxf(throughput.y, throughput.z)));
-            if (random_float(rng) > p) break;
-            throughput = throughput / p;
-        }
-
-        ro = hit.point + normal * 0.001f;
-
-        // cosine_sample_hemisphere with the per-quad frame (scene_params.hpp).
-        float r1 = random_float(rng);
-        float r2 = random_float(rng);
-        float phi = 6.28318548202514648f * r1;  // 2.0f * M_PI_F, exact product
-        float cos_theta = sqrtf(1.0f - r2);
-        float sin_theta = sqrtf(r2);
-        double sd, cd;
-        sincos(static_cast<double>(phi), &sd, &cd);
-        float sin_phi = static_cast<float>(sd);
-        float cos_phi = static_cast<float>(cd);
-
-        v3 fu = load_v3(q.frame_u);
-        v3 fv = load_v3(q.frame_v) * side;
-        v3 fw = load_v3(q.frame_w) * side;
-        v3 d = (fu * cos_phi) * sin_theta + (fv * sin_phi) * sin_theta + fw * cos_theta;
-        rd = normalize(d);
     }
-    return r;
+
+    // A challenger matters only if it could be in front of, or tie with, the sure
+    // winner. With no sure winner (best_t == inf) any challenger matters.
+    if (challenger_t < k_inf && challenger_t <= best_t * k_tie) {
+        trace_scene_exact(scene, ro, rd, hit);
+        return;
+    }
+    hit.index = best_i;
+    if (best_i < 0) return;
+    // The accepted hit, with the shader's operations: plugin.mm:173, 176, 179.
+    const float* sh = shade + best_i * k_shade_stride;
+    const v3 normal = load_v3(sh + k_sh_normal);
+    const float denom = dot(normal, rd);
+    hit.front = denom < 0.0f;
+    hit.t = (sh[k_sh_plane_d] - dot(normal, ro)) / denom;
+    hit.point = ro + rd * hit.t;
 }
 
 __device__ __forceinline__ float4 mix4(float4 a, float4 b, float w) {
@@ -174,63 +191,176 @@ __device__ __forceinline__ float4 mix4(float4 a, float4 b, float w) {
                        a.w + (b.w - a.w) * w);
 }
 
-constexpr int k_block_threads = 256;
+/// accumulate, plugin.mm:313-330, in place on one pixel of one layer. History
+/// before the first sample is defined as zero, so sample 0 is stored as is.
+__device__ __forceinline__ void accumulate_pixel(float4* __restrict__ layer, size_t idx,
+                                                 float4 sample, bool first, float weight) {
+    if (!first) sample = mix4(layer[idx], sample, weight);
+    layer[idx] = sample;
+}
 
-/// Block = 16x16 pixels; each warp owns an 8x4 tile so that primary rays stay
-/// coherent and every row of a tile is one 128-byte float4 segment.
-__global__ void __launch_bounds__(k_block_threads)
+constexpr int k_block_threads = 256;
+constexpr int k_blocks_per_sm = 4;
+constexpr int k_warps_per_block = k_block_threads / 32;
+
+template <int NQ>
+__global__ void __launch_bounds__(k_block_threads, k_blocks_per_sm)
 pathtrace_accumulate_kernel(const __grid_constant__ scene_params scene,
                             const __grid_constant__ frame_params frame, float4* __restrict__ beauty,
                             float4* __restrict__ albedo, float4* __restrict__ normal,
                             float4* __restrict__ depth, unsigned long long* __restrict__ ray_counter) {
-    const uint32_t warp = threadIdx.x >> 5;
+    __shared__ float s_shade[NQ * k_shade_stride];
+    for (int idx = threadIdx.x; idx < NQ * static_cast<int>(k_shade_floats); idx += k_block_threads) {
+        const int qi = idx / static_cast<int>(k_shade_floats);
+        const int k = idx - qi * static_cast<int>(k_shade_floats);
+        s_shade[qi * k_shade_stride + k] =
+            reinterpret_cast<const float*>(&scene.quads[qi])[k_shade_offset + k];
+    }
+    __syncthreads();
+
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t px = blockIdx.x * 16u + (warp & 1u) * 8u + (lane & 7u);
-    const uint32_t py = blockIdx.y * 16u + (warp >> 1) * 4u + (lane >> 3);
-    const bool inside = px < frame.width && py < frame.height;
+    const uint32_t lanes_below = (1u << lane) - 1u;
+    const uint32_t warp_global = blockIdx.x * k_warps_per_block + (threadIdx.x >> 5);
+    const uint32_t n_warps = gridDim.x * k_warps_per_block;
+    const uint32_t tiles_x = (frame.width + 7u) >> 3;
+    const uint32_t n_tiles = tiles_x * ((frame.height + 3u) >> 2);
+    const bool first_sample = frame.sample_index == 0;
+    const float weight = frame.weight;
+    const uint32_t max_bounces = scene.max_bounces;
+    const v3 cam_origin = load_v3(frame.position);
 
+    // Path state of this lane.
+    bool active = false;
+    v3 ro = cam_origin, rd = make_v3(0.0f, 0.0f, -1.0f);
+    v3 throughput = make_v3(1.0f, 1.0f, 1.0f), color = make_v3(0.0f, 0.0f, 0.0f);
+    uint32_t rng = 0, bounce = 0;
+    size_t pixel = 0;
     uint32_t rays = 0;
-    if (inside) {
-        // pathtrace_frag, plugin.mm:287-309; uv is the closed form of the
-        // rasteriser's interpolation, py = 0 at the top.
-        float uv_x = (static_cast<float>(px) + 0.5f) / static_cast<float>(frame.width);
-        float uv_y = 1.0f - (static_cast<float>(py) + 0.5f) / static_cast<float>(frame.height);
+    uint32_t next_item = 0;  // warp-uniform cursor into this warp's pixel sequence
 
-        uint32_t rng = pcg_hash(px + py * 1920u + frame.frame_index * 1920u * 1080u);
-
-        // get_camera_ray, plugin.mm:129-153: jitter x is drawn before jitter y.
-        float jx = random_float(rng);
-        float jy = random_float(rng);
-        uv_x += (jx - 0.5f) * 0.001f;
-        uv_y += (jy - 0.5f) * 0.001f;
-        v3 origin = load_v3(frame.position);
-        v3 target = load_v3(frame.lower_left) + load_v3(frame.horizontal) * uv_x +
-                    load_v3(frame.vertical) * uv_y;
-        v3 direction = normalize(target - origin);
-
-        path_result pt = path_trace(scene, origin, direction, rng);
-        rays = pt.rays;
-
-        float norm_depth = fminf(fmaxf((pt.depth - 1.0f) / 4.0f, 0.0f), 1.0f);
-        float4 s_beauty = make_float4(pt.color.x, pt.color.y, pt.color.z, 1.0f);
-        float4 s_albedo = make_float4(pt.albedo.x, pt.albedo.y, pt.albedo.z, 1.0f);
-        float4 s_normal = make_float4(pt.normal.x, pt.normal.y, pt.normal.z, 1.0f);
-        float4 s_depth = make_float4(norm_depth, norm_depth, norm_depth, 1.0f);
-
-        // accumulate, plugin.mm:313-330, in place. History before the first
-        // sample is defined as zero, so sample 0 is stored as is.
-        const size_t idx = static_cast<size_t>(py) * frame.width + px;
-        if (frame.sample_index != 0) {
-            const float w = frame.weight;
-            s_beauty = mix4(beauty[idx], s_beauty, w);
-            s_albedo = mix4(albedo[idx], s_albedo, w);
-            s_normal = mix4(normal[idx], s_normal, w);
-            s_depth = mix4(depth[idx], s_depth, w);
+    while (true) {
+        // Regeneration: idle lanes take the warp's next pixels, compacted.
+        const uint32_t idle = __ballot_sync(0xffffffffu, !active);
+        if (idle != 0u) {
+            if (!active) {
+                const uint32_t item = next_item + __popc(idle & lanes_below);
+                const uint32_t tile = warp_global + (item >> 5) * n_warps;
+                if (tile < n_tiles) {
+                    const uint32_t tile_y = tile / tiles_x;
+                    const uint32_t tile_x = tile - tile_y * tiles_x;
+                    const uint32_t px = tile_x * 8u + (item & 7u);
+                    const uint32_t py = tile_y * 4u + ((item >> 3) & 3u);
+                    if (px < frame.width && py < frame.height) {
+                        // pathtrace_frag, plugin.mm:287-309; uv is the closed form of
+                        // the rasteriser's interpolation, py = 0 on top.
+                        float uv_x = (static_cast<float>(px) + 0.5f) / static_cast<float>(frame.width);
+                        float uv_y = 1.0f - (static_cast<float>(py) + 0.5f) /
+                                                static_cast<float>(frame.height);
+                        rng = pcg_hash(px + py * 1920u + frame.frame_index * 1920u * 1080u);
+                        // get_camera_ray, plugin.mm:129-153: jitter x is drawn before y.
+                        const float jx = random_float(rng);
+                        const float jy = random_float(rng);
+                        uv_x += (jx - 0.5f) * 0.001f;
+                        uv_y += (jy - 0.5f) * 0.001f;
+                        const v3 target = load_v3(frame.lower_left) +
+                                          load_v3(frame.horizontal) * uv_x +
+                                          load_v3(frame.vertical) * uv_y;
+                        ro = cam_origin;
+                        rd = normalize(target - cam_origin);
+                        throughput = make_v3(1.0f, 1.0f, 1.0f);
+                        color = make_v3(0.0f, 0.0f, 0.0f);
+                        bounce = 0;
+                        pixel = static_cast<size_t>(py) * frame.width + px;
+                        active = true;
+                        // The history of this pixel is needed ~1000 cycles from now
+                        // (after the first trace); start pulling it out of HBM.
+                        if (!first_sample) {
+                            prefetch_l2(beauty + pixel);
+                            prefetch_l2(albedo + pixel);
+                            prefetch_l2(normal + pixel);
+                            prefetch_l2(depth + pixel);
+                        }
+                    }
+                }
+            }
+            next_item += __popc(idle);
         }
-        beauty[idx] = s_beauty;
-        albedo[idx] = s_albedo;
-        normal[idx] = s_normal;
-        depth[idx] = s_depth;
+        if (!__any_sync(0xffffffffu, active)) {
+            if (warp_global + (next_item >> 5) * n_warps >= n_tiles) break;
+            continue;  // only off-image pixels of an edge tile were handed out
+        }
+
+        if (active) {
+            // One bounce of path_trace, plugin.mm:232-273.
+            hit_record hit;
+            trace_scene<NQ>(scene, s_shade, ro, rd, hit);
+            rays++;
+            const bool is_hit = hit.index >= 0;
+            const float* sh = s_shade + (is_hit ? hit.index : 0) * k_shade_stride;
+            const float side = (is_hit && !hit.front) ? -1.0f : 1.0f;
+            const v3 n = load_v3(sh + k_sh_normal) * side;  // exact sign flip
+            const v3 q_emission = load_v3(sh + k_sh_emission);
+            const v3 q_albedo = load_v3(sh + k_sh_albedo);
+            const bool is_light = sh[k_sh_is_light] != 0.0f;
+
+            if (bounce == 0) {
+                // First-hit AOVs (plugin.mm:241-249, 300-307) go out now, so the
+                // lane does not carry them to the end of the path.
+                v3 a = make_v3(0.0f, 0.0f, 0.0f), nn = a;
+                float first_t = 0.0f;
+                if (is_hit) {
+                    a = is_light ? q_emission : q_albedo;
+                    nn = make_v3(n.x * 0.5f + 0.5f, n.y * 0.5f + 0.5f, n.z * 0.5f + 0.5f);
+                    first_t = hit.t;
+                }
+                const float nd = fminf(fmaxf((first_t - 1.0f) / 4.0f, 0.0f), 1.0f);
+                accumulate_pixel(albedo, pixel, make_float4(a.x, a.y, a.z, 1.0f), first_sample, weight);
+                accumulate_pixel(normal, pixel, make_float4(nn.x, nn.y, nn.z, 1.0f), first_sample, weight);
+                accumulate_pixel(depth, pixel, make_float4(nd, nd, nd, 1.0f), first_sample, weight);
+            }
+
+            bool done = !is_hit;
+            if (is_hit) {
+                color = color + throughput * q_emission;
+                done = is_light;
+                if (!done) {
+                    throughput = throughput * q_albedo;
+                    if (bounce > 2) {
+                        const float p = fmaxf(0.05f, fmaxf(throughput.x, fmaxf(throughput.y, throughput.z)));
+                        if (random_float(rng) > p) {
+                            done = true;
+                        } else {
+                            throughput = throughput / p;
+                        }
+                    }
+                }
+            }
+            bounce++;
+            done = done || bounce >= max_bounces;  // the shader's last scatter is never observed
+
+            if (!done) {
+                ro = hit.point + n * 0.001f;
+                // cosine_sample_hemisphere (plugin.mm:111-125) with the per-quad frame.
+                const float r1 = random_float(rng);
+                const float r2 = random_float(rng);
+                const float phi = 6.28318548202514648f * r1;  // 2.0f * M_PI_F, exact product
+                const float cos_theta = sqrtf(1.0f - r2);
+                const float sin_theta = sqrtf(r2);
+                double sd, cd;
+                sincos(static_cast<double>(phi), &sd, &cd);
+                const float sin_phi = static_cast<float>(sd);
+                const float cos_phi = static_cast<float>(cd);
+                const v3 fu = load_v3(sh + k_sh_frame_u);
+                const v3 fv = load_v3(sh + k_sh_frame_v) * side;
+                const v3 fw = load_v3(sh + k_sh_frame_w) * side;
+                const v3 d = (fu * cos_phi) * sin_theta + (fv * sin_phi) * sin_theta + fw * cos_theta;
+                rd = normalize(d);
+            } else {
+                accumulate_pixel(beauty, pixel, make_float4(color.x, color.y, color.z, 1.0f),
+                                 first_sample, weight);
+                active = false;
+            }
+        }
     }
 
     // One atomic per warp for the ray statistic (SURVEY.md 8d "Ray counting").
@@ -242,11 +372,23 @@ pathtrace_accumulate_kernel(const __grid_constant__ scene_params scene,
 
 cudaError_t launch_pathtrace_accumulate(const scene_params& scene, const frame_params& frame,
                                         float* const layers[4], unsigned long long* ray_counter,
-                                        cudaStream_t stream) {
-    dim3 grid((frame.width + 15u) / 16u, (frame.height + 15u) / 16u);
-    pathtrace_accumulate_kernel<<<grid, k_block_threads, 0, stream>>>(
-        scene, frame, reinterpret_cast<float4*>(layers[0]), reinterpret_cast<float4*>(layers[1]),
-        reinterpret_cast<float4*>(layers[2]), reinterpret_cast<float4*>(layers[3]), ray_counter);
+                                        int sm_count, cudaStream_t stream) {
+    const uint32_t n_tiles = ((frame.width + 7u) / 8u) * ((frame.height + 3u) / 4u);
+    uint32_t blocks = static_cast<uint32_t>(sm_count) * k_blocks_per_sm;
+    const uint32_t needed = (n_tiles + k_warps_per_block - 1u) / k_warps_per_block;
+    if (needed < blocks) blocks = needed;
+    if (blocks == 0) return cudaSuccess;
+    auto* b = reinterpret_cast<float4*>(layers[0]);
+    auto* a = reinterpret_cast<float4*>(layers[1]);
+    auto* n = reinterpret_cast<float4*>(layers[2]);
+    auto* d = reinterpret_cast<float4*>(layers[3]);
+    if (scene.quad_count <= 16) {
+        pathtrace_accumulate_kernel<16><<<blocks, k_block_threads, 0, stream>>>(scene, frame, b, a, n,
+                                                                              d, ray_counter);
+    } else {
+        pathtrace_accumulate_kernel<32><<<blocks, k_block_threads, 0, stream>>>(scene, frame, b, a, n,
+                                                                              d, ray_counter);
+    }
     return cudaGetLastError();
 }
 

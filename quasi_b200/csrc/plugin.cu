@@ -93,6 +93,7 @@ int g_instances = 0;
 struct plugin_state {
     Q_plugin_context* context = nullptr;
     int device = 0;
+    int sm_count = 148;
     uint32_t shard_index = 0;
     uint32_t shard_count = 1;
     cudaStream_t queue = nullptr;
@@ -129,25 +130,25 @@ bool check(const plugin_state* state, cudaError_t err, const char* what) {
 }
 
 void free_layers(plugin_state* state) {
-    for (auto& l : state->layers) {
-        if (l) cudaFree(l);
-        l = nullptr;
-    }
+    if (state->layers[0]) cudaFree(state->layers[0]);
+    for (auto& l : state->layers) l = nullptr;
 }
 
 /// Counterpart of create_textures (plugin.mm:491-535): four RGBA32F layers,
-/// accumulated in place, so 4 allocations instead of 12.
+/// accumulated in place, so one allocation of 64 B/px instead of twelve textures
+/// of 16 B/px. The layers are contiguous (beauty, albedo, normal, depth) so a
+/// multi-GPU host can reduce all four with a single collective.
 bool create_layers(plugin_state* state, uint32_t width, uint32_t height) {
     if (state->render_pending) cudaEventSynchronize(state->last_render);
     free_layers(state);
-    size_t bytes = static_cast<size_t>(width) * height * 4 * sizeof(float);
-    if (bytes != 0) {
-        for (auto& l : state->layers) {
-            if (!check(state, cudaMalloc(reinterpret_cast<void**>(&l), bytes), "cudaMalloc(layer)")) {
-                free_layers(state);
-                return false;
-            }
+    size_t floats = static_cast<size_t>(width) * height * 4;
+    if (floats != 0) {
+        float* block = nullptr;
+        if (!check(state, cudaMalloc(reinterpret_cast<void**>(&block),
+                                     floats * Q_AOV_COUNT * sizeof(float)), "cudaMalloc(layers)")) {
+            return false;
         }
+        for (int i = 0; i < Q_AOV_COUNT; i++) state->layers[i] = block + floats * i;
     }
     state->last_width = width;
     state->last_height = height;
@@ -229,6 +230,8 @@ Q_PLUGIN_EXPORT Q_plugin_handle* Q_plugin_create(Q_plugin_context* ctx) {
     }
 
     bool ok = check(state, cudaSetDevice(state->device), "cudaSetDevice");
+    ok = ok && check(state, cudaDeviceGetAttribute(&state->sm_count, cudaDevAttrMultiProcessorCount,
+                                                   state->device), "cudaDeviceGetAttribute");
     ok = ok && check(state, cudaEventCreateWithFlags(&state->last_render, cudaEventDisableTiming),
                      "cudaEventCreate");
     ok = ok && check(state, cudaMalloc(reinterpret_cast<void**>(&state->ray_counter),
@@ -320,12 +323,15 @@ Q_PLUGIN_EXPORT void Q_plugin_render(Q_plugin_handle* handle, Q_render_frame* fr
     Q::cuda::prepare_frame(frame->camera.position, frame->camera.target, frame->camera.up,
                            frame->camera.fov, width, height, frame_index, state->frame_count, fp);
 
+    Q::cuda::set_decision_margins(state->scene, frame->camera.position);
+
     // Frames may arrive on different streams (one per frame in flight); the
     // layers are shared, so order this frame after the previous one.
     order_after_render(state, stream);
 
     if (!check(state, Q::cuda::launch_pathtrace_accumulate(state->scene, fp, state->layers,
-                                                          state->ray_counter, stream),
+                                                          state->ray_counter, state->sm_count,
+                                                          stream),
                "pathtrace_accumulate")) {
         return;
     }

@@ -25,39 +25,52 @@ namespace Q::cuda {
 inline constexpr uint32_t k_max_quads = 32;   ///< plugin.mm:21, 30
 inline constexpr uint32_t k_max_bounces = 5;  ///< plugin.mm:22, 31
 
-/// One quad, pre-digested. 40 floats (160 bytes), 16-byte aligned rows so the
-/// constant-bank loads vectorise.
+/// One quad, pre-digested: 52 floats (208 bytes), 16-byte rows so constant-bank
+/// loads vectorise. Three groups: what the fast scan reads for every ray, what
+/// only the exact (literal) test reads, and what shading reads after a hit.
 struct alignas(16) quad_params {
-    float normal[3];   ///< n * rsqrt(dot(n,n)), n = cross(u,v)   (plugin.mm:165-170)
-    float plane_d;     ///< dot(normal, origin)                   (plugin.mm:171)
-    float w[3];        ///< n / dot(n,n)                          (plugin.mm:182)
-    float valid;       ///< 0 when dot(n,n) < 1e-8                (plugin.mm:168)
+    // -- fast scan --
+    float normal[3];        ///< n * rsqrt(dot(n,n)), n = cross(u,v)   (plugin.mm:165-170)
+    float plane_d;          ///< dot(normal, origin)                   (plugin.mm:171)
+    float fast_a[3];        ///< cross(v, w): alpha ~= dot(p - origin, fast_a)
+    float delta;            ///< decision margin for alpha/beta, see prepare_scene
+    float fast_b[3];        ///< cross(w, u): beta  ~= dot(p - origin, fast_b)
+    float one_minus_delta;
     float origin[3];
-    float pad0;
+    float one_plus_delta;
+    // -- exact test only --
+    float w[3];             ///< n / dot(n,n)                          (plugin.mm:182)
+    float valid;            ///< 0 when dot(n,n) < 1e-8                (plugin.mm:168)
     float u[3];
-    float pad1;
+    float fast_len;         ///< max(|fast_a|, |fast_b|), scales delta
     float v[3];
-    float pad2;
+    float pad1;
+    // -- shading (copied to shared memory, 24 floats) --
+    float shade_normal[3];  ///< == normal
+    float is_light;         ///< max(emission) > 0.1                   (plugin.mm:255-256)
     /// Cosine-sampling frame for a hit on the side the normal points to
     /// (plugin.mm:119-122). The other side is exactly (frame_u, -frame_v, -frame_w).
     float frame_u[3];
-    float pad3;
+    float shade_plane_d;    ///< == plane_d
     float frame_v[3];
-    float pad4;
+    float pad3;
     float frame_w[3];
-    float pad5;
+    float pad4;
     float albedo[3];
-    float is_light;    ///< max(emission) > 0.1                   (plugin.mm:255-256)
+    float pad5;
     float emission[3];
     float pad6;
 };
-static_assert(sizeof(quad_params) == 160);
+static_assert(sizeof(quad_params) == 208);
+inline constexpr uint32_t k_shade_offset = 28;  ///< first float of the shading group
+inline constexpr uint32_t k_shade_floats = 24;
 
 struct alignas(16) scene_params {
     quad_params quads[k_max_quads];
     uint32_t quad_count;
     uint32_t max_bounces;
-    uint32_t pad[2];
+    float corner_radius;    ///< farthest quad corner from the world origin
+    uint32_t pad;
 };
 
 /// Per-call camera and sample bookkeeping.
@@ -183,6 +196,16 @@ inline void prepare_scene(const scene_desc& desc, uint32_t max_bounces, scene_pa
     std::memset(&out, 0, sizeof out);
     out.quad_count = desc.quad_count < k_max_quads ? desc.quad_count : k_max_quads;
     out.max_bounces = max_bounces;
+
+    float corner_radius = 0.0f;
+    for (uint32_t i = 0; i < out.quad_count; i++) {
+        const quad_desc& q = desc.quads[i];
+        for (int c = 0; c < 4; c++) {
+            f3 corner = load3(q.origin) + load3(q.u) * float(c & 1) + load3(q.v) * float(c >> 1);
+            corner_radius = std::fmax(corner_radius, std::sqrt(dot(corner, corner)));
+        }
+    }
+    out.corner_radius = corner_radius;
     for (uint32_t i = 0; i < out.quad_count; i++) {
         const quad_desc& q = desc.quads[i];
         quad_params& g = out.quads[i];
@@ -204,8 +227,20 @@ inline void prepare_scene(const scene_desc& desc, uint32_t max_bounces, scene_pa
         g.valid = 1.0f;
         f3 normal = n * (1.0f / std::sqrt(area_sq));
         store3(g.normal, normal);
+        store3(g.shade_normal, normal);
         g.plane_d = dot(normal, origin);
-        store3(g.w, n / area_sq);
+        g.shade_plane_d = g.plane_d;
+        f3 wv = n / area_sq;
+        store3(g.w, wv);
+
+        // Fast-scan helpers. alpha = dot(w, cross(planar, v)) equals
+        // dot(planar, cross(v, w)) in exact arithmetic; in binary32 the two
+        // differ by a few ulps of |planar||a|. See set_decision_margins().
+        f3 fa = cross(v, wv);
+        f3 fb = cross(wv, u);
+        store3(g.fast_a, fa);
+        store3(g.fast_b, fb);
+        g.fast_len = std::fmax(std::sqrt(dot(fa, fa)), std::sqrt(dot(fb, fb)));
 
         // cosine_sample_hemisphere's basis for hit.normal == normal.
         f3 w = normalize(normal);
@@ -215,6 +250,29 @@ inline void prepare_scene(const scene_desc& desc, uint32_t max_bounces, scene_pa
         store3(g.frame_u, fu);
         store3(g.frame_v, fv);
         store3(g.frame_w, w);
+    }
+}
+
+/// @brief Sets the per-quad decision margin of the fast scan for a camera position.
+///
+/// The fast scan decides "is the plane hit inside the quad" from
+/// alpha' = dot(p' - origin, fast_a) with p' = ro + rd * t', t' = num * rcp(denom).
+/// Against the literal alpha of plugin.mm:179-184 that differs by at most about
+/// |fast_a| * R * (16 * 2^-24 + 2 * 2^-21) ~= 1.9e-6 * |fast_a| * R, where R
+/// bounds the distance of ray origins and hit points from the world origin
+/// (rounding of both forms plus the error of the approximate t). delta is 13x
+/// that bound. A candidate within delta of an edge is handed to the literal
+/// test, so delta trades speed for nothing else: it never reaches a pixel.
+inline void set_decision_margins(scene_params& scene, const float camera_position[3]) {
+    using namespace detail;
+    f3 c = load3(camera_position);
+    float radius = std::fmax(scene.corner_radius, std::sqrt(dot(c, c)));
+    for (uint32_t i = 0; i < scene.quad_count; i++) {
+        quad_params& g = scene.quads[i];
+        float delta = std::fmax(1e-5f, 2.5e-5f * g.fast_len * radius);
+        g.delta = delta;
+        g.one_minus_delta = 1.0f - delta;
+        g.one_plus_delta = 1.0f + delta;
     }
 }
 

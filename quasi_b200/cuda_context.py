@@ -63,7 +63,8 @@ class cuda_context:
 
     @classmethod
     def create(cls, width: int, height: int, device_ordinal: int = 0, shard_index: int = 0,
-               shard_count: int = 1, present: bool = False) -> "cuda_context":
+               shard_count: int = 1, present: bool = False,
+               single_stream: bool = False) -> "cuda_context":
         import torch
 
         if not torch.cuda.is_available():
@@ -77,7 +78,12 @@ class cuda_context:
         self._desc.shard_index = shard_index
         self._desc.shard_count = shard_count
         self._queue = torch.cuda.Stream(self.device)
-        self._streams = [torch.cuda.Stream(self.device) for _ in range(K_MAX_FRAMES_IN_FLIGHT)]
+        if single_stream:
+            # every frame on one stream (still at most 3 in flight): lets a caller
+            # bracket a run of frames with CUDA events on that stream
+            self._streams = [torch.cuda.Stream(self.device)] * K_MAX_FRAMES_IN_FLIGHT
+        else:
+            self._streams = [torch.cuda.Stream(self.device) for _ in range(K_MAX_FRAMES_IN_FLIGHT)]
         self._events = [None] * K_MAX_FRAMES_IN_FLIGHT
         self._gpu.backend = abi.Q_GPU_BACKEND_CUDA
         self._gpu.device = C.cast(C.pointer(self._desc), C.c_void_p)
@@ -122,6 +128,9 @@ class cuda_context:
         ev.record(self._streams[slot])
         self._events[slot] = ev
         self._frame_slot = (slot + 1) % K_MAX_FRAMES_IN_FLIGHT
+
+    def frame_stream(self, slot: int = 0):
+        return self._streams[slot]
 
     def drawable_tensor(self):
         return self._drawable_tensor

@@ -16,7 +16,8 @@ from .loader import dynamic_library, loader
 
 class headless_host:
     def __init__(self, width: int, height: int, plugin_path=PLUGIN_PATH, device_ordinal: int = 0,
-                 shard_index: int = 0, shard_count: int = 1, present: bool = False, log=None):
+                 shard_index: int = 0, shard_count: int = 1, present: bool = False, log=None,
+                 single_stream: bool = False):
         self.messages = []
         self._user_log = log
 
@@ -27,7 +28,7 @@ class headless_host:
                 self._user_log(text)
 
         self.context = cuda_context.create(width, height, device_ordinal, shard_index, shard_count,
-                                           present=present)
+                                           present=present, single_stream=single_stream)
         self.library = dynamic_library.open(plugin_path)
         self.plugin_context = self.context.make_plugin_context(log=_log)
         self.plugin = loader.load(self.library, self.plugin_context)
