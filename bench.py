@@ -104,17 +104,6 @@ class clock_sampler(threading.Thread):
                 "power_w_max": round(max(self.power), 1) if self.power else None, "samples": len(s)}
 
 
-def device_tensor(ptr: int, n_floats: int, device):
-    """A torch view of plugin-owned device memory (CUDA array interface, no copy)."""
-    import torch
-
-    class _holder:
-        __cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (ptr, False),
-                                    "version": 2, "strides": None}
-
-    return torch.as_tensor(_holder(), device=device)
-
-
 # ---------------------------------------------------------------- CPU arm ----
 
 def cpu_arm(budget_s: float, steps: int, warmup: int):
@@ -205,28 +194,22 @@ def run_ours(args):
     device = host.context.device
     stream = host.context.frame_stream()
     n_px = WIDTH * HEIGHT
-    combine = host.plugin.fn("Q_cuda_combine_shards")
-    result = torch.empty(n_px * 16, dtype=torch.float32, device=device) if world > 1 else None
+    reducer = None
+    if world > 1:
+        from quasi_b200.multi_gpu import shard_reducer
+
+        reducer = shard_reducer(host, dist, mode=args.reduce)
+        pinned = torch.empty(n_px * 16, dtype=torch.float32).pin_memory() if rank == 0 else None
 
     def render_frame_set():
         host.render_frame(camera_dirty=True)
         for _ in range(SPP - 1):
             host.render_frame(camera_dirty=False)
 
-    def reduce_to_root():
-        """One sum-reduce of all four layers over NVLink, then the 1/N scale on rank 0."""
-        layers = host.plugin.cuda_layers(stream.cuda_stream)
-        block = device_tensor(layers.device_ptr[0], n_px * 16, device)
-        with torch.cuda.stream(stream):
-            dist.reduce(block, dst=0, op=dist.ReduceOp.SUM)
-        if rank == 0:
-            ptrs = (C.c_void_p * 1)(layers.device_ptr[0])
-            combine(ptrs, 1, n_px * 4, 1.0 / world, result.data_ptr(), None, stream.cuda_stream)
-
     def step():
         render_frame_set()
-        if world > 1:
-            reduce_to_root()
+        if reducer is not None:
+            reducer.combine()  # one exchange per frame: sum over ranks, 1/N scale, result on rank 0
 
     def barrier():
         torch.cuda.synchronize(device)
@@ -251,15 +234,21 @@ def run_ours(args):
     ms_total = ev0.elapsed_time(ev1)
     s1 = host.stats()
     rays_local = s1.rays - s0.rays
-    launches_local = s1.kernel_launches - s0.kernel_launches + (args.steps if (world > 1 and rank == 0) else 0)
+    launches_local = s1.kernel_launches - s0.kernel_launches + (reducer.launches if reducer else 0)
 
     # ---- end to end through the public API with host buffers (e2e) ----
     def e2e_step():
         step()
-        if world == 1 or rank == 0:
+        if world == 1:
             rb = host.plugin.readback_aov()          # blocking D2H of the four layers
             assert rb.buffers[0].data, "readback returned no data"
             host.plugin.readback_aov_free(rb)
+        elif rank == 0:
+            from quasi_b200.multi_gpu import device_tensor
+
+            with torch.cuda.stream(stream):          # the combined layers, D2H into pinned memory
+                pinned.copy_(device_tensor(reducer.result_ptr, n_px * 16, device), non_blocking=True)
+            stream.synchronize()
 
     for _ in range(min(args.warmup, 3)):
         e2e_step()
@@ -306,7 +295,9 @@ def run_ours(args):
                 "workload": f"demo scene {WIDTH}x{HEIGHT}, {SPP} spp per GPU per frame "
                             f"({SPP * world} spp total), 5 bounces, 4 AOV layers, plugin C ABI",
                 "spp_per_gpu": SPP, "spp_total": SPP * world, "render_calls_per_step": SPP,
-                "parallelism": f"sample-sharded x{world}" + (", 1 NCCL sum-reduce/frame" if world > 1 else ""),
+                "parallelism": f"sample-sharded x{world}" + (
+                    f", 1 {args.reduce} combine/frame (sum over ranks, 1/N scale, result on rank 0)"
+                    if world > 1 else ""),
                 "l2": "no flush: each launch streams the 132.7 MB accumulation set, larger than the 126 MB L2",
                 "rays_per_step": rays_step,
             },
@@ -330,6 +321,13 @@ def run_ours(args):
             line["cpu_baseline"] = desc
         print(json.dumps(line), flush=True)
 
+    if reducer is not None:
+        dist.barrier()
+        if rank != 0:
+            reducer.close()   # unmap peers before their owners free
+        dist.barrier()
+        if rank == 0:
+            reducer.close()
     host.close()
     if dist is not None:
         dist.barrier()
@@ -342,6 +340,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--reduce", choices=["p2p", "nccl"], default="p2p",
+                    help="multi-GPU combine: fused peer-memory kernel (default) or NCCL reduce + scale")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--cpu-budget", type=float, default=0.0, help="seconds of CPU work for the CPU legs")
     args = ap.parse_args()

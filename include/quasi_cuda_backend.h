@@ -98,6 +98,26 @@ Q_PLUGIN_EXPORT int Q_cuda_combine_shards(const float* const* shards, uint32_t n
                                           uint64_t n_pixels, float scale, float* out, void* bgra,
                                           void* stream);
 
+/* ---- multi-process peer access (one process per GPU) --------
+ * The accumulation layers of every rank are made addressable from every other
+ * rank with CUDA IPC, so the sample-shard reduce can be ONE kernel per GPU that
+ * loads the peers' layers over NVLink and stores its slice of the result
+ * straight into the root GPU's buffer (Q_cuda_combine_shards on peer-mapped
+ * pointers): a reduce-scatter and a gather with no staging copy. */
+typedef struct Q_cuda_ipc_handle {
+    unsigned char bytes[64]; /* cudaIpcMemHandle_t */
+} Q_cuda_ipc_handle;
+
+/* Plain device memory owned by the library (cudaMalloc), exportable below. */
+Q_PLUGIN_EXPORT int Q_cuda_alloc(uint64_t bytes, void** out_device_ptr);
+Q_PLUGIN_EXPORT int Q_cuda_free(void* device_ptr);
+/* Export a Q_cuda_alloc'd buffer, or the plugin's contiguous layer block
+ * (device_ptr[0] of Q_cuda_plugin_layers). */
+Q_PLUGIN_EXPORT int Q_cuda_ipc_export(void* device_ptr, Q_cuda_ipc_handle* out);
+/* Map another process's buffer into this process; enables peer access lazily. */
+Q_PLUGIN_EXPORT int Q_cuda_ipc_open(const Q_cuda_ipc_handle* handle, void** out_device_ptr);
+Q_PLUGIN_EXPORT int Q_cuda_ipc_close(void* device_ptr);
+
 #ifdef __cplusplus
 } /* extern "C" */
 #endif

@@ -81,6 +81,10 @@ class Q_cuda_layers(C.Structure):
                 ("height", C.c_uint32), ("frame_count", C.c_uint32), ("reserved", C.c_uint32)]
 
 
+class Q_cuda_ipc_handle(C.Structure):
+    _fields_ = [("bytes", C.c_ubyte * 64)]
+
+
 # Sizes on x86-64 Linux (probed from the reference headers).
 assert C.sizeof(Q_plugin_context) == 40
 assert C.sizeof(Q_render_frame) == 72
@@ -99,5 +103,6 @@ OPTIONAL_SYMBOLS = (  # loader.hpp:115-128
 )
 CUDA_EXTENSION_SYMBOLS = (  # quasi_cuda_backend.h
     "Q_cuda_plugin_stats", "Q_cuda_plugin_layers", "Q_cuda_accumulate", "Q_cuda_tonemap_bgra8",
-    "Q_cuda_combine_shards",
+    "Q_cuda_combine_shards", "Q_cuda_alloc", "Q_cuda_free", "Q_cuda_ipc_export", "Q_cuda_ipc_open",
+    "Q_cuda_ipc_close",
 )

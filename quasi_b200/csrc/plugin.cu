@@ -477,4 +477,48 @@ Q_PLUGIN_EXPORT int Q_cuda_combine_shards(const float* const* shards, uint32_t n
                                           static_cast<cudaStream_t>(stream)) == cudaSuccess ? 0 : -1;
 }
 
+Q_PLUGIN_EXPORT int Q_cuda_alloc(uint64_t bytes, void** out_device_ptr) {
+    if (!out_device_ptr) return -1;
+    *out_device_ptr = nullptr;
+    if (cudaMalloc(out_device_ptr, bytes) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return -1;
+    }
+    return 0;
+}
+
+Q_PLUGIN_EXPORT int Q_cuda_free(void* device_ptr) {
+    if (!device_ptr) return 0;
+    return cudaFree(device_ptr) == cudaSuccess ? 0 : -1;
+}
+
+Q_PLUGIN_EXPORT int Q_cuda_ipc_export(void* device_ptr, Q_cuda_ipc_handle* out) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == sizeof(Q_cuda_ipc_handle));
+    if (!device_ptr || !out) return -1;
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, device_ptr) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return -1;
+    }
+    std::memcpy(out->bytes, &h, sizeof h);
+    return 0;
+}
+
+Q_PLUGIN_EXPORT int Q_cuda_ipc_open(const Q_cuda_ipc_handle* handle, void** out_device_ptr) {
+    if (!handle || !out_device_ptr) return -1;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle->bytes, sizeof h);
+    *out_device_ptr = nullptr;
+    if (cudaIpcOpenMemHandle(out_device_ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return -1;
+    }
+    return 0;
+}
+
+Q_PLUGIN_EXPORT int Q_cuda_ipc_close(void* device_ptr) {
+    if (!device_ptr) return 0;
+    return cudaIpcCloseMemHandle(device_ptr) == cudaSuccess ? 0 : -1;
+}
+
 }  // extern "C"
