@@ -22,13 +22,62 @@ PLUGIN_HDRS := $(CSRC)/kernels.hpp $(CSRC)/scene_params.hpp include/quasi_plugin
                include/quasi_cuda_backend.h
 PLUGIN_SO := quasi_b200/lib/libquasi_cuda.so
 
-all: plugin oracle
+all: plugin host oracle
 
 plugin: $(PLUGIN_SO)
 
 $(PLUGIN_SO): $(PLUGIN_SRCS) $(PLUGIN_HDRS)
 	mkdir -p $(dir $@)
 	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(PLUGIN_SRCS)
+
+# ---- C++ headless host (g++ -std=c++23, the reference's .bazelrc flags) ----
+HOST := quasi_b200/host
+CXX ?= g++
+HOST_CXXFLAGS := -std=c++23 -O2 -Wall -Wextra -Wpedantic -fcoroutines -pthread -fvisibility=hidden -fPIC \
+                 -ffp-contract=off -I$(HOST)/include -Iinclude -I/usr/local/cuda/include
+HOST_HDRS := $(shell find $(HOST)/include -name '*.hpp') include/quasi_plugin_abi.h include/quasi_cuda_backend.h
+HOST_BIN := quasi_b200/bin/quasi_headless
+
+host: $(HOST_BIN)
+
+$(HOST_BIN): $(HOST)/src/main.cpp $(HOST)/src/cuda_context.cpp $(HOST)/src/exr_writer.cpp $(HOST_HDRS)
+	mkdir -p $(dir $@)
+	$(CXX) $(HOST_CXXFLAGS) -o $@ $(HOST)/src/main.cpp $(HOST)/src/cuda_context.cpp $(HOST)/src/exr_writer.cpp \
+		-L/usr/local/cuda/lib64 -lcudart -lz -ldl
+
+# C++ tests: this repository's host tests (with a fake plugin fixture) and, where
+# /root/reference exists, the reference's own three test files compiled unmodified
+# from where they lie against this repository's headers.
+TESTDIR := quasi_b200/bin/tests
+# ASan + UBSan where the toolchain ships the runtime (some g++ installs do not).
+SANITIZE := $(shell echo 'int main(){}' | $(CXX) -fsanitize=address,undefined -x c++ - -o /dev/null 2>/dev/null \
+              && echo -fsanitize=address,undefined)
+TEST_CXXFLAGS := $(HOST_CXXFLAGS) -O1 -g $(SANITIZE) -I$(HOST)/test
+FAKE_SRC := $(HOST)/test/fake_plugin.cpp
+
+host-tests: $(TESTDIR)/host_test $(TESTDIR)/exr_write_tool
+	if [ -d $(REFERENCE)/test ]; then $(MAKE) reference-tests; fi
+
+$(TESTDIR)/host_test: $(HOST)/test/host_test.cpp $(HOST)/test/catch2_main.cpp $(HOST)/src/exr_writer.cpp \
+		$(FAKE_SRC) $(HOST_HDRS) $(HOST)/test/catch2/catch_test_macros.hpp
+	mkdir -p $(TESTDIR)
+	$(CXX) -std=c++20 -O1 -fPIC -shared -Iinclude -DFAKE_PLUGIN_GENERATION=1 $(FAKE_SRC) -o $(TESTDIR)/libfake_v1.so
+	$(CXX) -std=c++20 -O1 -fPIC -shared -Iinclude -DFAKE_PLUGIN_GENERATION=2 $(FAKE_SRC) -o $(TESTDIR)/libfake_v2.so
+	$(CXX) -std=c++20 -O1 -fPIC -shared -Iinclude -DFAKE_PLUGIN_ABI=99 $(FAKE_SRC) -o $(TESTDIR)/libfake_bad_abi.so
+	$(CXX) -std=c++20 -O1 -fPIC -shared -Iinclude -DFAKE_PLUGIN_NO_READBACK $(FAKE_SRC) -o $(TESTDIR)/libfake_minimal.so
+	$(CXX) $(TEST_CXXFLAGS) -o $@ $(HOST)/test/host_test.cpp $(HOST)/test/catch2_main.cpp \
+		$(HOST)/src/exr_writer.cpp -lz -ldl
+
+$(TESTDIR)/exr_write_tool: $(HOST)/test/exr_write_tool.cpp $(HOST)/src/exr_writer.cpp $(HOST_HDRS)
+	mkdir -p $(TESTDIR)
+	$(CXX) $(TEST_CXXFLAGS) -o $@ $(HOST)/test/exr_write_tool.cpp $(HOST)/src/exr_writer.cpp -lz
+
+reference-tests:
+	mkdir -p $(TESTDIR)
+	for t in async_test plugin_test exr_writer_test; do \
+		$(CXX) $(TEST_CXXFLAGS) -o $(TESTDIR)/ref_$$t $(REFERENCE)/test/$$t.cpp $(HOST)/test/catch2_main.cpp \
+			$(HOST)/src/exr_writer.cpp -lz -ldl || exit 1; \
+	done
 
 oracle:
 	$(MAKE) -C oracle all
@@ -38,7 +87,7 @@ ptxas-info:
 	$(NVCC) $(NVCCFLAGS) -Xptxas -v -shared -o /tmp/libquasi_cuda_v.so $(PLUGIN_SRCS)
 
 clean:
-	rm -rf quasi_b200/lib
+	rm -rf quasi_b200/lib quasi_b200/bin
 	$(MAKE) -C oracle clean
 
-.PHONY: all plugin oracle clean ptxas-info
+.PHONY: all plugin host host-tests reference-tests oracle clean ptxas-info
