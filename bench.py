@@ -55,7 +55,7 @@ def measured_peaks():
 
 
 class clock_sampler(threading.Thread):
-    """Samples SM clocks and throttle reasons of one GPU every 100 ms via NVML."""
+    """Samples SM clocks and throttle reasons of one GPU every 20 ms via NVML."""
 
     REASONS = {
         0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap",
@@ -91,7 +91,7 @@ class clock_sampler(threading.Thread):
                 self.power.append(self.nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
             except Exception:
                 pass
-            self._stop_evt.wait(0.1)
+            self._stop_evt.wait(0.02)
 
     def stop(self):
         self._stop_evt.set()
@@ -222,6 +222,7 @@ def run_ours(args):
         step()
     barrier()
     s0 = host.stats()
+    reducer_launches0 = reducer.launches if reducer else 0
     sampler = clock_sampler(local_rank)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -234,7 +235,7 @@ def run_ours(args):
     ms_total = ev0.elapsed_time(ev1)
     s1 = host.stats()
     rays_local = s1.rays - s0.rays
-    launches_local = s1.kernel_launches - s0.kernel_launches + (reducer.launches if reducer else 0)
+    launches_local = s1.kernel_launches - s0.kernel_launches + (reducer.launches - reducer_launches0 if reducer else 0)
 
     # ---- end to end through the public API with host buffers (e2e) ----
     def e2e_step():
@@ -285,7 +286,7 @@ def run_ours(args):
                     "dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        param_bytes = SPP * (C.sizeof(C.c_float) * 0 + 5136 + 80)  # scene_params + frame_params per launch
+        param_bytes = SPP * (7344 + 80)  # sizeof(scene_params) + sizeof(frame_params) per launch
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": "Mrays/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4),

@@ -98,6 +98,11 @@ Q_PLUGIN_EXPORT int Q_cuda_combine_shards(const float* const* shards, uint32_t n
                                           uint64_t n_pixels, float scale, float* out, void* bgra,
                                           void* stream);
 
+/* Test hook: the path tracer's sin/cos (correctly rounded binary32, evaluated in
+ * binary64) of n device floats phi[i] in [0, 2*pi]. */
+Q_PLUGIN_EXPORT int Q_cuda_probe_sincos(const float* phi, float* sin_out, float* cos_out,
+                                        uint64_t n, void* stream);
+
 /* ---- multi-process peer access (one process per GPU) --------
  * The accumulation layers of every rank are made addressable from every other
  * rank with CUDA IPC, so the sample-shard reduce can be ONE kernel per GPU that

@@ -43,6 +43,12 @@ static inline float q_max(float a, float b) { return a > b ? a : b; }
 float qo_sin(float x) { return (float)sin((double)x); }
 float qo_cos(float x) { return (float)cos((double)x); }
 float qo_tan(float x) { return (float)tan((double)x); }
+void qo_sincos_array(const float* phi, uint64_t n, float* sin_out, float* cos_out) {
+    for (uint64_t i = 0; i < n; i++) {
+        sin_out[i] = qo_sin(phi[i]);
+        cos_out[i] = qo_cos(phi[i]);
+    }
+}
 static inline float q_pow(float x, float y) { return (float)pow((double)x, (double)y); }
 
 #define Q_PI_F 3.14159265358979323846264338327950288f /* MSL M_PI_F */

@@ -150,6 +150,7 @@ void qo_combine_shards(const float* const* shards, uint32_t n_shards,
 float qo_sin(float x);
 float qo_cos(float x);
 float qo_tan(float x);
+void qo_sincos_array(const float* phi, uint64_t n, float* sin_out, float* cos_out);
 
 int qo_online_cores(void);
 

@@ -21,6 +21,10 @@ cudaError_t launch_pathtrace_accumulate(const scene_params& scene, const frame_p
                                         float* const layers[4], unsigned long long* ray_counter,
                                         int sm_count, cudaStream_t stream);
 
+/// @brief Test hook: the kernel's sin/cos of phi in [0, 2*pi], element-wise.
+cudaError_t launch_sincos_probe(const float* phi, float* sin_out, float* cos_out, uint64_t n,
+                                cudaStream_t stream);
+
 /// @brief output = mix(history, current, 1/(frame_count+1)) over n_pixels float4s.
 cudaError_t launch_accumulate(const float* current, const float* history, float* output,
                               uint64_t n_pixels, uint32_t frame_count, cudaStream_t stream);

@@ -53,7 +53,36 @@ __device__ __forceinline__ float dot(v3 a, v3 b) { return a.x * b.x + a.y * b.y 
 __device__ __forceinline__ v3 cross(v3 a, v3 b) {
     return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
 }
-__device__ __forceinline__ v3 normalize(v3 a) { return a / sqrtf(dot(a, a)); }
+
+/// One MUFU.RCP, relative error <= 2^-23.
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+/// {a.x/b, a.y/b, a.z/b}: three correctly rounded IEEE quotients sharing one
+/// reciprocal. This is the sequence nvcc itself emits for x / b (MUFU.RCP, two
+/// FFMAs to refine it, the product, the exact remainder, the correction) with the
+/// common part hoisted; it is exact when no intermediate can leave the normal
+/// range, which the guard checks. Anything else takes the plain divisions, so the
+/// result is always the bits of a.x / b, a.y / b, a.z / b.
+__device__ __forceinline__ v3 div3(v3 a, float b) {
+    constexpr float big = 0x1p+100f, tiny = 0x1p-100f;
+    auto in_range = [&](float x) { return (fabsf(x) >= tiny && fabsf(x) < big) || x == 0.0f; };
+    if (b > tiny && b < big && in_range(a.x) && in_range(a.y) && in_range(a.z)) {
+        const float r0 = rcp_approx(b);
+        const float r = __fmaf_rn(r0, __fmaf_rn(-b, r0, 1.0f), r0);
+        auto quotient = [&](float x) {
+            const float q = __fmul_rn(x, r);
+            return __fmaf_rn(__fmaf_rn(-q, b, x), r, q);
+        };
+        return {quotient(a.x), quotient(a.y), quotient(a.z)};
+    }
+    return a / b;
+}
+
+__device__ __forceinline__ v3 normalize(v3 a) { return div3(a, sqrtf(dot(a, a))); }
 
 /// plugin.mm:98-102
 __device__ __forceinline__ uint32_t pcg_hash(uint32_t input) {
@@ -67,13 +96,6 @@ __device__ __forceinline__ uint32_t pcg_hash(uint32_t input) {
 __device__ __forceinline__ float random_float(uint32_t& state) {
     state = pcg_hash(state);
     return __uint2float_rn(state) * 2.3283064365386963e-10f;
-}
-
-/// One MUFU.RCP, relative error <= 2^-23. Only ever feeds decisions with margins.
-__device__ __forceinline__ float rcp_approx(float x) {
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
 }
 
 __device__ __forceinline__ void prefetch_l2(const void* p) {
@@ -97,7 +119,8 @@ __device__ __noinline__ void trace_scene_exact(const scene_params& scene, v3 ro,
     closest.point = make_v3(0.0f, 0.0f, 0.0f);
     const uint32_t count = scene.quad_count;
 #pragma unroll 1
-    for (uint32_t i = 0; i < count; i++) {
+    for (uint32_t k = 0; k < count; k++) {  // original order: the later index wins a tie
+        const uint32_t i = scene.scene_order[k];
         const quad_params& q = scene.quads[i];
         if (q.valid == 0.0f) continue;
         v3 normal = load_v3(q.normal);
@@ -133,57 +156,207 @@ constexpr float k_t_min_lo = 0.001f * (1.0f - 4e-6f);  // below: surely t < t_mi
 constexpr float k_t_min_hi = 0.001f * (1.0f + 4e-6f);  // above: surely t >= t_min
 constexpr float k_tie = 1.0f + 4e-6f;                  // two hits closer than this: literal scan
 
-/// Closest hit of one ray against the NQ first quads. Same result, bit for bit,
+struct scan_state {
+    float best_t = k_inf;        ///< smallest t' among quads that are surely hit
+    float challenger_t = k_inf;  ///< smallest t' among every other quad that may be hit
+    int best_i = -1;
+};
+
+/// Files one plane hit. `m` = max(|alpha' - 1/2|, |beta' - 1/2|): the point is
+/// surely outside the quad beyond half_plus and surely inside within half_minus.
+__device__ __forceinline__ void consider(scan_state& s, const quad_params& q, int i, float t_fast,
+                                         float m) {
+    const bool maybe = m <= q.half_plus;
+    const bool sure = m < q.half_minus && t_fast > k_t_min_hi;
+    const bool better = sure && t_fast < s.best_t;
+    // Whoever does not become the winner challenges it.
+    const float loser = better ? s.best_t : (maybe ? t_fast : k_inf);
+    s.challenger_t = fminf(s.challenger_t, loser);
+    s.best_t = better ? t_fast : s.best_t;
+    s.best_i = better ? i : s.best_i;
+}
+
+__device__ __forceinline__ float axis(v3 a, int k) { return k == 0 ? a.x : (k == 1 ? a.y : a.z); }
+
+/// Quad whose normal is along axis K (two normal components are exactly zero, so
+/// the shader's three-term dot products collapse to one product, bit for bit)
+/// and whose barycentrics do not depend on coordinate K.
+template <int K>
+__device__ __forceinline__ void scan_flat(scan_state& s, const quad_params& q, int i, v3 ro, v3 rd) {
+    constexpr int I = (K + 1) % 3, J = (K + 2) % 3;
+    const float denom = q.normal[K] * axis(rd, K);
+    const float num = q.plane_d - q.normal[K] * axis(ro, K);
+    const float t_fast = num * rcp_approx(denom);
+    if (fabsf(denom) >= 1e-8f && t_fast > k_t_min_lo) {
+        const float pi = (axis(ro, I) + axis(rd, I) * t_fast) - q.center[I];
+        const float pj = (axis(ro, J) + axis(rd, J) * t_fast) - q.center[J];
+        const float alpha = pi * q.fast_a[I] + pj * q.fast_a[J];
+        const float beta = pi * q.fast_b[I] + pj * q.fast_b[J];
+        consider(s, q, i, t_fast, fmaxf(fabsf(alpha), fabsf(beta)));
+    }
+}
+
+/// Quad with a horizontal normal and one vertical edge (the side of a box
+/// standing on the floor): alpha lives in (x, z), beta along y.
+__device__ __forceinline__ void scan_upright(scan_state& s, const quad_params& q, int i, v3 ro, v3 rd) {
+    const float denom = q.normal[0] * rd.x + q.normal[2] * rd.z;
+    const float num = q.plane_d - (q.normal[0] * ro.x + q.normal[2] * ro.z);
+    const float t_fast = num * rcp_approx(denom);
+    if (fabsf(denom) >= 1e-8f && t_fast > k_t_min_lo) {
+        const float px = (ro.x + rd.x * t_fast) - q.center[0];
+        const float py = (ro.y + rd.y * t_fast) - q.center[1];
+        const float pz = (ro.z + rd.z * t_fast) - q.center[2];
+        const float alpha = px * q.fast_a[0] + pz * q.fast_a[2];
+        const float beta = py * q.fast_b[1];
+        consider(s, q, i, t_fast, fmaxf(fabsf(alpha), fabsf(beta)));
+    }
+}
+
+__device__ __forceinline__ void scan_general(scan_state& s, const quad_params& q, int i, v3 ro, v3 rd) {
+    const v3 normal = load_v3(q.normal);
+    const float denom = dot(normal, rd);            // the shader's value
+    const float num = q.plane_d - dot(normal, ro);  // the shader's value
+    const float t_fast = num * rcp_approx(denom);
+    if (fabsf(denom) >= 1e-8f && t_fast > k_t_min_lo) {
+        const v3 planar = (ro + rd * t_fast) - load_v3(q.center);
+        const float alpha = dot(planar, load_v3(q.fast_a));
+        const float beta = dot(planar, load_v3(q.fast_b));
+        consider(s, q, i, t_fast, fmaxf(fabsf(alpha), fabsf(beta)));
+    }
+}
+
+/// How many quads of each shape a scene has, known at compile time: the scan is
+/// then fully unrolled with every constant an immediate constant-bank operand.
+/// The sorted table order is general, flat_x, flat_y, flat_z, upright.
+template <int GEN, int FX, int FY, int FZ, int UP>
+struct fixed_layout {
+    static constexpr bool fixed = true;
+    static constexpr int general = GEN, flat_x = FX, flat_y = FY, flat_z = FZ, upright = UP;
+    static constexpr int begin_general = 0, begin_flat_x = GEN, begin_flat_y = GEN + FX,
+                         begin_flat_z = GEN + FX + FY, begin_upright = GEN + FX + FY + FZ;
+    static bool matches(const scene_params& s) {
+        const int want[k_shape_count + 1] = {0, GEN, GEN + FX, GEN + FX + FY, GEN + FX + FY + FZ,
+                                             GEN + FX + FY + FZ + UP};
+        for (uint32_t k = 0; k <= k_shape_count; k++) {
+            if (s.shape_begin[k] != static_cast<uint32_t>(want[k])) return false;
+        }
+        return true;
+    }
+};
+/// Any scene: one loop per shape with launch-uniform bounds.
+struct dynamic_layout {
+    static constexpr bool fixed = false;
+};
+/// The demo scene (make_cornell_box): 2 side walls, floor + ceiling + light + 2 box
+/// tops, the back wall, 8 box sides.
+using cornell_layout = fixed_layout<0, 2, 5, 1, 8>;
+
+/// Closest hit of one ray against the scene. Same result, bit for bit,
 /// as trace_scene_exact. `shade` is the shared-memory copy of the quads' shading
 /// records; the winner's plane is re-read from it for the literal finalisation.
-template <int NQ>
+///
+/// plugin.mm:174 (|denom| < 1e-8) is decided exactly in every form; plugin.mm:177
+/// (t < t_min) and plugin.mm:186 (alpha, beta in [0,1]) with margins.
+template <class Layout>
 __device__ __forceinline__ void trace_scene(const scene_params& scene, const float* shade, v3 ro,
                                             v3 rd, hit_record& hit) {
-    float best_t = k_inf;        // smallest t' among quads that are surely hit
-    float challenger_t = k_inf;  // smallest t' among every other quad that may be hit
-    int best_i = -1;
-
+    scan_state s;
+    if constexpr (Layout::fixed) {
 #pragma unroll
-    for (int i = 0; i < NQ; i++) {
-        const quad_params& q = scene.quads[i];
-        if (q.valid == 0.0f) continue;  // launch-uniform
-        const v3 normal = load_v3(q.normal);
-        const float denom = dot(normal, rd);            // the shader's value
-        const float num = q.plane_d - dot(normal, ro);  // the shader's value
-        const float t_fast = num * rcp_approx(denom);
-        // plugin.mm:174 exactly; plugin.mm:177 (t < t_min) with a margin
-        if (fabsf(denom) >= 1e-8f && t_fast > k_t_min_lo) {
-            const v3 planar = (ro + rd * t_fast) - load_v3(q.origin);
-            const float alpha = dot(planar, load_v3(q.fast_a));
-            const float beta = dot(planar, load_v3(q.fast_b));
-            const float lo = fminf(alpha, beta);
-            const float hi = fmaxf(alpha, beta);
-            const bool maybe = lo >= -q.delta && hi <= q.one_plus_delta;  // else surely outside
-            const bool sure = lo > q.delta && hi < q.one_minus_delta && t_fast > k_t_min_hi;
-            const bool better = maybe && sure && t_fast < best_t;
-            // Whoever does not become the winner challenges it.
-            const float loser = better ? best_t : (maybe ? t_fast : k_inf);
-            challenger_t = fminf(challenger_t, loser);
-            best_t = better ? t_fast : best_t;
-            best_i = better ? i : best_i;
+        for (int i = Layout::begin_flat_y; i < Layout::begin_flat_y + Layout::flat_y; i++) {
+            scan_flat<1>(s, scene.quads[i], i, ro, rd);
+        }
+#pragma unroll
+        for (int i = Layout::begin_upright; i < Layout::begin_upright + Layout::upright; i++) {
+            scan_upright(s, scene.quads[i], i, ro, rd);
+        }
+#pragma unroll
+        for (int i = Layout::begin_flat_x; i < Layout::begin_flat_x + Layout::flat_x; i++) {
+            scan_flat<0>(s, scene.quads[i], i, ro, rd);
+        }
+#pragma unroll
+        for (int i = Layout::begin_flat_z; i < Layout::begin_flat_z + Layout::flat_z; i++) {
+            scan_flat<2>(s, scene.quads[i], i, ro, rd);
+        }
+#pragma unroll
+        for (int i = Layout::begin_general; i < Layout::begin_general + Layout::general; i++) {
+            scan_general(s, scene.quads[i], i, ro, rd);
+        }
+    } else {
+        // One loop per shape over that shape's range of the sorted quad table.
+        // Trip counts and table offsets are launch-uniform.
+#pragma unroll 1
+        for (uint32_t i = scene.shape_begin[k_shape_flat_y]; i < scene.shape_begin[k_shape_flat_y + 1]; i++) {
+            scan_flat<1>(s, scene.quads[i], static_cast<int>(i), ro, rd);
+        }
+#pragma unroll 1
+        for (uint32_t i = scene.shape_begin[k_shape_upright]; i < scene.shape_begin[k_shape_upright + 1]; i++) {
+            scan_upright(s, scene.quads[i], static_cast<int>(i), ro, rd);
+        }
+#pragma unroll 1
+        for (uint32_t i = scene.shape_begin[k_shape_flat_x]; i < scene.shape_begin[k_shape_flat_x + 1]; i++) {
+            scan_flat<0>(s, scene.quads[i], static_cast<int>(i), ro, rd);
+        }
+#pragma unroll 1
+        for (uint32_t i = scene.shape_begin[k_shape_flat_z]; i < scene.shape_begin[k_shape_flat_z + 1]; i++) {
+            scan_flat<2>(s, scene.quads[i], static_cast<int>(i), ro, rd);
+        }
+#pragma unroll 1
+        for (uint32_t i = scene.shape_begin[k_shape_general]; i < scene.shape_begin[k_shape_general + 1]; i++) {
+            scan_general(s, scene.quads[i], static_cast<int>(i), ro, rd);
         }
     }
 
     // A challenger matters only if it could be in front of, or tie with, the sure
     // winner. With no sure winner (best_t == inf) any challenger matters.
-    if (challenger_t < k_inf && challenger_t <= best_t * k_tie) {
+    if (s.challenger_t < k_inf && s.challenger_t <= s.best_t * k_tie) {
         trace_scene_exact(scene, ro, rd, hit);
         return;
     }
-    hit.index = best_i;
-    if (best_i < 0) return;
+    hit.index = s.best_i;
+    if (s.best_i < 0) return;
     // The accepted hit, with the shader's operations: plugin.mm:173, 176, 179.
-    const float* sh = shade + best_i * k_shade_stride;
+    const float* sh = shade + s.best_i * k_shade_stride;
     const v3 normal = load_v3(sh + k_sh_normal);
     const float denom = dot(normal, rd);
     hit.front = denom < 0.0f;
     hit.t = (sh[k_sh_plane_d] - dot(normal, ro)) / denom;
     hit.point = ro + rd * hit.t;
+}
+
+/// Correctly rounded binary32 sin and cos of phi in [0, 2*pi]: evaluated in
+/// binary64 (Cody-Waite reduction by pi/2 in two pieces, then the classic
+/// degree-13 / degree-14 kernels on [-pi/4, pi/4]) and rounded once. The binary64
+/// result is within ~2^-52 relative of the true value, so the rounding to
+/// binary32 differs from the correctly rounded one with probability ~2^-28 per
+/// call; tests/test_cuda_parity.py compares 2^24 arguments against the oracle.
+/// About a third of the instructions of the general-range CUDA sincos().
+__device__ __forceinline__ void sincos_round_once(float phi, float& sin_phi, float& cos_phi) {
+    const double x = static_cast<double>(phi);
+    const double qd = rint(x * 0.63661977236758134308);  // 2/pi
+    const int quadrant = static_cast<int>(qd);
+    double r = fma(-qd, 1.57079632679489655800e+00, x);
+    r = fma(-qd, 6.12323399573676603587e-17, r);
+    const double z = r * r;
+    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    ps = fma(z, ps, 2.75573137070700676789e-06);
+    ps = fma(z, ps, -1.98412698298579493134e-04);
+    ps = fma(z, ps, 8.33333333332248946124e-03);
+    ps = fma(z, ps, -1.66666666666666324348e-01);
+    const double sin_r = fma(r * z, ps, r);
+    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    pc = fma(z, pc, -2.75573143513906633035e-07);
+    pc = fma(z, pc, 2.48015872894767294178e-05);
+    pc = fma(z, pc, -1.38888888888741095749e-03);
+    pc = fma(z, pc, 4.16666666666666019037e-02);
+    const double cos_r = fma(z * z, pc, fma(z, -0.5, 1.0));
+    const bool swap = (quadrant & 1) != 0;
+    double sv = swap ? cos_r : sin_r;
+    double cv = swap ? sin_r : cos_r;
+    if (quadrant & 2) sv = -sv;
+    if ((quadrant + 1) & 2) cv = -cv;
+    sin_phi = static_cast<float>(sv);
+    cos_phi = static_cast<float>(cv);
 }
 
 __device__ __forceinline__ float4 mix4(float4 a, float4 b, float w) {
@@ -203,7 +376,7 @@ constexpr int k_block_threads = 256;
 constexpr int k_blocks_per_sm = 4;
 constexpr int k_warps_per_block = k_block_threads / 32;
 
-template <int NQ>
+template <int NQ, class Layout>
 __global__ void __launch_bounds__(k_block_threads, k_blocks_per_sm)
 pathtrace_accumulate_kernel(const __grid_constant__ scene_params scene,
                             const __grid_constant__ frame_params frame, float4* __restrict__ beauty,
@@ -246,8 +419,14 @@ pathtrace_accumulate_kernel(const __grid_constant__ scene_params scene,
                 const uint32_t item = next_item + __popc(idle & lanes_below);
                 const uint32_t tile = warp_global + (item >> 5) * n_warps;
                 if (tile < n_tiles) {
-                    const uint32_t tile_y = tile / tiles_x;
-                    const uint32_t tile_x = tile - tile_y * tiles_x;
+                    // tile / tiles_x by multiply-high with floor(2^32 / tiles_x): at most
+                    // one too small for any 32-bit tile, fixed up by one compare.
+                    uint32_t tile_y = __umulhi(tile, frame.tiles_x_magic);
+                    uint32_t tile_x = tile - tile_y * tiles_x;
+                    if (tile_x >= tiles_x) {
+                        tile_x -= tiles_x;
+                        tile_y++;
+                    }
                     const uint32_t px = tile_x * 8u + (item & 7u);
                     const uint32_t py = tile_y * 4u + ((item >> 3) & 3u);
                     if (px < frame.width && py < frame.height) {
@@ -293,7 +472,7 @@ pathtrace_accumulate_kernel(const __grid_constant__ scene_params scene,
         if (active) {
             // One bounce of path_trace, plugin.mm:232-273.
             hit_record hit;
-            trace_scene<NQ>(scene, s_shade, ro, rd, hit);
+            trace_scene<Layout>(scene, s_shade, ro, rd, hit);
             rays++;
             const bool is_hit = hit.index >= 0;
             const float* sh = s_shade + (is_hit ? hit.index : 0) * k_shade_stride;
@@ -330,7 +509,7 @@ pathtrace_accumulate_kernel(const __grid_constant__ scene_params scene,
                         if (random_float(rng) > p) {
                             done = true;
                         } else {
-                            throughput = throughput / p;
+                            throughput = div3(throughput, p);
                         }
                     }
                 }
@@ -346,10 +525,8 @@ pathtrace_accumulate_kernel(const __grid_constant__ scene_params scene,
                 const float phi = 6.28318548202514648f * r1;  // 2.0f * M_PI_F, exact product
                 const float cos_theta = sqrtf(1.0f - r2);
                 const float sin_theta = sqrtf(r2);
-                double sd, cd;
-                sincos(static_cast<double>(phi), &sd, &cd);
-                const float sin_phi = static_cast<float>(sd);
-                const float cos_phi = static_cast<float>(cd);
+                float sin_phi, cos_phi;
+                sincos_round_once(phi, sin_phi, cos_phi);
                 const v3 fu = load_v3(sh + k_sh_frame_u);
                 const v3 fv = load_v3(sh + k_sh_frame_v) * side;
                 const v3 fw = load_v3(sh + k_sh_frame_w) * side;
@@ -368,7 +545,20 @@ pathtrace_accumulate_kernel(const __grid_constant__ scene_params scene,
     if (lane == 0 && rays != 0) atomicAdd(ray_counter, static_cast<unsigned long long>(rays));
 }
 
+__global__ void sincos_probe_kernel(const float* __restrict__ phi, float* __restrict__ sin_out,
+                                    float* __restrict__ cos_out, uint64_t n) {
+    const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) sincos_round_once(phi[i], sin_out[i], cos_out[i]);
+}
+
 }  // namespace
+
+cudaError_t launch_sincos_probe(const float* phi, float* sin_out, float* cos_out, uint64_t n,
+                                cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    sincos_probe_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(phi, sin_out, cos_out, n);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_pathtrace_accumulate(const scene_params& scene, const frame_params& frame,
                                         float* const layers[4], unsigned long long* ray_counter,
@@ -382,12 +572,12 @@ cudaError_t launch_pathtrace_accumulate(const scene_params& scene, const frame_p
     auto* a = reinterpret_cast<float4*>(layers[1]);
     auto* n = reinterpret_cast<float4*>(layers[2]);
     auto* d = reinterpret_cast<float4*>(layers[3]);
-    if (scene.quad_count <= 16) {
-        pathtrace_accumulate_kernel<16><<<blocks, k_block_threads, 0, stream>>>(scene, frame, b, a, n,
-                                                                              d, ray_counter);
+    if (cornell_layout::matches(scene)) {
+        pathtrace_accumulate_kernel<16, cornell_layout>
+            <<<blocks, k_block_threads, 0, stream>>>(scene, frame, b, a, n, d, ray_counter);
     } else {
-        pathtrace_accumulate_kernel<32><<<blocks, k_block_threads, 0, stream>>>(scene, frame, b, a, n,
-                                                                              d, ray_counter);
+        pathtrace_accumulate_kernel<32, dynamic_layout>
+            <<<blocks, k_block_threads, 0, stream>>>(scene, frame, b, a, n, d, ray_counter);
     }
     return cudaGetLastError();
 }

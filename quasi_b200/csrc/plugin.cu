@@ -477,6 +477,13 @@ Q_PLUGIN_EXPORT int Q_cuda_combine_shards(const float* const* shards, uint32_t n
                                           static_cast<cudaStream_t>(stream)) == cudaSuccess ? 0 : -1;
 }
 
+Q_PLUGIN_EXPORT int Q_cuda_probe_sincos(const float* phi, float* sin_out, float* cos_out,
+                                        uint64_t n, void* stream) {
+    if (!phi || !sin_out || !cos_out) return -1;
+    return Q::cuda::launch_sincos_probe(phi, sin_out, cos_out, n, static_cast<cudaStream_t>(stream)) ==
+                   cudaSuccess ? 0 : -1;
+}
+
 Q_PLUGIN_EXPORT int Q_cuda_alloc(uint64_t bytes, void** out_device_ptr) {
     if (!out_device_ptr) return -1;
     *out_device_ptr = nullptr;

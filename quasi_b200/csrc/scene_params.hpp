@@ -19,25 +19,38 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <utility>
 
 namespace Q::cuda {
 
 inline constexpr uint32_t k_max_quads = 32;   ///< plugin.mm:21, 30
 inline constexpr uint32_t k_max_bounces = 5;  ///< plugin.mm:22, 31
 
-/// One quad, pre-digested: 52 floats (208 bytes), 16-byte rows so constant-bank
+/// Which zero pattern a quad has, found on the host by looking for exact zeros.
+/// A pattern only selects a cheaper form of the same DECISION arithmetic in the
+/// scan (terms that are exactly zero are not computed); every pattern falls back
+/// to the same literal test, so a misclassification could cost speed, not bits.
+enum quad_shape : uint32_t {
+    k_shape_general = 0,
+    k_shape_flat_x = 1,    ///< normal along x; alpha, beta live in (y, z)   - side walls
+    k_shape_flat_y = 2,    ///< normal along y; alpha, beta live in (x, z)   - floor, ceiling, light, box tops
+    k_shape_flat_z = 3,    ///< normal along z; alpha, beta live in (x, y)   - back wall
+    k_shape_upright = 4,   ///< normal.y == 0, one edge vertical: alpha in (x, z), beta along y - box sides
+};
+
+/// One quad, pre-digested: 56 floats (224 bytes), 16-byte rows so constant-bank
 /// loads vectorise. Three groups: what the fast scan reads for every ray, what
 /// only the exact (literal) test reads, and what shading reads after a hit.
 struct alignas(16) quad_params {
     // -- fast scan --
     float normal[3];        ///< n * rsqrt(dot(n,n)), n = cross(u,v)   (plugin.mm:165-170)
     float plane_d;          ///< dot(normal, origin)                   (plugin.mm:171)
-    float fast_a[3];        ///< cross(v, w): alpha ~= dot(p - origin, fast_a)
-    float delta;            ///< decision margin for alpha/beta, see prepare_scene
-    float fast_b[3];        ///< cross(w, u): beta  ~= dot(p - origin, fast_b)
-    float one_minus_delta;
-    float origin[3];
-    float one_plus_delta;
+    float fast_a[3];        ///< cross(v, w): alpha - 1/2 ~= dot(p - center, fast_a)
+    float half_plus;        ///< 1/2 + delta: beyond it the point is surely outside
+    float fast_b[3];        ///< cross(w, u): beta  - 1/2 ~= dot(p - center, fast_b)
+    float half_minus;       ///< 1/2 - delta: within it the point is surely inside
+    float center[3];        ///< origin + u/2 + v/2
+    uint32_t shape;         ///< quad_shape: which specialised test applies
     // -- exact test only --
     float w[3];             ///< n / dot(n,n)                          (plugin.mm:182)
     float valid;            ///< 0 when dot(n,n) < 1e-8                (plugin.mm:168)
@@ -45,6 +58,8 @@ struct alignas(16) quad_params {
     float fast_len;         ///< max(|fast_a|, |fast_b|), scales delta
     float v[3];
     float pad1;
+    float origin[3];
+    float pad0;
     // -- shading (copied to shared memory, 24 floats) --
     float shade_normal[3];  ///< == normal
     float is_light;         ///< max(emission) > 0.1                   (plugin.mm:255-256)
@@ -61,12 +76,23 @@ struct alignas(16) quad_params {
     float emission[3];
     float pad6;
 };
-static_assert(sizeof(quad_params) == 208);
-inline constexpr uint32_t k_shade_offset = 28;  ///< first float of the shading group
+static_assert(sizeof(quad_params) == 224);
+inline constexpr uint32_t k_shade_offset = 32;  ///< first float of the shading group
 inline constexpr uint32_t k_shade_floats = 24;
 
+inline constexpr uint32_t k_shape_count = 5;
+
+/// The scene as the kernel sees it. `quads` is sorted by shape (stable), so the
+/// scan runs one tight loop per shape with that shape's arithmetic;
+/// shape_begin[s] .. shape_begin[s+1] is the range of shape s, degenerate quads
+/// sit behind the last range. The scan order does not matter for the result
+/// (closest hit; exact ties go to the literal test). The literal test walks
+/// `scene_order`, i.e. the ORIGINAL order, because plugin.mm:205-207 lets the
+/// later index win a tie. Hit indices on the device are positions in `quads`.
 struct alignas(16) scene_params {
     quad_params quads[k_max_quads];
+    uint32_t scene_order[k_max_quads];       ///< original index -> position in quads
+    uint32_t shape_begin[k_shape_count + 3]; ///< prefix ranges, padded to 8 entries
     uint32_t quad_count;
     uint32_t max_bounces;
     float corner_radius;    ///< farthest quad corner from the world origin
@@ -84,7 +110,8 @@ struct alignas(16) frame_params {
     float vertical[3];     ///< plugin.mm:144
     uint32_t frame_index;  ///< RNG frame index                   (plugin.mm:295)
     uint32_t sample_index; ///< render calls since the last restart
-    uint32_t pad[3];
+    uint32_t tiles_x_magic; ///< floor(2^32 / ceil(width / 8)), for the kernel's tile -> (x, y)
+    uint32_t pad[2];
 };
 
 /// The scene as the host describes it: the same 12+8 floats per quad the Metal
@@ -206,9 +233,11 @@ inline void prepare_scene(const scene_desc& desc, uint32_t max_bounces, scene_pa
         }
     }
     out.corner_radius = corner_radius;
+    quad_params digested[k_max_quads];
+    std::memset(digested, 0, sizeof digested);
     for (uint32_t i = 0; i < out.quad_count; i++) {
         const quad_desc& q = desc.quads[i];
-        quad_params& g = out.quads[i];
+        quad_params& g = digested[i];
         f3 origin = load3(q.origin), u = load3(q.u), v = load3(q.v);
         store3(g.origin, origin);
         store3(g.u, u);
@@ -238,9 +267,27 @@ inline void prepare_scene(const scene_desc& desc, uint32_t max_bounces, scene_pa
         // differ by a few ulps of |planar||a|. See set_decision_margins().
         f3 fa = cross(v, wv);
         f3 fb = cross(wv, u);
+        g.fast_len = std::fmax(std::sqrt(dot(fa, fa)), std::sqrt(dot(fb, fb)));
+        store3(g.center, origin + u * 0.5f + v * 0.5f);
+
+        // Zero patterns (exact comparisons on purpose, see quad_shape).
+        auto zero = [](float x) { return x == 0.0f; };
+        const float nn[3] = {normal.x, normal.y, normal.z};
+        const float aa[3] = {fa.x, fa.y, fa.z};
+        const float bb[3] = {fb.x, fb.y, fb.z};
+        g.shape = k_shape_general;
+        for (int k = 0; k < 3; k++) {
+            const int i = (k + 1) % 3, j = (k + 2) % 3;
+            if (zero(nn[i]) && zero(nn[j]) && zero(aa[k]) && zero(bb[k])) g.shape = k_shape_flat_x + k;
+        }
+        if (g.shape == k_shape_general && zero(nn[1])) {
+            // Only max(|alpha - 1/2|, |beta - 1/2|) is ever used, so the two
+            // barycentrics may trade places: put the vertical one in fast_b.
+            if (zero(aa[0]) && zero(aa[2]) && zero(bb[1])) std::swap(fa, fb);
+            if (zero(fb.x) && zero(fb.z) && zero(fa.y)) g.shape = k_shape_upright;
+        }
         store3(g.fast_a, fa);
         store3(g.fast_b, fb);
-        g.fast_len = std::fmax(std::sqrt(dot(fa, fa)), std::sqrt(dot(fb, fb)));
 
         // cosine_sample_hemisphere's basis for hit.normal == normal.
         f3 w = normalize(normal);
@@ -251,12 +298,31 @@ inline void prepare_scene(const scene_desc& desc, uint32_t max_bounces, scene_pa
         store3(g.frame_v, fv);
         store3(g.frame_w, w);
     }
+
+    // Stable sort by shape; degenerate quads (never hit) go last, outside every range.
+    uint32_t position = 0;
+    for (uint32_t shape = 0; shape <= k_shape_count; shape++) {
+        if (shape < k_shape_count) out.shape_begin[shape] = position;
+        for (uint32_t i = 0; i < out.quad_count; i++) {
+            const bool degenerate = digested[i].valid == 0.0f;
+            const bool take = shape < k_shape_count ? (!degenerate && digested[i].shape == shape) : degenerate;
+            if (take) {
+                out.quads[position] = digested[i];
+                out.scene_order[i] = position;
+                position++;
+            }
+        }
+        if (shape + 1 == k_shape_count) {
+            for (uint32_t k = k_shape_count; k < k_shape_count + 3; k++) out.shape_begin[k] = position;
+        }
+    }
 }
 
 /// @brief Sets the per-quad decision margin of the fast scan for a camera position.
 ///
 /// The fast scan decides "is the plane hit inside the quad" from
-/// alpha' = dot(p' - origin, fast_a) with p' = ro + rd * t', t' = num * rcp(denom).
+/// alpha' - 1/2 = dot(p' - center, fast_a) with p' = ro + rd * t', t' = num * rcp(denom)
+/// (center = origin + u/2 + v/2, so |alpha' - 1/2| <= 1/2 is the inside test).
 /// Against the literal alpha of plugin.mm:179-184 that differs by at most about
 /// |fast_a| * R * (16 * 2^-24 + 2 * 2^-21) ~= 1.9e-6 * |fast_a| * R, where R
 /// bounds the distance of ray origins and hit points from the world origin
@@ -270,9 +336,8 @@ inline void set_decision_margins(scene_params& scene, const float camera_positio
     for (uint32_t i = 0; i < scene.quad_count; i++) {
         quad_params& g = scene.quads[i];
         float delta = std::fmax(1e-5f, 2.5e-5f * g.fast_len * radius);
-        g.delta = delta;
-        g.one_minus_delta = 1.0f - delta;
-        g.one_plus_delta = 1.0f + delta;
+        g.half_plus = 0.5f + delta;
+        g.half_minus = 0.5f - delta;
     }
 }
 
@@ -319,6 +384,8 @@ inline void prepare_frame(const float position[3], const float target[3], const 
     out.frame_index = frame_index;
     out.sample_index = sample_index;
     out.weight = 1.0f / static_cast<float>(sample_index + 1u);
+    const uint64_t tiles_x = (static_cast<uint64_t>(width) + 7u) / 8u;
+    out.tiles_x_magic = tiles_x > 1 ? static_cast<uint32_t>((uint64_t{1} << 32) / tiles_x) : 0xffffffffu;
 }
 
 }  // namespace Q::cuda

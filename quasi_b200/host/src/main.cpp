@@ -106,7 +106,9 @@ Q::async::task<void> frame_loop(gpu_worker& w, const options& opt, clock_type::t
         if (opt.render_frames > 0 && w.frames >= static_cast<uint64_t>(opt.render_frames)) break;
         if (opt.progressive_s > 0.0 && clock_type::now() >= deadline) break;
 
-        if (!w.manager->is_loaded()) {  // mid-reload: nothing to render with
+        if (!w.manager->is_loaded() || w.manager->is_reloading()) {
+            // Mid-reload: submit nothing, so that the pre_unload hook sees the GPU
+            // go idle and the old library can be closed.
             co_await Q::async::yield();
             continue;
         }

@@ -156,6 +156,7 @@ class loader:
             "Q_cuda_ipc_export": (C.c_int, [C.c_void_p, C.POINTER(abi.Q_cuda_ipc_handle)]),
             "Q_cuda_ipc_open": (C.c_int, [C.POINTER(abi.Q_cuda_ipc_handle), C.POINTER(C.c_void_p)]),
             "Q_cuda_ipc_close": (C.c_int, [C.c_void_p]),
+            "Q_cuda_probe_sincos": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
         }
         for name, (res, args) in sig.items():
             if name in f:

@@ -102,6 +102,8 @@ class Oracle(_Base):
         for n in ("qo_sin", "qo_cos", "qo_tan"):
             getattr(lib, n).restype = f32
             getattr(lib, n).argtypes = [f32]
+        lib.qo_sincos_array.restype = None
+        lib.qo_sincos_array.argtypes = [fp, u64, fp, fp]
         lib.qo_online_cores.restype = i32
 
     # integer path
@@ -161,6 +163,12 @@ class Oracle(_Base):
         self.lib.qo_tonemap_bgra8(_fptr(np.ascontiguousarray(accumulated)), w, h,
                                   out.ctypes.data_as(C.POINTER(C.c_uint8)))
         return out
+
+    def sincos(self, phi):
+        phi = np.ascontiguousarray(phi, dtype=np.float32)
+        s, c = np.empty_like(phi), np.empty_like(phi)
+        self.lib.qo_sincos_array(_fptr(phi), phi.size, _fptr(s), _fptr(c))
+        return s, c
 
     def combine_shards(self, shards):
         shards = [np.ascontiguousarray(s, dtype=np.float32) for s in shards]

@@ -259,6 +259,34 @@ def test_standalone_passes_vs_oracle(torch_cuda, oracle):
     h.close()
 
 
+def test_sincos_probe_matches_correctly_rounded_values(torch_cuda, oracle):
+    """The kernel's own binary64 sin/cos, rounded once, against the oracle's on
+    2^24 arguments phi = 2*pi*r1 drawn the way the shader draws them, plus the
+    ends of the range and every quadrant boundary neighbourhood."""
+    torch = torch_cuda
+    h = host(8, 8)
+    rng = np.random.default_rng(11)
+    state = rng.integers(0, 2**32, size=1 << 24, dtype=np.uint64).astype(np.uint32)
+    r1 = state.astype(np.float32) * np.float32(2.0**-32)
+    phi = np.float32(6.28318548202514648) * r1
+    edges = np.array([0.0, 6.2831855, np.pi / 2, np.pi, 3 * np.pi / 2, np.pi / 4, 1e-30, 1e-10], dtype=np.float32)
+    near = np.concatenate([np.nextafter(edges, np.float32(10), dtype=np.float32),
+                           np.nextafter(edges, np.float32(-1), dtype=np.float32)])
+    phi = np.concatenate([phi, edges, near[(near >= 0) & (near <= np.float32(6.2831855))]]).astype(np.float32)
+    d = torch.from_numpy(phi).cuda()
+    ds, dc = torch.empty_like(d), torch.empty_like(d)
+    rc = h.plugin.fn("Q_cuda_probe_sincos")(d.data_ptr(), ds.data_ptr(), dc.data_ptr(), phi.size,
+                                             torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    want_s, want_c = oracle.sincos(phi)
+    bad_s = int((bits(ds.cpu().numpy()) != bits(want_s)).sum())
+    bad_c = int((bits(dc.cpu().numpy()) != bits(want_c)).sum())
+    h.close()
+    # 2^-28 per call would allow ~0.1 expected mismatches over 3.4e7 evaluations
+    assert bad_s + bad_c <= 1, (bad_s, bad_c)
+
+
 def test_sincos_correctly_rounded_over_the_rng_grid(torch_cuda, oracle):
     """cos/sin of phi = 2*pi*r1 decide bounce directions; the kernel's must be
     the correctly rounded binary32 values the oracle defines. Exercised through
