@@ -17,8 +17,8 @@ NVCCFLAGS := $(ARCH) -O3 -std=c++20 -lineinfo $(NVCC_NUMERICS) --cudart shared \
              -Xcompiler $(HOST_FLAGS) -Iinclude -Iquasi_b200/csrc
 
 CSRC := quasi_b200/csrc
-PLUGIN_SRCS := $(CSRC)/plugin.cu $(CSRC)/pathtrace.cu $(CSRC)/post.cu
-PLUGIN_HDRS := $(CSRC)/kernels.hpp $(CSRC)/scene_params.hpp include/quasi_plugin_abi.h \
+PLUGIN_SRCS := $(CSRC)/plugin.cu $(CSRC)/pathtrace.cu $(CSRC)/mesh_trace.cu $(CSRC)/post.cu
+PLUGIN_HDRS := $(CSRC)/kernels.hpp $(CSRC)/scene_params.hpp $(CSRC)/device_common.cuh $(CSRC)/mesh_scene.hpp include/quasi_plugin_abi.h \
                include/quasi_cuda_backend.h
 PLUGIN_SO := quasi_b200/lib/libquasi_cuda.so
 
@@ -55,7 +55,11 @@ SANITIZE := $(shell echo 'int main(){}' | $(CXX) -fsanitize=address,undefined -x
 TEST_CXXFLAGS := $(HOST_CXXFLAGS) -O1 -g $(SANITIZE) -I$(HOST)/test
 FAKE_SRC := $(HOST)/test/fake_plugin.cpp
 
-host-tests: $(TESTDIR)/host_test $(TESTDIR)/exr_write_tool
+host-tests: $(TESTDIR)/host_test $(TESTDIR)/exr_write_tool $(TESTDIR)/mesh_dump_tool
+
+$(TESTDIR)/mesh_dump_tool: $(HOST)/test/mesh_dump_tool.cpp quasi_b200/csrc/mesh_scene.hpp
+	mkdir -p $(TESTDIR)
+	$(CXX) -std=c++20 -O2 -ffp-contract=off -Wall -Wextra -Iquasi_b200/csrc -o $@ $(HOST)/test/mesh_dump_tool.cpp
 	if [ -d $(REFERENCE)/test ]; then $(MAKE) reference-tests; fi
 
 $(TESTDIR)/host_test: $(HOST)/test/host_test.cpp $(HOST)/test/catch2_main.cpp $(HOST)/src/exr_writer.cpp \

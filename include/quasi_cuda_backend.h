@@ -58,7 +58,24 @@ typedef struct Q_cuda_stats {
     uint32_t width;
     uint32_t height;
     uint32_t reserved;
+    uint64_t nodes_visited;    /* mesh scene: BVH box tests (32 B each); 0 for the quad scene */
+    uint64_t triangles_tested; /* mesh scene: triangle tests (48 B each) */
 } Q_cuda_stats;
+
+/* Host-side view of the mesh scene the plugin built (QUASI_CUDA_SCENE=mesh), for
+ * checking the builder against the oracle's: triangles in original order (48 B),
+ * nodes (32 B), leaf_order (slot -> original index). Pointers stay valid until
+ * Q_plugin_destroy. Returns -1 for the quad scene. */
+typedef struct Q_cuda_mesh_view {
+    const void* triangles;
+    const void* nodes;
+    const uint32_t* leaf_order;
+    uint32_t n_triangles;
+    uint32_t n_nodes;
+    uint32_t depth;
+    uint32_t reserved;
+} Q_cuda_mesh_view;
+Q_PLUGIN_EXPORT int Q_cuda_plugin_mesh_view(Q_plugin_handle* handle, Q_cuda_mesh_view* out);
 
 /* Device-side view of the accumulated RGBA32F layers (index = Q_aov_type),
  * each width*height*4 floats, row 0 = top, holding the mean of this GPU's

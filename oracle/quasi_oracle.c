@@ -14,28 +14,7 @@
 #include <string.h>
 #include <unistd.h>
 
-typedef struct {
-    float x, y, z;
-} v3;
-
-/* vec.hpp:40-50 (component-wise operators) */
-static inline v3 v3_make(float x, float y, float z) { v3 r = {x, y, z}; return r; }
-static inline v3 v3_add(v3 a, v3 b) { return v3_make(a.x + b.x, a.y + b.y, a.z + b.z); }
-static inline v3 v3_sub(v3 a, v3 b) { return v3_make(a.x - b.x, a.y - b.y, a.z - b.z); }
-static inline v3 v3_mul(v3 a, v3 b) { return v3_make(a.x * b.x, a.y * b.y, a.z * b.z); }
-static inline v3 v3_scale(v3 a, float s) { return v3_make(a.x * s, a.y * s, a.z * s); }
-static inline v3 v3_div(v3 a, float s) { return v3_make(a.x / s, a.y / s, a.z / s); }
-static inline v3 v3_neg(v3 a) { return v3_make(-a.x, -a.y, -a.z); }
-static inline v3 v3_adds(v3 a, float s) { return v3_make(a.x + s, a.y + s, a.z + s); }
-/* vec.hpp:92-94 */
-static inline float v3_dot(v3 a, v3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
-/* vec.hpp:100-106 */
-static inline v3 v3_cross(v3 a, v3 b) {
-    return v3_make(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
-}
-/* vec.hpp:108-114: v / length(v) */
-static inline v3 v3_normalize(v3 a) { return v3_div(a, sqrtf(v3_dot(a, a))); }
-static inline v3 v3_load(const float* p) { return v3_make(p[0], p[1], p[2]); }
+#include "quasi_oracle_internal.h"
 
 static inline float q_max(float a, float b) { return a > b ? a : b; }
 
@@ -72,11 +51,6 @@ uint32_t qo_seed(uint32_t px, uint32_t py, uint32_t frame_count) {
 }
 
 typedef struct {
-    v3 origin;
-    v3 direction;
-} ray_t;
-
-typedef struct {
     float t;
     v3 point;
     v3 normal;
@@ -85,7 +59,7 @@ typedef struct {
 } hit_t;
 
 /* plugin.mm:111-125 */
-static v3 cosine_sample_hemisphere(v3 normal, uint32_t* rng) {
+v3 qo_cosine_sample_hemisphere(v3 normal, uint32_t* rng) {
     float r1 = qo_random_float(rng);
     float r2 = qo_random_float(rng);
 
@@ -105,7 +79,7 @@ static v3 cosine_sample_hemisphere(v3 normal, uint32_t* rng) {
 }
 
 /* plugin.mm:129-153. Jitter draws x first, then y. */
-static ray_t get_camera_ray(const qo_camera* cam, float uv_x, float uv_y, uint32_t* rng) {
+ray_t qo_get_camera_ray(const qo_camera* cam, float uv_x, float uv_y, uint32_t* rng) {
     float jx = qo_random_float(rng);
     float jy = qo_random_float(rng);
     jx = jx - 0.5f;
@@ -231,7 +205,7 @@ static path_result_t path_trace(ray_t ray, const qo_scene_uniforms* scene, uint3
         }
 
         ray.origin = v3_add(hit.point, v3_scale(hit.normal, 0.001f));
-        ray.direction = cosine_sample_hemisphere(hit.normal, rng);
+        ray.direction = qo_cosine_sample_hemisphere(hit.normal, rng);
     }
     return result;
 }
@@ -244,7 +218,7 @@ uint32_t qo_pathtrace_pixel(const qo_scene_uniforms* scene, uint32_t px, uint32_
 
     uint32_t rng = qo_seed(px, py, scene->frame_count);
 
-    ray_t ray = get_camera_ray(&scene->camera, uv_x, uv_y, &rng);
+    ray_t ray = qo_get_camera_ray(&scene->camera, uv_x, uv_y, &rng);
     path_result_t pt = path_trace(ray, scene, &rng);
 
     float norm_depth = (pt.first_hit_depth - 1.0f) / 4.0f;

@@ -73,6 +73,12 @@ class Q_cuda_drawable(C.Structure):
 class Q_cuda_stats(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("paths", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("frame_count", C.c_uint32), ("width", C.c_uint32), ("height", C.c_uint32),
+                ("reserved", C.c_uint32), ("nodes_visited", C.c_uint64), ("triangles_tested", C.c_uint64)]
+
+
+class Q_cuda_mesh_view(C.Structure):
+    _fields_ = [("triangles", C.c_void_p), ("nodes", C.c_void_p), ("leaf_order", C.c_void_p),
+                ("n_triangles", C.c_uint32), ("n_nodes", C.c_uint32), ("depth", C.c_uint32),
                 ("reserved", C.c_uint32)]
 
 
@@ -104,5 +110,5 @@ OPTIONAL_SYMBOLS = (  # loader.hpp:115-128
 CUDA_EXTENSION_SYMBOLS = (  # quasi_cuda_backend.h
     "Q_cuda_plugin_stats", "Q_cuda_plugin_layers", "Q_cuda_accumulate", "Q_cuda_tonemap_bgra8",
     "Q_cuda_combine_shards", "Q_cuda_alloc", "Q_cuda_free", "Q_cuda_ipc_export", "Q_cuda_ipc_open",
-    "Q_cuda_ipc_close", "Q_cuda_probe_sincos",
+    "Q_cuda_ipc_close", "Q_cuda_probe_sincos", "Q_cuda_plugin_mesh_view",
 )

@@ -12,6 +12,21 @@
 namespace Q::cuda {
 
 inline constexpr uint32_t k_max_shards = 16;
+inline constexpr uint32_t k_mesh_stack_entries = 32;  ///< per-lane traversal stack; BVH depth must fit
+inline constexpr uint32_t k_mesh_materials = 8;
+
+/// Device view of the mesh scene (mesh_scene.hpp:pack_for_device).
+struct alignas(16) mesh_params {
+    const float4* nodes;    ///< 2 float4 per node: {min.xyz, left_first} {max.xyz, count}
+    const float4* tri_v0;   ///< leaf order: {v0.xyz, material}
+    const float4* tri_e1;   ///< leaf order: {e1.xyz, original index}
+    const float4* tri_e2;   ///< leaf order: {e2.xyz, 0}
+    uint32_t n_nodes;
+    uint32_t n_triangles;
+    uint32_t max_bounces;
+    uint32_t pad;
+    float materials[k_mesh_materials * 8];  ///< per material: albedo.xyz, 0, emission.xyz, 0
+};
 
 /// @brief One new sample per pixel, folded into the four accumulated layers in place.
 /// @param layers Device pointers to beauty, albedo, normal, depth (RGBA32F, row 0 = top).
@@ -20,6 +35,11 @@ inline constexpr uint32_t k_max_shards = 16;
 cudaError_t launch_pathtrace_accumulate(const scene_params& scene, const frame_params& frame,
                                         float* const layers[4], unsigned long long* ray_counter,
                                         int sm_count, cudaStream_t stream);
+
+/// @brief The mesh-scene form of launch_pathtrace_accumulate (BASELINE config 3).
+/// @param counters Device array of 3: rays, BVH nodes visited (box tests), triangles tested.
+cudaError_t launch_mesh_pathtrace(const mesh_params& scene, const frame_params& frame, float* const layers[4],
+                                  unsigned long long* counters, int sm_count, cudaStream_t stream);
 
 /// @brief Test hook: the kernel's sin/cos of phi in [0, 2*pi], element-wise.
 cudaError_t launch_sincos_probe(const float* phi, float* sin_out, float* cos_out, uint64_t n,

@@ -8,6 +8,7 @@
 /// CUDA fails, create returns NULL and render/readback do nothing.
 
 #include "kernels.hpp"
+#include "mesh_scene.hpp"
 
 #include <quasi_cuda_backend.h>
 
@@ -101,6 +102,12 @@ struct plugin_state {
     Q::cuda::scene_desc scene_desc;
     scene_params scene;
 
+    // Mesh scene (QUASI_CUDA_SCENE=mesh, BASELINE config 3); empty for the demo scene.
+    bool use_mesh = false;
+    Q::cuda::mesh::scene mesh;
+    Q::cuda::mesh_params mesh_device{};
+    void* mesh_buffers[4] = {nullptr, nullptr, nullptr, nullptr};
+
     float* layers[Q_AOV_COUNT] = {nullptr, nullptr, nullptr, nullptr};
     unsigned long long* ray_counter = nullptr;
     cudaEvent_t last_render = nullptr;
@@ -153,6 +160,54 @@ bool create_layers(plugin_state* state, uint32_t width, uint32_t height) {
     state->last_width = width;
     state->last_height = height;
     state->frame_count = 0;
+    return true;
+}
+
+void free_mesh(plugin_state* state) {
+    for (auto& b : state->mesh_buffers) {
+        if (b) cudaFree(b);
+        b = nullptr;
+    }
+}
+
+/// Generates the terrain-box scene, builds its BVH on the host and uploads both.
+bool create_mesh(plugin_state* state, uint32_t grid, uint32_t seed, uint32_t max_bounces) {
+    namespace mesh = Q::cuda::mesh;
+    mesh::generate_triangles(grid, seed, state->mesh);
+    mesh::build_bvh(state->mesh);
+    if (state->mesh.depth > Q::cuda::k_mesh_stack_entries) {
+        log_msg(state, "mesh BVH is deeper than the traversal stack");
+        return false;
+    }
+    std::vector<mesh::float4_t> packed[4];
+    mesh::pack_for_device(state->mesh, packed[0], packed[1], packed[2], packed[3]);
+    for (int i = 0; i < 4; i++) {
+        const size_t bytes = packed[i].size() * sizeof(mesh::float4_t);
+        if (!check(state, cudaMalloc(&state->mesh_buffers[i], bytes), "cudaMalloc(mesh)") ||
+            !check(state, cudaMemcpyAsync(state->mesh_buffers[i], packed[i].data(), bytes,
+                                          cudaMemcpyHostToDevice, state->queue), "upload(mesh)")) {
+            return false;
+        }
+    }
+    if (!check(state, cudaStreamSynchronize(state->queue), "upload(mesh) sync")) return false;
+    auto& d = state->mesh_device;
+    d.nodes = static_cast<const float4*>(state->mesh_buffers[0]);
+    d.tri_v0 = static_cast<const float4*>(state->mesh_buffers[1]);
+    d.tri_e1 = static_cast<const float4*>(state->mesh_buffers[2]);
+    d.tri_e2 = static_cast<const float4*>(state->mesh_buffers[3]);
+    d.n_nodes = static_cast<uint32_t>(state->mesh.nodes.size());
+    d.n_triangles = static_cast<uint32_t>(state->mesh.triangles.size());
+    d.max_bounces = max_bounces;
+    for (uint32_t m = 0; m < mesh::k_material_count; m++) {
+        for (int c = 0; c < 3; c++) {
+            d.materials[m * 8 + c] = state->mesh.materials[m].albedo[c];
+            d.materials[m * 8 + 4 + c] = state->mesh.materials[m].emission[c];
+        }
+    }
+    char buf[160];
+    std::snprintf(buf, sizeof buf, "Mesh scene: %u triangles, %u BVH nodes, depth %u", d.n_triangles, d.n_nodes,
+                  state->mesh.depth);
+    log_msg(state, buf);
     return true;
 }
 
@@ -234,9 +289,10 @@ Q_PLUGIN_EXPORT Q_plugin_handle* Q_plugin_create(Q_plugin_context* ctx) {
                                                    state->device), "cudaDeviceGetAttribute");
     ok = ok && check(state, cudaEventCreateWithFlags(&state->last_render, cudaEventDisableTiming),
                      "cudaEventCreate");
+    // counters: rays, BVH nodes visited, triangles tested
     ok = ok && check(state, cudaMalloc(reinterpret_cast<void**>(&state->ray_counter),
-                                       sizeof(unsigned long long)), "cudaMalloc(counter)");
-    ok = ok && check(state, cudaMemsetAsync(state->ray_counter, 0, sizeof(unsigned long long),
+                                       3 * sizeof(unsigned long long)), "cudaMalloc(counter)");
+    ok = ok && check(state, cudaMemsetAsync(state->ray_counter, 0, 3 * sizeof(unsigned long long),
                                             state->queue), "cudaMemset(counter)");
     if (ok) {
         // The plugin builds its own scene (plugin.mm:581-584). The ABI has no
@@ -244,9 +300,16 @@ Q_PLUGIN_EXPORT Q_plugin_handle* Q_plugin_create(Q_plugin_context* ctx) {
         state->scene_desc = Q::cuda::make_cornell_box();
         uint32_t bounces = env_u32("QUASI_CUDA_MAX_BOUNCES", Q::cuda::k_max_bounces, 1, 64);
         Q::cuda::prepare_scene(state->scene_desc, bounces, state->scene);
-        ok = create_layers(state, ctx->viewport_width, ctx->viewport_height);
+        const char* scene_name = std::getenv("QUASI_CUDA_SCENE");
+        if (scene_name && std::strcmp(scene_name, "mesh") == 0) {
+            state->use_mesh = true;
+            ok = create_mesh(state, env_u32("QUASI_CUDA_MESH_GRID", 707, 1, 4000),
+                             env_u32("QUASI_CUDA_MESH_SEED", 1, 0, 65535), bounces);
+        }
+        ok = ok && create_layers(state, ctx->viewport_width, ctx->viewport_height);
     }
     if (!ok) {
+        free_mesh(state);
         free_layers(state);
         if (state->ray_counter) cudaFree(state->ray_counter);
         if (state->last_render) cudaEventDestroy(state->last_render);
@@ -272,6 +335,7 @@ Q_PLUGIN_EXPORT void Q_plugin_destroy(Q_plugin_handle* handle) {
     cudaSetDevice(state->device);
     if (state->render_pending) cudaEventSynchronize(state->last_render);
     cudaStreamSynchronize(state->queue);
+    free_mesh(state);
     free_layers(state);
     if (state->ray_counter) cudaFree(state->ray_counter);
     if (state->last_render) cudaEventDestroy(state->last_render);
@@ -329,12 +393,12 @@ Q_PLUGIN_EXPORT void Q_plugin_render(Q_plugin_handle* handle, Q_render_frame* fr
     // layers are shared, so order this frame after the previous one.
     order_after_render(state, stream);
 
-    if (!check(state, Q::cuda::launch_pathtrace_accumulate(state->scene, fp, state->layers,
-                                                          state->ray_counter, state->sm_count,
-                                                          stream),
-               "pathtrace_accumulate")) {
-        return;
-    }
+    const cudaError_t launched =
+        state->use_mesh ? Q::cuda::launch_mesh_pathtrace(state->mesh_device, fp, state->layers,
+                                                         state->ray_counter, state->sm_count, stream)
+                        : Q::cuda::launch_pathtrace_accumulate(state->scene, fp, state->layers,
+                                                               state->ray_counter, state->sm_count, stream);
+    if (!check(state, launched, "pathtrace_accumulate")) return;
     state->kernel_launches++;
 
     // plugin.mm:776-788
@@ -422,15 +486,17 @@ Q_PLUGIN_EXPORT int Q_cuda_plugin_stats(Q_plugin_handle* handle, Q_cuda_stats* o
     auto* state = reinterpret_cast<plugin_state*>(handle);
     if (cudaSetDevice(state->device) != cudaSuccess) return -1;
     if (state->render_pending) cudaEventSynchronize(state->last_render);
-    unsigned long long rays = 0;
+    unsigned long long counters[3] = {0, 0, 0};
     order_after_render(state, state->queue);
-    if (!check(state, cudaMemcpyAsync(&rays, state->ray_counter, sizeof rays,
+    if (!check(state, cudaMemcpyAsync(counters, state->ray_counter, sizeof counters,
                                       cudaMemcpyDeviceToHost, state->queue), "stats copy") ||
         !check(state, cudaStreamSynchronize(state->queue), "stats sync")) {
         return -1;
     }
     std::memset(out, 0, sizeof *out);
-    out->rays = rays;
+    out->rays = counters[0];
+    out->nodes_visited = counters[1];
+    out->triangles_tested = counters[2];
     out->paths = state->paths;
     out->kernel_launches = state->kernel_launches;
     out->frame_count = state->frame_count;
@@ -450,6 +516,20 @@ Q_PLUGIN_EXPORT int Q_cuda_plugin_layers(Q_plugin_handle* handle, void* stream,
     out->width = state->last_width;
     out->height = state->last_height;
     out->frame_count = state->frame_count;
+    return 0;
+}
+
+Q_PLUGIN_EXPORT int Q_cuda_plugin_mesh_view(Q_plugin_handle* handle, Q_cuda_mesh_view* out) {
+    if (!handle || !out) return -1;
+    auto* state = reinterpret_cast<plugin_state*>(handle);
+    if (!state->use_mesh) return -1;
+    std::memset(out, 0, sizeof *out);
+    out->triangles = state->mesh.triangles.data();
+    out->nodes = state->mesh.nodes.data();
+    out->leaf_order = state->mesh.leaf_order.data();
+    out->n_triangles = static_cast<uint32_t>(state->mesh.triangles.size());
+    out->n_nodes = static_cast<uint32_t>(state->mesh.nodes.size());
+    out->depth = state->mesh.depth;
     return 0;
 }
 

@@ -17,7 +17,9 @@ from .loader import dynamic_library, loader
 class headless_host:
     def __init__(self, width: int, height: int, plugin_path=PLUGIN_PATH, device_ordinal: int = 0,
                  shard_index: int = 0, shard_count: int = 1, present: bool = False, log=None,
-                 single_stream: bool = False):
+                 single_stream: bool = False, env: dict | None = None):
+        """`env`: out-of-band plugin options (QUASI_CUDA_SCENE, QUASI_CUDA_MAX_BOUNCES, ...), set in
+        the process environment only while Q_plugin_create runs (the ABI has no slot for them)."""
         self.messages = []
         self._user_log = log
 
@@ -31,7 +33,18 @@ class headless_host:
                                            present=present, single_stream=single_stream)
         self.library = dynamic_library.open(plugin_path)
         self.plugin_context = self.context.make_plugin_context(log=_log)
-        self.plugin = loader.load(self.library, self.plugin_context)
+        import os
+
+        saved = {k: os.environ.get(k) for k in (env or {})}
+        os.environ.update({k: str(v) for k, v in (env or {}).items()})
+        try:
+            self.plugin = loader.load(self.library, self.plugin_context)
+        finally:
+            for k, v in saved.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
         self.camera = orbit_camera()
         self.camera.update_position()
         self.frames_rendered = 0

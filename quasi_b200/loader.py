@@ -156,6 +156,7 @@ class loader:
             "Q_cuda_ipc_export": (C.c_int, [C.c_void_p, C.POINTER(abi.Q_cuda_ipc_handle)]),
             "Q_cuda_ipc_open": (C.c_int, [C.POINTER(abi.Q_cuda_ipc_handle), C.POINTER(C.c_void_p)]),
             "Q_cuda_ipc_close": (C.c_int, [C.c_void_p]),
+            "Q_cuda_plugin_mesh_view": (C.c_int, [C.c_void_p, C.POINTER(abi.Q_cuda_mesh_view)]),
             "Q_cuda_probe_sincos": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
         }
         for name, (res, args) in sig.items():
@@ -255,6 +256,12 @@ class loader:
         if self._fn["Q_cuda_plugin_layers"](self._handle, stream_ptr, C.byref(l)) != 0:
             raise RuntimeError("Q_cuda_plugin_layers failed")
         return l
+
+    def cuda_mesh_view(self):
+        v = abi.Q_cuda_mesh_view()
+        if self._fn["Q_cuda_plugin_mesh_view"](self._handle, C.byref(v)) != 0:
+            return None
+        return v
 
     def fn(self, name: str):
         return self._fn[name]

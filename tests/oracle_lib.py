@@ -278,3 +278,72 @@ class Reference(_Base):
 def bits(a: np.ndarray) -> np.ndarray:
     """View float32 data as uint32 for bit-exact comparison."""
     return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+class MeshOracle:
+    """oracle/quasi_oracle_mesh.c: the triangle-mesh scene of BASELINE config 3."""
+
+    node_dtype = np.dtype([("bmin", "<f4", 3), ("left_first", "<u4"), ("bmax", "<f4", 3), ("count", "<u4")])
+    tri_dtype = np.dtype([("v0", "<f4", 3), ("material", "<u4"), ("e1", "<f4", 3), ("pad0", "<u4"),
+                          ("e2", "<f4", 3), ("pad1", "<u4")])
+
+    class _stats(C.Structure):
+        _fields_ = [("rays", C.c_uint64), ("nodes_visited", C.c_uint64), ("triangles_tested", C.c_uint64)]
+
+    def __init__(self, grid: int, seed: int = 1, path: Path = ORACLE_SO):
+        if not path.exists():
+            build_oracle(ref=False)
+        self.lib = lib = C.CDLL(str(path))
+        fp = C.POINTER(C.c_float)
+        lib.qm_scene_create.restype = C.c_void_p
+        lib.qm_scene_create.argtypes = [C.c_uint32, C.c_uint32]
+        lib.qm_scene_destroy.argtypes = [C.c_void_p]
+        for n in ("qm_triangle_count", "qm_node_count"):
+            getattr(lib, n).restype = C.c_uint32
+            getattr(lib, n).argtypes = [C.c_void_p]
+        for n in ("qm_triangles", "qm_nodes", "qm_leaf_order"):
+            getattr(lib, n).restype = C.c_void_p
+            getattr(lib, n).argtypes = [C.c_void_p]
+        lib.qm_render_frames.restype = None
+        lib.qm_render_frames.argtypes = [C.c_void_p, fp, fp, fp, C.c_float, C.c_uint32, C.c_uint32, C.c_uint32,
+                                         C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(fp), C.c_int,
+                                         C.POINTER(self._stats)]
+        self.grid, self.seed = grid, seed
+        self.scene = lib.qm_scene_create(grid, seed)
+
+    def __del__(self):
+        try:
+            self.lib.qm_scene_destroy(self.scene)
+        except Exception:
+            pass
+
+    @property
+    def n_triangles(self):
+        return self.lib.qm_triangle_count(self.scene)
+
+    @property
+    def n_nodes(self):
+        return self.lib.qm_node_count(self.scene)
+
+    def _array(self, ptr, dtype, n):
+        buf = (C.c_char * (np.dtype(dtype).itemsize * n)).from_address(ptr)
+        return np.frombuffer(buf, dtype=dtype, count=n).copy()
+
+    def triangles(self):
+        return self._array(self.lib.qm_triangles(self.scene), self.tri_dtype, self.n_triangles)
+
+    def nodes(self):
+        return self._array(self.lib.qm_nodes(self.scene), self.node_dtype, self.n_nodes)
+
+    def leaf_order(self):
+        return self._array(self.lib.qm_leaf_order(self.scene), np.uint32, self.n_triangles)
+
+    def render_frames(self, width, height, n_frames, max_bounces=4, use_bvh=True, camera=DEFAULT_CAMERA,
+                      frame_first=0, frame_stride=1, threads=0):
+        layers = [np.zeros((height, width, 4), dtype=np.float32) for _ in range(4)]
+        arr = (C.POINTER(C.c_float) * 4)(*[_fptr(a) for a in layers])
+        st = self._stats()
+        self.lib.qm_render_frames(self.scene, _f3(camera["position"]), _f3(camera["target"]), _f3(camera["up"]),
+                                  float(camera["fov"]), width, height, frame_first, frame_stride, n_frames,
+                                  max_bounces, 1 if use_bvh else 0, arr, threads, C.byref(st))
+        return layers, dict(rays=st.rays, nodes_visited=st.nodes_visited, triangles_tested=st.triangles_tested)
