@@ -41,6 +41,10 @@ constexpr int k_block_threads = 256;
 constexpr int k_blocks_per_sm = 3;
 constexpr int k_warps_per_block = k_block_threads / 32;
 constexpr uint32_t k_miss = 0xffffffffu;
+#ifndef QUASI_MESH_MIN_WAITING
+#define QUASI_MESH_MIN_WAITING 8
+#endif
+constexpr int k_min_waiting = QUASI_MESH_MIN_WAITING;  ///< waiting lanes that trigger a service phase
 
 struct mesh_hit {
     float t;
@@ -82,69 +86,61 @@ __device__ __forceinline__ void intersect(float4 v0m, float4 e1p, float4 e2_, ui
     best.slot = slot;
 }
 
-/// Closest hit through the BVH. `stack` points at this thread's column of the
-/// shared-memory stack; consecutive entries are k_block_threads words apart.
-__device__ __forceinline__ mesh_hit trace_mesh(const mesh_params& scene, uint2* stack, v3 o, v3 d,
-                                               uint32_t& nodes_visited, uint32_t& tris_tested) {
-    mesh_hit best{1e30f, k_miss, 0u};
-    const v3 idir = make_v3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-    const float4* __restrict__ nodes = scene.nodes;
+constexpr uint32_t k_done = 0xffffffffu;  ///< node reference: traversal finished
 
-    float tn;
-    float4 lo = __ldg(nodes), hi = __ldg(nodes + 1);
-    nodes_visited++;
-    if (!box_hit(lo, hi, o, idir, best.t, tn)) return best;
-    uint32_t left_first = __float_as_uint(lo.w), count = __float_as_uint(hi.w);
-    int sp = 0;
-
-    for (;;) {
-        if (count == 0u) {
-            // interior: both children are one 64-byte line
-            const float4* c = nodes + 2u * static_cast<size_t>(left_first);
-            const float4 l_lo = __ldg(c), l_hi = __ldg(c + 1), r_lo = __ldg(c + 2), r_hi = __ldg(c + 3);
-            nodes_visited += 2u;
-            float tl, tr;
-            const bool hit_l = box_hit(l_lo, l_hi, o, idir, best.t, tl);
-            const bool hit_r = box_hit(r_lo, r_hi, o, idir, best.t, tr);
-            if (hit_l || hit_r) {
-                const bool go_left = hit_l && (!hit_r || tl <= tr);
-                if (hit_l && hit_r) {
-                    // defer the far child: {left_first << 3 | count, entry distance}
-                    const float4 f_lo = go_left ? r_lo : l_lo, f_hi = go_left ? r_hi : l_hi;
-                    stack[sp * k_block_threads] =
-                        make_uint2((__float_as_uint(f_lo.w) << 3) | __float_as_uint(f_hi.w),
-                                   __float_as_uint(go_left ? tr : tl));
-                    sp++;
-                }
-                left_first = __float_as_uint(go_left ? l_lo.w : r_lo.w);
-                count = __float_as_uint(go_left ? l_hi.w : r_hi.w);
-                continue;
-            }
-        } else {
-            for (uint32_t k = 0; k < count; k++) {
-                const uint32_t slot = left_first + k;
-                intersect(__ldg(scene.tri_v0 + slot), __ldg(scene.tri_e1 + slot), __ldg(scene.tri_e2 + slot),
-                          slot, o, d, best);
-            }
-            tris_tested += count;
-        }
-        // pop the next deferred subtree that can still hold a closer (or tying) hit
-        bool found = false;
-        while (sp > 0) {
-            sp--;
-            const uint2 e = stack[sp * k_block_threads];
-            if (__uint_as_float(e.y) <= best.t) {
-                left_first = e.x >> 3;
-                count = e.x & 7u;
-                found = true;
-                break;
-            }
-        }
-        if (!found) break;
-    }
-    return best;
+/// Node references are {left_first << 3 | count}: count 0 = interior, 1..4 = leaf.
+__device__ __forceinline__ uint32_t node_ref(float4 lo, float4 hi) {
+    return (__float_as_uint(lo.w) << 3) | __float_as_uint(hi.w);
 }
 
+/// Next deferred subtree that can still hold a closer (or tying) hit, or k_done.
+__device__ __forceinline__ uint32_t pop(const uint2* stack, int& sp, float closest) {
+    while (sp > 0) {
+        sp--;
+        const uint2 e = stack[sp * k_block_threads];
+        if (__uint_as_float(e.y) <= closest) return e.x;
+    }
+    return k_done;
+}
+
+/// One interior step: tests both children (one 64-byte line), descends into the
+/// nearer one that is hit and defers the other, or pops.
+__device__ __forceinline__ void interior_step(const float4* __restrict__ nodes, uint2* stack, v3 o, v3 idir,
+                                              float closest, uint32_t& cur, int& sp) {
+    const float4* c = nodes + 2u * static_cast<size_t>(cur >> 3);
+    const float4 l_lo = __ldg(c), l_hi = __ldg(c + 1), r_lo = __ldg(c + 2), r_hi = __ldg(c + 3);
+    float tl, tr;
+    const bool hit_l = box_hit(l_lo, l_hi, o, idir, closest, tl);
+    const bool hit_r = box_hit(r_lo, r_hi, o, idir, closest, tr);
+    const uint32_t ref_l = node_ref(l_lo, l_hi), ref_r = node_ref(r_lo, r_hi);
+    if (hit_l && hit_r) {
+        const bool go_left = tl <= tr;
+        stack[sp * k_block_threads] = make_uint2(go_left ? ref_r : ref_l, __float_as_uint(go_left ? tr : tl));
+        sp++;
+        cur = go_left ? ref_l : ref_r;
+    } else if (hit_l || hit_r) {
+        cur = hit_l ? ref_l : ref_r;
+    } else {
+        cur = pop(stack, sp, closest);
+    }
+}
+
+/// Persistent warps; every lane is a small state machine:
+///   idle      no path (start, or the warp's pixels have run out)
+///   tracing   `cur` != k_done: a closest-hit query is in flight (cursor, stack
+///             pointer, best hit and ray live in registers, the stack in shared memory)
+///   waiting   the query has finished; the hit has to be shaded
+/// The warp alternates between two phases and reconverges between them:
+///   service   waiting lanes shade their hit (next bounce, or write the pixel);
+///             lanes without a path take the warp's next pixels (ballot + popc
+///             compaction); every lane with a new ray tests the root and starts tracing.
+///   traverse  warp-synchronous while-while (interior descent until every tracing
+///             lane holds a leaf; leaf triangles; repeat) until k_min_waiting lanes
+///             are waiting or nobody is tracing.
+/// So a lane whose ray left the scene after 3 nodes does not sit out the 150
+/// nodes of its neighbour: it is given the next ray as soon as enough lanes
+/// are waiting to make the service phase worth issuing (Aila & Laine's
+/// persistent while-while with dynamic fetch, with paths instead of rays).
 __global__ void __launch_bounds__(k_block_threads, k_blocks_per_sm)
 mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_constant__ frame_params frame,
                       float4* __restrict__ beauty, float4* __restrict__ albedo, float4* __restrict__ normal,
@@ -156,6 +152,7 @@ mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_co
     }
     __syncthreads();
     uint2* my_stack = s_stack + threadIdx.x;
+    const float4* __restrict__ nodes = scene.nodes;
 
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lanes_below = (1u << lane) - 1u;
@@ -168,73 +165,31 @@ mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_co
     const uint32_t max_bounces = scene.max_bounces;
     const v3 cam_origin = load_v3(frame.position);
 
+    // path state
     bool active = false;
     v3 ro = cam_origin, rd = make_v3(0.0f, 0.0f, -1.0f);
     v3 throughput = make_v3(1.0f, 1.0f, 1.0f), color = make_v3(0.0f, 0.0f, 0.0f);
-    uint32_t rng = 0, bounce = 0;
-    size_t pixel = 0;
+    uint32_t rng = 0, bounce = 0, pixel = 0;
+    // query state
+    uint32_t cur = k_done;
+    int sp = 0;
+    mesh_hit best{1e30f, k_miss, 0u};
+    v3 idir = make_v3(0.0f, 0.0f, 0.0f);
+
     uint32_t rays = 0, nodes_visited = 0, tris_tested = 0;
-    uint32_t next_item = 0;
+    uint32_t next_item = 0;  // warp-uniform cursor into this warp's pixel sequence
 
     while (true) {
-        // Regeneration: idle lanes take the warp's next pixels (see pathtrace.cu).
-        const uint32_t idle = __ballot_sync(0xffffffffu, !active);
-        if (idle != 0u) {
-            if (!active) {
-                const uint32_t item = next_item + __popc(idle & lanes_below);
-                const uint32_t tile = warp_global + (item >> 5) * n_warps;
-                if (tile < n_tiles) {
-                    uint32_t tile_y = __umulhi(tile, frame.tiles_x_magic);
-                    uint32_t tile_x = tile - tile_y * tiles_x;
-                    if (tile_x >= tiles_x) {
-                        tile_x -= tiles_x;
-                        tile_y++;
-                    }
-                    const uint32_t px = tile_x * 8u + (item & 7u);
-                    const uint32_t py = tile_y * 4u + ((item >> 3) & 3u);
-                    if (px < frame.width && py < frame.height) {
-                        float uv_x = (static_cast<float>(px) + 0.5f) / static_cast<float>(frame.width);
-                        float uv_y = 1.0f - (static_cast<float>(py) + 0.5f) / static_cast<float>(frame.height);
-                        rng = pcg_hash(px + py * 1920u + frame.frame_index * 1920u * 1080u);
-                        const float jx = random_float(rng);
-                        const float jy = random_float(rng);
-                        uv_x += (jx - 0.5f) * 0.001f;
-                        uv_y += (jy - 0.5f) * 0.001f;
-                        const v3 target = load_v3(frame.lower_left) + load_v3(frame.horizontal) * uv_x +
-                                          load_v3(frame.vertical) * uv_y;
-                        ro = cam_origin;
-                        rd = normalize(target - cam_origin);
-                        throughput = make_v3(1.0f, 1.0f, 1.0f);
-                        color = make_v3(0.0f, 0.0f, 0.0f);
-                        bounce = 0;
-                        pixel = static_cast<size_t>(py) * frame.width + px;
-                        active = true;
-                        if (!first_sample) {
-                            prefetch_l2(beauty + pixel);
-                            prefetch_l2(albedo + pixel);
-                            prefetch_l2(normal + pixel);
-                            prefetch_l2(depth + pixel);
-                        }
-                    }
-                }
-            }
-            next_item += __popc(idle);
-        }
-        if (!__any_sync(0xffffffffu, active)) {
-            if (warp_global + (next_item >> 5) * n_warps >= n_tiles) break;
-            continue;
-        }
-
-        if (active) {
-            const mesh_hit hit = trace_mesh(scene, my_stack, ro, rd, nodes_visited, tris_tested);
-            rays++;
-            const bool is_hit = hit.prim != k_miss;
-
+        // ---------------------------------------------------------- service ----
+        bool new_ray = false;
+        if (active && cur == k_done) {
+            // One bounce of path_trace (plugin.mm:232-273) around the finished query.
+            const bool is_hit = best.prim != k_miss;
             v3 n = make_v3(0.0f, 0.0f, 0.0f), q_emission = n, q_albedo = n;
             bool is_light = false;
             if (is_hit) {
-                const float4 v0m = __ldg(scene.tri_v0 + hit.slot);
-                const float4 e1 = __ldg(scene.tri_e1 + hit.slot), e2 = __ldg(scene.tri_e2 + hit.slot);
+                const float4 v0m = __ldg(scene.tri_v0 + best.slot);
+                const float4 e1 = __ldg(scene.tri_e1 + best.slot), e2 = __ldg(scene.tri_e2 + best.slot);
                 const float* m = s_material + __float_as_uint(v0m.w) * 8u;
                 q_albedo = load_v3(m);
                 q_emission = load_v3(m + 4);
@@ -249,7 +204,7 @@ mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_co
                 if (is_hit) {
                     a = is_light ? q_emission : q_albedo;
                     nn = make_v3(n.x * 0.5f + 0.5f, n.y * 0.5f + 0.5f, n.z * 0.5f + 0.5f);
-                    first_t = hit.t;
+                    first_t = best.t;
                 }
                 const float nd = fminf(fmaxf((first_t - 1.0f) / 4.0f, 0.0f), 1.0f);
                 accumulate_pixel(albedo, pixel, make_float4(a.x, a.y, a.z, 1.0f), first_sample, weight);
@@ -277,7 +232,7 @@ mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_co
             done = done || bounce >= max_bounces;
 
             if (!done) {
-                const v3 point = ro + rd * hit.t;
+                const v3 point = ro + rd * best.t;
                 ro = point + n * 0.001f;
                 // cosine_sample_hemisphere, plugin.mm:111-125, literally
                 const float r1 = random_float(rng);
@@ -293,11 +248,95 @@ mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_co
                 const v3 u = cross(w, v);
                 const v3 dir = (u * cos_phi) * sin_theta + (v * sin_phi) * sin_theta + w * cos_theta;
                 rd = normalize(dir);
+                new_ray = true;
             } else {
                 accumulate_pixel(beauty, pixel, make_float4(color.x, color.y, color.z, 1.0f), first_sample,
                                  weight);
                 active = false;
             }
+        }
+        __syncwarp();
+
+        // Regeneration: lanes without a path take the warp's next pixels (see pathtrace.cu).
+        const uint32_t idle = __ballot_sync(0xffffffffu, !active);
+        if (idle != 0u && warp_global + (next_item >> 5) * n_warps < n_tiles) {
+            if (!active) {
+                const uint32_t item = next_item + __popc(idle & lanes_below);
+                const uint32_t tile = warp_global + (item >> 5) * n_warps;
+                if (tile < n_tiles) {
+                    uint32_t tile_y = __umulhi(tile, frame.tiles_x_magic);
+                    uint32_t tile_x = tile - tile_y * tiles_x;
+                    if (tile_x >= tiles_x) {
+                        tile_x -= tiles_x;
+                        tile_y++;
+                    }
+                    const uint32_t px = tile_x * 8u + (item & 7u);
+                    const uint32_t py = tile_y * 4u + ((item >> 3) & 3u);
+                    if (px < frame.width && py < frame.height) {
+                        float uv_x = (static_cast<float>(px) + 0.5f) / static_cast<float>(frame.width);
+                        float uv_y = 1.0f - (static_cast<float>(py) + 0.5f) / static_cast<float>(frame.height);
+                        rng = pcg_hash(px + py * 1920u + frame.frame_index * 1920u * 1080u);
+                        const float jx = random_float(rng);
+                        const float jy = random_float(rng);
+                        uv_x += (jx - 0.5f) * 0.001f;
+                        uv_y += (jy - 0.5f) * 0.001f;
+                        const v3 target = load_v3(frame.lower_left) + load_v3(frame.horizontal) * uv_x +
+                                          load_v3(frame.vertical) * uv_y;
+                        ro = cam_origin;
+                        rd = normalize(target - cam_origin);
+                        throughput = make_v3(1.0f, 1.0f, 1.0f);
+                        color = make_v3(0.0f, 0.0f, 0.0f);
+                        bounce = 0;
+                        pixel = py * frame.width + px;
+                        active = true;
+                        new_ray = true;
+                        if (!first_sample) {
+                            prefetch_l2(beauty + pixel);
+                            prefetch_l2(albedo + pixel);
+                            prefetch_l2(normal + pixel);
+                            prefetch_l2(depth + pixel);
+                        }
+                    }
+                }
+            }
+            next_item += __popc(idle);
+        }
+
+        // Every lane with a new ray: root test, start of the query.
+        if (new_ray) {
+            rays++;
+            best = mesh_hit{1e30f, k_miss, 0u};
+            idir = make_v3(1.0f / rd.x, 1.0f / rd.y, 1.0f / rd.z);
+            sp = 0;
+            float tn;
+            const float4 lo = __ldg(nodes), hi = __ldg(nodes + 1);
+            nodes_visited++;
+            cur = box_hit(lo, hi, ro, idir, best.t, tn) ? node_ref(lo, hi) : k_done;
+        }
+        if (!__any_sync(0xffffffffu, active)) {
+            if (warp_global + (next_item >> 5) * n_warps >= n_tiles) break;  // no paths, no pixels left
+            continue;  // only off-image pixels of an edge tile were handed out
+        }
+
+        // --------------------------------------------------------- traverse ----
+        while (__any_sync(0xffffffffu, cur != k_done)) {
+            while ((cur & 7u) == 0u) {
+                nodes_visited += 2u;
+                interior_step(nodes, my_stack, ro, idir, best.t, cur, sp);
+            }
+            __syncwarp();
+            if (cur != k_done) {
+                const uint32_t first = cur >> 3, count = cur & 7u;
+                for (uint32_t k = 0; k < count; k++) {
+                    const uint32_t slot = first + k;
+                    intersect(__ldg(scene.tri_v0 + slot), __ldg(scene.tri_e1 + slot), __ldg(scene.tri_e2 + slot),
+                              slot, ro, rd, best);
+                }
+                tris_tested += count;
+                cur = pop(my_stack, sp, best.t);
+            }
+            const uint32_t waiting = __ballot_sync(0xffffffffu, active && cur == k_done);
+            if (__popc(waiting) >= k_min_waiting) break;
         }
     }
 
