@@ -12,7 +12,7 @@
 namespace Q::cuda {
 
 inline constexpr uint32_t k_max_shards = 16;
-inline constexpr uint32_t k_mesh_stack_entries = 32;  ///< per-lane traversal stack; BVH depth must fit
+inline constexpr uint32_t k_mesh_stack_entries = 48;  ///< per-lane traversal stack (shared + local part); BVH depth must fit
 inline constexpr uint32_t k_mesh_materials = 8;
 
 /// Device view of the mesh scene (mesh_scene.hpp:pack_for_device).
@@ -21,6 +21,7 @@ struct alignas(16) mesh_params {
     const float4* tri_v0;   ///< leaf order: {v0.xyz, material}
     const float4* tri_e1;   ///< leaf order: {e1.xyz, original index}
     const float4* tri_e2;   ///< leaf order: {e2.xyz, 0}
+    const float4* tri_shade;  ///< leaf order, 3 per triangle: mesh_scene.hpp:shading_record
     uint32_t n_nodes;
     uint32_t n_triangles;
     uint32_t max_bounces;

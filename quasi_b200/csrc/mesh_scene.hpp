@@ -18,7 +18,8 @@
 /// {min.xyz, left_first} {max.xyz, count}; triangles in LEAF ORDER as three
 /// float4 arrays {v0.xyz, material} {e1.xyz, original index} {e2.xyz, 0}, so a
 /// node is two 16-byte loads, a pair of sibling nodes one 64-byte line, and a
-/// triangle three 16-byte loads.
+/// triangle three 16-byte loads; plus, per triangle, a 48-byte shading record
+/// (normal and cosine-sampling frame) read once per hit.
 
 #pragma once
 
@@ -332,9 +333,48 @@ inline void build_bvh(scene& s) {
     }
 }
 
+namespace detail {
+
+struct vec3 {
+    float x, y, z;
+};
+inline vec3 cross3(vec3 a, vec3 b) {
+    return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+/// v / sqrt((v.x*v.x + v.y*v.y) + v.z*v.z): the reference's normalize (math/vec.hpp:92-114).
+inline vec3 normalize3(vec3 v) {
+    const float len = std::sqrt(v.x * v.x + v.y * v.y + v.z * v.z);
+    return {v.x / len, v.y / len, v.z / len};
+}
+
+}  // namespace detail
+
+/// @brief What shading a hit on a triangle needs, none of which depends on the ray
+/// except for one sign: the geometric normal ng = normalize(cross(e1, e2)) and the
+/// cosine-sampling frame of plugin.mm:115-121 for n = +ng, i.e. w = normalize(ng),
+/// a = |w.x| > 0.9 ? (0,1,0) : (1,0,0), v = normalize(cross(w, a)), u = cross(w, v).
+/// Each operation is one correctly rounded binary32 operation in the shader's
+/// order (this file is compiled with -ffp-contract=off), so the values are the
+/// ones the per-hit evaluation of oracle/quasi_oracle_mesh.c produces. For
+/// n = -ng the frame is (-w, -v, u), exactly (negation commutes with every step).
+/// Packed as three float4: {ng.xyz, w.x} {w.y, w.z, v.x, v.y} {v.z, u.xyz}.
+inline void shading_record(const triangle& t, float4_t out[3]) {
+    using namespace detail;
+    const vec3 ng = normalize3(cross3({t.e1[0], t.e1[1], t.e1[2]}, {t.e2[0], t.e2[1], t.e2[2]}));
+    const vec3 w = normalize3(ng);
+    const vec3 a = std::fabs(w.x) > 0.9f ? vec3{0.0f, 1.0f, 0.0f} : vec3{1.0f, 0.0f, 0.0f};
+    const vec3 v = normalize3(cross3(w, a));
+    const vec3 u = cross3(w, v);
+    out[0] = {ng.x, ng.y, ng.z, w.x};
+    out[1] = {w.y, w.z, v.x, v.y};
+    out[2] = {v.z, u.x, u.y, u.z};
+}
+
 /// @brief Flattens nodes and leaf-ordered triangles into the float4 arrays the kernel reads.
+/// `tri_shade` gets three float4 per leaf slot (shading_record).
 inline void pack_for_device(const scene& s, std::vector<float4_t>& nodes, std::vector<float4_t>& tri_v0,
-                            std::vector<float4_t>& tri_e1, std::vector<float4_t>& tri_e2) {
+                            std::vector<float4_t>& tri_e1, std::vector<float4_t>& tri_e2,
+                            std::vector<float4_t>& tri_shade) {
     nodes.resize(s.nodes.size() * 2);
     for (size_t i = 0; i < s.nodes.size(); i++) {
         const node& n = s.nodes[i];
@@ -345,12 +385,14 @@ inline void pack_for_device(const scene& s, std::vector<float4_t>& nodes, std::v
     tri_v0.resize(n);
     tri_e1.resize(n);
     tri_e2.resize(n);
+    tri_shade.resize(n * 3);
     for (size_t slot = 0; slot < n; slot++) {
         const uint32_t original = s.leaf_order[slot];
         const triangle& t = s.triangles[original];
         tri_v0[slot] = {t.v0[0], t.v0[1], t.v0[2], bits_to_float(t.material)};
         tri_e1[slot] = {t.e1[0], t.e1[1], t.e1[2], bits_to_float(original)};
         tri_e2[slot] = {t.e2[0], t.e2[1], t.e2[2], 0.0f};
+        shading_record(t, &tri_shade[slot * 3]);
     }
 }
 

@@ -8,23 +8,37 @@
 /// path; the arithmetic contract is oracle/quasi_oracle_mesh.h and the result is
 /// bit-identical to it.
 ///
-/// Bound: L2 / latency, not HBM and not FP32 issue. The
-/// working set (20.6 MB of nodes + 48 MB of triangles) sits in the 126 MB L2, so
-/// the kernel is built around memory-level parallelism and coherence:
+/// Bound: instruction issue at low SIMD efficiency, then L1/L2 latency; not HBM
+/// (the 20.6 MB of nodes + 48 MB of triangles sit in the
+/// 126 MB L2). What the kernel is built around, in the order it mattered (ncu,
+/// profiles/r1_mesh_*):
+///  - Lanes of a warp that follow different rays must be kept together by hand.
+///    Every lane is a small state machine (idle / at an interior node / holding a
+///    leaf / waiting to be shaded) and the warp picks ONE kind of work per
+///    iteration by ballot: descend one level for the lanes at interior nodes;
+///    test triangles once k_leaf_batch lanes hold a leaf; shade and hand out new
+///    rays once k_min_waiting lanes have finished their query (persistent
+///    while-while with dynamic fetch, with paths instead of rays). The first
+///    version, a per-lane loop, ran at 5.5 of 32 lanes per instruction.
 ///  - 32-byte nodes read as two float4; siblings are adjacent, so visiting an
 ///    interior node is one 64-byte line (4 x LDG.128, read-only path).
+///  - The slab test is 6 FFMA against precomputed origin * 1/dir. It only
+///    prunes, so it may be approximate as long as it is conservative: boxes are
+///    padded by 1e-4 of their extent + 1e-5, the test's error is below 2e-6.
 ///  - Triangles in leaf order as three float4 arrays (SoA): 3 x LDG.128 each,
-///    consecutive slots of a leaf are consecutive addresses.
-///  - Per-lane traversal stack in shared memory, laid out [entry][thread] so a
-///    push or pop by the whole warp touches 32 different banks. Entries carry
-///    the entry distance, and a popped subtree that has fallen behind the
-///    current closest hit is skipped without touching memory.
-///  - Near child first, far child pushed (while-while traversal).
-///  - Persistent warps with path regeneration (ballot + popc compaction), as in
-///    pathtrace.cu: all lanes of a warp are always inside the same bounce.
-/// The order in which nodes are visited cannot change the result: boxes are
-/// padded (they only prune what the ray provably misses) and an equal t is won
-/// by the higher triangle index.
+///    consecutive slots of a leaf are consecutive addresses. Moeller-Trumbore
+///    in the oracle's operation order: the accepted t reaches the pixel.
+///  - Normal and cosine-sampling frame per triangle are precomputed on the host
+///    with the shader's operations (mesh_scene.hpp:shading_record) and read
+///    once per hit: three normalisations less per bounce.
+///  - Per-lane traversal stack: the first k_smem_stack entries in shared
+///    memory, laid out [entry][thread] so a push or pop by the whole warp
+///    touches 32 different banks, the rest (rarely reached) in local memory.
+///    Entries carry the entry distance, and a popped subtree that has fallen
+///    behind the current closest hit is skipped without touching memory.
+/// The order in which nodes are visited cannot change the result: boxes only
+/// prune what the ray provably misses, and an equal t is won by the higher
+/// triangle index.
 
 #include "device_common.cuh"
 #include "kernels.hpp"
@@ -37,14 +51,28 @@ namespace {
 
 using namespace dev;
 
-constexpr int k_block_threads = 256;
-constexpr int k_blocks_per_sm = 3;
-constexpr int k_warps_per_block = k_block_threads / 32;
-constexpr uint32_t k_miss = 0xffffffffu;
-#ifndef QUASI_MESH_MIN_WAITING
-#define QUASI_MESH_MIN_WAITING 8
+#ifndef QUASI_MESH_BLOCKS_PER_SM
+#define QUASI_MESH_BLOCKS_PER_SM 4
 #endif
-constexpr int k_min_waiting = QUASI_MESH_MIN_WAITING;  ///< waiting lanes that trigger a service phase
+#ifndef QUASI_MESH_MIN_WAITING
+#define QUASI_MESH_MIN_WAITING 16
+#endif
+#ifndef QUASI_MESH_LEAF_BATCH
+#define QUASI_MESH_LEAF_BATCH 12
+#endif
+#ifndef QUASI_MESH_SMEM_STACK
+#define QUASI_MESH_SMEM_STACK 16
+#endif
+
+constexpr int k_block_threads = 256;
+constexpr int k_blocks_per_sm = QUASI_MESH_BLOCKS_PER_SM;
+constexpr int k_warps_per_block = k_block_threads / 32;
+constexpr int k_min_waiting = QUASI_MESH_MIN_WAITING;  ///< finished queries that trigger a service phase
+constexpr int k_leaf_batch = QUASI_MESH_LEAF_BATCH;    ///< lanes holding a leaf that trigger the triangle phase
+constexpr int k_smem_stack = QUASI_MESH_SMEM_STACK;    ///< stack entries per lane kept in shared memory
+constexpr int k_local_stack = static_cast<int>(k_mesh_stack_entries) - k_smem_stack;
+constexpr uint32_t k_miss = 0xffffffffu;
+constexpr uint32_t k_done = 0xffffffffu;  ///< node reference: the query has finished
 
 struct mesh_hit {
     float t;
@@ -52,15 +80,47 @@ struct mesh_hit {
     uint32_t slot;  ///< position in leaf order (where its float4s are)
 };
 
-/// Slab test of oracle/quasi_oracle_mesh.c:box_hit; also returns the entry distance.
-__device__ __forceinline__ bool box_hit(float4 lo, float4 hi, v3 o, v3 idir, float closest, float& t_near) {
-    const float t0x = (lo.x - o.x) * idir.x, t1x = (hi.x - o.x) * idir.x;
-    const float t0y = (lo.y - o.y) * idir.y, t1y = (hi.y - o.y) * idir.y;
-    const float t0z = (lo.z - o.z) * idir.z, t1z = (hi.z - o.z) * idir.z;
+/// Per-lane traversal stack: entries {node reference, entry distance}.
+struct lane_stack {
+    uint2* shared;  ///< this thread's column; consecutive entries are k_block_threads apart
+    uint2 local[k_local_stack];
+    int sp = 0;
+
+    __device__ __forceinline__ void push(uint2 e) {
+        if (sp < k_smem_stack) {
+            shared[sp * k_block_threads] = e;
+        } else {
+            local[sp - k_smem_stack] = e;
+        }
+        sp++;
+    }
+    /// Next deferred subtree that can still hold a closer (or tying) hit, or k_done.
+    __device__ __forceinline__ uint32_t pop(float closest) {
+        while (sp > 0) {
+            sp--;
+            const uint2 e = sp < k_smem_stack ? shared[sp * k_block_threads] : local[sp - k_smem_stack];
+            if (__uint_as_float(e.y) <= closest) return e.x;
+        }
+        return k_done;
+    }
+};
+
+/// Slab test against a padded box: `inv` = 1/dir (clamped to +-2^100), `oi` =
+/// origin * inv. Returns the entry distance in t_near. Conservative, not exact
+/// (see the file comment); NaNs cannot occur because inv is finite.
+__device__ __forceinline__ bool box_hit(float4 lo, float4 hi, v3 inv, v3 oi, float closest, float& t_near) {
+    const float t0x = __fmaf_rn(lo.x, inv.x, -oi.x), t1x = __fmaf_rn(hi.x, inv.x, -oi.x);
+    const float t0y = __fmaf_rn(lo.y, inv.y, -oi.y), t1y = __fmaf_rn(hi.y, inv.y, -oi.y);
+    const float t0z = __fmaf_rn(lo.z, inv.z, -oi.z), t1z = __fmaf_rn(hi.z, inv.z, -oi.z);
     const float tn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.0f));
     const float tf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), closest));
     t_near = tn;
     return tn <= tf;
+}
+
+/// 1/x for the slab test: one MUFU.RCP, clamped so that origin * result stays finite.
+__device__ __forceinline__ float slab_reciprocal(float x) {
+    return fminf(fmaxf(rcp_approx(x), -0x1p+100f), 0x1p+100f);
 }
 
 /// Moeller-Trumbore in the operation order of oracle/quasi_oracle_mesh.c:qm_intersect.
@@ -86,72 +146,44 @@ __device__ __forceinline__ void intersect(float4 v0m, float4 e1p, float4 e2_, ui
     best.slot = slot;
 }
 
-constexpr uint32_t k_done = 0xffffffffu;  ///< node reference: traversal finished
-
 /// Node references are {left_first << 3 | count}: count 0 = interior, 1..4 = leaf.
 __device__ __forceinline__ uint32_t node_ref(float4 lo, float4 hi) {
     return (__float_as_uint(lo.w) << 3) | __float_as_uint(hi.w);
 }
 
-/// Next deferred subtree that can still hold a closer (or tying) hit, or k_done.
-__device__ __forceinline__ uint32_t pop(const uint2* stack, int& sp, float closest) {
-    while (sp > 0) {
-        sp--;
-        const uint2 e = stack[sp * k_block_threads];
-        if (__uint_as_float(e.y) <= closest) return e.x;
-    }
-    return k_done;
-}
-
 /// One interior step: tests both children (one 64-byte line), descends into the
 /// nearer one that is hit and defers the other, or pops.
-__device__ __forceinline__ void interior_step(const float4* __restrict__ nodes, uint2* stack, v3 o, v3 idir,
-                                              float closest, uint32_t& cur, int& sp) {
+__device__ __forceinline__ void interior_step(const float4* __restrict__ nodes, lane_stack& stack, v3 inv, v3 oi,
+                                              float closest, uint32_t& cur) {
     const float4* c = nodes + 2u * static_cast<size_t>(cur >> 3);
     const float4 l_lo = __ldg(c), l_hi = __ldg(c + 1), r_lo = __ldg(c + 2), r_hi = __ldg(c + 3);
     float tl, tr;
-    const bool hit_l = box_hit(l_lo, l_hi, o, idir, closest, tl);
-    const bool hit_r = box_hit(r_lo, r_hi, o, idir, closest, tr);
+    const bool hit_l = box_hit(l_lo, l_hi, inv, oi, closest, tl);
+    const bool hit_r = box_hit(r_lo, r_hi, inv, oi, closest, tr);
     const uint32_t ref_l = node_ref(l_lo, l_hi), ref_r = node_ref(r_lo, r_hi);
     if (hit_l && hit_r) {
         const bool go_left = tl <= tr;
-        stack[sp * k_block_threads] = make_uint2(go_left ? ref_r : ref_l, __float_as_uint(go_left ? tr : tl));
-        sp++;
+        stack.push(make_uint2(go_left ? ref_r : ref_l, __float_as_uint(go_left ? tr : tl)));
         cur = go_left ? ref_l : ref_r;
     } else if (hit_l || hit_r) {
         cur = hit_l ? ref_l : ref_r;
     } else {
-        cur = pop(stack, sp, closest);
+        cur = stack.pop(closest);
     }
 }
 
-/// Persistent warps; every lane is a small state machine:
-///   idle      no path (start, or the warp's pixels have run out)
-///   tracing   `cur` != k_done: a closest-hit query is in flight (cursor, stack
-///             pointer, best hit and ray live in registers, the stack in shared memory)
-///   waiting   the query has finished; the hit has to be shaded
-/// The warp alternates between two phases and reconverges between them:
-///   service   waiting lanes shade their hit (next bounce, or write the pixel);
-///             lanes without a path take the warp's next pixels (ballot + popc
-///             compaction); every lane with a new ray tests the root and starts tracing.
-///   traverse  warp-synchronous while-while (interior descent until every tracing
-///             lane holds a leaf; leaf triangles; repeat) until k_min_waiting lanes
-///             are waiting or nobody is tracing.
-/// So a lane whose ray left the scene after 3 nodes does not sit out the 150
-/// nodes of its neighbour: it is given the next ray as soon as enough lanes
-/// are waiting to make the service phase worth issuing (Aila & Laine's
-/// persistent while-while with dynamic fetch, with paths instead of rays).
 __global__ void __launch_bounds__(k_block_threads, k_blocks_per_sm)
 mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_constant__ frame_params frame,
                       float4* __restrict__ beauty, float4* __restrict__ albedo, float4* __restrict__ normal,
                       float4* __restrict__ depth, unsigned long long* __restrict__ counters) {
-    extern __shared__ uint2 s_stack[];  // [k_mesh_stack_entries][k_block_threads]
+    __shared__ uint2 s_stack[k_smem_stack * k_block_threads];
     __shared__ float s_material[k_mesh_materials * 8];
     for (int i = threadIdx.x; i < static_cast<int>(k_mesh_materials) * 8; i += k_block_threads) {
         s_material[i] = scene.materials[i];
     }
     __syncthreads();
-    uint2* my_stack = s_stack + threadIdx.x;
+    lane_stack stack;
+    stack.shared = s_stack + threadIdx.x;
     const float4* __restrict__ nodes = scene.nodes;
 
     const uint32_t lane = threadIdx.x & 31u;
@@ -172,9 +204,8 @@ mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_co
     uint32_t rng = 0, bounce = 0, pixel = 0;
     // query state
     uint32_t cur = k_done;
-    int sp = 0;
     mesh_hit best{1e30f, k_miss, 0u};
-    v3 idir = make_v3(0.0f, 0.0f, 0.0f);
+    v3 inv = make_v3(0.0f, 0.0f, 0.0f), oi = inv;
 
     uint32_t rays = 0, nodes_visited = 0, tris_tested = 0;
     uint32_t next_item = 0;  // warp-uniform cursor into this warp's pixel sequence
@@ -186,16 +217,22 @@ mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_co
             // One bounce of path_trace (plugin.mm:232-273) around the finished query.
             const bool is_hit = best.prim != k_miss;
             v3 n = make_v3(0.0f, 0.0f, 0.0f), q_emission = n, q_albedo = n;
+            v3 fu = n, fv = n, fw = n;
             bool is_light = false;
             if (is_hit) {
-                const float4 v0m = __ldg(scene.tri_v0 + best.slot);
-                const float4 e1 = __ldg(scene.tri_e1 + best.slot), e2 = __ldg(scene.tri_e2 + best.slot);
-                const float* m = s_material + __float_as_uint(v0m.w) * 8u;
+                const float4* rec = scene.tri_shade + 3u * static_cast<size_t>(best.slot);
+                const float4 s0 = __ldg(rec), s1 = __ldg(rec + 1), s2 = __ldg(rec + 2);
+                const float* m = s_material + __float_as_uint(__ldg(scene.tri_v0 + best.slot).w) * 8u;
                 q_albedo = load_v3(m);
                 q_emission = load_v3(m + 4);
                 is_light = fmaxf(q_emission.x, fmaxf(q_emission.y, q_emission.z)) > 0.1f;
-                const v3 ng = normalize(cross(make_v3(e1.x, e1.y, e1.z), make_v3(e2.x, e2.y, e2.z)));
-                n = dot(ng, rd) < 0.0f ? ng : make_v3(-ng.x, -ng.y, -ng.z);
+                // normal faces the ray; the frame of -ng is (u, -v, -w), exactly
+                const v3 ng = make_v3(s0.x, s0.y, s0.z);
+                const float side = dot(ng, rd) < 0.0f ? 1.0f : -1.0f;
+                n = ng * side;
+                fw = make_v3(s0.w, s1.x, s1.y) * side;
+                fv = make_v3(s1.z, s1.w, s2.x) * side;
+                fu = make_v3(s2.y, s2.z, s2.w);
             }
 
             if (bounce == 0) {
@@ -234,7 +271,7 @@ mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_co
             if (!done) {
                 const v3 point = ro + rd * best.t;
                 ro = point + n * 0.001f;
-                // cosine_sample_hemisphere, plugin.mm:111-125, literally
+                // cosine_sample_hemisphere (plugin.mm:111-125) with the per-triangle frame
                 const float r1 = random_float(rng);
                 const float r2 = random_float(rng);
                 const float phi = 6.28318548202514648f * r1;
@@ -242,11 +279,7 @@ mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_co
                 const float sin_theta = sqrtf(r2);
                 float sin_phi, cos_phi;
                 sincos_round_once(phi, sin_phi, cos_phi);
-                const v3 w = normalize(n);
-                const v3 a = fabsf(w.x) > 0.9f ? make_v3(0.0f, 1.0f, 0.0f) : make_v3(1.0f, 0.0f, 0.0f);
-                const v3 v = normalize(cross(w, a));
-                const v3 u = cross(w, v);
-                const v3 dir = (u * cos_phi) * sin_theta + (v * sin_phi) * sin_theta + w * cos_theta;
+                const v3 dir = (fu * cos_phi) * sin_theta + (fv * sin_phi) * sin_theta + fw * cos_theta;
                 rd = normalize(dir);
                 new_ray = true;
             } else {
@@ -306,26 +339,36 @@ mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_co
         if (new_ray) {
             rays++;
             best = mesh_hit{1e30f, k_miss, 0u};
-            idir = make_v3(1.0f / rd.x, 1.0f / rd.y, 1.0f / rd.z);
-            sp = 0;
+            inv = make_v3(slab_reciprocal(rd.x), slab_reciprocal(rd.y), slab_reciprocal(rd.z));
+            oi = ro * inv;
+            stack.sp = 0;
             float tn;
             const float4 lo = __ldg(nodes), hi = __ldg(nodes + 1);
             nodes_visited++;
-            cur = box_hit(lo, hi, ro, idir, best.t, tn) ? node_ref(lo, hi) : k_done;
+            cur = box_hit(lo, hi, inv, oi, best.t, tn) ? node_ref(lo, hi) : k_done;
         }
-        if (!__any_sync(0xffffffffu, active)) {
+        const uint32_t m_active = __ballot_sync(0xffffffffu, active);
+        if (m_active == 0u) {
             if (warp_global + (next_item >> 5) * n_warps >= n_tiles) break;  // no paths, no pixels left
             continue;  // only off-image pixels of an edge tile were handed out
         }
 
         // --------------------------------------------------------- traverse ----
-        while (__any_sync(0xffffffffu, cur != k_done)) {
-            while ((cur & 7u) == 0u) {
-                nodes_visited += 2u;
-                interior_step(nodes, my_stack, ro, idir, best.t, cur, sp);
-            }
-            __syncwarp();
-            if (cur != k_done) {
+        while (true) {
+            const bool at_interior = (cur & 7u) == 0u;  // k_done has its low bits set
+            const uint32_t m_interior = __ballot_sync(0xffffffffu, at_interior);
+            const uint32_t m_leaf = __ballot_sync(0xffffffffu, !at_interior && cur != k_done);
+            const uint32_t m_tracing = m_interior | m_leaf;
+            // enough finished queries to make shading worth issuing, or nothing to traverse
+            if (m_tracing == 0u || __popc(m_active & ~m_tracing) >= k_min_waiting) break;
+            if (m_interior != 0u && __popc(m_leaf) < k_leaf_batch) {
+                // Descend one level. Lanes that already hold a leaf sit this out; they are
+                // served together once k_leaf_batch of them have gathered.
+                if (at_interior) {
+                    nodes_visited += 2u;
+                    interior_step(nodes, stack, inv, oi, best.t, cur);
+                }
+            } else if (!at_interior && cur != k_done) {
                 const uint32_t first = cur >> 3, count = cur & 7u;
                 for (uint32_t k = 0; k < count; k++) {
                     const uint32_t slot = first + k;
@@ -333,10 +376,8 @@ mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_co
                               slot, ro, rd, best);
                 }
                 tris_tested += count;
-                cur = pop(my_stack, sp, best.t);
+                cur = stack.pop(best.t);
             }
-            const uint32_t waiting = __ballot_sync(0xffffffffu, active && cur == k_done);
-            if (__popc(waiting) >= k_min_waiting) break;
         }
     }
 
@@ -354,17 +395,12 @@ mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_co
 
 cudaError_t launch_mesh_pathtrace(const mesh_params& scene, const frame_params& frame, float* const layers[4],
                                   unsigned long long* counters, int sm_count, cudaStream_t stream) {
-    static const cudaError_t attr = cudaFuncSetAttribute(
-        mesh_pathtrace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-        static_cast<int>(k_mesh_stack_entries * k_block_threads * sizeof(uint2)));
-    if (attr != cudaSuccess) return attr;
     const uint32_t n_tiles = ((frame.width + 7u) / 8u) * ((frame.height + 3u) / 4u);
     uint32_t blocks = static_cast<uint32_t>(sm_count) * k_blocks_per_sm;
     const uint32_t needed = (n_tiles + k_warps_per_block - 1u) / k_warps_per_block;
     if (needed < blocks) blocks = needed;
     if (blocks == 0) return cudaSuccess;
-    const size_t smem = static_cast<size_t>(k_mesh_stack_entries) * k_block_threads * sizeof(uint2);
-    mesh_pathtrace_kernel<<<blocks, k_block_threads, smem, stream>>>(
+    mesh_pathtrace_kernel<<<blocks, k_block_threads, 0, stream>>>(
         scene, frame, reinterpret_cast<float4*>(layers[0]), reinterpret_cast<float4*>(layers[1]),
         reinterpret_cast<float4*>(layers[2]), reinterpret_cast<float4*>(layers[3]), counters);
     return cudaGetLastError();

@@ -106,7 +106,7 @@ struct plugin_state {
     bool use_mesh = false;
     Q::cuda::mesh::scene mesh;
     Q::cuda::mesh_params mesh_device{};
-    void* mesh_buffers[4] = {nullptr, nullptr, nullptr, nullptr};
+    void* mesh_buffers[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 
     float* layers[Q_AOV_COUNT] = {nullptr, nullptr, nullptr, nullptr};
     unsigned long long* ray_counter = nullptr;
@@ -179,9 +179,9 @@ bool create_mesh(plugin_state* state, uint32_t grid, uint32_t seed, uint32_t max
         log_msg(state, "mesh BVH is deeper than the traversal stack");
         return false;
     }
-    std::vector<mesh::float4_t> packed[4];
-    mesh::pack_for_device(state->mesh, packed[0], packed[1], packed[2], packed[3]);
-    for (int i = 0; i < 4; i++) {
+    std::vector<mesh::float4_t> packed[5];
+    mesh::pack_for_device(state->mesh, packed[0], packed[1], packed[2], packed[3], packed[4]);
+    for (int i = 0; i < 5; i++) {
         const size_t bytes = packed[i].size() * sizeof(mesh::float4_t);
         if (!check(state, cudaMalloc(&state->mesh_buffers[i], bytes), "cudaMalloc(mesh)") ||
             !check(state, cudaMemcpyAsync(state->mesh_buffers[i], packed[i].data(), bytes,
@@ -195,6 +195,7 @@ bool create_mesh(plugin_state* state, uint32_t grid, uint32_t seed, uint32_t max
     d.tri_v0 = static_cast<const float4*>(state->mesh_buffers[1]);
     d.tri_e1 = static_cast<const float4*>(state->mesh_buffers[2]);
     d.tri_e2 = static_cast<const float4*>(state->mesh_buffers[3]);
+    d.tri_shade = static_cast<const float4*>(state->mesh_buffers[4]);
     d.n_nodes = static_cast<uint32_t>(state->mesh.nodes.size());
     d.n_triangles = static_cast<uint32_t>(state->mesh.triangles.size());
     d.max_bounces = max_bounces;
