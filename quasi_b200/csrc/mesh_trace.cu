@@ -60,6 +60,9 @@ using namespace dev;
 #ifndef QUASI_MESH_LEAF_BATCH
 #define QUASI_MESH_LEAF_BATCH 12
 #endif
+#ifndef QUASI_MESH_RUN_EXIT
+#define QUASI_MESH_RUN_EXIT 4
+#endif
 #ifndef QUASI_MESH_SMEM_STACK
 #define QUASI_MESH_SMEM_STACK 16
 #endif
@@ -69,10 +72,12 @@ constexpr int k_blocks_per_sm = QUASI_MESH_BLOCKS_PER_SM;
 constexpr int k_warps_per_block = k_block_threads / 32;
 constexpr int k_min_waiting = QUASI_MESH_MIN_WAITING;  ///< finished queries that trigger a service phase
 constexpr int k_leaf_batch = QUASI_MESH_LEAF_BATCH;    ///< lanes holding a leaf that trigger the triangle phase
+constexpr int k_run_exit = QUASI_MESH_RUN_EXIT;        ///< lanes leaving a descent run that end it
 constexpr int k_smem_stack = QUASI_MESH_SMEM_STACK;    ///< stack entries per lane kept in shared memory
 constexpr int k_local_stack = static_cast<int>(k_mesh_stack_entries) - k_smem_stack;
 constexpr uint32_t k_miss = 0xffffffffu;
 constexpr uint32_t k_done = 0xffffffffu;  ///< node reference: the query has finished
+constexpr uint32_t k_pop = 0xfffffffeu;   ///< node reference: take the next entry off the stack
 
 struct mesh_hit {
     float t;
@@ -94,15 +99,16 @@ struct lane_stack {
         }
         sp++;
     }
-    /// Next deferred subtree that can still hold a closer (or tying) hit, or k_done.
-    __device__ __forceinline__ uint32_t pop(float closest) {
-        while (sp > 0) {
-            sp--;
-            const uint2 e = sp < k_smem_stack ? shared[sp * k_block_threads] : local[sp - k_smem_stack];
-            if (__uint_as_float(e.y) <= closest) return e.x;
-        }
-        return k_done;
+    /// Takes one entry off (sp > 0). Returns its node reference if that subtree can
+    /// still hold a closer (or tying) hit; otherwise k_pop if entries remain, else k_done.
+    __device__ __forceinline__ uint32_t pop_one(float closest) {
+        sp--;
+        const uint2 e = sp < k_smem_stack ? shared[sp * k_block_threads] : local[sp - k_smem_stack];
+        if (__uint_as_float(e.y) <= closest) return e.x;
+        return sp > 0 ? k_pop : k_done;
     }
+    /// What a lane that has used up its node holds next.
+    __device__ __forceinline__ uint32_t after_node() const { return sp > 0 ? k_pop : k_done; }
 };
 
 /// Slab test against a padded box: `inv` = 1/dir (clamped to +-2^100), `oi` =
@@ -123,27 +129,32 @@ __device__ __forceinline__ float slab_reciprocal(float x) {
     return fminf(fmaxf(rcp_approx(x), -0x1p+100f), 0x1p+100f);
 }
 
-/// Moeller-Trumbore in the operation order of oracle/quasi_oracle_mesh.c:qm_intersect.
+/// Moeller-Trumbore with the operations, their order and the decisions of
+/// oracle/quasi_oracle_mesh.c:qm_intersect, evaluated without branches: every
+/// lane computes u, v and t and the early returns become one predicate. Values
+/// computed past a failed test are never used (NaN and infinity compare false).
 __device__ __forceinline__ void intersect(float4 v0m, float4 e1p, float4 e2_, uint32_t slot, v3 o, v3 d,
                                           mesh_hit& best) {
     const v3 e1 = make_v3(e1p.x, e1p.y, e1p.z), e2 = make_v3(e2_.x, e2_.y, e2_.z);
     const v3 pvec = cross(d, e2);
     const float det = dot(e1, pvec);
-    if (fabsf(det) < 1e-12f) return;
     const float inv_det = 1.0f / det;
     const v3 tvec = o - make_v3(v0m.x, v0m.y, v0m.z);
     const float u = dot(tvec, pvec) * inv_det;
-    if (u < 0.0f || u > 1.0f) return;
     const v3 qvec = cross(tvec, e1);
     const float v = dot(d, qvec) * inv_det;
-    if (v < 0.0f || u + v > 1.0f) return;
     const float t = dot(e2, qvec) * inv_det;
-    if (t < 0.001f || t > best.t) return;
     const uint32_t prim = __float_as_uint(e1p.w);
-    if (t == best.t && best.prim != k_miss && prim < best.prim) return;
-    best.t = t;
-    best.prim = prim;
-    best.slot = slot;
+    // the oracle's rejections, literally (so that an unordered compare decides the same way)
+    bool reject = fabsf(det) < 1e-12f;
+    reject = reject || u < 0.0f || u > 1.0f;
+    reject = reject || v < 0.0f || u + v > 1.0f;
+    reject = reject || t < 0.001f || t > best.t;
+    reject = reject || (t == best.t && best.prim != k_miss && prim < best.prim);
+    const bool ok = !reject;
+    best.t = ok ? t : best.t;
+    best.prim = ok ? prim : best.prim;
+    best.slot = ok ? slot : best.slot;
 }
 
 /// Node references are {left_first << 3 | count}: count 0 = interior, 1..4 = leaf.
@@ -152,7 +163,7 @@ __device__ __forceinline__ uint32_t node_ref(float4 lo, float4 hi) {
 }
 
 /// One interior step: tests both children (one 64-byte line), descends into the
-/// nearer one that is hit and defers the other, or pops.
+/// nearer one that is hit and defers the other, or asks for the next stack entry.
 __device__ __forceinline__ void interior_step(const float4* __restrict__ nodes, lane_stack& stack, v3 inv, v3 oi,
                                               float closest, uint32_t& cur) {
     const float4* c = nodes + 2u * static_cast<size_t>(cur >> 3);
@@ -168,7 +179,7 @@ __device__ __forceinline__ void interior_step(const float4* __restrict__ nodes, 
     } else if (hit_l || hit_r) {
         cur = hit_l ? ref_l : ref_r;
     } else {
-        cur = stack.pop(closest);
+        cur = stack.after_node();
     }
 }
 
@@ -355,20 +366,26 @@ mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_co
 
         // --------------------------------------------------------- traverse ----
         while (true) {
-            const bool at_interior = (cur & 7u) == 0u;  // k_done has its low bits set
-            const uint32_t m_interior = __ballot_sync(0xffffffffu, at_interior);
-            const uint32_t m_leaf = __ballot_sync(0xffffffffu, !at_interior && cur != k_done);
-            const uint32_t m_tracing = m_interior | m_leaf;
+            // low 3 bits of cur: 0 interior, 1..4 leaf with that many triangles, 6 k_pop, 7 k_done
+            const bool descending = (cur & 7u) == 0u || cur == k_pop;
+            const uint32_t m_descending = __ballot_sync(0xffffffffu, descending);
+            const uint32_t m_leaf = __ballot_sync(0xffffffffu, (cur & 7u) - 1u < 4u);
+            const uint32_t m_tracing = m_descending | m_leaf;
             // enough finished queries to make shading worth issuing, or nothing to traverse
             if (m_tracing == 0u || __popc(m_active & ~m_tracing) >= k_min_waiting) break;
-            if (m_interior != 0u && __popc(m_leaf) < k_leaf_batch) {
-                // Descend one level. Lanes that already hold a leaf sit this out; they are
-                // served together once k_leaf_batch of them have gathered.
-                if (at_interior) {
-                    nodes_visited += 2u;
-                    interior_step(nodes, stack, inv, oi, best.t, cur);
-                }
-            } else if (!at_interior && cur != k_done) {
+            if (m_descending != 0u && __popc(m_leaf) < k_leaf_batch) {
+                // Descent run: one level per iteration for every lane that is not holding a
+                // leaf, until k_run_exit of them have reached a leaf or finished. Leaf
+                // holders sit this out; they are served once k_leaf_batch have gathered.
+                const int keep = max(__popc(m_descending) - k_run_exit, 0);
+                do {
+                    if (cur == k_pop) cur = stack.pop_one(best.t);
+                    if ((cur & 7u) == 0u) {
+                        nodes_visited += 2u;
+                        interior_step(nodes, stack, inv, oi, best.t, cur);
+                    }
+                } while (__popc(__ballot_sync(0xffffffffu, (cur & 7u) == 0u || cur == k_pop)) > keep);
+            } else if ((cur & 7u) - 1u < 4u) {
                 const uint32_t first = cur >> 3, count = cur & 7u;
                 for (uint32_t k = 0; k < count; k++) {
                     const uint32_t slot = first + k;
@@ -376,7 +393,7 @@ mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_co
                               slot, ro, rd, best);
                 }
                 tris_tested += count;
-                cur = stack.pop(best.t);
+                cur = stack.after_node();
             }
         }
     }
