@@ -12,7 +12,7 @@
 namespace Q::cuda {
 
 inline constexpr uint32_t k_max_shards = 16;
-inline constexpr uint32_t k_mesh_stack_entries = 48;  ///< per-lane traversal stack (shared + local part); BVH depth must fit
+inline constexpr uint32_t k_mesh_stack_entries = 32;  ///< per-lane traversal stack; BVH depth must fit
 inline constexpr uint32_t k_mesh_materials = 8;
 
 /// Device view of the mesh scene (mesh_scene.hpp:pack_for_device).

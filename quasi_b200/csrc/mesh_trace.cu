@@ -31,11 +31,11 @@
 ///  - Normal and cosine-sampling frame per triangle are precomputed on the host
 ///    with the shader's operations (mesh_scene.hpp:shading_record) and read
 ///    once per hit: three normalisations less per bounce.
-///  - Per-lane traversal stack: the first k_smem_stack entries in shared
-///    memory, laid out [entry][thread] so a push or pop by the whole warp
-///    touches 32 different banks, the rest (rarely reached) in local memory.
-///    Entries carry the entry distance, and a popped subtree that has fallen
-///    behind the current closest hit is skipped without touching memory.
+///  - Per-lane traversal stack in shared memory, laid out [entry][thread] so a
+///    push or pop by the whole warp touches 32 different banks. Entries carry
+///    the entry distance (16 bits, rounded down), and a popped subtree that has
+///    fallen behind the current closest hit is skipped without touching memory.
+///    6 bytes per entry: 48 KB per CTA, four CTAs per SM.
 /// The order in which nodes are visited cannot change the result: boxes only
 /// prune what the ray provably misses, and an equal t is won by the higher
 /// triangle index.
@@ -63,9 +63,6 @@ using namespace dev;
 #ifndef QUASI_MESH_RUN_EXIT
 #define QUASI_MESH_RUN_EXIT 4
 #endif
-#ifndef QUASI_MESH_SMEM_STACK
-#define QUASI_MESH_SMEM_STACK 16
-#endif
 
 constexpr int k_block_threads = 256;
 constexpr int k_blocks_per_sm = QUASI_MESH_BLOCKS_PER_SM;
@@ -73,8 +70,7 @@ constexpr int k_warps_per_block = k_block_threads / 32;
 constexpr int k_min_waiting = QUASI_MESH_MIN_WAITING;  ///< finished queries that trigger a service phase
 constexpr int k_leaf_batch = QUASI_MESH_LEAF_BATCH;    ///< lanes holding a leaf that trigger the triangle phase
 constexpr int k_run_exit = QUASI_MESH_RUN_EXIT;        ///< lanes leaving a descent run that end it
-constexpr int k_smem_stack = QUASI_MESH_SMEM_STACK;    ///< stack entries per lane kept in shared memory
-constexpr int k_local_stack = static_cast<int>(k_mesh_stack_entries) - k_smem_stack;
+constexpr size_t k_stack_bytes = static_cast<size_t>(k_mesh_stack_entries) * k_block_threads * 6;
 constexpr uint32_t k_miss = 0xffffffffu;
 constexpr uint32_t k_done = 0xffffffffu;  ///< node reference: the query has finished
 constexpr uint32_t k_pop = 0xfffffffeu;   ///< node reference: take the next entry off the stack
@@ -85,29 +81,27 @@ struct mesh_hit {
     uint32_t slot;  ///< position in leaf order (where its float4s are)
 };
 
-/// Per-lane traversal stack: entries {node reference, entry distance}.
+/// Per-lane traversal stack, all of it in shared memory: node references as
+/// uint32 [entry][thread], entry distances as the upper 16 bits of the float
+/// (truncation rounds a non-negative float down, which only makes the cull on
+/// pop a little less eager) as uint16 [entry][thread]. 6 bytes per entry.
 struct lane_stack {
-    uint2* shared;  ///< this thread's column; consecutive entries are k_block_threads apart
-    uint2 local[k_local_stack];
+    uint32_t* refs;
+    uint16_t* dist;
     int sp = 0;
 
     __device__ __forceinline__ void push(uint2 e) {
-        if (sp < k_smem_stack) {
-            shared[sp * k_block_threads] = e;
-        } else {
-            local[sp - k_smem_stack] = e;
-        }
+        refs[sp * k_block_threads] = e.x;
+        dist[sp * k_block_threads] = static_cast<uint16_t>(e.y >> 16);
         sp++;
     }
-    /// Takes one entry off (sp > 0). Returns its node reference if that subtree can
-    /// still hold a closer (or tying) hit; otherwise k_pop if entries remain, else k_done.
     __device__ __forceinline__ uint32_t pop_one(float closest) {
         sp--;
-        const uint2 e = sp < k_smem_stack ? shared[sp * k_block_threads] : local[sp - k_smem_stack];
-        if (__uint_as_float(e.y) <= closest) return e.x;
-        return sp > 0 ? k_pop : k_done;
+        const uint32_t ref = refs[sp * k_block_threads];
+        const float t_near = __uint_as_float(static_cast<uint32_t>(dist[sp * k_block_threads]) << 16);
+        const uint32_t rest = sp > 0 ? k_pop : k_done;
+        return t_near <= closest ? ref : rest;
     }
-    /// What a lane that has used up its node holds next.
     __device__ __forceinline__ uint32_t after_node() const { return sp > 0 ? k_pop : k_done; }
 };
 
@@ -187,14 +181,15 @@ __global__ void __launch_bounds__(k_block_threads, k_blocks_per_sm)
 mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_constant__ frame_params frame,
                       float4* __restrict__ beauty, float4* __restrict__ albedo, float4* __restrict__ normal,
                       float4* __restrict__ depth, unsigned long long* __restrict__ counters) {
-    __shared__ uint2 s_stack[k_smem_stack * k_block_threads];
+    extern __shared__ uint32_t s_refs[];  // [k_mesh_stack_entries][k_block_threads], then the uint16 distances
     __shared__ float s_material[k_mesh_materials * 8];
     for (int i = threadIdx.x; i < static_cast<int>(k_mesh_materials) * 8; i += k_block_threads) {
         s_material[i] = scene.materials[i];
     }
     __syncthreads();
     lane_stack stack;
-    stack.shared = s_stack + threadIdx.x;
+    stack.refs = s_refs + threadIdx.x;
+    stack.dist = reinterpret_cast<uint16_t*>(s_refs + k_mesh_stack_entries * k_block_threads) + threadIdx.x;
     const float4* __restrict__ nodes = scene.nodes;
 
     const uint32_t lane = threadIdx.x & 31u;
@@ -417,7 +412,10 @@ cudaError_t launch_mesh_pathtrace(const mesh_params& scene, const frame_params& 
     const uint32_t needed = (n_tiles + k_warps_per_block - 1u) / k_warps_per_block;
     if (needed < blocks) blocks = needed;
     if (blocks == 0) return cudaSuccess;
-    mesh_pathtrace_kernel<<<blocks, k_block_threads, 0, stream>>>(
+    static const cudaError_t attr = cudaFuncSetAttribute(
+        mesh_pathtrace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(k_stack_bytes));
+    if (attr != cudaSuccess) return attr;
+    mesh_pathtrace_kernel<<<blocks, k_block_threads, k_stack_bytes, stream>>>(
         scene, frame, reinterpret_cast<float4*>(layers[0]), reinterpret_cast<float4*>(layers[1]),
         reinterpret_cast<float4*>(layers[2]), reinterpret_cast<float4*>(layers[3]), counters);
     return cudaGetLastError();
