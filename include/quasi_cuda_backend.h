@@ -133,12 +133,28 @@ typedef struct Q_cuda_ipc_handle {
 /* Plain device memory owned by the library (cudaMalloc), exportable below. */
 Q_PLUGIN_EXPORT int Q_cuda_alloc(uint64_t bytes, void** out_device_ptr);
 Q_PLUGIN_EXPORT int Q_cuda_free(void* device_ptr);
+Q_PLUGIN_EXPORT int Q_cuda_memset_async(void* device_ptr, int value, uint64_t bytes, void* stream);
 /* Export a Q_cuda_alloc'd buffer, or the plugin's contiguous layer block
  * (device_ptr[0] of Q_cuda_plugin_layers). */
 Q_PLUGIN_EXPORT int Q_cuda_ipc_export(void* device_ptr, Q_cuda_ipc_handle* out);
 /* Map another process's buffer into this process; enables peer access lazily. */
 Q_PLUGIN_EXPORT int Q_cuda_ipc_open(const Q_cuda_ipc_handle* handle, void** out_device_ptr);
 Q_PLUGIN_EXPORT int Q_cuda_ipc_close(void* device_ptr);
+
+/* Q_cuda_combine_shards with the cross-GPU synchronisation INSIDE the kernel, so
+ * the exchange of a frame is one launch per GPU and no host barrier: rank `rank`
+ * of n_shards passes its slice of every rank's layer block (shards[g]), every
+ * rank's flag block (flags[g]: Q_CUDA_SYNC_WORDS uint32, zeroed once with
+ * Q_cuda_memset_async, mapped with the IPC calls above) and the frame's epoch
+ * (1, 2, 3, ... identical on all ranks). The kernel waits until every rank's
+ * render of this epoch has finished, combines, and returns only when every
+ * rank's slice has landed in `out`'s owner and nobody still reads this rank's
+ * layers. Every rank must launch it for every epoch (n_pixels may be 0). */
+#define Q_CUDA_SYNC_WORDS 33u
+Q_PLUGIN_EXPORT int Q_cuda_combine_shards_sync(const float* const* shards, uint32_t* const* flags,
+                                               uint32_t n_shards, uint32_t rank, uint32_t epoch,
+                                               uint64_t n_pixels, float scale, float* out, void* bgra,
+                                               void* stream);
 
 #ifdef __cplusplus
 } /* extern "C" */

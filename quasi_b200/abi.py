@@ -110,5 +110,6 @@ OPTIONAL_SYMBOLS = (  # loader.hpp:115-128
 CUDA_EXTENSION_SYMBOLS = (  # quasi_cuda_backend.h
     "Q_cuda_plugin_stats", "Q_cuda_plugin_layers", "Q_cuda_accumulate", "Q_cuda_tonemap_bgra8",
     "Q_cuda_combine_shards", "Q_cuda_alloc", "Q_cuda_free", "Q_cuda_ipc_export", "Q_cuda_ipc_open",
-    "Q_cuda_ipc_close", "Q_cuda_probe_sincos", "Q_cuda_plugin_mesh_view",
+    "Q_cuda_ipc_close", "Q_cuda_probe_sincos", "Q_cuda_plugin_mesh_view", "Q_cuda_combine_shards_sync",
+    "Q_cuda_memset_async",
 )

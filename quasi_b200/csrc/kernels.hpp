@@ -60,4 +60,15 @@ cudaError_t launch_combine_shards(const float* const* shards, uint32_t n_shards,
                                   uint64_t n_pixels, float scale, float* out, void* bgra,
                                   cudaStream_t stream);
 
+/// Words in a rank's flag block for launch_combine_shards_sync: arrive[16], done[16], CTA counter.
+inline constexpr uint32_t k_sync_words = 2 * k_max_shards + 1;
+
+/// @brief launch_combine_shards with the cross-GPU synchronisation inside the kernel.
+/// `shards[g]` / `flags[g]` are rank g's slice of its layer block and its zero-initialised
+/// flag block (k_sync_words uint32), both addressable from this GPU; `epoch` counts frames
+/// from 1 and is the same on every rank. See combine_shards_sync_kernel.
+cudaError_t launch_combine_shards_sync(const float* const* shards, uint32_t* const* flags, uint32_t n_shards,
+                                       uint32_t rank, uint32_t epoch, uint64_t n_pixels, float scale, float* out,
+                                       void* bgra, cudaStream_t stream);
+
 }  // namespace Q::cuda

@@ -558,6 +558,20 @@ Q_PLUGIN_EXPORT int Q_cuda_combine_shards(const float* const* shards, uint32_t n
                                           static_cast<cudaStream_t>(stream)) == cudaSuccess ? 0 : -1;
 }
 
+Q_PLUGIN_EXPORT int Q_cuda_combine_shards_sync(const float* const* shards, uint32_t* const* flags,
+                                               uint32_t n_shards, uint32_t rank, uint32_t epoch,
+                                               uint64_t n_pixels, float scale, float* out, void* bgra,
+                                               void* stream) {
+    if (!shards || !flags || !out || epoch == 0) return -1;
+    return Q::cuda::launch_combine_shards_sync(shards, flags, n_shards, rank, epoch, n_pixels, scale, out,
+                                               bgra, static_cast<cudaStream_t>(stream)) == cudaSuccess ? 0 : -1;
+}
+
+Q_PLUGIN_EXPORT int Q_cuda_memset_async(void* device_ptr, int value, uint64_t bytes, void* stream) {
+    if (!device_ptr) return -1;
+    return cudaMemsetAsync(device_ptr, value, bytes, static_cast<cudaStream_t>(stream)) == cudaSuccess ? 0 : -1;
+}
+
 Q_PLUGIN_EXPORT int Q_cuda_probe_sincos(const float* phi, float* sin_out, float* cos_out,
                                         uint64_t n, void* stream) {
     if (!phi || !sin_out || !cos_out) return -1;

@@ -102,6 +102,84 @@ combine_shards_kernel(const __grid_constant__ shard_list shards, uint32_t n_shar
     }
 }
 
+struct sync_list {
+    uint32_t* flags[k_max_shards];  ///< rank g's flag block (k_sync_words uint32), peer-mapped
+};
+
+constexpr uint32_t k_sync_arrive = 0;               ///< [from rank]: that rank's layers are final for this epoch
+constexpr uint32_t k_sync_done = k_max_shards;      ///< [from rank]: that rank has read and written all it will
+constexpr uint32_t k_sync_blocks = 2 * k_max_shards;  ///< local: CTAs of this launch that have finished
+
+__device__ __forceinline__ void store_release_system(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t load_acquire_system(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+/// Spins until the epoch stored at p has reached `epoch` (wrap-safe).
+__device__ __forceinline__ void wait_epoch(const uint32_t* p, uint32_t epoch) {
+    while (static_cast<int32_t>(load_acquire_system(p) - epoch) < 0) __nanosleep(64);
+}
+
+/// The whole multi-GPU exchange of one frame as ONE kernel per GPU, with no host
+/// synchronisation: every rank runs this on its 1/G slice of the contiguous layer block.
+///   arrive   the kernel starts after this rank's render (stream order): it stores
+///            `epoch` into every peer's arrive[rank], then waits until every peer has
+///            arrived in its own flag block. From here on all layers are final.
+///   combine  rank-ordered sum of the G per-rank means over NVLink (16-byte peer
+///            loads), 1/G scale, slice stored straight into the root GPU's result
+///            buffer (a peer store for every rank but the root): reduce-scatter and
+///            gather, no staging.
+///   done     the last CTA of this launch stores `epoch` into every peer's done[rank] and
+///            waits for every peer's done: when the kernel ends on the root all slices have
+///            landed there, and when it ends anywhere nobody still reads this rank's
+///            layers, so the next render may overwrite them.
+/// Nothing here waits for another CTA of the same launch, and a peer's flags are written by
+/// a kernel that itself waits only for `arrive`, so there is no cycle as long as every rank
+/// launches the kernel for the same epoch.
+__global__ void __launch_bounds__(k_threads)
+combine_shards_sync_kernel(const __grid_constant__ shard_list shards, const __grid_constant__ sync_list sync,
+                           uint32_t n_shards, uint32_t rank, uint32_t epoch, uint64_t n, float scale,
+                           float4* __restrict__ out, uchar4* __restrict__ bgra) {
+    uint32_t* mine = sync.flags[rank];
+    if (blockIdx.x == 0 && threadIdx.x < n_shards) {
+        store_release_system(sync.flags[threadIdx.x] + k_sync_arrive + rank, epoch);
+    }
+    if (threadIdx.x < n_shards) wait_epoch(mine + k_sync_arrive + threadIdx.x, epoch);
+    __syncthreads();
+
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * k_threads;
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * k_threads + threadIdx.x; i < n; i += stride) {
+        float4 s = ld_stream(shards.ptr[0] + i);
+        for (uint32_t g = 1; g < n_shards; g++) {
+            float4 v = ld_stream(shards.ptr[g] + i);
+            s.x = s.x + v.x;
+            s.y = s.y + v.y;
+            s.z = s.z + v.z;
+            s.w = s.w + v.w;
+        }
+        s = make_float4(s.x * scale, s.y * scale, s.z * scale, s.w * scale);
+        out[i] = s;
+        if (bgra != nullptr) bgra[i] = tonemap_pixel(s);
+    }
+
+    __threadfence_system();  // this thread's slice stores are visible before the done flag is
+    __syncthreads();
+    __shared__ bool s_last;
+    if (threadIdx.x == 0) {
+        s_last = atomicAdd(mine + k_sync_blocks, 1u) == gridDim.x - 1u;
+        if (s_last) mine[k_sync_blocks] = 0u;  // for the next launch (ordered by the stream)
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x < n_shards) {
+        __threadfence_system();
+        store_release_system(sync.flags[threadIdx.x] + k_sync_done + rank, epoch);
+        wait_epoch(mine + k_sync_done + threadIdx.x, epoch);
+    }
+}
+
 }  // namespace
 
 cudaError_t launch_accumulate(const float* current, const float* history, float* output,
@@ -134,6 +212,28 @@ cudaError_t launch_combine_shards(const float* const* shards, uint32_t n_shards,
     if (scale == 0.0f) scale = 1.0f / static_cast<float>(n_shards);
     combine_shards_kernel<<<grid_for(n_pixels), k_threads, 0, stream>>>(
         list, n_shards, n_pixels, scale, reinterpret_cast<float4*>(out),
+        static_cast<uchar4*>(bgra));
+    return cudaGetLastError();
+}
+
+}  // namespace Q::cuda
+
+namespace Q::cuda {
+
+cudaError_t launch_combine_shards_sync(const float* const* shards, uint32_t* const* flags, uint32_t n_shards,
+                                       uint32_t rank, uint32_t epoch, uint64_t n_pixels, float scale, float* out,
+                                       void* bgra, cudaStream_t stream) {
+    if (n_shards == 0 || n_shards > k_max_shards || rank >= n_shards) return cudaErrorInvalidValue;
+    shard_list list{};
+    sync_list sync{};
+    for (uint32_t g = 0; g < n_shards; g++) {
+        list.ptr[g] = reinterpret_cast<const float4*>(shards[g]);
+        sync.flags[g] = flags[g];
+        if (flags[g] == nullptr) return cudaErrorInvalidValue;
+    }
+    if (scale == 0.0f) scale = 1.0f / static_cast<float>(n_shards);
+    combine_shards_sync_kernel<<<grid_for(n_pixels), k_threads, 0, stream>>>(
+        list, sync, n_shards, rank, epoch, n_pixels, scale, reinterpret_cast<float4*>(out),
         static_cast<uchar4*>(bgra));
     return cudaGetLastError();
 }

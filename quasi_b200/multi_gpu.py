@@ -10,12 +10,15 @@ means) * (1/N). Two implementations of that exchange:
   nccl  torch.distributed.reduce(SUM) of the contiguous 4-layer block to rank 0
         on the frame stream, then the 1/N scale kernel on rank 0. The baseline.
   p2p   the layer blocks of all ranks are mapped into every process with CUDA
-        IPC. Each rank runs ONE kernel (Q_cuda_combine_shards on peer pointers)
-        that loads its 1/N slice of every rank's layers over NVLink in rank
-        order, scales, and stores the slice straight into rank 0's result
-        buffer: reduce-scatter + gather fused, no staging copy, and unlike NCCL's
-        ring/tree the summation order is fixed, so the result is bit-identical
-        to the oracle's rank-ordered combine.
+        IPC. Each rank runs ONE kernel (Q_cuda_combine_shards_sync on peer
+        pointers) that waits on device-side flags until every rank's render has
+        finished, loads its 1/N slice of every rank's layers over NVLink in rank
+        order, scales, stores the slice straight into rank 0's result buffer and
+        signals completion: reduce-scatter + gather fused, no staging copy, no
+        host barrier, and unlike NCCL's ring/tree the summation order is fixed,
+        so the result is bit-identical to the oracle's rank-ordered combine.
+  p2p_host  the same data path with Q_cuda_combine_shards and two host barriers
+        per frame instead of the flags (the first form; kept for comparison).
 
 The reference has no multi-GPU path; the oracle for the combine
 is oracle/quasi_oracle.c:qo_combine_shards.
@@ -80,7 +83,10 @@ class shard_reducer:
         self.result_ptr = None            # rank 0: the combined layers (own memory)
         self._opened = []
         self.launches = 0
-        if mode == "p2p":
+        self.epoch = 0
+        self.flag_ptrs = None
+        self._own_flags = None
+        if mode in ("p2p", "p2p_host"):
             self._setup_p2p()
         elif mode == "nccl":
             self._setup_nccl()
@@ -113,14 +119,27 @@ class shard_reducer:
             if self.fn("Q_cuda_ipc_export")(self.result_ptr, C.byref(rh)) != 0:
                 raise RuntimeError("Q_cuda_ipc_export(result) failed")
             result_handle = bytes(rh.bytes)
+        # this rank's flag block for the in-kernel synchronisation, zeroed before anyone can see it
+        p = C.c_void_p()
+        if self.fn("Q_cuda_alloc")(256, C.byref(p)) != 0:
+            raise RuntimeError("Q_cuda_alloc(flags) failed")
+        self._own_flags = p.value
+        if self.fn("Q_cuda_memset_async")(self._own_flags, 0, 256, self.stream.cuda_stream) != 0:
+            raise RuntimeError("Q_cuda_memset_async(flags) failed")
+        self.stream.synchronize()
+        fh = abi.Q_cuda_ipc_handle()
+        if self.fn("Q_cuda_ipc_export")(self._own_flags, C.byref(fh)) != 0:
+            raise RuntimeError("Q_cuda_ipc_export(flags) failed")
         gathered = [None] * self.world
-        self.dist.all_gather_object(gathered, (bytes(mine.bytes), result_handle))
-        self.block_ptrs = []
-        for g, (layer_handle, _) in enumerate(gathered):
+        self.dist.all_gather_object(gathered, (bytes(mine.bytes), result_handle, bytes(fh.bytes)))
+        self.block_ptrs, self.flag_ptrs = [], []
+        for g, (layer_handle, _, flag_handle) in enumerate(gathered):
             if g == self.rank:
                 self.block_ptrs.append(block)
+                self.flag_ptrs.append(self._own_flags)
             else:
                 self.block_ptrs.append(self._open(layer_handle))
+                self.flag_ptrs.append(self._open(flag_handle))
         self.out_ptr = self.result_ptr if self.rank == 0 else self._open(gathered[0][1])
 
     def _open(self, raw: bytes) -> int:
@@ -136,8 +155,10 @@ class shard_reducer:
     def combine(self):
         if self.mode == "nccl":
             self._combine_nccl()
-        else:
+        elif self.mode == "p2p":
             self._combine_p2p()
+        else:
+            self._combine_p2p_host()
 
     def _combine_nccl(self):
         torch, dist = self.torch, self.dist
@@ -152,6 +173,19 @@ class shard_reducer:
             self.launches += 1
 
     def _combine_p2p(self):
+        """One launch per rank, enqueue only: the kernel itself waits for the peers' renders
+        and for their slices (combine_shards_sync_kernel)."""
+        self.epoch += 1
+        lo, hi = slice_bounds(self.total_float4, self.world, self.rank)
+        off = lo * 16
+        ptrs = (C.c_void_p * self.world)(*[p + off for p in self.block_ptrs])
+        flags = (C.c_void_p * self.world)(*self.flag_ptrs)
+        rc = self.fn("Q_cuda_combine_shards_sync")(ptrs, flags, self.world, self.rank, self.epoch, hi - lo, 0.0,
+                                                   self.out_ptr + off, None, self.stream.cuda_stream)
+        assert rc == 0
+        self.launches += 1
+
+    def _combine_p2p_host(self):
         # All ranks must have finished rendering before anyone reads their layers,
         # and all slices must have landed before rank 0 uses the result (or anyone
         # restarts accumulation). Host-side barriers; the kernels are one per rank.
@@ -181,6 +215,9 @@ class shard_reducer:
         for p in self._opened:
             self.fn("Q_cuda_ipc_close")(p)
         self._opened = []
-        if self.mode == "p2p" and self.rank == 0 and self.result_ptr:
+        if self.mode != "nccl" and self.rank == 0 and self.result_ptr:
             self.fn("Q_cuda_free")(self.result_ptr)
             self.result_ptr = None
+        if self._own_flags:
+            self.fn("Q_cuda_free")(self._own_flags)
+            self._own_flags = None

@@ -35,7 +35,7 @@ def main():
     w, h, per_rank = 320, 180, 5
     host = headless_host(w, h, device_ordinal=local, shard_index=rank, shard_count=world, single_stream=True)
     results = {}
-    for mode in ("p2p", "nccl"):
+    for mode in ("p2p", "p2p_host", "nccl"):
         reducer = shard_reducer(host, dist, mode=mode)
         host.render_frame(camera_dirty=True)
         for _ in range(per_rank - 1):
@@ -43,6 +43,18 @@ def main():
         mine = host.readback_aov()           # this rank's shard mean (before the in-place NCCL sum)
         reducer.combine()
         results[mode] = reducer.result_numpy()
+        if mode == "p2p":
+            # back-to-back frames with no host synchronisation in between: the in-kernel
+            # flags alone must order render -> combine -> next render across the GPUs
+            for _ in range(3):
+                host.render_frame(camera_dirty=True)
+                for _ in range(per_rank - 1):
+                    host.render_frame(camera_dirty=False)
+                reducer.combine()
+            again = reducer.result_numpy()
+            if rank == 0 and not all(np.array_equal(bits(a), bits(b)) for a, b in zip(again, results[mode])):
+                print("FAIL p2p: repeated frames without host barriers differ")
+                results["p2p_repeat_failed"] = True
         dist.barrier()
         if rank != 0:
             reducer.close()
@@ -67,9 +79,13 @@ def main():
             if not np.array_equal(bits(results["p2p"][l]), bits(combined)):
                 print(f"FAIL p2p combine layer {l}: {(bits(results['p2p'][l]) != bits(combined)).sum()} floats differ")
                 ok = False
+            if not np.array_equal(bits(results["p2p_host"][l]), bits(combined)):
+                print(f"FAIL p2p_host combine layer {l}")
+                ok = False
             if not np.allclose(results["nccl"][l], combined, rtol=2e-6, atol=2e-6):
                 print(f"FAIL nccl combine layer {l}")
                 ok = False
+        ok = ok and not results.get("p2p_repeat_failed", False)
         print("MULTI_GPU_CHECK", "OK" if ok else "FAILED", f"world={world} {w}x{h} {per_rank} spp/rank")
     host.close()
     dist.barrier()
