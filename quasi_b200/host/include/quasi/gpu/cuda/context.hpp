@@ -105,7 +105,8 @@ private:
         void* end_event = nullptr;    // cudaEvent_t
         bool in_flight = false;
         Q_cuda_drawable drawable{};
-        uint8_t* pixels = nullptr;    // pinned host, 4 * width * height
+        uint8_t* pixels = nullptr;    // pinned host, 4 * width * height: what the host "presents"
+        void* device_pixels = nullptr;  // the drawable the plugin tonemaps into, same size, in HBM
     };
 
     void release();

@@ -115,7 +115,17 @@ bool context::allocate_drawables() {
             return false;
         }
         s.pixels = static_cast<uint8_t*>(p);
-        s.drawable.pixels = p;  // pinned host memory is device-addressable under UVA
+        // The plugin writes the drawable in HBM; end_frame brings it to the pinned
+        // buffer with the copy engine, which overlaps the next frame's kernels. (A
+        // kernel storing 8-bit pixels straight into pinned host memory crosses
+        // PCIe at a third of the DMA rate and made the frame PCIe-bound.)
+        void* d = nullptr;
+        if (bytes != 0 && cudaMalloc(&d, bytes) != cudaSuccess) {
+            (void)cudaGetLastError();
+            return false;
+        }
+        s.device_pixels = d;
+        s.drawable.pixels = d;
         s.drawable.pitch_bytes = 4u * width_;
         s.drawable.reserved = 0;
     }
@@ -125,7 +135,9 @@ bool context::allocate_drawables() {
 void context::free_drawables() {
     for (auto& s : slots_) {
         if (s.pixels) cudaFreeHost(s.pixels);
+        if (s.device_pixels) cudaFree(s.device_pixels);
         s.pixels = nullptr;
+        s.device_pixels = nullptr;
         s.drawable = Q_cuda_drawable{};
     }
 }
@@ -199,6 +211,11 @@ void context::end_frame(render_frame& frame) {
     for (int i = 0; i < k_max_frames_in_flight; i++) {
         slot& s = slots_[i];
         if (s.stream == frame.command_buffer) {
+            if (frame.drawable && s.device_pixels && s.pixels) {
+                // "presentDrawable" (context.mm:166-188): the finished image goes to the host.
+                cudaMemcpyAsync(s.pixels, s.device_pixels, static_cast<size_t>(width_) * height_ * 4,
+                                cudaMemcpyDeviceToHost, as_stream(s.stream));
+            }
             cudaEventRecord(as_event(s.end_event), as_stream(s.stream));
             s.in_flight = true;
             next_slot_ = (i + 1) % k_max_frames_in_flight;
