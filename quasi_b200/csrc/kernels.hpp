@@ -32,15 +32,17 @@ struct alignas(16) mesh_params {
 /// @brief One new sample per pixel, folded into the four accumulated layers in place.
 /// @param layers Device pointers to beauty, albedo, normal, depth (RGBA32F, row 0 = top).
 /// @param ray_counter Device counter incremented by the number of closest-hit queries.
+/// @param tile_counters Two zero-initialised device uints: the tile work queue (device_common.cuh:tile_feed).
 /// @param sm_count Multiprocessors of the device; the grid is 4 resident CTAs per SM.
 cudaError_t launch_pathtrace_accumulate(const scene_params& scene, const frame_params& frame,
                                         float* const layers[4], unsigned long long* ray_counter,
-                                        int sm_count, cudaStream_t stream);
+                                        unsigned int* tile_counters, int sm_count, cudaStream_t stream);
 
 /// @brief The mesh-scene form of launch_pathtrace_accumulate (BASELINE config 3).
 /// @param counters Device array of 3: rays, BVH nodes visited (box tests), triangles tested.
 cudaError_t launch_mesh_pathtrace(const mesh_params& scene, const frame_params& frame, float* const layers[4],
-                                  unsigned long long* counters, int sm_count, cudaStream_t stream);
+                                  unsigned long long* counters, unsigned int* tile_counters, int sm_count,
+                                  cudaStream_t stream);
 
 /// @brief Test hook: the kernel's sin/cos of phi in [0, 2*pi], element-wise.
 cudaError_t launch_sincos_probe(const float* phi, float* sin_out, float* cos_out, uint64_t n,

@@ -180,7 +180,8 @@ __device__ __forceinline__ void interior_step(const float4* __restrict__ nodes, 
 __global__ void __launch_bounds__(k_block_threads, k_blocks_per_sm)
 mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_constant__ frame_params frame,
                       float4* __restrict__ beauty, float4* __restrict__ albedo, float4* __restrict__ normal,
-                      float4* __restrict__ depth, unsigned long long* __restrict__ counters) {
+                      float4* __restrict__ depth, unsigned long long* __restrict__ counters,
+                      unsigned int* __restrict__ tile_counters) {
     extern __shared__ uint32_t s_refs[];  // [k_mesh_stack_entries][k_block_threads], then the uint16 distances
     __shared__ float s_material[k_mesh_materials * 8];
     for (int i = threadIdx.x; i < static_cast<int>(k_mesh_materials) * 8; i += k_block_threads) {
@@ -194,8 +195,6 @@ mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_co
 
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lanes_below = (1u << lane) - 1u;
-    const uint32_t warp_global = blockIdx.x * k_warps_per_block + (threadIdx.x >> 5);
-    const uint32_t n_warps = gridDim.x * k_warps_per_block;
     const uint32_t tiles_x = (frame.width + 7u) >> 3;
     const uint32_t n_tiles = tiles_x * ((frame.height + 3u) >> 2);
     const bool first_sample = frame.sample_index == 0;
@@ -215,6 +214,7 @@ mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_co
 
     uint32_t rays = 0, nodes_visited = 0, tris_tested = 0;
     uint32_t next_item = 0;  // warp-uniform cursor into this warp's pixel sequence
+    tile_feed feed{tile_counters, n_tiles};
 
     while (true) {
         // ---------------------------------------------------------- service ----
@@ -298,10 +298,11 @@ mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_co
 
         // Regeneration: lanes without a path take the warp's next pixels (see pathtrace.cu).
         const uint32_t idle = __ballot_sync(0xffffffffu, !active);
-        if (idle != 0u && warp_global + (next_item >> 5) * n_warps < n_tiles) {
+        if (idle != 0u) {
+            feed.open(next_item, next_item + __popc(idle) - 1u);
             if (!active) {
                 const uint32_t item = next_item + __popc(idle & lanes_below);
-                const uint32_t tile = warp_global + (item >> 5) * n_warps;
+                const uint32_t tile = feed.tile_of(item);
                 if (tile < n_tiles) {
                     uint32_t tile_y = __umulhi(tile, frame.tiles_x_magic);
                     uint32_t tile_x = tile - tile_y * tiles_x;
@@ -355,7 +356,7 @@ mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_co
         }
         const uint32_t m_active = __ballot_sync(0xffffffffu, active);
         if (m_active == 0u) {
-            if (warp_global + (next_item >> 5) * n_warps >= n_tiles) break;  // no paths, no pixels left
+            if (feed.exhausted(next_item)) break;  // no paths, no pixels left
             continue;  // only off-image pixels of an edge tile were handed out
         }
 
@@ -393,6 +394,7 @@ mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_co
         }
     }
 
+    feed.finish(gridDim.x * k_warps_per_block);
     rays = __reduce_add_sync(0xffffffffu, rays);
     nodes_visited = __reduce_add_sync(0xffffffffu, nodes_visited);
     tris_tested = __reduce_add_sync(0xffffffffu, tris_tested);
@@ -406,7 +408,8 @@ mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_co
 }  // namespace
 
 cudaError_t launch_mesh_pathtrace(const mesh_params& scene, const frame_params& frame, float* const layers[4],
-                                  unsigned long long* counters, int sm_count, cudaStream_t stream) {
+                                  unsigned long long* counters, unsigned int* tile_counters, int sm_count,
+                                  cudaStream_t stream) {
     const uint32_t n_tiles = ((frame.width + 7u) / 8u) * ((frame.height + 3u) / 4u);
     uint32_t blocks = static_cast<uint32_t>(sm_count) * k_blocks_per_sm;
     const uint32_t needed = (n_tiles + k_warps_per_block - 1u) / k_warps_per_block;
@@ -417,7 +420,7 @@ cudaError_t launch_mesh_pathtrace(const mesh_params& scene, const frame_params& 
     if (attr != cudaSuccess) return attr;
     mesh_pathtrace_kernel<<<blocks, k_block_threads, k_stack_bytes, stream>>>(
         scene, frame, reinterpret_cast<float4*>(layers[0]), reinterpret_cast<float4*>(layers[1]),
-        reinterpret_cast<float4*>(layers[2]), reinterpret_cast<float4*>(layers[3]), counters);
+        reinterpret_cast<float4*>(layers[2]), reinterpret_cast<float4*>(layers[3]), counters, tile_counters);
     return cudaGetLastError();
 }
 

@@ -10,7 +10,8 @@
 ///
 /// Execution model (DESIGN.md "Kernels"):
 ///  - Persistent warps with path regeneration. The grid is resident CTAs only
-///    (4 per SM); each warp owns every n_warps-th 8x4 pixel tile. A lane whose
+///    (4 per SM); warps take 8x4 pixel tiles from a device-wide work queue (one
+///    atomic per tile, device_common.cuh:tile_feed). A lane whose
 ///    path ended writes its pixel and immediately starts the warp's next pixel
 ///    (ballot + popc compaction of the idle lanes), so every lane of the warp is
 ///    always inside the same bounce step. In the thread-per-pixel form the warp
@@ -126,10 +127,11 @@ __device__ __forceinline__ void scan_flat(scan_state& s, const quad_params& q, i
     const float num = q.plane_d - q.normal[K] * axis(ro, K);
     const float t_fast = num * rcp_approx(denom);
     if (fabsf(denom) >= 1e-8f && t_fast > k_t_min_lo) {
-        const float pi = (axis(ro, I) + axis(rd, I) * t_fast) - q.center[I];
-        const float pj = (axis(ro, J) + axis(rd, J) * t_fast) - q.center[J];
-        const float alpha = pi * q.fast_a[I] + pj * q.fast_a[J];
-        const float beta = pi * q.fast_b[I] + pj * q.fast_b[J];
+        // p', alpha', beta' only feed margin decisions: contracted (FFMA), unlike num and denom
+        const float pi = __fmaf_rn(axis(rd, I), t_fast, axis(ro, I)) - q.center[I];
+        const float pj = __fmaf_rn(axis(rd, J), t_fast, axis(ro, J)) - q.center[J];
+        const float alpha = __fmaf_rn(pi, q.fast_a[I], pj * q.fast_a[J]);
+        const float beta = __fmaf_rn(pi, q.fast_b[I], pj * q.fast_b[J]);
         consider(s, q, i, t_fast, fmaxf(fabsf(alpha), fabsf(beta)));
     }
 }
@@ -141,10 +143,10 @@ __device__ __forceinline__ void scan_upright(scan_state& s, const quad_params& q
     const float num = q.plane_d - (q.normal[0] * ro.x + q.normal[2] * ro.z);
     const float t_fast = num * rcp_approx(denom);
     if (fabsf(denom) >= 1e-8f && t_fast > k_t_min_lo) {
-        const float px = (ro.x + rd.x * t_fast) - q.center[0];
-        const float py = (ro.y + rd.y * t_fast) - q.center[1];
-        const float pz = (ro.z + rd.z * t_fast) - q.center[2];
-        const float alpha = px * q.fast_a[0] + pz * q.fast_a[2];
+        const float px = __fmaf_rn(rd.x, t_fast, ro.x) - q.center[0];
+        const float py = __fmaf_rn(rd.y, t_fast, ro.y) - q.center[1];
+        const float pz = __fmaf_rn(rd.z, t_fast, ro.z) - q.center[2];
+        const float alpha = __fmaf_rn(px, q.fast_a[0], pz * q.fast_a[2]);
         const float beta = py * q.fast_b[1];
         consider(s, q, i, t_fast, fmaxf(fabsf(alpha), fabsf(beta)));
     }
@@ -156,9 +158,11 @@ __device__ __forceinline__ void scan_general(scan_state& s, const quad_params& q
     const float num = q.plane_d - dot(normal, ro);  // the shader's value
     const float t_fast = num * rcp_approx(denom);
     if (fabsf(denom) >= 1e-8f && t_fast > k_t_min_lo) {
-        const v3 planar = (ro + rd * t_fast) - load_v3(q.center);
-        const float alpha = dot(planar, load_v3(q.fast_a));
-        const float beta = dot(planar, load_v3(q.fast_b));
+        const v3 planar = make_v3(__fmaf_rn(rd.x, t_fast, ro.x) - q.center[0],
+                                  __fmaf_rn(rd.y, t_fast, ro.y) - q.center[1],
+                                  __fmaf_rn(rd.z, t_fast, ro.z) - q.center[2]);
+        const float alpha = __fmaf_rn(planar.x, q.fast_a[0], __fmaf_rn(planar.y, q.fast_a[1], planar.z * q.fast_a[2]));
+        const float beta = __fmaf_rn(planar.x, q.fast_b[0], __fmaf_rn(planar.y, q.fast_b[1], planar.z * q.fast_b[2]));
         consider(s, q, i, t_fast, fmaxf(fabsf(alpha), fabsf(beta)));
     }
 }
@@ -271,7 +275,8 @@ __global__ void __launch_bounds__(k_block_threads, k_blocks_per_sm)
 pathtrace_accumulate_kernel(const __grid_constant__ scene_params scene,
                             const __grid_constant__ frame_params frame, float4* __restrict__ beauty,
                             float4* __restrict__ albedo, float4* __restrict__ normal,
-                            float4* __restrict__ depth, unsigned long long* __restrict__ ray_counter) {
+                            float4* __restrict__ depth, unsigned long long* __restrict__ ray_counter,
+                            unsigned int* __restrict__ tile_counters) {
     __shared__ float s_shade[NQ * k_shade_stride];
     for (int idx = threadIdx.x; idx < NQ * static_cast<int>(k_shade_floats); idx += k_block_threads) {
         const int qi = idx / static_cast<int>(k_shade_floats);
@@ -283,8 +288,6 @@ pathtrace_accumulate_kernel(const __grid_constant__ scene_params scene,
 
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lanes_below = (1u << lane) - 1u;
-    const uint32_t warp_global = blockIdx.x * k_warps_per_block + (threadIdx.x >> 5);
-    const uint32_t n_warps = gridDim.x * k_warps_per_block;
     const uint32_t tiles_x = (frame.width + 7u) >> 3;
     const uint32_t n_tiles = tiles_x * ((frame.height + 3u) >> 2);
     const bool first_sample = frame.sample_index == 0;
@@ -300,14 +303,16 @@ pathtrace_accumulate_kernel(const __grid_constant__ scene_params scene,
     size_t pixel = 0;
     uint32_t rays = 0;
     uint32_t next_item = 0;  // warp-uniform cursor into this warp's pixel sequence
+    tile_feed feed{tile_counters, n_tiles};
 
     while (true) {
         // Regeneration: idle lanes take the warp's next pixels, compacted.
         const uint32_t idle = __ballot_sync(0xffffffffu, !active);
         if (idle != 0u) {
+            feed.open(next_item, next_item + __popc(idle) - 1u);
             if (!active) {
                 const uint32_t item = next_item + __popc(idle & lanes_below);
-                const uint32_t tile = warp_global + (item >> 5) * n_warps;
+                const uint32_t tile = feed.tile_of(item);
                 if (tile < n_tiles) {
                     // tile / tiles_x by multiply-high with floor(2^32 / tiles_x): at most
                     // one too small for any 32-bit tile, fixed up by one compare.
@@ -355,7 +360,7 @@ pathtrace_accumulate_kernel(const __grid_constant__ scene_params scene,
             next_item += __popc(idle);
         }
         if (!__any_sync(0xffffffffu, active)) {
-            if (warp_global + (next_item >> 5) * n_warps >= n_tiles) break;
+            if (feed.exhausted(next_item)) break;
             continue;  // only off-image pixels of an edge tile were handed out
         }
 
@@ -430,6 +435,7 @@ pathtrace_accumulate_kernel(const __grid_constant__ scene_params scene,
         }
     }
 
+    feed.finish(gridDim.x * k_warps_per_block);
     // One atomic per warp for the ray statistic (SURVEY.md 8d "Ray counting").
     rays = __reduce_add_sync(0xffffffffu, rays);
     if (lane == 0 && rays != 0) atomicAdd(ray_counter, static_cast<unsigned long long>(rays));
@@ -452,7 +458,7 @@ cudaError_t launch_sincos_probe(const float* phi, float* sin_out, float* cos_out
 
 cudaError_t launch_pathtrace_accumulate(const scene_params& scene, const frame_params& frame,
                                         float* const layers[4], unsigned long long* ray_counter,
-                                        int sm_count, cudaStream_t stream) {
+                                        unsigned int* tile_counters, int sm_count, cudaStream_t stream) {
     const uint32_t n_tiles = ((frame.width + 7u) / 8u) * ((frame.height + 3u) / 4u);
     uint32_t blocks = static_cast<uint32_t>(sm_count) * k_blocks_per_sm;
     const uint32_t needed = (n_tiles + k_warps_per_block - 1u) / k_warps_per_block;
@@ -464,10 +470,10 @@ cudaError_t launch_pathtrace_accumulate(const scene_params& scene, const frame_p
     auto* d = reinterpret_cast<float4*>(layers[3]);
     if (cornell_layout::matches(scene)) {
         pathtrace_accumulate_kernel<16, cornell_layout>
-            <<<blocks, k_block_threads, 0, stream>>>(scene, frame, b, a, n, d, ray_counter);
+            <<<blocks, k_block_threads, 0, stream>>>(scene, frame, b, a, n, d, ray_counter, tile_counters);
     } else {
         pathtrace_accumulate_kernel<32, dynamic_layout>
-            <<<blocks, k_block_threads, 0, stream>>>(scene, frame, b, a, n, d, ray_counter);
+            <<<blocks, k_block_threads, 0, stream>>>(scene, frame, b, a, n, d, ray_counter, tile_counters);
     }
     return cudaGetLastError();
 }

@@ -290,11 +290,12 @@ Q_PLUGIN_EXPORT Q_plugin_handle* Q_plugin_create(Q_plugin_context* ctx) {
                                                    state->device), "cudaDeviceGetAttribute");
     ok = ok && check(state, cudaEventCreateWithFlags(&state->last_render, cudaEventDisableTiming),
                      "cudaEventCreate");
-    // counters: rays, BVH nodes visited, triangles tested
+    // counters: rays, BVH nodes visited, triangles tested; then the tile work queue (2 x uint32)
     ok = ok && check(state, cudaMalloc(reinterpret_cast<void**>(&state->ray_counter),
-                                       3 * sizeof(unsigned long long)), "cudaMalloc(counter)");
-    ok = ok && check(state, cudaMemsetAsync(state->ray_counter, 0, 3 * sizeof(unsigned long long),
+                                       4 * sizeof(unsigned long long)), "cudaMalloc(counter)");
+    ok = ok && check(state, cudaMemsetAsync(state->ray_counter, 0, 4 * sizeof(unsigned long long),
                                             state->queue), "cudaMemset(counter)");
+    ok = ok && check(state, cudaStreamSynchronize(state->queue), "cudaMemset(counter) sync");
     if (ok) {
         // The plugin builds its own scene (plugin.mm:581-584). The ABI has no
         // slot for options, so they come from the environment.
@@ -394,11 +395,13 @@ Q_PLUGIN_EXPORT void Q_plugin_render(Q_plugin_handle* handle, Q_render_frame* fr
     // layers are shared, so order this frame after the previous one.
     order_after_render(state, stream);
 
+    auto* tile_counters = reinterpret_cast<unsigned int*>(state->ray_counter + 3);
     const cudaError_t launched =
         state->use_mesh ? Q::cuda::launch_mesh_pathtrace(state->mesh_device, fp, state->layers,
-                                                         state->ray_counter, state->sm_count, stream)
+                                                         state->ray_counter, tile_counters, state->sm_count, stream)
                         : Q::cuda::launch_pathtrace_accumulate(state->scene, fp, state->layers,
-                                                               state->ray_counter, state->sm_count, stream);
+                                                               state->ray_counter, tile_counters, state->sm_count,
+                                                               stream);
     if (!check(state, launched, "pathtrace_accumulate")) return;
     state->kernel_launches++;
 
