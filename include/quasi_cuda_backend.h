@@ -49,6 +49,36 @@ typedef struct Q_cuda_drawable {
     uint32_t reserved;
 } Q_cuda_drawable;
 
+/* Q_gpu_context::layer (CAMetalLayer* for Metal, plugin.mm:573) points at one of
+ * these, or is NULL. It lets the accumulation survive Q_plugin_destroy /
+ * Q_plugin_create, i.e. a hot reload (SURVEY.md section 5 "checkpoint / resume",
+ * section 8f rank 4): in the reference all state lives in the plugin handle and a
+ * reload restarts at sample 0 (plugin.mm:594-617).
+ *   destroy  with a state attached the backend does NOT free its layer block: it
+ *            records it here (pointer, size, sample count, the scene and shard it
+ *            belongs to). The block now belongs to the host, which releases it
+ *            with cudaFree (or Q_cuda_free) when it is done.
+ *   create   if the recorded block fits (same viewport, scene tag and shard) the
+ *            backend adopts it and continues at sample `frame_count` (the RNG frame
+ *            index continues, so the image is bit-identical to an uninterrupted
+ *            run); otherwise it frees the block and starts from zero.
+ * The host still decides whether to continue: camera_dirty on the next frame
+ * restarts the accumulation as always. Zero-initialise it; set struct_size. */
+typedef struct Q_cuda_persistent_state {
+    uint32_t struct_size;  /* sizeof(Q_cuda_persistent_state) */
+    uint32_t valid;        /* written by the backend: the fields below describe a block */
+    void* layers;          /* device: 4 contiguous RGBA32F layers (beauty, albedo, normal, depth) */
+    uint64_t bytes;        /* 64 * width * height */
+    uint32_t width;
+    uint32_t height;
+    uint32_t frame_count;  /* samples accumulated per pixel by this shard */
+    uint32_t scene_tag;    /* hash of scene kind and options */
+    uint32_t shard_index;
+    uint32_t shard_count;
+    int32_t device_ordinal;
+    uint32_t reserved;
+} Q_cuda_persistent_state;
+
 /* Counters since Q_plugin_create (not reset by camera_dirty). */
 typedef struct Q_cuda_stats {
     uint64_t rays;            /* closest-hit queries = trace_scene calls (plugin.mm:199) */

@@ -66,6 +66,13 @@ class Q_cuda_device_desc(C.Structure):
                 ("shard_index", C.c_uint32), ("shard_count", C.c_uint32)]
 
 
+class Q_cuda_persistent_state(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("valid", C.c_uint32), ("layers", C.c_void_p),
+                ("bytes", C.c_uint64), ("width", C.c_uint32), ("height", C.c_uint32),
+                ("frame_count", C.c_uint32), ("scene_tag", C.c_uint32), ("shard_index", C.c_uint32),
+                ("shard_count", C.c_uint32), ("device_ordinal", C.c_int32), ("reserved", C.c_uint32)]
+
+
 class Q_cuda_drawable(C.Structure):
     _fields_ = [("pixels", C.c_void_p), ("pitch_bytes", C.c_uint32), ("reserved", C.c_uint32)]
 

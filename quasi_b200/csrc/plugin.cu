@@ -119,6 +119,9 @@ struct plugin_state {
 
     uint64_t paths = 0;
     uint64_t kernel_launches = 0;
+
+    Q_cuda_persistent_state* persistent = nullptr;  ///< host-owned, Q_gpu_context::layer (may be null)
+    uint32_t scene_tag = 0;
 };
 
 void log_msg(const plugin_state* state, const char* msg) {
@@ -160,6 +163,50 @@ bool create_layers(plugin_state* state, uint32_t width, uint32_t height) {
     state->last_width = width;
     state->last_height = height;
     state->frame_count = 0;
+    return true;
+}
+
+/// Takes over the layer block a previous instance left with the host
+/// (Q_cuda_persistent_state), if it belongs to this viewport, scene and shard.
+/// A block that does not fit is released here, so the host never holds a stale one.
+bool adopt_layers(plugin_state* state, uint32_t width, uint32_t height) {
+    Q_cuda_persistent_state* p = state->persistent;
+    if (!p || !p->valid || !p->layers) return false;
+    const uint64_t bytes = static_cast<uint64_t>(width) * height * 4 * Q_AOV_COUNT * sizeof(float);
+    const bool fits = p->width == width && p->height == height && p->bytes == bytes && bytes != 0 &&
+                      p->scene_tag == state->scene_tag && p->shard_index == state->shard_index &&
+                      p->shard_count == state->shard_count && p->device_ordinal == state->device;
+    auto* block = static_cast<float*>(p->layers);
+    p->valid = 0;
+    p->layers = nullptr;
+    if (!fits) {
+        cudaFree(block);
+        return false;
+    }
+    const size_t floats = static_cast<size_t>(width) * height * 4;
+    for (int i = 0; i < Q_AOV_COUNT; i++) state->layers[i] = block + floats * i;
+    state->last_width = width;
+    state->last_height = height;
+    state->frame_count = p->frame_count;
+    log_msg(state, "Accumulation adopted from the host's persistent state");
+    return true;
+}
+
+/// Hands the layer block to the host instead of freeing it (see adopt_layers).
+bool leave_layers_with_host(plugin_state* state) {
+    Q_cuda_persistent_state* p = state->persistent;
+    if (!p || !state->layers[0] || state->frame_count == 0) return false;
+    p->layers = state->layers[0];
+    p->bytes = static_cast<uint64_t>(state->last_width) * state->last_height * 4 * Q_AOV_COUNT * sizeof(float);
+    p->width = state->last_width;
+    p->height = state->last_height;
+    p->frame_count = state->frame_count;
+    p->scene_tag = state->scene_tag;
+    p->shard_index = state->shard_index;
+    p->shard_count = state->shard_count;
+    p->device_ordinal = state->device;
+    p->valid = 1;
+    for (auto& l : state->layers) l = nullptr;
     return true;
 }
 
@@ -308,7 +355,14 @@ Q_PLUGIN_EXPORT Q_plugin_handle* Q_plugin_create(Q_plugin_context* ctx) {
             ok = create_mesh(state, env_u32("QUASI_CUDA_MESH_GRID", 707, 1, 4000),
                              env_u32("QUASI_CUDA_MESH_SEED", 1, 0, 65535), bounces);
         }
-        ok = ok && create_layers(state, ctx->viewport_width, ctx->viewport_height);
+        state->scene_tag = state->use_mesh
+                               ? 0x6d000000u ^ (env_u32("QUASI_CUDA_MESH_GRID", 707, 1, 4000) << 8) ^
+                                     (env_u32("QUASI_CUDA_MESH_SEED", 1, 0, 65535) << 20) ^ bounces
+                               : 0x71000000u ^ bounces;
+        auto* persistent = static_cast<Q_cuda_persistent_state*>(ctx->gpu->layer);
+        if (persistent && persistent->struct_size >= sizeof(Q_cuda_persistent_state)) state->persistent = persistent;
+        ok = ok && (adopt_layers(state, ctx->viewport_width, ctx->viewport_height) ||
+                    create_layers(state, ctx->viewport_width, ctx->viewport_height));
     }
     if (!ok) {
         free_mesh(state);
@@ -338,7 +392,7 @@ Q_PLUGIN_EXPORT void Q_plugin_destroy(Q_plugin_handle* handle) {
     if (state->render_pending) cudaEventSynchronize(state->last_render);
     cudaStreamSynchronize(state->queue);
     free_mesh(state);
-    free_layers(state);
+    if (!leave_layers_with_host(state)) free_layers(state);
     if (state->ray_counter) cudaFree(state->ray_counter);
     if (state->last_render) cudaEventDestroy(state->last_render);
     delete state;

@@ -64,7 +64,7 @@ class cuda_context:
     @classmethod
     def create(cls, width: int, height: int, device_ordinal: int = 0, shard_index: int = 0,
                shard_count: int = 1, present: bool = False,
-               single_stream: bool = False) -> "cuda_context":
+               single_stream: bool = False, keep_accumulation: bool = False) -> "cuda_context":
         import torch
 
         if not torch.cuda.is_available():
@@ -88,7 +88,10 @@ class cuda_context:
         self._gpu.backend = abi.Q_GPU_BACKEND_CUDA
         self._gpu.device = C.cast(C.pointer(self._desc), C.c_void_p)
         self._gpu.queue = self._queue.cuda_stream
-        self._gpu.layer = None
+        # Q_cuda_persistent_state: lets the accumulation outlive a plugin instance
+        self.persistent = abi.Q_cuda_persistent_state()
+        self.persistent.struct_size = C.sizeof(abi.Q_cuda_persistent_state)
+        self._gpu.layer = C.cast(C.pointer(self.persistent), C.c_void_p) if keep_accumulation else None
         self._present = present
         self.resize(width, height)
         return self

@@ -9,6 +9,8 @@ that pytest and bench.py can drive the same ABI without a subprocess.
 """
 from __future__ import annotations
 
+import ctypes as C
+
 from . import PLUGIN_PATH, abi
 from .cuda_context import cuda_context, orbit_camera
 from .loader import dynamic_library, loader
@@ -17,7 +19,7 @@ from .loader import dynamic_library, loader
 class headless_host:
     def __init__(self, width: int, height: int, plugin_path=PLUGIN_PATH, device_ordinal: int = 0,
                  shard_index: int = 0, shard_count: int = 1, present: bool = False, log=None,
-                 single_stream: bool = False, env: dict | None = None):
+                 single_stream: bool = False, env: dict | None = None, keep_accumulation: bool = False):
         """`env`: out-of-band plugin options (QUASI_CUDA_SCENE, QUASI_CUDA_MAX_BOUNCES, ...), set in
         the process environment only while Q_plugin_create runs (the ABI has no slot for them)."""
         self.messages = []
@@ -30,11 +32,20 @@ class headless_host:
                 self._user_log(text)
 
         self.context = cuda_context.create(width, height, device_ordinal, shard_index, shard_count,
-                                           present=present, single_stream=single_stream)
-        self.library = dynamic_library.open(plugin_path)
+                                           present=present, single_stream=single_stream,
+                                           keep_accumulation=keep_accumulation)
+        self._plugin_path, self._env = plugin_path, env
         self.plugin_context = self.context.make_plugin_context(log=_log)
+        self._load()
+        self.camera = orbit_camera()
+        self.camera.update_position()
+        self.frames_rendered = 0
+
+    def _load(self):
         import os
 
+        self.library = dynamic_library.open(self._plugin_path)
+        env = self._env
         saved = {k: os.environ.get(k) for k in (env or {})}
         os.environ.update({k: str(v) for k, v in (env or {}).items()})
         try:
@@ -45,9 +56,14 @@ class headless_host:
                     os.environ.pop(k, None)
                 else:
                     os.environ[k] = v
-        self.camera = orbit_camera()
-        self.camera.update_position()
-        self.frames_rendered = 0
+
+    def reload(self):
+        """What Q::plugin::manager does on a hot reload (manager.hpp:209-268): destroy the
+        instance, close the library, open it again, create a new instance on the same context."""
+        self.context.synchronize()
+        self.plugin.destroy()
+        self.library.close()
+        self._load()
 
     def render_frame(self, camera_dirty=None):
         """One iteration of the main loop, main.cpp:243-270. Enqueue only."""
@@ -74,4 +90,8 @@ class headless_host:
 
     def close(self):
         self.plugin.destroy()
+        p = self.context.persistent
+        if p.valid and p.layers:  # a block parked by the destroyed instance belongs to the host
+            self.library.get_symbol("Q_cuda_free")(C.c_void_p(p.layers))
+            p.valid, p.layers = 0, None
         self.library.close()

@@ -46,6 +46,9 @@ struct context_options {
     uint32_t shard_index = 0;  ///< this GPU's sample shard
     uint32_t shard_count = 1;
     bool present = false;      ///< allocate BGRA8 presentable buffers (pinned host memory)
+    /// Offer the backend a Q_cuda_persistent_state through Q_gpu_context::layer, so the
+    /// accumulation outlives a plugin instance (a hot reload continues instead of restarting).
+    bool keep_accumulation = false;
 };
 
 class context {
@@ -122,6 +125,8 @@ private:
     uint32_t width_ = 0;
     uint32_t height_ = 0;
     bool present_ = false;
+    bool keep_accumulation_ = false;
+    Q_cuda_persistent_state persistent_{};  ///< owned here; the backend parks its layer block in it
     bool valid_ = false;
 };
 

@@ -36,6 +36,8 @@ context::result<context> context::create(uint32_t width, uint32_t height, contex
     ctx.width_ = width;
     ctx.height_ = height;
     ctx.present_ = options.present;
+    ctx.keep_accumulation_ = options.keep_accumulation;
+    ctx.persistent_.struct_size = sizeof(Q_cuda_persistent_state);
     ctx.device_desc_.struct_size = sizeof(Q_cuda_device_desc);
     ctx.device_desc_.device_ordinal = options.device_ordinal;
     ctx.device_desc_.shard_index = options.shard_index;
@@ -78,6 +80,8 @@ context& context::operator=(context&& other) noexcept {
         width_ = other.width_;
         height_ = other.height_;
         present_ = other.present_;
+        keep_accumulation_ = other.keep_accumulation_;
+        persistent_ = std::exchange(other.persistent_, {});
         valid_ = std::exchange(other.valid_, false);
     }
     // The plugin keeps the address of gpu_ctx_ and reads device_desc_ through it,
@@ -86,7 +90,7 @@ context& context::operator=(context&& other) noexcept {
     gpu_ctx_.backend = valid_ ? k_backend_cuda : k_backend_none;
     gpu_ctx_.device = valid_ ? &device_desc_ : nullptr;
     gpu_ctx_.queue = queue_;
-    gpu_ctx_.layer = nullptr;
+    gpu_ctx_.layer = (valid_ && keep_accumulation_) ? &persistent_ : nullptr;
     return *this;
 }
 
@@ -95,6 +99,8 @@ void context::release() {
     cudaSetDevice(device_desc_.device_ordinal);
     synchronize();
     free_drawables();
+    if (persistent_.valid && persistent_.layers) cudaFree(persistent_.layers);  // parked by a destroyed plugin
+    persistent_ = {};
     for (auto& s : slots_) {
         if (s.begin_event) cudaEventDestroy(as_event(s.begin_event));
         if (s.end_event) cudaEventDestroy(as_event(s.end_event));

@@ -84,6 +84,7 @@ struct options {
     bool watch = false;
     bool present = false;
     bool json = false;
+    bool keep_accumulation = false;  ///< --keep-accumulation: a reloaded backend continues the image
 };
 
 struct gpu_worker {
@@ -148,7 +149,7 @@ float percentile(std::vector<float> v, double p) {
 void usage(const char* argv0) {
     std::fprintf(stderr,
                  "Usage: %s [--render N] [--progressive SECONDS] [--width W] [--height H] [--out FILE.exr]\n"
-                 "          [--gpus G] [--device D] [--watch] [--present] [--json] <plugin.so>\n",
+                 "          [--gpus G] [--device D] [--watch] [--keep-accumulation] [--present] [--json] <plugin.so>\n",
                  argv0);
 }
 
@@ -196,6 +197,8 @@ bool parse(int argc, char* argv[], options& opt) {
             opt.present = true;
         } else if (arg == "--json") {
             opt.json = true;
+        } else if (arg == "--keep-accumulation") {
+            opt.keep_accumulation = true;
         } else if (!arg.empty() && arg[0] != '-') {
             opt.plugin_path = arg;
         } else {
@@ -290,7 +293,8 @@ int main(int argc, char* argv[]) {
         auto ctx = Q::gpu::cuda::context::create(
             opt.width, opt.height,
             {.device_ordinal = opt.first_device + g, .shard_index = static_cast<uint32_t>(g),
-             .shard_count = static_cast<uint32_t>(opt.gpus), .present = opt.present});
+             .shard_count = static_cast<uint32_t>(opt.gpus), .present = opt.present,
+             .keep_accumulation = opt.keep_accumulation});
         if (!ctx) {
             std::fprintf(stderr, "Failed to create CUDA context: %s\n", Q::gpu::cuda::to_string(ctx.error()));
             return EXIT_FAILURE;
@@ -303,8 +307,10 @@ int main(int argc, char* argv[]) {
         hooks.pre_unload = [raw]() -> Q::async::task<void> {
             co_await raw->context.wait_idle();  // nothing of the old library may still be running
         };
-        hooks.post_load = [raw]() -> Q::async::task<void> {
-            raw->camera.dirty = true;  // the new instance starts from sample 0
+        hooks.post_load = [raw, keep = opt.keep_accumulation]() -> Q::async::task<void> {
+            // The new instance starts from sample 0 (the reference's behaviour), unless the
+            // context offered it the old instance's layers (Q_cuda_persistent_state).
+            if (!keep) raw->camera.dirty = true;
             co_return;
         };
         hooks.on_error = [](const std::string& msg) { std::fprintf(stderr, "[Host] reload error: %s\n", msg.c_str()); };

@@ -111,6 +111,8 @@ int main(void) {
   printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(Q_plugin_context), sizeof(Q_render_frame),
     sizeof(Q_gpu_context), sizeof(Q_camera), sizeof(Q_readback_result), sizeof(Q_readback_aov_result),
     sizeof(Q_cuda_device_desc), sizeof(Q_cuda_drawable), sizeof(Q_cuda_stats), sizeof(Q_cuda_layers));
+  printf("%zu %zu %zu %zu\n", sizeof(Q_cuda_persistent_state), offsetof(Q_cuda_persistent_state, layers),
+    offsetof(Q_cuda_persistent_state, frame_count), offsetof(Q_cuda_persistent_state, device_ordinal));
   printf("%zu %zu %zu %zu\n", offsetof(Q_render_frame, camera), offsetof(Q_render_frame, camera_dirty),
     offsetof(Q_plugin_context, gpu), offsetof(Q_plugin_context, request_shutdown));
   return 0; }''')
@@ -122,7 +124,9 @@ int main(void) {
                                    abi.Q_cuda_drawable, abi.Q_cuda_stats, abi.Q_cuda_layers)]
     assert [int(x) for x in out[:10]] == sizes
     assert sizes[:6] == [40, 72, 32, 40, 24, 96]  # SURVEY.md 8b, probed from the reference headers
-    assert [int(x) for x in out[10:]] == [abi.Q_render_frame.camera.offset, abi.Q_render_frame.camera_dirty.offset,
+    P = abi.Q_cuda_persistent_state
+    assert [int(x) for x in out[10:14]] == [C.sizeof(P), P.layers.offset, P.frame_count.offset, P.device_ordinal.offset]
+    assert [int(x) for x in out[14:]] == [abi.Q_render_frame.camera.offset, abi.Q_render_frame.camera_dirty.offset,
                                           abi.Q_plugin_context.gpu.offset, abi.Q_plugin_context.request_shutdown.offset]
 
 

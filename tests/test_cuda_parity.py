@@ -296,3 +296,51 @@ def test_sincos_correctly_rounded_over_the_rng_grid(torch_cuda, oracle):
     want, rays = oracle.render_frames(oracle.scene(48, 27), 48, 27, 96)
     assert_bit_exact(got, want)
     assert stats.rays == rays
+
+
+def test_accumulation_survives_a_plugin_reload_when_the_host_keeps_it(torch_cuda, oracle):
+    """SURVEY.md 8f rank 4: with a Q_cuda_persistent_state in Q_gpu_context::layer the
+    destroyed instance parks its layers with the host and the next instance continues at
+    the same sample index: 5 + reload + 5 frames are the bits of 10 uninterrupted frames.
+    Without it a reload restarts at sample 0, as in the reference (plugin.mm:594-617)."""
+    from quasi_b200.headless import headless_host
+
+    w, h = 200, 120
+    want10, _ = oracle.render_frames(oracle.scene(w, h), w, h, 10)
+    want5, _ = oracle.render_frames(oracle.scene(w, h), w, h, 5)
+
+    host = headless_host(w, h, keep_accumulation=True)
+    host.render(5)
+    host.reload()
+    assert any("adopted" in m for m in host.messages)
+    assert host.context.persistent.valid == 0          # the block is the plugin's again
+    kept = host.readback_aov()                          # readable before the first new frame
+    for g, wv in zip(kept, want5):
+        assert np.array_equal(bits(g), bits(wv))
+    host.render(5)
+    for name, g, wv in zip(LAYERS, host.readback_aov(), want10):
+        assert np.array_equal(bits(g), bits(wv)), name
+    assert host.stats().frame_count == 10
+
+    # a parked block that does not fit (other viewport) is released, not adopted
+    host.context.synchronize()
+    host.plugin.destroy()
+    assert host.context.persistent.valid == 1 and host.context.persistent.frame_count == 10
+    host.context.persistent.width += 1
+    host.library.close()
+    host._load()
+    assert host.context.persistent.valid == 0 and host.plugin.readback_aov_numpy() is None
+    host.render_frame(camera_dirty=False)
+    host.render(4)
+    for g, wv in zip(host.readback_aov(), want5):
+        assert np.array_equal(bits(g), bits(wv))
+    host.close()
+
+    plain = headless_host(w, h)
+    plain.render(5)
+    plain.reload()
+    assert plain.plugin.readback_aov_numpy() is None    # nothing rendered yet in the new instance
+    plain.render(5)
+    for g, wv in zip(plain.readback_aov(), want5):
+        assert np.array_equal(bits(g), bits(wv))
+    plain.close()

@@ -153,3 +153,36 @@ def test_headless_host_hot_reload_continuity(host_built, tmp_path):
     # the gap is dominated by the 300 ms settle wait + <=100 ms poll (manager.hpp:126,230)
     assert 300 <= stats["frame_ms_max"] < 2000
     assert stats["frame_ms_p50"] < 20
+
+
+@pytest.mark.gpu
+def test_headless_host_keeps_the_accumulation_across_a_reload(host_built, tmp_path):
+    """--keep-accumulation: the context offers a Q_cuda_persistent_state, the destroyed
+    instance parks its layers there and the reloaded one continues."""
+    import json
+    import shutil
+    import time
+
+    import quasi_b200
+
+    lib = tmp_path / "libquasi_cuda.so"
+    shutil.copy(quasi_b200.PLUGIN_PATH, lib)
+    proc = subprocess.Popen(["stdbuf", "-oL", str(BIN / "quasi_headless"), "--progressive", "4", "--width", "640",
+                             "--height", "360", "--watch", "--keep-accumulation", str(lib)],
+                            stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    head = ""
+    while "Loaded plugin:" not in head:
+        line = proc.stdout.readline()
+        assert line, "host exited early:\n" + head
+        head += line
+    time.sleep(1.0)
+    tmp = tmp_path / "libquasi_cuda.so.new"
+    shutil.copy(quasi_b200.PLUGIN_PATH, tmp)
+    os.replace(tmp, lib)
+    rest, _ = proc.communicate(timeout=120)
+    out = head + rest
+    assert proc.returncode == 0, out[-3000:]
+    stats = json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
+    assert stats["reloads"] == 1 and stats["reload_failures"] == 0
+    assert out.count("Accumulation adopted from the host's persistent state") == 1
+    assert out.index("Path tracer destroyed") < out.index("Accumulation adopted")

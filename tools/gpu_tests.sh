@@ -1,0 +1,4 @@
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; rc=$?; echo "pytest exit $rc" >> gpurun_out/pytest_gpu.log
+tail -3 gpurun_out/pytest_gpu.log
+if [ $rc -ne 0 ]; then grep -E "Error|assert|FAIL|^E " gpurun_out/pytest_gpu.log | head -30; fi
