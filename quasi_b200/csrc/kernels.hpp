@@ -44,6 +44,27 @@ cudaError_t launch_mesh_pathtrace(const mesh_params& scene, const frame_params& 
                                   unsigned long long* counters, unsigned int* tile_counters, int sm_count,
                                   cudaStream_t stream);
 
+/// Triangles in ORIGINAL order on the device: what build_lbvh reads.
+struct lbvh_input {
+    const float4* tri_v0;     ///< {v0.xyz, material}
+    const float4* tri_e1;     ///< {e1.xyz, -}
+    const float4* tri_e2;     ///< {e2.xyz, -}
+    const float4* tri_shade;  ///< 3 per triangle (mesh_scene.hpp:shading_record)
+    uint32_t n_triangles;
+};
+/// Device buffers build_lbvh fills: the layout mesh_params describes.
+struct lbvh_output {
+    float4* nodes;         ///< 2 * (2 n - 1) float4
+    float4* tri_v0;        ///< n, leaf order
+    float4* tri_e1;        ///< n, w = original index
+    float4* tri_e2;        ///< n
+    float4* tri_shade;     ///< 3 n
+    uint32_t* leaf_order;  ///< n: slot -> original index
+    uint32_t* depth;       ///< 1: longest root-to-leaf path in nodes
+};
+/// @brief Builds a linear BVH over the triangles on the GPU (lbvh_build.cu) and waits for it.
+cudaError_t build_lbvh(const lbvh_input& in, const lbvh_output& out, cudaStream_t stream);
+
 /// @brief Test hook: the kernel's sin/cos of phi in [0, 2*pi], element-wise.
 cudaError_t launch_sincos_probe(const float* phi, float* sin_out, float* cos_out, uint64_t n,
                                 cudaStream_t stream);

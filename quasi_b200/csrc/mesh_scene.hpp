@@ -396,4 +396,21 @@ inline void pack_for_device(const scene& s, std::vector<float4_t>& nodes, std::v
     }
 }
 
+/// @brief The triangles in ORIGINAL order as the float4 arrays the GPU builder reads.
+inline void pack_original_order(const scene& s, std::vector<float4_t>& tri_v0, std::vector<float4_t>& tri_e1,
+                                std::vector<float4_t>& tri_e2, std::vector<float4_t>& tri_shade) {
+    const size_t n = s.triangles.size();
+    tri_v0.resize(n);
+    tri_e1.resize(n);
+    tri_e2.resize(n);
+    tri_shade.resize(n * 3);
+    for (size_t i = 0; i < n; i++) {
+        const triangle& t = s.triangles[i];
+        tri_v0[i] = {t.v0[0], t.v0[1], t.v0[2], bits_to_float(t.material)};
+        tri_e1[i] = {t.e1[0], t.e1[1], t.e1[2], 0.0f};
+        tri_e2[i] = {t.e2[0], t.e2[1], t.e2[2], 0.0f};
+        shading_record(t, &tri_shade[i * 3]);
+    }
+}
+
 }  // namespace Q::cuda::mesh

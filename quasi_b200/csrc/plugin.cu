@@ -217,26 +217,8 @@ void free_mesh(plugin_state* state) {
     }
 }
 
-/// Generates the terrain-box scene, builds its BVH on the host and uploads both.
-bool create_mesh(plugin_state* state, uint32_t grid, uint32_t seed, uint32_t max_bounces) {
+void finish_mesh_params(plugin_state* state, uint32_t max_bounces) {
     namespace mesh = Q::cuda::mesh;
-    mesh::generate_triangles(grid, seed, state->mesh);
-    mesh::build_bvh(state->mesh);
-    if (state->mesh.depth > Q::cuda::k_mesh_stack_entries) {
-        log_msg(state, "mesh BVH is deeper than the traversal stack");
-        return false;
-    }
-    std::vector<mesh::float4_t> packed[5];
-    mesh::pack_for_device(state->mesh, packed[0], packed[1], packed[2], packed[3], packed[4]);
-    for (int i = 0; i < 5; i++) {
-        const size_t bytes = packed[i].size() * sizeof(mesh::float4_t);
-        if (!check(state, cudaMalloc(&state->mesh_buffers[i], bytes), "cudaMalloc(mesh)") ||
-            !check(state, cudaMemcpyAsync(state->mesh_buffers[i], packed[i].data(), bytes,
-                                          cudaMemcpyHostToDevice, state->queue), "upload(mesh)")) {
-            return false;
-        }
-    }
-    if (!check(state, cudaStreamSynchronize(state->queue), "upload(mesh) sync")) return false;
     auto& d = state->mesh_device;
     d.nodes = static_cast<const float4*>(state->mesh_buffers[0]);
     d.tri_v0 = static_cast<const float4*>(state->mesh_buffers[1]);
@@ -252,9 +234,113 @@ bool create_mesh(plugin_state* state, uint32_t grid, uint32_t seed, uint32_t max
             d.materials[m * 8 + 4 + c] = state->mesh.materials[m].emission[c];
         }
     }
+}
+
+/// BVH on the GPU (lbvh_build.cu): uploads the triangles in original order, builds,
+/// gathers into leaf order on the device; the nodes and the leaf order come back to
+/// the host only for Q_cuda_plugin_mesh_view. Returns false (nothing kept) if the
+/// build fails or the tree is deeper than the traversal stack.
+bool build_mesh_on_gpu(plugin_state* state) {
+    namespace mesh = Q::cuda::mesh;
+    const size_t n = state->mesh.triangles.size();
+    std::vector<mesh::float4_t> original[4];
+    mesh::pack_original_order(state->mesh, original[0], original[1], original[2], original[3]);
+    void* input[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint32_t* order = nullptr;
+    uint32_t* depth = nullptr;
+    cudaEvent_t begin = nullptr, end = nullptr;
+    auto cleanup = [&](bool keep) {
+        for (auto& b : input) {
+            if (b) cudaFree(b);
+        }
+        if (order) cudaFree(order);
+        if (depth) cudaFree(depth);
+        if (begin) cudaEventDestroy(begin);
+        if (end) cudaEventDestroy(end);
+        if (!keep) free_mesh(state);
+        return keep;
+    };
+    bool ok = true;
+    for (int i = 0; i < 4 && ok; i++) {
+        const size_t bytes = original[i].size() * sizeof(mesh::float4_t);
+        ok = check(state, cudaMalloc(&input[i], bytes), "cudaMalloc(lbvh input)") &&
+             check(state, cudaMemcpyAsync(input[i], original[i].data(), bytes, cudaMemcpyHostToDevice, state->queue),
+                   "upload(lbvh input)");
+    }
+    const size_t out_bytes[5] = {sizeof(float4) * 2 * (2 * n - 1), sizeof(float4) * n, sizeof(float4) * n,
+                                 sizeof(float4) * n, sizeof(float4) * 3 * n};
+    for (int i = 0; i < 5 && ok; i++) ok = check(state, cudaMalloc(&state->mesh_buffers[i], out_bytes[i]), "cudaMalloc(mesh)");
+    ok = ok && check(state, cudaMalloc(reinterpret_cast<void**>(&order), sizeof(uint32_t) * n), "cudaMalloc(order)") &&
+         check(state, cudaMalloc(reinterpret_cast<void**>(&depth), sizeof(uint32_t)), "cudaMalloc(depth)") &&
+         check(state, cudaEventCreate(&begin), "cudaEventCreate") && check(state, cudaEventCreate(&end), "cudaEventCreate");
+    if (!ok) return cleanup(false);
+
+    Q::cuda::lbvh_input in{static_cast<const float4*>(input[0]), static_cast<const float4*>(input[1]),
+                           static_cast<const float4*>(input[2]), static_cast<const float4*>(input[3]),
+                           static_cast<uint32_t>(n)};
+    Q::cuda::lbvh_output out{static_cast<float4*>(state->mesh_buffers[0]), static_cast<float4*>(state->mesh_buffers[1]),
+                             static_cast<float4*>(state->mesh_buffers[2]), static_cast<float4*>(state->mesh_buffers[3]),
+                             static_cast<float4*>(state->mesh_buffers[4]), order, depth};
+    cudaEventRecord(begin, state->queue);
+    const cudaError_t built = Q::cuda::build_lbvh(in, out, state->queue);
+    cudaEventRecord(end, state->queue);
+    if (!check(state, built, "build_lbvh") || !check(state, cudaEventSynchronize(end), "build_lbvh sync")) {
+        return cleanup(false);
+    }
+    float build_ms = 0.0f;
+    cudaEventElapsedTime(&build_ms, begin, end);
+
+    state->mesh.nodes.resize(2 * n - 1);
+    state->mesh.leaf_order.resize(n);
+    ok = check(state, cudaMemcpy(&state->mesh.depth, depth, sizeof(uint32_t), cudaMemcpyDeviceToHost), "download(depth)") &&
+         check(state, cudaMemcpy(state->mesh.nodes.data(), state->mesh_buffers[0], out_bytes[0], cudaMemcpyDeviceToHost),
+               "download(nodes)") &&
+         check(state, cudaMemcpy(state->mesh.leaf_order.data(), order, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost),
+               "download(order)");
+    if (!ok) return cleanup(false);
+    char buf[200];
+    if (state->mesh.depth > Q::cuda::k_mesh_stack_entries) {
+        std::snprintf(buf, sizeof buf, "GPU-built BVH has depth %u, the traversal stack holds %u: using the host builder",
+                      state->mesh.depth, Q::cuda::k_mesh_stack_entries);
+        log_msg(state, buf);
+        return cleanup(false);
+    }
+    std::snprintf(buf, sizeof buf, "Mesh BVH built on the GPU in %.3f ms (LBVH, %zu node slots, depth %u)", build_ms,
+                  2 * n - 1, state->mesh.depth);
+    log_msg(state, buf);
+    return cleanup(true);
+}
+
+/// Generates the terrain-box scene, builds its BVH (binned SAH on the host by default,
+/// LBVH on the GPU with QUASI_CUDA_MESH_BUILDER=lbvh) and leaves both on the device.
+bool create_mesh(plugin_state* state, uint32_t grid, uint32_t seed, uint32_t max_bounces) {
+    namespace mesh = Q::cuda::mesh;
+    mesh::generate_triangles(grid, seed, state->mesh);
+    const char* builder = std::getenv("QUASI_CUDA_MESH_BUILDER");
+    bool on_gpu = builder && std::strcmp(builder, "lbvh") == 0 && state->mesh.triangles.size() > 4 &&
+                  build_mesh_on_gpu(state);
+    if (!on_gpu) {
+        mesh::build_bvh(state->mesh);
+        if (state->mesh.depth > Q::cuda::k_mesh_stack_entries) {
+            log_msg(state, "mesh BVH is deeper than the traversal stack");
+            return false;
+        }
+        std::vector<mesh::float4_t> packed[5];
+        mesh::pack_for_device(state->mesh, packed[0], packed[1], packed[2], packed[3], packed[4]);
+        for (int i = 0; i < 5; i++) {
+            const size_t bytes = packed[i].size() * sizeof(mesh::float4_t);
+            if (!check(state, cudaMalloc(&state->mesh_buffers[i], bytes), "cudaMalloc(mesh)") ||
+                !check(state, cudaMemcpyAsync(state->mesh_buffers[i], packed[i].data(), bytes,
+                                              cudaMemcpyHostToDevice, state->queue), "upload(mesh)")) {
+                return false;
+            }
+        }
+        if (!check(state, cudaStreamSynchronize(state->queue), "upload(mesh) sync")) return false;
+    }
+    finish_mesh_params(state, max_bounces);
     char buf[160];
-    std::snprintf(buf, sizeof buf, "Mesh scene: %u triangles, %u BVH nodes, depth %u", d.n_triangles, d.n_nodes,
-                  state->mesh.depth);
+    std::snprintf(buf, sizeof buf, "Mesh scene: %u triangles, %u BVH nodes, depth %u", state->mesh_device.n_triangles,
+                  state->mesh_device.n_nodes, state->mesh.depth);
     log_msg(state, buf);
     return true;
 }

@@ -11,15 +11,16 @@ from oracle_lib import MeshOracle, bits
 pytestmark = pytest.mark.gpu
 
 
-def mesh_host(width, height, grid, bounces=4, seed=1):
+def mesh_host(width, height, grid, bounces=4, seed=1, builder="sah"):
     from quasi_b200.headless import headless_host
 
     return headless_host(width, height, env={"QUASI_CUDA_SCENE": "mesh", "QUASI_CUDA_MESH_GRID": grid,
-                                             "QUASI_CUDA_MESH_SEED": seed, "QUASI_CUDA_MAX_BOUNCES": bounces})
+                                             "QUASI_CUDA_MESH_SEED": seed, "QUASI_CUDA_MAX_BOUNCES": bounces,
+                                             "QUASI_CUDA_MESH_BUILDER": builder})
 
 
-def render(width, height, frames, grid, bounces=4):
-    h = mesh_host(width, height, grid, bounces)
+def render(width, height, frames, grid, bounces=4, builder="sah"):
+    h = mesh_host(width, height, grid, bounces, builder=builder)
     h.render(frames)
     layers = h.readback_aov()
     stats = h.stats()
@@ -87,3 +88,55 @@ def test_config3_full_size_properties():
         assert np.all(a[..., 3] == 1.0) and np.isfinite(a).all() and a.min() >= 0.0
     assert got[0][:, :300, :3].max() == 0.0              # the margins beside the box stay black
     assert got[0][..., :3].mean() > 0.02
+
+
+@pytest.mark.parametrize("grid,size,frames", [(3, (64, 36), 2), (24, (160, 90), 3), (100, (97, 61), 2),
+                                              (707, (480, 270), 2)])
+def test_gpu_built_bvh_renders_the_oracle_image(grid, size, frames):
+    """The tree built on the GPU (lbvh_build.cu) is a different tree from the oracle's SAH
+    tree; the closest hit does not depend on the tree, so the image is the same bits."""
+    w, h = size
+    got, stats = render(w, h, frames, grid, builder="lbvh")
+    want, st = MeshOracle(grid).render_frames(w, h, frames, max_bounces=4, use_bvh=True)
+    assert_bit_exact(got, want)
+    assert stats.rays == st["rays"]
+    assert stats.nodes_visited > 0 and stats.triangles_tested > 0
+
+
+def test_gpu_built_bvh_is_a_tree_over_all_triangles():
+    grid = 40
+    h = mesh_host(16, 16, grid, builder="lbvh")
+    assert any("built on the GPU" in s for s in h.messages), h.messages
+    v = h.plugin.cuda_mesh_view()
+    n = v.n_triangles
+    assert n == 12 + 2 * grid * grid and v.n_nodes == 2 * n - 1
+    nodes = np.frombuffer(C.string_at(v.nodes, 32 * v.n_nodes), dtype=np.dtype(
+        [("lo", "<f4", 3), ("left_first", "<u4"), ("hi", "<f4", 3), ("count", "<u4")]))
+    tris = np.frombuffer(C.string_at(v.triangles, 48 * n), dtype=np.dtype(
+        [("v0", "<f4", 3), ("m", "<u4"), ("e1", "<f4", 3), ("p0", "<u4"), ("e2", "<f4", 3), ("p1", "<u4")]))
+    order = np.frombuffer(C.string_at(v.leaf_order, 4 * n), dtype=np.uint32)
+    assert np.array_equal(np.sort(order), np.arange(n, dtype=np.uint32))     # a permutation
+    corners = np.stack([tris["v0"], tris["v0"] + tris["e1"], tris["v0"] + tris["e2"]], axis=1)  # (n, 3, 3)
+    seen = np.zeros(n, dtype=np.int32)
+    depth = 0
+    stack = [(0, 1, None, None)]
+    while stack:
+        i, d, plo, phi = stack.pop()
+        node = nodes[i]
+        depth = max(depth, d)
+        if plo is not None:   # a child's box lies inside its parent's (both padded)
+            assert np.all(node["lo"] >= plo - 1e-4) and np.all(node["hi"] <= phi + 1e-4)
+        if node["count"] == 0:
+            left = int(node["left_first"])
+            stack.append((left, d + 1, node["lo"], node["hi"]))
+            stack.append((left + 1, d + 1, node["lo"], node["hi"]))
+        else:
+            assert 1 <= node["count"] <= 4
+            for slot in range(int(node["left_first"]), int(node["left_first"] + node["count"])):
+                t = int(order[slot])
+                seen[t] += 1
+                assert np.all(corners[t] >= node["lo"]) and np.all(corners[t] <= node["hi"])
+                assert np.all(corners[t] - node["lo"] >= 9e-6) and np.all(node["hi"] - corners[t] >= 9e-6)  # padding
+    assert np.all(seen == 1)
+    assert depth == v.depth <= 32
+    h.close()

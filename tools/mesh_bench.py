@@ -28,6 +28,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--json", default=None)
+    ap.add_argument("--builder", choices=["sah", "lbvh"], default="sah",
+                    help="BVH builder: binned SAH on the host (default) or LBVH on the GPU")
     ap.add_argument("--plugin", default=None, help="path of a libquasi_cuda.so build to measure")
     args = ap.parse_args()
 
@@ -40,7 +42,8 @@ def main():
     host = headless_host(args.width, args.height, single_stream=True,
                          plugin_path=args.plugin or quasi_b200.PLUGIN_PATH,
                          env={"QUASI_CUDA_SCENE": "mesh", "QUASI_CUDA_MESH_GRID": args.grid,
-                              "QUASI_CUDA_MESH_SEED": 1, "QUASI_CUDA_MAX_BOUNCES": args.bounces})
+                              "QUASI_CUDA_MESH_SEED": 1, "QUASI_CUDA_MAX_BOUNCES": args.bounces,
+                              "QUASI_CUDA_MESH_BUILDER": args.builder})
     stream = host.context.frame_stream()
 
     def step():
