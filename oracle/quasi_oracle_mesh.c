@@ -137,10 +137,12 @@ typedef struct {
     uint32_t* scratch;
     qm_node* nodes;
     uint32_t n_nodes;
+    uint32_t outlier_first; /* leaf slots from here on hold the outliers split off at the root */
 } builder_t;
 
 #define QM_BINS 16
 #define QM_LEAF_MAX 4
+#define QM_OUTLIER_FRACTION (1.0f / 64.0f)
 
 static void build_node(builder_t* b, uint32_t node_index, uint32_t first, uint32_t count) {
     box_t bounds, cbounds;
@@ -157,10 +159,37 @@ static void build_node(builder_t* b, uint32_t node_index, uint32_t first, uint32
         node->bmin[a] = bounds.lo[a] - pad;
         node->bmax[a] = bounds.hi[a] + pad;
     }
-    if (count <= QM_LEAF_MAX) {
+    if (count <= (first >= b->outlier_first ? 1u : QM_LEAF_MAX)) {
         node->left_first = first;
         node->count = count;
         return;
+    }
+
+    /* Root only: triangles whose box is larger than 1/64 of the scene's box (walls, floor)
+     * go to the right subtree as they are, in leaves of one; everything else goes left. A
+     * greedy SAH never isolates them by itself and each would inflate one box per level. */
+    if (node_index == 0) {
+        float limit = box_area(&bounds) * QM_OUTLIER_FRACTION;
+        uint32_t nl = 0, nr = 0;
+        for (uint32_t k = first; k < first + count; k++) { /* stable partition */
+            uint32_t t = b->order[k];
+            if (box_area(&b->prim_box[t]) > limit) {
+                b->scratch[nr++] = t;
+            } else {
+                b->order[first + nl++] = t;
+            }
+        }
+        memcpy(&b->order[first + nl], b->scratch, (size_t)nr * sizeof(uint32_t));
+        if (nl > 0 && nr > 0) {
+            b->outlier_first = first + nl;
+            uint32_t left = b->n_nodes;
+            b->n_nodes += 2;
+            node->left_first = left;
+            node->count = 0;
+            build_node(b, left, first, nl);
+            build_node(b, left + 1u, first + nl, nr);
+            return;
+        }
     }
 
     /* 16-bin SAH over the centroid bounds; first strictly smaller cost wins. */
@@ -249,6 +278,7 @@ static void build_bvh(qm_scene* s) {
     b.scratch = (uint32_t*)malloc((size_t)n * sizeof(uint32_t));
     b.nodes = (qm_node*)calloc((size_t)2 * n, sizeof(qm_node));
     b.n_nodes = 1;
+    b.outlier_first = 0xffffffffu;
     for (uint32_t t = 0; t < n; t++) {
         const qm_triangle* tri = &s->tris[t];
         float p1[3], p2[3];

@@ -13,8 +13,11 @@
 /// Karras 2012:
 ///   1. primitive boxes + centroids, scene centroid bounds (block reduction, one
 ///      ordered-integer atomic per block and axis)
-///   2. 30-bit Morton code of the centroid; key = code << 32 | triangle index, so
-///      keys are unique and ties need no special case
+///   2. 30-bit Morton code of the centroid; key = outlier << 62 | code << 32 |
+///      triangle index, so keys are unique and ties need no special case. An
+///      outlier is a triangle whose box exceeds 1/64 of the scene's box (the rule
+///      of mesh_scene.hpp:build_bvh): the top bit makes the root split outliers |
+///      everything else, instead of letting each wall inflate one box per level
 ///   3. 64-bit radix sort of the keys (cub::DeviceRadixSort, library code)
 ///   4. one thread per internal node: range and split from the common-prefix
 ///      lengths of neighbouring keys
@@ -22,8 +25,9 @@
 ///      to arrive at a node merges its children
 ///   6. emission into the traversal layout: 32-byte nodes, the two children of
 ///      internal node i at 1 + 2i and 2 + 2i (siblings share a 64-byte line), a
-///      subtree of at most 4 triangles becomes one leaf (its range of the sorted
-///      order is contiguous), boxes padded by 1e-4 of their extent + 1e-5
+///      subtree of at most 4 triangles that are not outliers becomes one leaf (its
+///      range of the sorted order is contiguous), boxes padded by 1e-4 of their
+///      extent + 1e-5
 ///   7. triangles and shading records gathered into leaf (= sorted) order
 /// The build of the 999 710-triangle scene takes a few milliseconds against 2.3 s
 /// for the binned-SAH build on one host core; the tree is shallower in quality
@@ -43,6 +47,8 @@ namespace {
 constexpr int k_threads = 256;
 constexpr uint32_t k_leaf_flag = 0x80000000u;  ///< child reference: leaf k (position in sorted order)
 constexpr uint32_t k_leaf_max = 4;
+constexpr uint64_t k_outlier_bit = 1ull << 62;
+constexpr float k_outlier_fraction = 1.0f / 64.0f;  // mesh_scene.hpp:k_outlier_fraction
 
 inline unsigned blocks_for(uint32_t n) { return (n + k_threads - 1) / k_threads; }
 
@@ -62,7 +68,7 @@ struct build_arrays {
     float4* prim_lo;       ///< [n] box of triangle t, w = centroid.x
     float4* prim_hi;       ///< [n] w = centroid.y; centroid.z in cz
     float* prim_cz;        ///< [n]
-    uint32_t* scene;       ///< [6] ordered-uint centroid bounds: lo xyz, hi xyz
+    uint32_t* scene;       ///< [12] ordered-uint: centroid bounds lo xyz, hi xyz, then scene box lo xyz, hi xyz
     uint64_t* keys;        ///< [n] sorted keys (after the sort)
     uint32_t* child;       ///< [2 (n-1)] children of internal node i at 2i, 2i+1
     uint32_t* range;       ///< [2 (n-1)] first, last sorted position covered by internal node i
@@ -76,6 +82,7 @@ __global__ void __launch_bounds__(k_threads)
 prim_bounds_kernel(build_arrays a, uint32_t n) {
     const uint32_t t = blockIdx.x * k_threads + threadIdx.x;
     float c[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, d[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    float b_lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, b_hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
     if (t < n) {
         const float4 v0 = a.tri_v0[t], e1 = a.tri_e1[t], e2 = a.tri_e2[t];
         const float p0[3] = {v0.x, v0.y, v0.z};
@@ -86,15 +93,17 @@ prim_bounds_kernel(build_arrays a, uint32_t n) {
             lo[k] = fminf(p0[k], fminf(p1[k], p2[k]));
             hi[k] = fmaxf(p0[k], fmaxf(p1[k], p2[k]));
             c[k] = d[k] = ((p0[k] + p1[k]) + p2[k]) * (1.0f / 3.0f);
+            b_lo[k] = lo[k];
+            b_hi[k] = hi[k];
         }
         a.prim_lo[t] = make_float4(lo[0], lo[1], lo[2], c[0]);
         a.prim_hi[t] = make_float4(hi[0], hi[1], hi[2], c[1]);
         a.prim_cz[t] = c[2];
     }
-    // block reduction of the centroid bounds, then one atomic per block and axis
-    __shared__ float s_lo[3][k_threads / 32], s_hi[3][k_threads / 32];
-    for (int k = 0; k < 3; k++) {
-        float lo = c[k], hi = d[k];
+    // block reduction of the centroid bounds and of the scene box, then one atomic per block and axis
+    __shared__ float s_lo[6][k_threads / 32], s_hi[6][k_threads / 32];
+    for (int k = 0; k < 6; k++) {
+        float lo = k < 3 ? c[k] : b_lo[k - 3], hi = k < 3 ? d[k] : b_hi[k - 3];
         for (int o = 16; o > 0; o >>= 1) {
             lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
             hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
@@ -105,14 +114,15 @@ prim_bounds_kernel(build_arrays a, uint32_t n) {
         }
     }
     __syncthreads();
-    if (threadIdx.x < 3) {
+    if (threadIdx.x < 6) {
         float lo = s_lo[threadIdx.x][0], hi = s_hi[threadIdx.x][0];
         for (int w = 1; w < k_threads / 32; w++) {
             lo = fminf(lo, s_lo[threadIdx.x][w]);
             hi = fmaxf(hi, s_hi[threadIdx.x][w]);
         }
-        atomicMin(a.scene + threadIdx.x, ordered(lo));
-        atomicMax(a.scene + 3 + threadIdx.x, ordered(hi));
+        const uint32_t group = threadIdx.x < 3 ? 0u : 6u, axis = threadIdx.x % 3u;
+        atomicMin(a.scene + group + axis, ordered(lo));
+        atomicMax(a.scene + group + 3 + axis, ordered(hi));
     }
 }
 
@@ -138,7 +148,18 @@ morton_kernel(build_arrays a, uint64_t* keys_out, uint32_t n) {
         q[k] = static_cast<uint32_t>(fminf(fmaxf(u * 1024.0f, 0.0f), 1023.0f));
     }
     const uint32_t code = (expand_bits(q[0]) << 2) | (expand_bits(q[1]) << 1) | expand_bits(q[2]);
-    keys_out[t] = (static_cast<uint64_t>(code) << 32) | t;
+    // outlier: box area above 1/64 of the scene box's (both 2 (dx dy + dy dz + dz dx), mesh_scene.hpp)
+    float ext[3], own[3];
+    const float4 lo4 = a.prim_lo[t], hi4 = a.prim_hi[t];
+    const float own_lo[3] = {lo4.x, lo4.y, lo4.z}, own_hi[3] = {hi4.x, hi4.y, hi4.z};
+    for (int k = 0; k < 3; k++) {
+        ext[k] = unordered(a.scene[9 + k]) - unordered(a.scene[6 + k]);
+        own[k] = own_hi[k] - own_lo[k];
+    }
+    const float scene_area = 2.0f * ((ext[0] * ext[1] + ext[1] * ext[2]) + ext[2] * ext[0]);
+    const float own_area = 2.0f * ((own[0] * own[1] + own[1] * own[2]) + own[2] * own[0]);
+    const uint64_t outlier = own_area > scene_area * k_outlier_fraction ? k_outlier_bit : 0ull;
+    keys_out[t] = outlier | (static_cast<uint64_t>(code) << 32) | t;
 }
 
 /// Length of the common prefix of keys i and j; -1 outside the array (Karras 2012, section 4).
@@ -221,6 +242,12 @@ __device__ __forceinline__ void write_node(float4* nodes, uint32_t at, float4 lo
     nodes[2 * at + 1] = make_float4(hi.x + px, hi.y + py, hi.z + pz, __uint_as_float(count));
 }
 
+/// An internal node becomes one leaf if it covers at most 4 triangles, none of them an outlier.
+__device__ __forceinline__ bool collapses(const build_arrays& a, uint32_t node) {
+    const uint32_t first = a.range[2 * node], size = a.range[2 * node + 1] - first + 1u;
+    return size <= k_leaf_max && (a.keys[a.range[2 * node + 1]] & k_outlier_bit) == 0ull;
+}
+
 __device__ __forceinline__ void emit_child(const build_arrays& a, float4* nodes, uint32_t at, uint32_t ref) {
     float4 lo, hi;
     if (ref & k_leaf_flag) {
@@ -232,7 +259,7 @@ __device__ __forceinline__ void emit_child(const build_arrays& a, float4* nodes,
     lo = a.box_lo[ref];
     hi = a.box_hi[ref];
     const uint32_t first = a.range[2 * ref], size = a.range[2 * ref + 1] - first + 1u;
-    if (size <= k_leaf_max) {
+    if (collapses(a, ref)) {
         write_node(nodes, at, lo, hi, first, size);  // the whole subtree as one leaf
     } else {
         write_node(nodes, at, lo, hi, 1u + 2u * ref, 0u);
@@ -256,8 +283,7 @@ depth_and_order_kernel(build_arrays a, uint32_t* leaf_order, uint32_t* depth, ui
     leaf_order[k] = static_cast<uint32_t>(a.keys[k]);
     uint32_t node = a.parent[(n - 1) + k], levels = 1u;  // the leaf node itself
     for (;;) {
-        const uint32_t size = a.range[2 * node + 1] - a.range[2 * node] + 1u;
-        if (size > k_leaf_max) levels++;  // an interior node of the emitted tree
+        if (!collapses(a, node)) levels++;  // an interior node of the emitted tree
         if (node == 0u) break;
         node = a.parent[node];
     }
@@ -294,7 +320,7 @@ cudaError_t build_lbvh(const lbvh_input& in, const lbvh_output& out, cudaStream_
         return at;
     };
     const size_t o_prim_lo = carve(sizeof(float4) * n), o_prim_hi = carve(sizeof(float4) * n);
-    const size_t o_prim_cz = carve(sizeof(float) * n), o_scene = carve(sizeof(uint32_t) * 6);
+    const size_t o_prim_cz = carve(sizeof(float) * n), o_scene = carve(sizeof(uint32_t) * 12);
     const size_t o_keys_a = carve(sizeof(uint64_t) * n), o_keys_b = carve(sizeof(uint64_t) * n);
     const size_t o_child = carve(sizeof(uint32_t) * 2 * n), o_range = carve(sizeof(uint32_t) * 2 * n);
     const size_t o_parent = carve(sizeof(uint32_t) * 2 * n), o_visits = carve(sizeof(uint32_t) * n);
@@ -330,7 +356,8 @@ cudaError_t build_lbvh(const lbvh_input& in, const lbvh_output& out, cudaStream_
         return e;
     };
     // ordered(+FLT_MAX) for the minima, ordered(-FLT_MAX) for the maxima
-    const uint32_t scene_init[6] = {0xff7fffffu, 0xff7fffffu, 0xff7fffffu, 0x00800000u, 0x00800000u, 0x00800000u};
+    const uint32_t scene_init[12] = {0xff7fffffu, 0xff7fffffu, 0xff7fffffu, 0x00800000u, 0x00800000u, 0x00800000u,
+                                     0xff7fffffu, 0xff7fffffu, 0xff7fffffu, 0x00800000u, 0x00800000u, 0x00800000u};
     if ((err = cudaMemcpyAsync(a.scene, scene_init, sizeof scene_init, cudaMemcpyHostToDevice, stream)) != cudaSuccess ||
         (err = cudaMemsetAsync(a.visits, 0, sizeof(uint32_t) * n, stream)) != cudaSuccess ||
         (err = cudaMemsetAsync(out.depth, 0, sizeof(uint32_t), stream)) != cudaSuccess ||
