@@ -58,7 +58,7 @@ using namespace dev;
 #define QUASI_MESH_MIN_WAITING 16
 #endif
 #ifndef QUASI_MESH_LEAF_BATCH
-#define QUASI_MESH_LEAF_BATCH 12
+#define QUASI_MESH_LEAF_BATCH 8
 #endif
 #ifndef QUASI_MESH_RUN_EXIT
 #define QUASI_MESH_RUN_EXIT 4
