@@ -278,12 +278,12 @@ def run_ours(args):
         peak, peak_src = measured_peaks()
         kernel_ms = ms_step / SPP  # the step is SPP back-to-back launches of the one kernel (N=1)
         achieved = ALGORITHMIC_BYTES_PER_PIXEL_PER_CALL * n_px / (kernel_ms * 1e-3) / 1e9
-        traffic = None
+        traffic, issue_util = None, None
         summary = ROOT / "profiles" / "ncu_summary.json"
         if summary.exists():
             try:
-                traffic = json.loads(summary.read_text()).get("pathtrace_accumulate_kernel", {}).get(
-                    "dram_bytes_per_launch")
+                k = json.loads(summary.read_text()).get("pathtrace_accumulate_kernel", {})
+                traffic, issue_util = k.get("dram_bytes_per_launch"), k.get("issue_slot_utilization")
             except Exception:
                 traffic = None
         param_bytes = SPP * (7344 + 80)  # sizeof(scene_params) + sizeof(frame_params) per launch
@@ -313,8 +313,10 @@ def run_ours(args):
                 "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": ALGORITHMIC_BYTES_PER_PIXEL_PER_CALL * n_px,
                 "kernel_ms": round(kernel_ms, 5),
-                "note": "FP32-issue-bound kernel (16-quad scan per ray); HBM fraction is low by design, "
-                        "see DESIGN.md and profiles/",
+                "issue_slot_utilization_ncu": issue_util,
+                "note": "instruction-issue-bound kernel (16-quad scan per ray, ~36 warp instructions per ray): the "
+                        "HBM fraction is low by design, the issue slots are the resource that is full "
+                        "(ncu, profiles/ncu_summary.json); see DESIGN.md section 4.1",
             },
         }
         if world == 1 and not args.no_cpu:

@@ -11,7 +11,11 @@ from pathlib import Path
 
 PACKAGE_DIR = Path(__file__).resolve().parent
 REPO_ROOT = PACKAGE_DIR.parent
-PLUGIN_PATH = PACKAGE_DIR / "lib" / "libquasi_cuda.so"
+import os as _os
+
+# QUASI_PLUGIN_OVERRIDE: measure another build of the backend (tools/build_variant.sh) with the same host code
+PLUGIN_PATH = Path(_os.environ["QUASI_PLUGIN_OVERRIDE"]) if _os.environ.get("QUASI_PLUGIN_OVERRIDE") else \
+    PACKAGE_DIR / "lib" / "libquasi_cuda.so"
 
 from .abi import (  # noqa: E402,F401
     Q_AOV_BEAUTY, Q_AOV_ALBEDO, Q_AOV_NORMAL, Q_AOV_DEPTH, Q_AOV_COUNT,

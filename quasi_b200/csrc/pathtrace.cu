@@ -103,10 +103,15 @@ struct scan_state {
 
 /// Files one plane hit. `m` = max(|alpha' - 1/2|, |beta' - 1/2|): the point is
 /// surely outside the quad beyond half_plus and surely inside within half_minus.
+/// `ahead`: the plane is hit at all (|denom| >= 1e-8, decided exactly) and not surely
+/// behind t_min. The scan evaluates every quad for every lane without a branch: the
+/// inside test is 20 instructions, a divergent branch around it costs 3 and nearly
+/// always has a lane that takes it. What a lane computes past a failed `ahead` (possibly
+/// from an infinite t') is discarded here.
 __device__ __forceinline__ void consider(scan_state& s, const quad_params& q, int i, float t_fast,
-                                         float m) {
-    const bool maybe = m <= q.half_plus;
-    const bool sure = m < q.half_minus && t_fast > k_t_min_hi;
+                                         float m, bool ahead) {
+    const bool maybe = ahead && m <= q.half_plus;
+    const bool sure = ahead && m < q.half_minus && t_fast > k_t_min_hi;
     const bool better = sure && t_fast < s.best_t;
     // Whoever does not become the winner challenges it.
     const float loser = better ? s.best_t : (maybe ? t_fast : k_inf);
@@ -126,14 +131,13 @@ __device__ __forceinline__ void scan_flat(scan_state& s, const quad_params& q, i
     const float denom = q.normal[K] * axis(rd, K);
     const float num = q.plane_d - q.normal[K] * axis(ro, K);
     const float t_fast = num * rcp_approx(denom);
-    if (fabsf(denom) >= 1e-8f && t_fast > k_t_min_lo) {
-        // p', alpha', beta' only feed margin decisions: contracted (FFMA), unlike num and denom
-        const float pi = __fmaf_rn(axis(rd, I), t_fast, axis(ro, I)) - q.center[I];
-        const float pj = __fmaf_rn(axis(rd, J), t_fast, axis(ro, J)) - q.center[J];
-        const float alpha = __fmaf_rn(pi, q.fast_a[I], pj * q.fast_a[J]);
-        const float beta = __fmaf_rn(pi, q.fast_b[I], pj * q.fast_b[J]);
-        consider(s, q, i, t_fast, fmaxf(fabsf(alpha), fabsf(beta)));
-    }
+    const bool ahead = fabsf(denom) >= 1e-8f && t_fast > k_t_min_lo;
+    // p', alpha', beta' only feed margin decisions: contracted (FFMA), unlike num and denom
+    const float pi = __fmaf_rn(axis(rd, I), t_fast, axis(ro, I)) - q.center[I];
+    const float pj = __fmaf_rn(axis(rd, J), t_fast, axis(ro, J)) - q.center[J];
+    const float alpha = __fmaf_rn(pi, q.fast_a[I], pj * q.fast_a[J]);
+    const float beta = __fmaf_rn(pi, q.fast_b[I], pj * q.fast_b[J]);
+    consider(s, q, i, t_fast, fmaxf(fabsf(alpha), fabsf(beta)), ahead);
 }
 
 /// Quad with a horizontal normal and one vertical edge (the side of a box
@@ -142,14 +146,13 @@ __device__ __forceinline__ void scan_upright(scan_state& s, const quad_params& q
     const float denom = q.normal[0] * rd.x + q.normal[2] * rd.z;
     const float num = q.plane_d - (q.normal[0] * ro.x + q.normal[2] * ro.z);
     const float t_fast = num * rcp_approx(denom);
-    if (fabsf(denom) >= 1e-8f && t_fast > k_t_min_lo) {
-        const float px = __fmaf_rn(rd.x, t_fast, ro.x) - q.center[0];
-        const float py = __fmaf_rn(rd.y, t_fast, ro.y) - q.center[1];
-        const float pz = __fmaf_rn(rd.z, t_fast, ro.z) - q.center[2];
-        const float alpha = __fmaf_rn(px, q.fast_a[0], pz * q.fast_a[2]);
-        const float beta = py * q.fast_b[1];
-        consider(s, q, i, t_fast, fmaxf(fabsf(alpha), fabsf(beta)));
-    }
+    const bool ahead = fabsf(denom) >= 1e-8f && t_fast > k_t_min_lo;
+    const float px = __fmaf_rn(rd.x, t_fast, ro.x) - q.center[0];
+    const float py = __fmaf_rn(rd.y, t_fast, ro.y) - q.center[1];
+    const float pz = __fmaf_rn(rd.z, t_fast, ro.z) - q.center[2];
+    const float alpha = __fmaf_rn(px, q.fast_a[0], pz * q.fast_a[2]);
+    const float beta = py * q.fast_b[1];
+    consider(s, q, i, t_fast, fmaxf(fabsf(alpha), fabsf(beta)), ahead);
 }
 
 __device__ __forceinline__ void scan_general(scan_state& s, const quad_params& q, int i, v3 ro, v3 rd) {
@@ -157,13 +160,14 @@ __device__ __forceinline__ void scan_general(scan_state& s, const quad_params& q
     const float denom = dot(normal, rd);            // the shader's value
     const float num = q.plane_d - dot(normal, ro);  // the shader's value
     const float t_fast = num * rcp_approx(denom);
-    if (fabsf(denom) >= 1e-8f && t_fast > k_t_min_lo) {
+    const bool ahead = fabsf(denom) >= 1e-8f && t_fast > k_t_min_lo;
+    {
         const v3 planar = make_v3(__fmaf_rn(rd.x, t_fast, ro.x) - q.center[0],
                                   __fmaf_rn(rd.y, t_fast, ro.y) - q.center[1],
                                   __fmaf_rn(rd.z, t_fast, ro.z) - q.center[2]);
         const float alpha = __fmaf_rn(planar.x, q.fast_a[0], __fmaf_rn(planar.y, q.fast_a[1], planar.z * q.fast_a[2]));
         const float beta = __fmaf_rn(planar.x, q.fast_b[0], __fmaf_rn(planar.y, q.fast_b[1], planar.z * q.fast_b[2]));
-        consider(s, q, i, t_fast, fmaxf(fabsf(alpha), fabsf(beta)));
+        consider(s, q, i, t_fast, fmaxf(fabsf(alpha), fabsf(beta)), ahead);
     }
 }
 
