@@ -141,7 +141,7 @@ typedef struct {
 } builder_t;
 
 #define QM_BINS 16
-#define QM_LEAF_MAX 4
+#define QM_LEAF_MAX 2
 #define QM_OUTLIER_FRACTION (1.0f / 64.0f)
 
 static void build_node(builder_t* b, uint32_t node_index, uint32_t first, uint32_t count) {

@@ -27,7 +27,7 @@
  *
  * BVH: binary, built top-down with 16-bin SAH on centroids; children are
  * allocated in pairs when their parent is split, left subtree built first;
- * leaves hold <= 4 triangles. One rule precedes the SAH, at the root only:
+ * leaves hold <= 2 triangles. One rule precedes the SAH, at the root only:
  * triangles whose box area exceeds 1/64 of the scene box's (the room's walls)
  * are split off, in order, into the right subtree, which is then built the same
  * way with leaves of one triangle. Node boxes are padded by 1e-4*extent + 1e-5 so

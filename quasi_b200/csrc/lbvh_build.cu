@@ -25,13 +25,13 @@
 ///      to arrive at a node merges its children
 ///   6. emission into the traversal layout: 32-byte nodes, the two children of
 ///      internal node i at 1 + 2i and 2 + 2i (siblings share a 64-byte line), a
-///      subtree of at most 4 triangles that are not outliers becomes one leaf (its
+///      subtree of at most 2 triangles that are not outliers becomes one leaf (its
 ///      range of the sorted order is contiguous), boxes padded by 1e-4 of their
 ///      extent + 1e-5
 ///   7. triangles and shading records gathered into leaf (= sorted) order
 /// The build of the 999 710-triangle scene takes 2.1 ms against 2.3 s for the
-/// binned-SAH build on one host core; rays visit 41 boxes on this tree against 36
-/// on the SAH tree (frame 30.0 ms against 27.4 ms), the usual LBVH trade.
+/// binned-SAH build on one host core; rays visit 42 boxes on this tree against 37
+/// on the SAH tree (frame 28.5 ms against 26.2 ms), the usual LBVH trade.
 
 #include "kernels.hpp"
 
@@ -46,7 +46,7 @@ namespace {
 
 constexpr int k_threads = 256;
 constexpr uint32_t k_leaf_flag = 0x80000000u;  ///< child reference: leaf k (position in sorted order)
-constexpr uint32_t k_leaf_max = 4;
+constexpr uint32_t k_leaf_max = 2;
 constexpr uint64_t k_outlier_bit = 1ull << 62;
 constexpr float k_outlier_fraction = 1.0f / 64.0f;  // mesh_scene.hpp:k_outlier_fraction
 
@@ -242,7 +242,7 @@ __device__ __forceinline__ void write_node(float4* nodes, uint32_t at, float4 lo
     nodes[2 * at + 1] = make_float4(hi.x + px, hi.y + py, hi.z + pz, __uint_as_float(count));
 }
 
-/// An internal node becomes one leaf if it covers at most 4 triangles, none of them an outlier.
+/// An internal node becomes one leaf if it covers at most k_leaf_max triangles, none of them an outlier.
 __device__ __forceinline__ bool collapses(const build_arrays& a, uint32_t node) {
     const uint32_t first = a.range[2 * node], size = a.range[2 * node + 1] - first + 1u;
     return size <= k_leaf_max && (a.keys[a.range[2 * node + 1]] & k_outlier_bit) == 0ull;

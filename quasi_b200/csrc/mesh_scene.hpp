@@ -65,7 +65,7 @@ struct material {
 
 inline constexpr uint32_t k_material_count = 5;
 inline constexpr uint32_t k_sah_bins = 16;
-inline constexpr uint32_t k_leaf_max = 4;
+inline constexpr uint32_t k_leaf_max = 2;
 /// Triangles whose box area exceeds this fraction of the scene's are split off at the root.
 inline constexpr float k_outlier_fraction = 1.0f / 64.0f;
 
