@@ -308,9 +308,14 @@ pathtrace_accumulate_kernel(const __grid_constant__ scene_params scene,
     uint32_t rays = 0;
     uint32_t next_item = 0;  // warp-uniform cursor into this warp's pixel sequence
     tile_feed feed{tile_counters, n_tiles};
+    // Where a continuing path scatters from: the quad it hit, complemented when it was hit
+    // from behind. Set by the shading step, consumed at the top of the next iteration.
+    int scatter = 0;
 
     while (true) {
         // Regeneration: idle lanes take the warp's next pixels, compacted.
+        bool fresh = false;
+        float uv_x = 0.0f, uv_y = 0.0f;
         const uint32_t idle = __ballot_sync(0xffffffffu, !active);
         if (idle != 0u) {
             feed.open(next_item, next_item + __popc(idle) - 1u);
@@ -331,20 +336,10 @@ pathtrace_accumulate_kernel(const __grid_constant__ scene_params scene,
                     if (px < frame.width && py < frame.height) {
                         // pathtrace_frag, plugin.mm:287-309; uv is the closed form of
                         // the rasteriser's interpolation, py = 0 on top.
-                        float uv_x = (static_cast<float>(px) + 0.5f) / static_cast<float>(frame.width);
-                        float uv_y = 1.0f - (static_cast<float>(py) + 0.5f) /
-                                                static_cast<float>(frame.height);
+                        uv_x = (static_cast<float>(px) + 0.5f) / static_cast<float>(frame.width);
+                        uv_y = 1.0f - (static_cast<float>(py) + 0.5f) / static_cast<float>(frame.height);
                         rng = pcg_hash(px + py * 1920u + frame.frame_index * 1920u * 1080u);
-                        // get_camera_ray, plugin.mm:129-153: jitter x is drawn before y.
-                        const float jx = random_float(rng);
-                        const float jy = random_float(rng);
-                        uv_x += (jx - 0.5f) * 0.001f;
-                        uv_y += (jy - 0.5f) * 0.001f;
-                        const v3 target = load_v3(frame.lower_left) +
-                                          load_v3(frame.horizontal) * uv_x +
-                                          load_v3(frame.vertical) * uv_y;
-                        ro = cam_origin;
-                        rd = normalize(target - cam_origin);
+                        fresh = true;
                         throughput = make_v3(1.0f, 1.0f, 1.0f);
                         color = make_v3(0.0f, 0.0f, 0.0f);
                         bounce = 0;
@@ -369,6 +364,36 @@ pathtrace_accumulate_kernel(const __grid_constant__ scene_params scene,
         }
 
         if (active) {
+            // Every path needs a direction now: a new one its camera ray (get_camera_ray,
+            // plugin.mm:129-153, jitter x drawn before y), a continuing one its scattered ray
+            // (cosine_sample_hemisphere, plugin.mm:111-125, r1 before r2, with the per-quad
+            // frame). Both take two draws and end in a normalisation; those are issued once
+            // for the whole warp instead of once per kind of lane.
+            const float draw_a = random_float(rng);
+            const float draw_b = random_float(rng);
+            v3 d;
+            if (fresh) {
+                uv_x += (draw_a - 0.5f) * 0.001f;
+                uv_y += (draw_b - 0.5f) * 0.001f;
+                const v3 target = load_v3(frame.lower_left) + load_v3(frame.horizontal) * uv_x +
+                                  load_v3(frame.vertical) * uv_y;
+                ro = cam_origin;
+                d = target - cam_origin;
+            } else {
+                const float* from = s_shade + (scatter < 0 ? ~scatter : scatter) * k_shade_stride;
+                const float side = scatter < 0 ? -1.0f : 1.0f;
+                const float phi = 6.28318548202514648f * draw_a;  // 2.0f * M_PI_F, exact product
+                const float cos_theta = sqrtf(1.0f - draw_b);
+                const float sin_theta = sqrtf(draw_b);
+                float sin_phi, cos_phi;
+                sincos_round_once(phi, sin_phi, cos_phi);
+                const v3 fu = load_v3(from + k_sh_frame_u);
+                const v3 fv = load_v3(from + k_sh_frame_v) * side;
+                const v3 fw = load_v3(from + k_sh_frame_w) * side;
+                d = (fu * cos_phi) * sin_theta + (fv * sin_phi) * sin_theta + fw * cos_theta;
+            }
+            rd = normalize(d);
+
             // One bounce of path_trace, plugin.mm:232-273.
             hit_record hit;
             trace_scene<Layout>(scene, s_shade, ro, rd, hit);
@@ -418,19 +443,7 @@ pathtrace_accumulate_kernel(const __grid_constant__ scene_params scene,
 
             if (!done) {
                 ro = hit.point + n * 0.001f;
-                // cosine_sample_hemisphere (plugin.mm:111-125) with the per-quad frame.
-                const float r1 = random_float(rng);
-                const float r2 = random_float(rng);
-                const float phi = 6.28318548202514648f * r1;  // 2.0f * M_PI_F, exact product
-                const float cos_theta = sqrtf(1.0f - r2);
-                const float sin_theta = sqrtf(r2);
-                float sin_phi, cos_phi;
-                sincos_round_once(phi, sin_phi, cos_phi);
-                const v3 fu = load_v3(sh + k_sh_frame_u);
-                const v3 fv = load_v3(sh + k_sh_frame_v) * side;
-                const v3 fw = load_v3(sh + k_sh_frame_w) * side;
-                const v3 d = (fu * cos_phi) * sin_theta + (fv * sin_phi) * sin_theta + fw * cos_theta;
-                rd = normalize(d);
+                scatter = hit.front ? hit.index : ~hit.index;  // the direction is drawn at the top
             } else {
                 accumulate_pixel(beauty, pixel, make_float4(color.x, color.y, color.z, 1.0f),
                                  first_sample, weight);
