@@ -218,12 +218,13 @@ mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_co
 
     while (true) {
         // ---------------------------------------------------------- service ----
-        bool new_ray = false;
+        bool new_ray = false, fresh = false;
+        v3 fu = make_v3(0.0f, 0.0f, 0.0f), fv = fu, fw = fu;  // scattering frame of a continuing path
+        float uv_x = 0.0f, uv_y = 0.0f;                        // pixel centre of a new path
         if (active && cur == k_done) {
             // One bounce of path_trace (plugin.mm:232-273) around the finished query.
             const bool is_hit = best.prim != k_miss;
             v3 n = make_v3(0.0f, 0.0f, 0.0f), q_emission = n, q_albedo = n;
-            v3 fu = n, fv = n, fw = n;
             bool is_light = false;
             if (is_hit) {
                 const float4* rec = scene.tri_shade + 3u * static_cast<size_t>(best.slot);
@@ -277,17 +278,7 @@ mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_co
             if (!done) {
                 const v3 point = ro + rd * best.t;
                 ro = point + n * 0.001f;
-                // cosine_sample_hemisphere (plugin.mm:111-125) with the per-triangle frame
-                const float r1 = random_float(rng);
-                const float r2 = random_float(rng);
-                const float phi = 6.28318548202514648f * r1;
-                const float cos_theta = sqrtf(1.0f - r2);
-                const float sin_theta = sqrtf(r2);
-                float sin_phi, cos_phi;
-                sincos_round_once(phi, sin_phi, cos_phi);
-                const v3 dir = (fu * cos_phi) * sin_theta + (fv * sin_phi) * sin_theta + fw * cos_theta;
-                rd = normalize(dir);
-                new_ray = true;
+                new_ray = true;  // the direction is drawn below, together with the new paths' camera rays
             } else {
                 accumulate_pixel(beauty, pixel, make_float4(color.x, color.y, color.z, 1.0f), first_sample,
                                  weight);
@@ -313,17 +304,10 @@ mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_co
                     const uint32_t px = tile_x * 8u + (item & 7u);
                     const uint32_t py = tile_y * 4u + ((item >> 3) & 3u);
                     if (px < frame.width && py < frame.height) {
-                        float uv_x = (static_cast<float>(px) + 0.5f) / static_cast<float>(frame.width);
-                        float uv_y = 1.0f - (static_cast<float>(py) + 0.5f) / static_cast<float>(frame.height);
+                        uv_x = (static_cast<float>(px) + 0.5f) / static_cast<float>(frame.width);
+                        uv_y = 1.0f - (static_cast<float>(py) + 0.5f) / static_cast<float>(frame.height);
                         rng = pcg_hash(px + py * 1920u + frame.frame_index * 1920u * 1080u);
-                        const float jx = random_float(rng);
-                        const float jy = random_float(rng);
-                        uv_x += (jx - 0.5f) * 0.001f;
-                        uv_y += (jy - 0.5f) * 0.001f;
-                        const v3 target = load_v3(frame.lower_left) + load_v3(frame.horizontal) * uv_x +
-                                          load_v3(frame.vertical) * uv_y;
-                        ro = cam_origin;
-                        rd = normalize(target - cam_origin);
+                        fresh = true;
                         throughput = make_v3(1.0f, 1.0f, 1.0f);
                         color = make_v3(0.0f, 0.0f, 0.0f);
                         bounce = 0;
@@ -342,8 +326,30 @@ mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_co
             next_item += __popc(idle);
         }
 
-        // Every lane with a new ray: root test, start of the query.
+        // Every lane with a new ray: its direction (get_camera_ray, plugin.mm:129-153, for a new
+        // path; cosine_sample_hemisphere, plugin.mm:111-125, with the per-triangle frame for a
+        // continuing one: two draws and a normalisation either way, issued once for both kinds),
+        // then the root test and the start of the query.
         if (new_ray) {
+            const float draw_a = random_float(rng);
+            const float draw_b = random_float(rng);
+            v3 dir;
+            if (fresh) {
+                uv_x += (draw_a - 0.5f) * 0.001f;
+                uv_y += (draw_b - 0.5f) * 0.001f;
+                const v3 target = load_v3(frame.lower_left) + load_v3(frame.horizontal) * uv_x +
+                                  load_v3(frame.vertical) * uv_y;
+                ro = cam_origin;
+                dir = target - cam_origin;
+            } else {
+                const float phi = 6.28318548202514648f * draw_a;
+                const float cos_theta = sqrtf(1.0f - draw_b);
+                const float sin_theta = sqrtf(draw_b);
+                float sin_phi, cos_phi;
+                sincos_round_once(phi, sin_phi, cos_phi);
+                dir = (fu * cos_phi) * sin_theta + (fv * sin_phi) * sin_theta + fw * cos_theta;
+            }
+            rd = normalize(dir);
             rays++;
             best = mesh_hit{1e30f, k_miss, 0u};
             inv = make_v3(slab_reciprocal(rd.x), slab_reciprocal(rd.y), slab_reciprocal(rd.z));
