@@ -270,8 +270,14 @@ __device__ __forceinline__ void trace_scene(const scene_params& scene, const flo
     hit.point = ro + rd * hit.t;
 }
 
-constexpr int k_block_threads = 256;
-constexpr int k_blocks_per_sm = 4;
+#ifndef QUASI_QUAD_BLOCK_THREADS
+#define QUASI_QUAD_BLOCK_THREADS 256
+#endif
+#ifndef QUASI_QUAD_BLOCKS_PER_SM
+#define QUASI_QUAD_BLOCKS_PER_SM 4
+#endif
+constexpr int k_block_threads = QUASI_QUAD_BLOCK_THREADS;
+constexpr int k_blocks_per_sm = QUASI_QUAD_BLOCKS_PER_SM;
 constexpr int k_warps_per_block = k_block_threads / 32;
 
 template <int NQ, class Layout>
