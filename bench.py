@@ -286,7 +286,7 @@ def run_ours(args):
                 traffic, issue_util = k.get("dram_bytes_per_launch"), k.get("issue_slot_utilization")
             except Exception:
                 traffic = None
-        param_bytes = SPP * (7344 + 80)  # sizeof(scene_params) + sizeof(frame_params) per launch
+        param_bytes = SPP * (7856 + 80)  # sizeof(scene_params) + sizeof(frame_params) per launch
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": "Mrays/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4),

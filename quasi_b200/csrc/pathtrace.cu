@@ -32,6 +32,7 @@
 
 #include "device_common.cuh"
 #include "kernels.hpp"
+#include "scan_decide.hpp"
 
 #include <cuda_runtime.h>
 
@@ -40,6 +41,7 @@ namespace Q::cuda {
 namespace {
 
 using namespace dev;
+using namespace scan;
 
 struct hit_record {
     float t;
@@ -88,96 +90,13 @@ constexpr int k_shade_stride = 25;  // odd: lanes reading different quads hit di
 constexpr int k_sh_normal = 0, k_sh_is_light = 3, k_sh_frame_u = 4, k_sh_plane_d = 7,
               k_sh_frame_v = 8, k_sh_frame_w = 12, k_sh_albedo = 16, k_sh_emission = 20;
 
-// Margins of the fast scan. t' = num * rcp(denom) is within 2^-21 relative of the
-// IEEE quotient t; the bands below are ten times wider than that.
-constexpr float k_inf = __builtin_huge_valf();
-constexpr float k_t_min_lo = 0.001f * (1.0f - 4e-6f);  // below: surely t < t_min
-constexpr float k_t_min_hi = 0.001f * (1.0f + 4e-6f);  // above: surely t >= t_min
-constexpr float k_tie = 1.0f + 4e-6f;                  // two hits closer than this: literal scan
-
-struct scan_state {
-    float best_t = k_inf;        ///< smallest t' among quads that are surely hit
-    float challenger_t = k_inf;  ///< smallest t' among every other quad that may be hit
-    int best_i = -1;
-};
-
-/// Files one plane hit. `m` = max(|alpha' - 1/2|, |beta' - 1/2|): the point is
-/// surely outside the quad beyond half_plus and surely inside within half_minus.
-/// `ahead`: the plane is hit at all (|denom| >= 1e-8, decided exactly) and not surely
-/// behind t_min. The scan evaluates every quad for every lane without a branch: the
-/// inside test is 20 instructions, a divergent branch around it costs 3 and nearly
-/// always has a lane that takes it. What a lane computes past a failed `ahead` (possibly
-/// from an infinite t') is discarded here.
-__device__ __forceinline__ void consider(scan_state& s, const quad_params& q, int i, float t_fast,
-                                         float m, bool ahead) {
-    const bool maybe = ahead && m <= q.half_plus;
-    const bool sure = ahead && m < q.half_minus && t_fast > k_t_min_hi;
-    const bool better = sure && t_fast < s.best_t;
-    // Whoever does not become the winner challenges it.
-    const float loser = better ? s.best_t : (maybe ? t_fast : k_inf);
-    s.challenger_t = fminf(s.challenger_t, loser);
-    s.best_t = better ? t_fast : s.best_t;
-    s.best_i = better ? i : s.best_i;
-}
-
-__device__ __forceinline__ float axis(v3 a, int k) { return k == 0 ? a.x : (k == 1 ? a.y : a.z); }
-
-/// Quad whose normal is along axis K (two normal components are exactly zero, so
-/// the shader's three-term dot products collapse to one product, bit for bit)
-/// and whose barycentrics do not depend on coordinate K.
-template <int K>
-__device__ __forceinline__ void scan_flat(scan_state& s, const quad_params& q, int i, v3 ro, v3 rd) {
-    constexpr int I = (K + 1) % 3, J = (K + 2) % 3;
-    const float denom = q.normal[K] * axis(rd, K);
-    const float num = q.plane_d - q.normal[K] * axis(ro, K);
-    const float t_fast = num * rcp_approx(denom);
-    const bool ahead = fabsf(denom) >= 1e-8f && t_fast > k_t_min_lo;
-    // p', alpha', beta' only feed margin decisions: contracted (FFMA), unlike num and denom
-    const float pi = __fmaf_rn(axis(rd, I), t_fast, axis(ro, I)) - q.center[I];
-    const float pj = __fmaf_rn(axis(rd, J), t_fast, axis(ro, J)) - q.center[J];
-    const float alpha = __fmaf_rn(pi, q.fast_a[I], pj * q.fast_a[J]);
-    const float beta = __fmaf_rn(pi, q.fast_b[I], pj * q.fast_b[J]);
-    consider(s, q, i, t_fast, fmaxf(fabsf(alpha), fabsf(beta)), ahead);
-}
-
-/// Quad with a horizontal normal and one vertical edge (the side of a box
-/// standing on the floor): alpha lives in (x, z), beta along y.
-__device__ __forceinline__ void scan_upright(scan_state& s, const quad_params& q, int i, v3 ro, v3 rd) {
-    const float denom = q.normal[0] * rd.x + q.normal[2] * rd.z;
-    const float num = q.plane_d - (q.normal[0] * ro.x + q.normal[2] * ro.z);
-    const float t_fast = num * rcp_approx(denom);
-    const bool ahead = fabsf(denom) >= 1e-8f && t_fast > k_t_min_lo;
-    const float px = __fmaf_rn(rd.x, t_fast, ro.x) - q.center[0];
-    const float py = __fmaf_rn(rd.y, t_fast, ro.y) - q.center[1];
-    const float pz = __fmaf_rn(rd.z, t_fast, ro.z) - q.center[2];
-    const float alpha = __fmaf_rn(px, q.fast_a[0], pz * q.fast_a[2]);
-    const float beta = py * q.fast_b[1];
-    consider(s, q, i, t_fast, fmaxf(fabsf(alpha), fabsf(beta)), ahead);
-}
-
-__device__ __forceinline__ void scan_general(scan_state& s, const quad_params& q, int i, v3 ro, v3 rd) {
-    const v3 normal = load_v3(q.normal);
-    const float denom = dot(normal, rd);            // the shader's value
-    const float num = q.plane_d - dot(normal, ro);  // the shader's value
-    const float t_fast = num * rcp_approx(denom);
-    const bool ahead = fabsf(denom) >= 1e-8f && t_fast > k_t_min_lo;
-    {
-        const v3 planar = make_v3(__fmaf_rn(rd.x, t_fast, ro.x) - q.center[0],
-                                  __fmaf_rn(rd.y, t_fast, ro.y) - q.center[1],
-                                  __fmaf_rn(rd.z, t_fast, ro.z) - q.center[2]);
-        const float alpha = __fmaf_rn(planar.x, q.fast_a[0], __fmaf_rn(planar.y, q.fast_a[1], planar.z * q.fast_a[2]));
-        const float beta = __fmaf_rn(planar.x, q.fast_b[0], __fmaf_rn(planar.y, q.fast_b[1], planar.z * q.fast_b[2]));
-        consider(s, q, i, t_fast, fmaxf(fabsf(alpha), fabsf(beta)), ahead);
-    }
-}
-
 /// How many quads of each shape a scene has, known at compile time: the scan is
 /// then fully unrolled with every constant an immediate constant-bank operand.
 /// The sorted table order is general, flat_x, flat_y, flat_z, upright.
-template <int GEN, int FX, int FY, int FZ, int UP>
+template <int GEN, int FX, int FY, int FZ, int UP, int BOX>
 struct fixed_layout {
     static constexpr bool fixed = true;
-    static constexpr int general = GEN, flat_x = FX, flat_y = FY, flat_z = FZ, upright = UP;
+    static constexpr int general = GEN, flat_x = FX, flat_y = FY, flat_z = FZ, upright = UP, boxes = BOX;
     static constexpr int begin_general = 0, begin_flat_x = GEN, begin_flat_y = GEN + FX,
                          begin_flat_z = GEN + FX + FY, begin_upright = GEN + FX + FY + FZ;
     static bool matches(const scene_params& s) {
@@ -186,16 +105,16 @@ struct fixed_layout {
         for (uint32_t k = 0; k <= k_shape_count; k++) {
             if (s.shape_begin[k] != static_cast<uint32_t>(want[k])) return false;
         }
-        return true;
+        return s.box_count == static_cast<uint32_t>(BOX);
     }
 };
 /// Any scene: one loop per shape with launch-uniform bounds.
 struct dynamic_layout {
     static constexpr bool fixed = false;
 };
-/// The demo scene (make_cornell_box): 2 side walls, floor + ceiling + light + 2 box
-/// tops, the back wall, 8 box sides.
-using cornell_layout = fixed_layout<0, 2, 5, 1, 8>;
+/// The demo scene (make_cornell_box): 2 side walls, floor + ceiling + light, the back
+/// wall, and two boxes of five faces each.
+using cornell_layout = fixed_layout<0, 2, 3, 1, 0, 2>;
 
 /// Closest hit of one ray against the scene. Same result, bit for bit,
 /// as trace_scene_exact. `shade` is the shared-memory copy of the quads' shading
@@ -228,6 +147,8 @@ __device__ __forceinline__ void trace_scene(const scene_params& scene, const flo
         for (int i = Layout::begin_general; i < Layout::begin_general + Layout::general; i++) {
             scan_general(s, scene.quads[i], i, ro, rd);
         }
+#pragma unroll
+        for (int n = 0; n < Layout::boxes; n++) scan_box(s, scene.boxes[n], ro, rd);
     } else {
         // One loop per shape over that shape's range of the sorted quad table.
         // Trip counts and table offsets are launch-uniform.
@@ -251,11 +172,11 @@ __device__ __forceinline__ void trace_scene(const scene_params& scene, const flo
         for (uint32_t i = scene.shape_begin[k_shape_general]; i < scene.shape_begin[k_shape_general + 1]; i++) {
             scan_general(s, scene.quads[i], static_cast<int>(i), ro, rd);
         }
+#pragma unroll 1
+        for (uint32_t n = 0; n < scene.box_count; n++) scan_box(s, scene.boxes[n], ro, rd);
     }
 
-    // A challenger matters only if it could be in front of, or tie with, the sure
-    // winner. With no sure winner (best_t == inf) any challenger matters.
-    if (s.challenger_t < k_inf && s.challenger_t <= s.best_t * k_tie) {
+    if (needs_literal_scan(s)) {
         trace_scene_exact(scene, ro, rd, hit);
         return;
     }

@@ -23,6 +23,11 @@
 
 namespace Q::cuda {
 
+/// Three floats; the vector type of the kernels (device_common.cuh) and of scan_decide.hpp.
+struct v3 {
+    float x, y, z;
+};
+
 inline constexpr uint32_t k_max_quads = 32;   ///< plugin.mm:21, 30
 inline constexpr uint32_t k_max_bounces = 5;  ///< plugin.mm:22, 31
 
@@ -36,6 +41,7 @@ enum quad_shape : uint32_t {
     k_shape_flat_y = 2,    ///< normal along y; alpha, beta live in (x, z)   - floor, ceiling, light, box tops
     k_shape_flat_z = 3,    ///< normal along z; alpha, beta live in (x, y)   - back wall
     k_shape_upright = 4,   ///< normal.y == 0, one edge vertical: alpha in (x, z), beta along y - box sides
+    k_shape_boxed = 5,     ///< a face of a detected box (box_params): scanned with its box, not on its own
 };
 
 /// One quad, pre-digested: 56 floats (224 bytes), 16-byte rows so constant-bank
@@ -80,12 +86,39 @@ static_assert(sizeof(quad_params) == 224);
 inline constexpr uint32_t k_shade_offset = 32;  ///< first float of the shading group
 inline constexpr uint32_t k_shade_floats = 24;
 
-inline constexpr uint32_t k_shape_count = 5;
+inline constexpr uint32_t k_shape_count = 5;  ///< shapes the scan walks quad by quad (boxed faces are not among them)
+inline constexpr uint32_t k_max_boxes = 4;
+
+/// Four upright quads in two parallel pairs closed by a flat_y quad on top, standing on
+/// something (no bottom face): the two blocks of the demo scene. A convex solid is entered
+/// at most once, so the closest hit among its five faces is where the ray enters the
+/// intersection of the three slabs, and ONE slab test (3 plane distances, one point, 3
+/// interval tests) DECIDES what the five separate quad tests decide; pathtrace.cu:scan_box.
+/// Like everything in the fast scan this only decides: distances use each face's own plane
+/// constants in the shader's form, an entry within `delta` of an edge, a ray parallel to a
+/// slab or an entry through the open bottom hand the ray to the literal test, and the
+/// accepted hit is recomputed with the literal operations of its face.
+struct alignas(16) box_params {
+    float axis[2][2];         ///< (x, z) of the two horizontal slab directions (stored normal of one side each)
+    float side_normal[2][2][2];  ///< [slab][low, high side][x, z]: that face's own stored normal
+    float side_d[2][2];       ///< [slab][low, high side]: that face's own plane_d
+    uint32_t side_index[2][2];   ///< [slab][low, high side]: position of the face in scene_params::quads
+    float top_normal_y;       ///< stored normal of the top face is (0, top_normal_y, 0)
+    float top_d;
+    uint32_t top_index;
+    float y_bottom;
+    float mid[3];             ///< centre of the box in (slab 0, slab 1, y) coordinates
+    float half[3];            ///< half extents in the same coordinates
+    float delta;              ///< decision margin, in length units (set_decision_margins)
+    float edge_scale;         ///< longest face edge: turns a face's alpha margin into a length
+};
+static_assert(sizeof(box_params) % 16 == 0);
 
 /// The scene as the kernel sees it. `quads` is sorted by shape (stable), so the
 /// scan runs one tight loop per shape with that shape's arithmetic;
-/// shape_begin[s] .. shape_begin[s+1] is the range of shape s, degenerate quads
-/// sit behind the last range. The scan order does not matter for the result
+/// shape_begin[s] .. shape_begin[s+1] is the range of shape s; the faces of detected
+/// boxes (shape_begin[5] .. shape_begin[6]) and then the degenerate quads sit behind
+/// the ranges the scan walks. The scan order does not matter for the result
 /// (closest hit; exact ties go to the literal test). The literal test walks
 /// `scene_order`, i.e. the ORIGINAL order, because plugin.mm:205-207 lets the
 /// later index win a tie. Hit indices on the device are positions in `quads`.
@@ -96,7 +129,8 @@ struct alignas(16) scene_params {
     uint32_t quad_count;
     uint32_t max_bounces;
     float corner_radius;    ///< farthest quad corner from the world origin
-    uint32_t pad;
+    uint32_t box_count;
+    box_params boxes[k_max_boxes];
 };
 
 /// Per-call camera and sample bookkeeping.
@@ -299,22 +333,133 @@ inline void prepare_scene(const scene_desc& desc, uint32_t max_bounces, scene_pa
         store3(g.frame_w, w);
     }
 
-    // Stable sort by shape; degenerate quads (never hit) go last, outside every range.
+    // Boxes: a flat_y quad whose four corners are the top ends of four upright quads that
+    // form two parallel pairs at right angles and share one bottom height.
+    struct found_box {
+        uint32_t top, side[2][2];
+    };
+    found_box found[k_max_boxes];
+    uint32_t n_found = 0;
+    auto corner_of = [&](uint32_t i, int c) {
+        const quad_params& g = digested[i];
+        return load3(g.origin) + load3(g.u) * float(c & 1) + load3(g.v) * float(c >> 1);
+    };
+    auto near_xz = [](f3 a, f3 b) { return std::fabs(a.x - b.x) < 1e-5f && std::fabs(a.z - b.z) < 1e-5f; };
+    for (uint32_t t = 0; t < out.quad_count && n_found < k_max_boxes; t++) {
+        if (digested[t].valid == 0.0f || digested[t].shape != k_shape_flat_y) continue;
+        const float y_top = digested[t].origin[1];
+        uint32_t sides[4];
+        uint32_t n_sides = 0;
+        float y_bottom = 0.0f;
+        bool consistent = true;
+        for (uint32_t i = 0; i < out.quad_count; i++) {
+            if (digested[i].valid == 0.0f || digested[i].shape != k_shape_upright) continue;
+            float lo = 1e30f, hi = -1e30f;
+            for (int c = 0; c < 4; c++) {
+                lo = std::fmin(lo, corner_of(i, c).y);
+                hi = std::fmax(hi, corner_of(i, c).y);
+            }
+            if (std::fabs(hi - y_top) > 1e-5f) continue;
+            int matched = 0;  // top corners of the side that are corners of the top quad
+            for (int c = 0; c < 4; c++) {
+                const f3 p = corner_of(i, c);
+                if (std::fabs(p.y - hi) > 1e-5f) continue;
+                for (int k = 0; k < 4; k++) matched += near_xz(p, corner_of(t, k)) ? 1 : 0;
+            }
+            if (matched != 2) continue;
+            if (n_sides == 4) {
+                consistent = false;
+                break;
+            }
+            if (n_sides == 0) y_bottom = lo;
+            consistent = consistent && std::fabs(lo - y_bottom) < 1e-5f;
+            sides[n_sides++] = i;
+        }
+        if (!consistent || n_sides != 4) continue;
+        // pair the sides: sides[0] with the one parallel to it, the other two with each other
+        auto hdot = [&](uint32_t a, uint32_t b) {
+            return digested[a].normal[0] * digested[b].normal[0] + digested[a].normal[2] * digested[b].normal[2];
+        };
+        int partner = -1;
+        for (int k = 1; k < 4; k++) {
+            if (std::fabs(hdot(sides[0], sides[k])) > 1.0f - 1e-5f) partner = partner < 0 ? k : 4;
+        }
+        if (partner < 1 || partner > 3) continue;
+        uint32_t other[2];
+        int n_other = 0;
+        for (int k = 1; k < 4; k++) {
+            if (k != partner) other[n_other++] = sides[k];
+        }
+        if (std::fabs(hdot(other[0], other[1])) <= 1.0f - 1e-5f || std::fabs(hdot(sides[0], other[0])) > 1e-4f) continue;
+        found_box& b = found[n_found++];
+        b.top = t;
+        b.side[0][0] = sides[0];
+        b.side[0][1] = sides[partner];
+        b.side[1][0] = other[0];
+        b.side[1][1] = other[1];
+        digested[t].shape = k_shape_boxed;
+        for (uint32_t k = 0; k < 4; k++) digested[sides[k]].shape = k_shape_boxed;
+    }
+
+    // Stable sort by shape; boxed faces, then degenerate quads (never hit), go last, outside
+    // every range the scan walks.
     uint32_t position = 0;
-    for (uint32_t shape = 0; shape <= k_shape_count; shape++) {
-        if (shape < k_shape_count) out.shape_begin[shape] = position;
+    for (uint32_t shape = 0; shape <= k_shape_boxed + 1; shape++) {
+        if (shape <= k_shape_boxed) out.shape_begin[shape] = position;
         for (uint32_t i = 0; i < out.quad_count; i++) {
             const bool degenerate = digested[i].valid == 0.0f;
-            const bool take = shape < k_shape_count ? (!degenerate && digested[i].shape == shape) : degenerate;
+            const bool take = shape <= k_shape_boxed ? (!degenerate && digested[i].shape == shape) : degenerate;
             if (take) {
                 out.quads[position] = digested[i];
                 out.scene_order[i] = position;
                 position++;
             }
         }
-        if (shape + 1 == k_shape_count) {
-            for (uint32_t k = k_shape_count; k < k_shape_count + 3; k++) out.shape_begin[k] = position;
+        if (shape == k_shape_boxed) {
+            for (uint32_t k = k_shape_boxed + 1; k < k_shape_count + 3; k++) out.shape_begin[k] = position;
         }
+    }
+
+    out.box_count = n_found;
+    for (uint32_t n = 0; n < n_found; n++) {
+        box_params& b = out.boxes[n];
+        const quad_params& top = digested[found[n].top];
+        b.top_normal_y = top.normal[1];
+        b.top_d = top.plane_d;
+        b.top_index = out.scene_order[found[n].top];
+        float y_bottom = 1e30f, longest = 0.0f, shortest = 1e30f;
+        for (int slab = 0; slab < 2; slab++) {
+            const quad_params& first = digested[found[n].side[slab][0]];
+            b.axis[slab][0] = first.normal[0];
+            b.axis[slab][1] = first.normal[2];
+            float offset[2];
+            for (int k = 0; k < 2; k++) {
+                const quad_params& g = digested[found[n].side[slab][k]];
+                offset[k] = b.axis[slab][0] * g.center[0] + b.axis[slab][1] * g.center[2];
+                for (int c = 0; c < 4; c++) y_bottom = std::fmin(y_bottom, corner_of(found[n].side[slab][k], c).y);
+                const float lu = std::sqrt(dot(load3(g.u), load3(g.u))), lv = std::sqrt(dot(load3(g.v), load3(g.v)));
+                longest = std::fmax(longest, std::fmax(lu, lv));
+                shortest = std::fmin(shortest, std::fmin(lu, lv));
+            }
+            const int low = offset[0] <= offset[1] ? 0 : 1;
+            for (int k = 0; k < 2; k++) {
+                const uint32_t original = found[n].side[slab][k == 0 ? low : 1 - low];
+                const quad_params& g = digested[original];
+                b.side_normal[slab][k][0] = g.normal[0];
+                b.side_normal[slab][k][1] = g.normal[2];
+                b.side_d[slab][k] = g.plane_d;
+                b.side_index[slab][k] = out.scene_order[original];
+            }
+            b.mid[slab] = (offset[0] + offset[1]) * 0.5f;
+            b.half[slab] = std::fabs(offset[1] - offset[0]) * 0.5f;
+        }
+        const float y_top = top.origin[1];
+        b.y_bottom = y_bottom;
+        b.mid[2] = (y_bottom + y_top) * 0.5f;
+        b.half[2] = (y_top - y_bottom) * 0.5f;
+        b.edge_scale = longest;
+        (void)shortest;
+        b.delta = 1e-4f;  // set_decision_margins
     }
 }
 
@@ -338,6 +483,16 @@ inline void set_decision_margins(scene_params& scene, const float camera_positio
         float delta = std::fmax(1e-5f, 2.5e-5f * g.fast_len * radius);
         g.half_plus = 0.5f + delta;
         g.half_minus = 0.5f - delta;
+    }
+    // A box decides in length units: the widest alpha margin of its faces times its longest
+    // edge, i.e. the widest band any of its faces keeps around its own edges.
+    for (uint32_t n = 0; n < scene.box_count; n++) {
+        box_params& b = scene.boxes[n];
+        float widest = 0.0f;
+        const uint32_t faces[5] = {b.top_index, b.side_index[0][0], b.side_index[0][1], b.side_index[1][0],
+                                   b.side_index[1][1]};
+        for (uint32_t f : faces) widest = std::fmax(widest, scene.quads[f].half_plus - 0.5f);
+        b.delta = widest * b.edge_scale;
     }
 }
 

@@ -1,0 +1,155 @@
+// Host check of the quad scene's fast scan (quasi_b200/csrc/scan_decide.hpp) against the
+// literal loop of /root/reference/backends/metal/plugin.mm:157-212 (trace_scene +
+// intersect_quad, restated below in the shader's operation order), on the demo scene.
+// Whenever the fast scan does not ask for the literal loop, its winner must be the
+// literal winner. Rays: camera rays, bounce rays from random points of every quad, and
+// rays aimed at what is hard: the edges of the boxes' faces, the floor within t_min of a
+// box, directions almost parallel to a face.
+//   usage: scan_decide_check [rays]   -> prints counts, exit code 1 on any mismatch
+#include "scan_decide.hpp"
+
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+
+using namespace Q::cuda;
+
+namespace {
+
+float dot3(const float* a, v3 b) { return a[0] * b.x + a[1] * b.y + a[2] * b.z; }
+
+int literal_winner(const scene_params& scene, v3 ro, v3 rd) {
+    float closest = 1e30f;
+    int index = -1;
+    for (uint32_t k = 0; k < scene.quad_count; k++) {
+        const uint32_t i = scene.scene_order[k];
+        const quad_params& q = scene.quads[i];
+        if (q.valid == 0.0f) continue;
+        const float denom = dot3(q.normal, rd);
+        if (std::fabs(denom) < 1e-8f) continue;
+        const float t = (q.plane_d - dot3(q.normal, ro)) / denom;
+        if (t < 0.001f || t > closest) continue;
+        const v3 planar{ro.x + rd.x * t - q.origin[0], ro.y + rd.y * t - q.origin[1], ro.z + rd.z * t - q.origin[2]};
+        const v3 pv{planar.y * q.v[2] - planar.z * q.v[1], planar.z * q.v[0] - planar.x * q.v[2],
+                    planar.x * q.v[1] - planar.y * q.v[0]};
+        const v3 up{q.u[1] * planar.z - q.u[2] * planar.y, q.u[2] * planar.x - q.u[0] * planar.z,
+                    q.u[0] * planar.y - q.u[1] * planar.x};
+        const float alpha = dot3(q.w, pv), beta = dot3(q.w, up);
+        if (alpha < 0.0f || alpha > 1.0f || beta < 0.0f || beta > 1.0f) continue;
+        closest = t;
+        index = static_cast<int>(i);
+    }
+    return index;
+}
+
+bool inside_a_box_or_outside_the_room(const scene_params& scene, v3 p) {
+    if (std::fabs(p.x) > 1.0f || p.y < 0.0f || p.y > 2.0f || p.z < -1.0f) return true;
+    for (uint32_t n = 0; n < scene.box_count; n++) {
+        const box_params& b = scene.boxes[n];
+        const float c0 = b.axis[0][0] * p.x + b.axis[0][1] * p.z, c1 = b.axis[1][0] * p.x + b.axis[1][1] * p.z;
+        if (std::fabs(c0 - b.mid[0]) < b.half[0] && std::fabs(c1 - b.mid[1]) < b.half[1] &&
+            std::fabs(p.y - b.mid[2]) < b.half[2]) {
+            return true;
+        }
+    }
+    return false;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+    const long rays = argc > 1 ? std::atol(argv[1]) : 3000000;
+    scene_params scene;
+    const scene_desc desc = make_cornell_box();
+    prepare_scene(desc, 5, scene);
+    const float camera[3] = {0.0f, 1.0f, 3.5f};
+    set_decision_margins(scene, camera);
+    if (scene.box_count != 2) {
+        std::printf("expected the two blocks of the demo scene to be detected, found %u\n", scene.box_count);
+        return 1;
+    }
+    uint32_t floor_position = 0;  // the floor is quad 0 of make_cornell_box
+    floor_position = scene.scene_order[0];
+
+    std::mt19937 rng(7);
+    std::uniform_real_distribution<float> uniform(0.0f, 1.0f);
+    auto coin = [&] { return (rng() & 1u) != 0u; };
+    long tested = 0, decided = 0, literal = 0, mismatches = 0;
+    for (long it = 0; it < rays; it++) {
+        v3 ro{}, rd{};
+        const int kind = static_cast<int>(it % 4);
+        if (kind == 0) {  // camera rays
+            ro = {0.0f, 1.0f, 3.5f};
+            rd = {-0.6f + 1.2f * uniform(rng), -0.5f + uniform(rng), -1.0f};
+        } else {
+            uint32_t qi = rng() % scene.quad_count;
+            if (kind >= 2) qi = coin() ? floor_position : scene.shape_begin[k_shape_boxed] + rng() % 10u;
+            const quad_params& q = scene.quads[qi];
+            float a = uniform(rng), b = uniform(rng), side = coin() ? 1.0f : -1.0f;
+            if (kind >= 2 && qi != floor_position) {  // hug the edges of a box face
+                if (coin()) a = coin() ? uniform(rng) * 0.01f : 1.0f - uniform(rng) * 0.01f;
+                if (coin()) b = coin() ? uniform(rng) * 0.01f : 1.0f - uniform(rng) * 0.01f;
+            }
+            if (kind >= 2 && qi == floor_position) {  // the floor around the foot of a box
+                const box_params& box = scene.boxes[rng() % scene.box_count];
+                float c0 = box.mid[0] + (2.0f * uniform(rng) - 1.0f) * (box.half[0] + 0.004f);
+                float c1 = box.mid[1] + (2.0f * uniform(rng) - 1.0f) * (box.half[1] + 0.004f);
+                const float off = uniform(rng) * 0.004f - 0.0005f;
+                if (coin()) {
+                    c0 = box.mid[0] + (coin() ? 1.0f : -1.0f) * (box.half[0] + off);
+                } else {
+                    c1 = box.mid[1] + (coin() ? 1.0f : -1.0f) * (box.half[1] + off);
+                }
+                const float x = box.axis[0][0] * c0 + box.axis[1][0] * c1, z = box.axis[0][1] * c0 + box.axis[1][1] * c1;
+                a = (x + 1.0f) * 0.5f;
+                b = (z + 1.0f) * 0.5f;
+                side = -1.0f;  // the floor's stored normal points down
+            }
+            ro = {q.origin[0] + q.u[0] * a + q.v[0] * b + q.normal[0] * 0.001f * side,
+                  q.origin[1] + q.u[1] * a + q.v[1] * b + q.normal[1] * 0.001f * side,
+                  q.origin[2] + q.u[2] * a + q.v[2] * b + q.normal[2] * 0.001f * side};
+            float len2;
+            do {
+                rd = {2.0f * uniform(rng) - 1.0f, 2.0f * uniform(rng) - 1.0f, 2.0f * uniform(rng) - 1.0f};
+                len2 = rd.x * rd.x + rd.y * rd.y + rd.z * rd.z;
+            } while (len2 > 1.0f || len2 < 1e-4f);
+            if (kind == 3 && coin()) {  // almost parallel to a face of a box or to the floor
+                const box_params& box = scene.boxes[rng() % scene.box_count];
+                const int which = static_cast<int>(rng() % 3u);
+                const float tiny = (uniform(rng) - 0.5f) * 4e-6f;
+                if (which == 2) {
+                    rd.y = tiny;
+                } else {  // remove the component along the slab direction, leave a tiny one
+                    const float along = box.axis[which][0] * rd.x + box.axis[which][1] * rd.z;
+                    rd.x += (tiny - along) * box.axis[which][0];
+                    rd.z += (tiny - along) * box.axis[which][1];
+                }
+            }
+            if ((rd.x * q.normal[0] + rd.y * q.normal[1] + rd.z * q.normal[2]) * side < 0.0f) {
+                rd = {-rd.x, -rd.y, -rd.z};
+            }
+            if (inside_a_box_or_outside_the_room(scene, ro)) continue;  // no path ever starts there
+        }
+        const float len = std::sqrt(rd.x * rd.x + rd.y * rd.y + rd.z * rd.z);
+        rd = {rd.x / len, rd.y / len, rd.z / len};
+
+        scan::scan_state state;
+        scan::scan_scene(state, scene, ro, rd);
+        tested++;
+        if (scan::needs_literal_scan(state)) {
+            literal++;
+            continue;
+        }
+        decided++;
+        const int want = literal_winner(scene, ro, rd);
+        if (state.best_i != want) {
+            if (mismatches < 10) {
+                std::printf("MISMATCH fast %d literal %d ro %.9g %.9g %.9g rd %.9g %.9g %.9g\n", state.best_i, want, ro.x,
+                            ro.y, ro.z, rd.x, rd.y, rd.z);
+            }
+            mismatches++;
+        }
+    }
+    std::printf("rays %ld decided %ld literal %ld mismatches %ld\n", tested, decided, literal, mismatches);
+    return mismatches == 0 ? 0 : 1;
+}

@@ -1,0 +1,39 @@
+"""The deciding arithmetic of the quad scene's closest-hit scan (quasi_b200/csrc/scan_decide.hpp,
+the code the CUDA kernel compiles) run on the host against the literal loop of the reference
+shader: whenever the fast scan does not hand a ray to the literal loop, it must name the
+literal winner. tests/scan_decide_check.cpp aims the rays at the hard places (edges of the
+blocks' faces, the floor within t_min of a block, directions almost parallel to a face)."""
+import subprocess
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def build(tmp_path, include_dir):
+    exe = tmp_path / "scan_decide_check"
+    subprocess.run(["g++", "-std=c++20", "-O2", "-ffp-contract=off", "-Wall", "-Wextra", f"-I{include_dir}",
+                    str(ROOT / "tests" / "scan_decide_check.cpp"), "-o", str(exe)], check=True)
+    return exe
+
+
+def test_fast_scan_names_the_literal_winner(tmp_path):
+    exe = build(tmp_path, ROOT / "quasi_b200" / "csrc")
+    out = subprocess.run([str(exe), "4000000"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout[-2000:]
+    counts = dict(zip(out.stdout.split()[0::2], out.stdout.split()[1::2]))
+    assert int(counts["mismatches"]) == 0 and int(counts["decided"]) > 2_000_000
+    assert int(counts["literal"]) > 0          # the margins do fire on these rays
+
+
+def test_the_check_notices_a_missing_rule(tmp_path):
+    """Without the rule that sends rays starting within t_min of a block's face to the literal
+    loop, the scan names the wrong quad for some of them: the check must see that."""
+    mutated = tmp_path / "mutated"
+    mutated.mkdir()
+    src = (ROOT / "quasi_b200" / "csrc" / "scan_decide.hpp").read_text()
+    assert "(parallel || tunnels)" in src
+    (mutated / "scan_decide.hpp").write_text(src.replace("(parallel || tunnels)", "(parallel)"))
+    (mutated / "scene_params.hpp").write_text((ROOT / "quasi_b200" / "csrc" / "scene_params.hpp").read_text())
+    exe = build(tmp_path, mutated)
+    out = subprocess.run([str(exe), "3000000"], capture_output=True, text=True)
+    assert out.returncode == 1 and "MISMATCH" in out.stdout

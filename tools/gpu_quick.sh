@@ -1,7 +1,5 @@
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; rc=$?; echo "pytest exit $rc" >> gpurun_out/pytest_gpu.log
 tail -3 gpurun_out/pytest_gpu.log
-if [ $rc -ne 0 ]; then grep -E "Error|assert|FAIL" gpurun_out/pytest_gpu.log | head -20; exit 1; fi
-timeout 200 python bench.py --no-cpu > gpurun_out/bench.json 2> gpurun_out/bench.err; cut -c1-420 gpurun_out/bench.json
-timeout 120 python tools/mesh_bench.py --json gpurun_out/mesh_bench.json 2>&1 | tail -1 | cut -c1-300
-bash tools/gpu_configs.sh 1 2>&1 | cut -c1-330
+if [ $rc -ne 0 ]; then grep -E "Error|assert|FAIL|^E " gpurun_out/pytest_gpu.log | head -20; exit 1; fi
+timeout 200 python bench.py --no-cpu > gpurun_out/bench.json 2> gpurun_out/bench.err; cut -c1-300 gpurun_out/bench.json
