@@ -78,15 +78,25 @@ int main(int argc, char** argv) {
     for (long it = 0; it < rays; it++) {
         v3 ro{}, rd{};
         const int kind = static_cast<int>(it % 4);
-        if (kind == 0) {  // camera rays
+        if (kind == 0 && coin()) {  // camera rays of the default camera
             ro = {0.0f, 1.0f, 3.5f};
             rd = {-0.6f + 1.2f * uniform(rng), -0.5f + uniform(rng), -1.0f};
+        } else if (kind == 0) {  // a camera anywhere around the room, looking at a point in or near it
+            float len2;
+            do {
+                ro = {2.0f * uniform(rng) - 1.0f, 2.0f * uniform(rng) - 1.0f, 2.0f * uniform(rng) - 1.0f};
+                len2 = ro.x * ro.x + ro.y * ro.y + ro.z * ro.z;
+            } while (len2 > 1.0f || len2 < 0.01f);
+            const float radius = (2.0f + 3.0f * uniform(rng)) / std::sqrt(len2);
+            ro = {ro.x * radius, 1.0f + ro.y * radius, ro.z * radius};
+            const v3 target{2.4f * uniform(rng) - 1.2f, 2.4f * uniform(rng) - 0.2f, 2.4f * uniform(rng) - 1.2f};
+            rd = {target.x - ro.x, target.y - ro.y, target.z - ro.z};
         } else {
             uint32_t qi = rng() % scene.quad_count;
-            if (kind >= 2) qi = coin() ? floor_position : scene.shape_begin[k_shape_boxed] + rng() % 10u;
+            if (kind >= 2) qi = coin() ? floor_position : scene.shape_begin[k_shape_boxed] + rng() % (scene.shape_begin[k_shape_boxed + 1] - scene.shape_begin[k_shape_boxed]);
             const quad_params& q = scene.quads[qi];
             float a = uniform(rng), b = uniform(rng), side = coin() ? 1.0f : -1.0f;
-            if (kind >= 2 && qi != floor_position) {  // hug the edges of a box face
+            if (kind >= 2 && qi != floor_position) {  // hug the edges of a face of a box or of the room
                 if (coin()) a = coin() ? uniform(rng) * 0.01f : 1.0f - uniform(rng) * 0.01f;
                 if (coin()) b = coin() ? uniform(rng) * 0.01f : 1.0f - uniform(rng) * 0.01f;
             }
