@@ -34,9 +34,12 @@ struct alignas(16) mesh_params {
 /// @param ray_counter Device counter incremented by the number of closest-hit queries.
 /// @param tile_counters Two zero-initialised device uints: the tile work queue (device_common.cuh:tile_feed).
 /// @param sm_count Multiprocessors of the device; the grid is 4 resident CTAs per SM.
+/// @param generic_scan Use the any-scene kernel (one loop per quad shape) even where a kernel
+///        unrolled for the scene's layout exists.
 cudaError_t launch_pathtrace_accumulate(const scene_params& scene, const frame_params& frame,
                                         float* const layers[4], unsigned long long* ray_counter,
-                                        unsigned int* tile_counters, int sm_count, cudaStream_t stream);
+                                        unsigned int* tile_counters, int sm_count, cudaStream_t stream,
+                                        bool generic_scan = false);
 
 /// @brief The mesh-scene form of launch_pathtrace_accumulate (BASELINE config 3).
 /// @param counters Device array of 3: rays, BVH nodes visited (box tests), triangles tested.

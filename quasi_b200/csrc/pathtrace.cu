@@ -115,6 +115,8 @@ struct dynamic_layout {
 /// The demo scene (make_cornell_box): 2 side walls, floor + ceiling + light, the back
 /// wall, and two boxes of five faces each.
 using cornell_layout = fixed_layout<0, 2, 3, 1, 0, 2>;
+/// The same scene with every quad on its own (QUASI_CUDA_SCAN=quads).
+using cornell_quads_layout = fixed_layout<0, 2, 5, 1, 8, 0>;
 
 /// Closest hit of one ray against the scene. Same result, bit for bit,
 /// as trace_scene_exact. `shade` is the shared-memory copy of the quads' shading
@@ -402,7 +404,8 @@ cudaError_t launch_sincos_probe(const float* phi, float* sin_out, float* cos_out
 
 cudaError_t launch_pathtrace_accumulate(const scene_params& scene, const frame_params& frame,
                                         float* const layers[4], unsigned long long* ray_counter,
-                                        unsigned int* tile_counters, int sm_count, cudaStream_t stream) {
+                                        unsigned int* tile_counters, int sm_count, cudaStream_t stream,
+                                        bool generic_scan) {
     const uint32_t n_tiles = ((frame.width + 7u) / 8u) * ((frame.height + 3u) / 4u);
     uint32_t blocks = static_cast<uint32_t>(sm_count) * k_blocks_per_sm;
     const uint32_t needed = (n_tiles + k_warps_per_block - 1u) / k_warps_per_block;
@@ -412,8 +415,11 @@ cudaError_t launch_pathtrace_accumulate(const scene_params& scene, const frame_p
     auto* a = reinterpret_cast<float4*>(layers[1]);
     auto* n = reinterpret_cast<float4*>(layers[2]);
     auto* d = reinterpret_cast<float4*>(layers[3]);
-    if (cornell_layout::matches(scene)) {
+    if (!generic_scan && cornell_layout::matches(scene)) {
         pathtrace_accumulate_kernel<16, cornell_layout>
+            <<<blocks, k_block_threads, 0, stream>>>(scene, frame, b, a, n, d, ray_counter, tile_counters);
+    } else if (!generic_scan && cornell_quads_layout::matches(scene)) {
+        pathtrace_accumulate_kernel<16, cornell_quads_layout>
             <<<blocks, k_block_threads, 0, stream>>>(scene, frame, b, a, n, d, ray_counter, tile_counters);
     } else {
         pathtrace_accumulate_kernel<32, dynamic_layout>

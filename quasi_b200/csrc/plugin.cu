@@ -120,6 +120,7 @@ struct plugin_state {
     uint64_t paths = 0;
     uint64_t kernel_launches = 0;
 
+    bool generic_scan = false;  ///< QUASI_CUDA_SCAN=generic: the any-scene kernel
     Q_cuda_persistent_state* persistent = nullptr;  ///< host-owned, Q_gpu_context::layer (may be null)
     uint32_t scene_tag = 0;
 };
@@ -434,7 +435,12 @@ Q_PLUGIN_EXPORT Q_plugin_handle* Q_plugin_create(Q_plugin_context* ctx) {
         // slot for options, so they come from the environment.
         state->scene_desc = Q::cuda::make_cornell_box();
         uint32_t bounces = env_u32("QUASI_CUDA_MAX_BOUNCES", Q::cuda::k_max_bounces, 1, 64);
-        Q::cuda::prepare_scene(state->scene_desc, bounces, state->scene);
+        // QUASI_CUDA_SCAN: "generic" = the any-scene kernel, "quads" = no block grouping,
+        // "generic-quads" = both; default: grouped blocks, kernel unrolled for the demo scene.
+        const char* scan = std::getenv("QUASI_CUDA_SCAN");
+        state->generic_scan = scan && std::strncmp(scan, "generic", 7) == 0;
+        const bool group_boxes = !(scan && std::strstr(scan, "quads") != nullptr);
+        Q::cuda::prepare_scene(state->scene_desc, bounces, state->scene, group_boxes);
         const char* scene_name = std::getenv("QUASI_CUDA_SCENE");
         if (scene_name && std::strcmp(scene_name, "mesh") == 0) {
             state->use_mesh = true;
@@ -541,7 +547,7 @@ Q_PLUGIN_EXPORT void Q_plugin_render(Q_plugin_handle* handle, Q_render_frame* fr
                                                          state->ray_counter, tile_counters, state->sm_count, stream)
                         : Q::cuda::launch_pathtrace_accumulate(state->scene, fp, state->layers,
                                                                state->ray_counter, tile_counters, state->sm_count,
-                                                               stream);
+                                                               stream, state->generic_scan);
     if (!check(state, launched, "pathtrace_accumulate")) return;
     state->kernel_launches++;
 

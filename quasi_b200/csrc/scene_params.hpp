@@ -252,7 +252,9 @@ inline scene_desc make_cornell_box() {
 }
 
 /// @brief Derives the per-quad constants the shader recomputes per ray.
-inline void prepare_scene(const scene_desc& desc, uint32_t max_bounces, scene_params& out) {
+/// @param group_boxes Detect blocks (box_params) and scan each with one slab test; false keeps
+/// every quad on its own (QUASI_CUDA_SCAN=quads, for tests and comparisons).
+inline void prepare_scene(const scene_desc& desc, uint32_t max_bounces, scene_params& out, bool group_boxes = true) {
     using namespace detail;
     std::memset(&out, 0, sizeof out);
     out.quad_count = desc.quad_count < k_max_quads ? desc.quad_count : k_max_quads;
@@ -345,7 +347,7 @@ inline void prepare_scene(const scene_desc& desc, uint32_t max_bounces, scene_pa
         return load3(g.origin) + load3(g.u) * float(c & 1) + load3(g.v) * float(c >> 1);
     };
     auto near_xz = [](f3 a, f3 b) { return std::fabs(a.x - b.x) < 1e-5f && std::fabs(a.z - b.z) < 1e-5f; };
-    for (uint32_t t = 0; t < out.quad_count && n_found < k_max_boxes; t++) {
+    for (uint32_t t = 0; group_boxes && t < out.quad_count && n_found < k_max_boxes; t++) {
         if (digested[t].valid == 0.0f || digested[t].shape != k_shape_flat_y) continue;
         const float y_top = digested[t].origin[1];
         uint32_t sides[4];

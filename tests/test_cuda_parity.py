@@ -344,3 +344,21 @@ def test_accumulation_survives_a_plugin_reload_when_the_host_keeps_it(torch_cuda
     for g, wv in zip(plain.readback_aov(), want5):
         assert np.array_equal(bits(g), bits(wv))
     plain.close()
+
+
+@pytest.mark.parametrize("scan", ["generic", "quads", "generic-quads"])
+def test_every_scan_variant_is_bit_exact(torch_cuda, oracle, scan):
+    """QUASI_CUDA_SCAN selects the any-scene kernel (one loop per quad shape instead of the
+    code unrolled for the demo scene) and/or switches the grouping of blocks off. All of
+    them decide the same closest hit."""
+    from quasi_b200.headless import headless_host
+
+    w, h, frames = 211, 119, 4
+    host = headless_host(w, h, env={"QUASI_CUDA_SCAN": scan})
+    host.render(frames)
+    got, stats = host.readback_aov(), host.stats()
+    host.close()
+    want, rays = oracle.render_frames(oracle.scene(w, h), w, h, frames)
+    for name, g, wv in zip(LAYERS, got, want):
+        assert np.array_equal(bits(g), bits(wv)), f"{scan}: {name}"
+    assert stats.rays == rays
