@@ -3,4 +3,4 @@ timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1
 tail -3 gpurun_out/pytest_gpu.log
 if [ $rc -ne 0 ]; then grep -E "Error|assert|FAIL|^E " gpurun_out/pytest_gpu.log | head -20; exit 1; fi
 timeout 200 python bench.py --no-cpu > gpurun_out/bench.json 2> gpurun_out/bench.err; cut -c1-300 gpurun_out/bench.json
-for scan in generic quads generic-quads; do QUASI_CUDA_SCAN=$scan timeout 200 python bench.py --no-cpu --steps 10 2>/dev/null | cut -c60-200 | sed "s/^/$scan: /"; done
+timeout 120 python tools/mesh_bench.py --json gpurun_out/mesh_bench.json 2>&1 | tail -1 | cut -c1-300
