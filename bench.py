@@ -337,6 +337,102 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------- config 3 (not the headline) ----
+
+def run_mesh(args):
+    """BASELINE configs[2]: the 1 M-triangle terrain scene (SAH BVH, or LBVH built on the GPU with
+    --mesh-builder lbvh), 1920x1080, 16 spp, 4 bounces, one GPU. Same conventions as the headline:
+    a step is one 16-spp frame, `value` is device-timed, `e2e` includes the readback, the CPU
+    baseline is the mesh oracle on every host core on a bounded sample."""
+    import torch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; libquasi_cuda.so has no CPU fallback")
+    from quasi_b200.headless import headless_host
+
+    spp, bounces, grid = 16, 4, 707
+    host = headless_host(WIDTH, HEIGHT, single_stream=True,
+                         env={"QUASI_CUDA_SCENE": "mesh", "QUASI_CUDA_MESH_GRID": grid, "QUASI_CUDA_MESH_SEED": 1,
+                              "QUASI_CUDA_MAX_BOUNCES": bounces, "QUASI_CUDA_MESH_BUILDER": args.mesh_builder})
+    stream = host.context.frame_stream()
+
+    def step():
+        host.render_frame(camera_dirty=True)
+        for _ in range(spp - 1):
+            host.render_frame(camera_dirty=False)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    s0 = host.stats()
+    sampler = clock_sampler(0)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms_step = ev0.elapsed_time(ev1) / args.steps
+    s1 = host.stats()
+    rays = (s1.rays - s0.rays) / args.steps
+    nodes = (s1.nodes_visited - s0.nodes_visited) / args.steps
+    tris = (s1.triangles_tested - s0.triangles_tested) / args.steps
+    launches = s1.kernel_launches - s0.kernel_launches
+
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+        rb = host.plugin.readback_aov()
+        assert rb.buffers[0].data, "readback returned no data"
+        host.plugin.readback_aov_free(rb)
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    messages = [m for m in host.messages if "esh" in m]
+    host.close()
+
+    peak, peak_src = measured_peaks()
+    bytes_step = nodes * 32 + tris * 48  # SURVEY.md 8d: nodes visited x 32 B + triangles tested x 48 B
+    line = {
+        "metric": "Mrays/s @1080p 16spp (1 M-triangle mesh scene, 4 bounces, headless via plugin C ABI)",
+        "value": round(rays / (ms_step * 1e-3) / 1e6, 2), "unit": "Mrays/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic (procedural terrain box from pcg_hash, no inputs to load)",
+        "config": {"workload": f"terrain mesh grid {grid} ({12 + 2 * grid * grid} triangles), {WIDTH}x{HEIGHT}, {spp} spp, "
+                               f"{bounces} bounces, BVH builder {args.mesh_builder}",
+                   "rays_per_step": rays, "nodes_per_ray": round(nodes / rays, 2),
+                   "triangles_per_ray": round(tris / rays, 2), "plugin_messages": messages,
+                   "l2": "no flush: the scene (20-37 MB of nodes, 96 MB of triangles and shading records) is meant "
+                         "to be served by L2; the 132.7 MB accumulation set is streamed every launch"},
+        "e2e": {"value": round(rays / e2e_s / 1e6, 2), "unit": "Mrays/s", "ms_per_step": round(e2e_s * 1e3, 4),
+                "h2d_bytes_per_step": spp * (320 + 80), "d2h_bytes_per_step": WIDTH * HEIGHT * 64},
+        "gpu_launches": launches, "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "mesh_pathtrace_kernel",
+                     "achieved": round(bytes_step / (ms_step * 1e-3) / 1e9, 1), "peak": peak, "unit": "GB/s",
+                     "frac": round(bytes_step / (ms_step * 1e-3) / 1e9 / peak, 4), "traffic": None,
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": round(bytes_step / spp),
+                     "kernel_ms": round(ms_step / spp, 5),
+                     "note": "algorithmic bytes (nodes x 32 B + triangles x 48 B) are served by L1/L2, not HBM "
+                             "(DRAM traffic is ~0.8 GB per launch, profiles/ncu_summary.json): the kernel is "
+                             "bound by instruction issue at 14.6 of 32 lanes, see DESIGN.md section 4.3"},
+    }
+    if not args.no_cpu:
+        from oracle_lib import MeshOracle
+
+        cw, ch, cframes = 960, 540, 4
+        oracle = MeshOracle(grid)
+        oracle.render_frames(cw, ch, 1, max_bounces=bounces)  # pages the library in
+        t0 = time.perf_counter()
+        _, st = oracle.render_frames(cw, ch, cframes, max_bounces=bounces)
+        cpu_s = time.perf_counter() - t0
+        line["cpu_baseline"] = {
+            "value": round(st["rays"] / cpu_s / 1e6, 3), "unit": "Mrays/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{cw}x{ch}, {cframes} spp of the same scene and BVH (oracle/quasi_oracle_mesh.c, gcc -O2 "
+                      f"-ffp-contract=off, one thread per core), {st['rays']} rays in {cpu_s:.2f} s"}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -348,10 +444,15 @@ def main():
                          "GPUs) or the fused peer-memory kernel (p2p: fixed summation order, bit-exact vs the oracle)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--cpu-budget", type=float, default=0.0, help="seconds of CPU work for the CPU legs")
+    ap.add_argument("--workload", choices=["demo", "mesh"], default="demo",
+                    help="demo = the headline (BASELINE configs[1]); mesh = configs[2], the 1 M-triangle scene, 1 GPU")
+    ap.add_argument("--mesh-builder", choices=["sah", "lbvh"], default="sah")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "mesh":
+        run_mesh(args)
     else:
         run_ours(args)
 
