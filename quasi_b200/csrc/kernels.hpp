@@ -66,7 +66,9 @@ struct lbvh_output {
     uint32_t* depth;       ///< 1: longest root-to-leaf path in nodes
 };
 /// @brief Builds a linear BVH over the triangles on the GPU (lbvh_build.cu) and waits for it.
-cudaError_t build_lbvh(const lbvh_input& in, const lbvh_output& out, cudaStream_t stream);
+/// @param build_ms If not null: device time of the build's kernels (CUDA events; the
+///        allocation of the scratch space is not included).
+cudaError_t build_lbvh(const lbvh_input& in, const lbvh_output& out, cudaStream_t stream, float* build_ms = nullptr);
 
 /// @brief Test hook: the kernel's sin/cos of phi in [0, 2*pi], element-wise.
 cudaError_t launch_sincos_probe(const float* phi, float* sin_out, float* cos_out, uint64_t n,

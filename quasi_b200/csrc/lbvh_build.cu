@@ -29,7 +29,7 @@
 ///      range of the sorted order is contiguous), boxes padded by 1e-4 of their
 ///      extent + 1e-5
 ///   7. triangles and shading records gathered into leaf (= sorted) order
-/// The build of the 999 710-triangle scene takes 2.1 ms against 2.3 s for the
+/// The build of the 999 710-triangle scene takes 0.57 ms of kernels against 2.3 s for the
 /// binned-SAH build on one host core; rays visit 42 boxes on this tree against 37
 /// on the SAH tree (frame 28.5 ms against 26.2 ms), the usual LBVH trade.
 
@@ -308,7 +308,7 @@ gather_kernel(const uint32_t* __restrict__ leaf_order, const float4* __restrict_
 
 }  // namespace
 
-cudaError_t build_lbvh(const lbvh_input& in, const lbvh_output& out, cudaStream_t stream) {
+cudaError_t build_lbvh(const lbvh_input& in, const lbvh_output& out, cudaStream_t stream, float* build_ms) {
     const uint32_t n = in.n_triangles;
     if (n <= k_leaf_max || n >= k_leaf_flag) return cudaErrorInvalidValue;
 
@@ -365,6 +365,19 @@ cudaError_t build_lbvh(const lbvh_input& in, const lbvh_output& out, cudaStream_
             cudaSuccess) {
         return finish(err);
     }
+    // Timed: the kernels of the build, not the allocation of its scratch space above.
+    cudaEvent_t begin = nullptr, end = nullptr;
+    if (build_ms != nullptr) {
+        *build_ms = 0.0f;
+        if (cudaEventCreate(&begin) != cudaSuccess || cudaEventCreate(&end) != cudaSuccess) {
+            (void)cudaGetLastError();
+            if (begin) cudaEventDestroy(begin);
+            begin = end = nullptr;
+        } else {
+            cudaStreamSynchronize(stream);  // the memsets above are not part of the measurement either
+            cudaEventRecord(begin, stream);
+        }
+    }
     prim_bounds_kernel<<<blocks_for(n), k_threads, 0, stream>>>(a, n);
     morton_kernel<<<blocks_for(n), k_threads, 0, stream>>>(a, keys_unsorted, n);
     err = cub::DeviceRadixSort::SortKeys(scratch + o_sort, sort_bytes, keys_unsorted, a.keys, static_cast<int>(n), 0, 64,
@@ -376,8 +389,14 @@ cudaError_t build_lbvh(const lbvh_input& in, const lbvh_output& out, cudaStream_
     depth_and_order_kernel<<<blocks_for(n), k_threads, 0, stream>>>(a, out.leaf_order, out.depth, n);
     gather_kernel<<<blocks_for(n), k_threads, 0, stream>>>(out.leaf_order, in.tri_v0, in.tri_e1, in.tri_e2, in.tri_shade,
                                                            out.tri_v0, out.tri_e1, out.tri_e2, out.tri_shade, n);
-    if ((err = cudaGetLastError()) != cudaSuccess) return finish(err);
-    return finish(cudaStreamSynchronize(stream));
+    if (end != nullptr) cudaEventRecord(end, stream);
+    if ((err = cudaGetLastError()) == cudaSuccess) err = cudaStreamSynchronize(stream);
+    if (end != nullptr) {
+        if (err == cudaSuccess) cudaEventElapsedTime(build_ms, begin, end);
+        cudaEventDestroy(begin);
+        cudaEventDestroy(end);
+    }
+    return finish(err);
 }
 
 }  // namespace Q::cuda

@@ -249,15 +249,12 @@ bool build_mesh_on_gpu(plugin_state* state) {
     void* input[4] = {nullptr, nullptr, nullptr, nullptr};
     uint32_t* order = nullptr;
     uint32_t* depth = nullptr;
-    cudaEvent_t begin = nullptr, end = nullptr;
     auto cleanup = [&](bool keep) {
         for (auto& b : input) {
             if (b) cudaFree(b);
         }
         if (order) cudaFree(order);
         if (depth) cudaFree(depth);
-        if (begin) cudaEventDestroy(begin);
-        if (end) cudaEventDestroy(end);
         if (!keep) free_mesh(state);
         return keep;
     };
@@ -272,8 +269,7 @@ bool build_mesh_on_gpu(plugin_state* state) {
                                  sizeof(float4) * n, sizeof(float4) * 3 * n};
     for (int i = 0; i < 5 && ok; i++) ok = check(state, cudaMalloc(&state->mesh_buffers[i], out_bytes[i]), "cudaMalloc(mesh)");
     ok = ok && check(state, cudaMalloc(reinterpret_cast<void**>(&order), sizeof(uint32_t) * n), "cudaMalloc(order)") &&
-         check(state, cudaMalloc(reinterpret_cast<void**>(&depth), sizeof(uint32_t)), "cudaMalloc(depth)") &&
-         check(state, cudaEventCreate(&begin), "cudaEventCreate") && check(state, cudaEventCreate(&end), "cudaEventCreate");
+         check(state, cudaMalloc(reinterpret_cast<void**>(&depth), sizeof(uint32_t)), "cudaMalloc(depth)");
     if (!ok) return cleanup(false);
 
     Q::cuda::lbvh_input in{static_cast<const float4*>(input[0]), static_cast<const float4*>(input[1]),
@@ -282,14 +278,8 @@ bool build_mesh_on_gpu(plugin_state* state) {
     Q::cuda::lbvh_output out{static_cast<float4*>(state->mesh_buffers[0]), static_cast<float4*>(state->mesh_buffers[1]),
                              static_cast<float4*>(state->mesh_buffers[2]), static_cast<float4*>(state->mesh_buffers[3]),
                              static_cast<float4*>(state->mesh_buffers[4]), order, depth};
-    cudaEventRecord(begin, state->queue);
-    const cudaError_t built = Q::cuda::build_lbvh(in, out, state->queue);
-    cudaEventRecord(end, state->queue);
-    if (!check(state, built, "build_lbvh") || !check(state, cudaEventSynchronize(end), "build_lbvh sync")) {
-        return cleanup(false);
-    }
     float build_ms = 0.0f;
-    cudaEventElapsedTime(&build_ms, begin, end);
+    if (!check(state, Q::cuda::build_lbvh(in, out, state->queue, &build_ms), "build_lbvh")) return cleanup(false);
 
     state->mesh.nodes.resize(2 * n - 1);
     state->mesh.leaf_order.resize(n);
