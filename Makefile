@@ -59,7 +59,7 @@ host-tests: $(TESTDIR)/host_test $(TESTDIR)/exr_write_tool $(TESTDIR)/mesh_dump_
 
 $(TESTDIR)/mesh_dump_tool: $(HOST)/test/mesh_dump_tool.cpp quasi_b200/csrc/mesh_scene.hpp
 	mkdir -p $(TESTDIR)
-	$(CXX) -std=c++20 -O2 -ffp-contract=off -Wall -Wextra -Iquasi_b200/csrc -o $@ $(HOST)/test/mesh_dump_tool.cpp
+	$(CXX) -std=c++20 -O2 -ffp-contract=off -Wall -Wextra -pthread -Iquasi_b200/csrc -o $@ $(HOST)/test/mesh_dump_tool.cpp
 	if [ -d $(REFERENCE)/test ]; then $(MAKE) reference-tests; fi
 
 $(TESTDIR)/host_test: $(HOST)/test/host_test.cpp $(HOST)/test/catch2_main.cpp $(HOST)/src/exr_writer.cpp \

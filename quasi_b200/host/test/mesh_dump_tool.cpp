@@ -1,7 +1,7 @@
 /// @file mesh_dump_tool.cpp
 /// @brief Test helper: builds the backend's mesh scene + BVH on the CPU and dumps it.
 ///
-/// Usage: mesh_dump_tool <grid> <seed> <out.bin>
+/// Usage: mesh_dump_tool <grid> <seed> <out.bin> [task_limit]
 /// out.bin = uint32 n_triangles, n_nodes, depth, 0; triangles (48 B each, original
 /// order); nodes (32 B each); leaf_order (uint32 each). tests/test_mesh_cpu.py
 /// compares it bit for bit with oracle/quasi_oracle_mesh.c's independent build.
@@ -16,7 +16,7 @@ int main(int argc, char** argv) {
     Q::cuda::mesh::scene s;
     Q::cuda::mesh::generate_triangles(static_cast<uint32_t>(std::atoi(argv[1])),
                                       static_cast<uint32_t>(std::atoi(argv[2])), s);
-    Q::cuda::mesh::build_bvh(s);
+    Q::cuda::mesh::build_bvh(s, argc > 4 ? static_cast<uint32_t>(std::atoi(argv[4])) : 32768u);
     std::FILE* f = std::fopen(argv[3], "wb");
     if (!f) return 1;
     const uint32_t hdr[4] = {static_cast<uint32_t>(s.triangles.size()), static_cast<uint32_t>(s.nodes.size()),

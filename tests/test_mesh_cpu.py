@@ -14,10 +14,10 @@ ROOT = Path(__file__).resolve().parent.parent
 TOOL = ROOT / "quasi_b200" / "bin" / "tests" / "mesh_dump_tool"
 
 
-def backend_build(grid, seed, tmp_path):
+def backend_build(grid, seed, tmp_path, task_limit=None):
     subprocess.run(["make", "-s", "-C", str(ROOT), str(TOOL.relative_to(ROOT))], check=True)
     out = tmp_path / f"mesh_{grid}.bin"
-    subprocess.run([str(TOOL), str(grid), str(seed), str(out)], check=True)
+    subprocess.run([str(TOOL), str(grid), str(seed), str(out)] + ([str(task_limit)] if task_limit else []), check=True)
     raw = out.read_bytes()
     nt, nn, depth, _ = np.frombuffer(raw, dtype=np.uint32, count=4)
     o = 16
@@ -36,6 +36,16 @@ def test_backend_builder_equals_oracle_builder(grid, seed, tmp_path):
     assert nodes == m.nodes().tobytes()          # the bit-exact BVH build-order contract
     assert np.array_equal(order, m.leaf_order())
     assert sorted(order.tolist()) == list(range(nt))
+
+
+@pytest.mark.parametrize("task_limit", [16, 500, 4000])
+def test_concurrent_build_is_the_sequential_build(task_limit, tmp_path):
+    """The backend builds ranges above `task_limit` triangles by splitting them and building the
+    halves on different threads (mesh_scene.hpp:build_parallel); whatever the limit, the node
+    array and the leaf order are the oracle's, which is built by one thread, byte for byte."""
+    nt, nn, depth, tris, nodes, order = backend_build(60, 5, tmp_path, task_limit)
+    m = MeshOracle(60, 5)
+    assert nn == m.n_nodes and nodes == m.nodes().tobytes() and np.array_equal(order, m.leaf_order())
 
 
 def test_million_triangle_build_matches_and_fits_the_traversal_stack(tmp_path):
