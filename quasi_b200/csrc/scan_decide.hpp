@@ -17,6 +17,8 @@
 #include "scene_params.hpp"
 
 #include <cmath>
+#include <cstdint>
+#include <cstring>
 
 #if defined(__CUDACC__)
 #define QUASI_SCAN_FN __device__ __forceinline__
@@ -36,6 +38,17 @@ QUASI_SCAN_FN float rcp(float x) {
     return r;
 }
 QUASI_SCAN_FN float fma_rn(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+#elif defined(QUASI_SCAN_CHECK_PERTURB)
+/// Host check only: the exact quotient moved two units in the last place up or down
+/// (which way depends on the argument's last bit), twice the error MUFU.RCP may have.
+QUASI_SCAN_FN float rcp(float x) {
+    const float r = 1.0f / x;
+    std::uint32_t bits;
+    std::memcpy(&bits, &x, sizeof bits);
+    const float towards = (bits & 1u) != 0u ? INFINITY : -INFINITY;
+    return std::nextafter(std::nextafter(r, towards), towards);
+}
+QUASI_SCAN_FN float fma_rn(float a, float b, float c) { return a * b + c; }  // and no contraction either
 #else
 QUASI_SCAN_FN float rcp(float x) { return 1.0f / x; }
 QUASI_SCAN_FN float fma_rn(float a, float b, float c) { return std::fmaf(a, b, c); }

@@ -9,9 +9,9 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 
 
-def build(tmp_path, include_dir):
-    exe = tmp_path / "scan_decide_check"
-    subprocess.run(["g++", "-std=c++20", "-O2", "-ffp-contract=off", "-Wall", "-Wextra", f"-I{include_dir}",
+def build(tmp_path, include_dir, *flags):
+    exe = tmp_path / ("scan_decide_check" + "".join(f.replace("-D", "_") for f in flags))
+    subprocess.run(["g++", "-std=c++20", "-O2", "-ffp-contract=off", "-Wall", "-Wextra", f"-I{include_dir}", *flags,
                     str(ROOT / "tests" / "scan_decide_check.cpp"), "-o", str(exe)], check=True)
     return exe
 
@@ -23,6 +23,17 @@ def test_fast_scan_names_the_literal_winner(tmp_path):
     counts = dict(zip(out.stdout.split()[0::2], out.stdout.split()[1::2]))
     assert int(counts["mismatches"]) == 0 and int(counts["decided"]) > 2_000_000
     assert int(counts["literal"]) > 0          # the margins do fire on these rays
+
+
+def test_margins_absorb_an_approximate_reciprocal(tmp_path):
+    """On the device 1/x in the deciding arithmetic is one MUFU.RCP (relative error 2^-23) and
+    a*b+c is one FFMA; on the host they are exact quotient and fmaf. With the reciprocal pushed
+    two ulps either way and the FFMAs replaced by separately rounded operations the scan must
+    still never name a quad the literal loop does not."""
+    exe = build(tmp_path, ROOT / "quasi_b200" / "csrc", "-DQUASI_SCAN_CHECK_PERTURB")
+    out = subprocess.run([str(exe), "4000000"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout[-2000:]
+    assert "mismatches 0" in out.stdout
 
 
 def test_the_check_notices_a_missing_rule(tmp_path):
