@@ -112,11 +112,11 @@ struct fixed_layout {
 struct dynamic_layout {
     static constexpr bool fixed = false;
 };
-/// The demo scene (make_cornell_box): 2 side walls, floor + ceiling + light, the back
-/// wall, and two boxes of five faces each.
-using cornell_layout = fixed_layout<0, 2, 3, 1, 0, 2>;
-/// The same scene with every quad on its own (QUASI_CUDA_SCAN=quads).
+/// The demo scene (make_cornell_box): 2 side walls, floor + ceiling + light + 2 block tops,
+/// the back wall, 8 block sides.
 using cornell_quads_layout = fixed_layout<0, 2, 5, 1, 8, 0>;
+/// The same scene with each block's five faces as one slab test (QUASI_CUDA_SCAN=boxes).
+using cornell_layout = fixed_layout<0, 2, 3, 1, 0, 2>;
 
 /// Closest hit of one ray against the scene. Same result, bit for bit,
 /// as trace_scene_exact. `shade` is the shared-memory copy of the quads' shading

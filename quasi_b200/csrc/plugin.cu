@@ -425,11 +425,12 @@ Q_PLUGIN_EXPORT Q_plugin_handle* Q_plugin_create(Q_plugin_context* ctx) {
         // slot for options, so they come from the environment.
         state->scene_desc = Q::cuda::make_cornell_box();
         uint32_t bounces = env_u32("QUASI_CUDA_MAX_BOUNCES", Q::cuda::k_max_bounces, 1, 64);
-        // QUASI_CUDA_SCAN: "generic" = the any-scene kernel, "quads" = no block grouping,
-        // "generic-quads" = both; default: grouped blocks, kernel unrolled for the demo scene.
+        // QUASI_CUDA_SCAN: "generic" = the any-scene kernel, "boxes" = the five faces of a block
+        // in one slab test (scan_decide.hpp:scan_box), "generic-boxes" = both; default: every
+        // quad on its own in the kernel unrolled for the demo scene, the fastest form.
         const char* scan = std::getenv("QUASI_CUDA_SCAN");
         state->generic_scan = scan && std::strncmp(scan, "generic", 7) == 0;
-        const bool group_boxes = !(scan && std::strstr(scan, "quads") != nullptr);
+        const bool group_boxes = scan && std::strstr(scan, "boxes") != nullptr;
         Q::cuda::prepare_scene(state->scene_desc, bounces, state->scene, group_boxes);
         const char* scene_name = std::getenv("QUASI_CUDA_SCENE");
         if (scene_name && std::strcmp(scene_name, "mesh") == 0) {

@@ -192,12 +192,26 @@ QUASI_SCAN_FN void scan_box(scan_state& s, const box_params& b, v3 ro, v3 rd) {
     const float m1 = std::fabs(fma_rn(a1, 0.001f, s1) - b.mid[1]) - b.half[1];
     const float m2 = std::fabs(fma_rn(rd.y, 0.001f, ro.y) - b.mid[2]) - b.half[2];
     const bool tunnels = std::fmax(m0, std::fmax(m1, m2)) <= b.delta;
+    // "Surely inside slab k" is e_k < -delta, measured at the entry point. Seen from the face
+    // of slab k the same edge is approached at the speed the ray crosses the ENTRY slab: when
+    // that is the slower one (a ray almost in the plane of the entry face) the ray is still
+    // within delta of the box while it crosses the plane of slab k, well before the entry, and
+    // the literal test may count THAT face as hit. So the margin of slab k is delta times the
+    // ratio of the two speeds where that exceeds one: e_k * v_entry + delta * max(v_entry, v_k) < 0.
+    const float v0 = std::fabs(a0), v1 = std::fabs(a1), v2 = std::fabs(rd.y);
+    const float v_entry = entry_slab == 0 ? v0 : (entry_slab == 1 ? v1 : v2);
+    const float q0 = fma_rn(e0, v_entry, b.delta * std::fmax(v_entry, v0));
+    const float q1 = fma_rn(e1, v_entry, b.delta * std::fmax(v_entry, v1));
+    const float q2 = fma_rn(e2, v_entry, b.delta * std::fmax(v_entry, v2));
+    const float edge = std::fmax(entry_slab == 0 ? -k_inf : q0, std::fmax(entry_slab == 1 ? -k_inf : q1,
+                                                                    entry_slab == 2 ? -k_inf : q2));
     const bool ahead = t_entry > k_t_min_lo;
     const bool maybe = ahead && outside <= b.delta;
     // a ray parallel to a slab, or entering where there is no face, is never decided here
-    const bool sure = ahead && outside < -b.delta && t_entry > k_t_min_hi && !parallel && face >= 0;
+    const bool sure = ahead && edge < 0.0f && t_entry > k_t_min_hi && !parallel && face >= 0;
     const bool better = sure && t_entry < s.best_t;
-    float loser = better ? s.best_t : (maybe ? t_entry : k_inf);
+    // a box that may be hit but is not surely hit at the entry may be hit earlier, on another face
+    float loser = better ? s.best_t : (maybe ? 0.0f : k_inf);
     loser = (parallel || tunnels) ? 0.0f : loser;  // forces the literal scan
     s.challenger_t = std::fmin(s.challenger_t, loser);
     s.best_t = better ? t_entry : s.best_t;

@@ -252,9 +252,9 @@ inline scene_desc make_cornell_box() {
 }
 
 /// @brief Derives the per-quad constants the shader recomputes per ray.
-/// @param group_boxes Detect blocks (box_params) and scan each with one slab test; false keeps
-/// every quad on its own (QUASI_CUDA_SCAN=quads, for tests and comparisons).
-inline void prepare_scene(const scene_desc& desc, uint32_t max_bounces, scene_params& out, bool group_boxes = true) {
+/// @param group_boxes Detect blocks (box_params) and scan each with one slab test
+/// (QUASI_CUDA_SCAN=boxes); false keeps every quad on its own, the default.
+inline void prepare_scene(const scene_desc& desc, uint32_t max_bounces, scene_params& out, bool group_boxes = false) {
     using namespace detail;
     std::memset(&out, 0, sizeof out);
     out.quad_count = desc.quad_count < k_max_quads ? desc.quad_count : k_max_quads;

@@ -5,12 +5,14 @@
 // literal winner. Rays: camera rays, bounce rays from random points of every quad, and
 // rays aimed at what is hard: the edges of the boxes' faces, the floor within t_min of a
 // box, directions almost parallel to a face.
-//   usage: scan_decide_check [rays]   -> prints counts, exit code 1 on any mismatch
+//   usage: scan_decide_check [rays] [quads]   -> prints counts, exit code 1 on any mismatch
+//   "quads": every quad on its own (the backend's default); otherwise the blocks are grouped
 #include "scan_decide.hpp"
 
 #include <cstdio>
 #include <cstdlib>
 #include <random>
+#include <string>
 
 using namespace Q::cuda;
 
@@ -42,7 +44,7 @@ int literal_winner(const scene_params& scene, v3 ro, v3 rd) {
     return index;
 }
 
-bool inside_a_box_or_outside_the_room(const scene_params& scene, v3 p) {
+bool inside_a_box_or_outside_the_room(const scene_params& scene, v3 p) {  // `scene`: the grouped form
     if (std::fabs(p.x) > 1.0f || p.y < 0.0f || p.y > 2.0f || p.z < -1.0f) return true;
     for (uint32_t n = 0; n < scene.box_count; n++) {
         const box_params& b = scene.boxes[n];
@@ -59,15 +61,20 @@ bool inside_a_box_or_outside_the_room(const scene_params& scene, v3 p) {
 
 int main(int argc, char** argv) {
     const long rays = argc > 1 ? std::atol(argv[1]) : 3000000;
+    const bool group_boxes = !(argc > 2 && std::string(argv[2]) == "quads");
     scene_params scene;
     const scene_desc desc = make_cornell_box();
-    prepare_scene(desc, 5, scene);
+    prepare_scene(desc, 5, scene, group_boxes);
     const float camera[3] = {0.0f, 1.0f, 3.5f};
     set_decision_margins(scene, camera);
-    if (scene.box_count != 2) {
+    if (scene.box_count != (group_boxes ? 2u : 0u)) {
         std::printf("expected the two blocks of the demo scene to be detected, found %u\n", scene.box_count);
         return 1;
     }
+    scene_params grouped;  // the blocks' geometry, for aiming rays, whichever form is checked
+    prepare_scene(desc, 5, grouped, true);
+    set_decision_margins(grouped, camera);
+    const uint32_t block_faces = 10;  // quads 6..15 of make_cornell_box
     uint32_t floor_position = 0;  // the floor is quad 0 of make_cornell_box
     floor_position = scene.scene_order[0];
 
@@ -93,19 +100,27 @@ int main(int argc, char** argv) {
             rd = {target.x - ro.x, target.y - ro.y, target.z - ro.z};
         } else {
             uint32_t qi = rng() % scene.quad_count;
-            if (kind >= 2) qi = coin() ? floor_position : scene.shape_begin[k_shape_boxed] + rng() % (scene.shape_begin[k_shape_boxed + 1] - scene.shape_begin[k_shape_boxed]);
+            if (kind >= 2) qi = coin() ? floor_position : scene.scene_order[6u + rng() % block_faces];
             const quad_params& q = scene.quads[qi];
             float a = uniform(rng), b = uniform(rng), side = coin() ? 1.0f : -1.0f;
+            int grazed_box = -1, grazed_slab = 0;  // kind 3: a floor point in the plane of a box side
             if (kind >= 2 && qi != floor_position) {  // hug the edges of a face of a box or of the room
                 if (coin()) a = coin() ? uniform(rng) * 0.01f : 1.0f - uniform(rng) * 0.01f;
                 if (coin()) b = coin() ? uniform(rng) * 0.01f : 1.0f - uniform(rng) * 0.01f;
             }
             if (kind >= 2 && qi == floor_position) {  // the floor around the foot of a box
-                const box_params& box = scene.boxes[rng() % scene.box_count];
+                const uint32_t which_box = rng() % grouped.box_count;
+                const box_params& box = grouped.boxes[which_box];
                 float c0 = box.mid[0] + (2.0f * uniform(rng) - 1.0f) * (box.half[0] + 0.004f);
                 float c1 = box.mid[1] + (2.0f * uniform(rng) - 1.0f) * (box.half[1] + 0.004f);
-                const float off = uniform(rng) * 0.004f - 0.0005f;
-                if (coin()) {
+                float off = uniform(rng) * 0.004f - 0.0005f;
+                const bool first_slab = coin();
+                if (kind == 3 && coin()) {  // within a few 1e-8 of the plane of a side, to be grazed below
+                    off = (uniform(rng) - 0.5f) * 2e-7f;
+                    grazed_box = static_cast<int>(which_box);
+                    grazed_slab = first_slab ? 0 : 1;
+                }
+                if (first_slab) {
                     c0 = box.mid[0] + (coin() ? 1.0f : -1.0f) * (box.half[0] + off);
                 } else {
                     c1 = box.mid[1] + (coin() ? 1.0f : -1.0f) * (box.half[1] + off);
@@ -123,10 +138,10 @@ int main(int argc, char** argv) {
                 rd = {2.0f * uniform(rng) - 1.0f, 2.0f * uniform(rng) - 1.0f, 2.0f * uniform(rng) - 1.0f};
                 len2 = rd.x * rd.x + rd.y * rd.y + rd.z * rd.z;
             } while (len2 > 1.0f || len2 < 1e-4f);
-            if (kind == 3 && coin()) {  // almost parallel to a face of a box or to the floor
-                const box_params& box = scene.boxes[rng() % scene.box_count];
-                const int which = static_cast<int>(rng() % 3u);
-                const float tiny = (uniform(rng) - 0.5f) * 4e-6f;
+            if (kind == 3 && (grazed_box >= 0 || coin())) {  // almost parallel to a face of a box or to the floor
+                const box_params& box = grouped.boxes[grazed_box >= 0 ? static_cast<uint32_t>(grazed_box) : rng() % grouped.box_count];
+                const int which = grazed_box >= 0 ? grazed_slab : static_cast<int>(rng() % 3u);
+                const float tiny = (uniform(rng) - 0.5f) * (coin() ? 4e-6f : 4e-4f);
                 if (which == 2) {
                     rd.y = tiny;
                 } else {  // remove the component along the slab direction, leave a tiny one
@@ -138,7 +153,7 @@ int main(int argc, char** argv) {
             if ((rd.x * q.normal[0] + rd.y * q.normal[1] + rd.z * q.normal[2]) * side < 0.0f) {
                 rd = {-rd.x, -rd.y, -rd.z};
             }
-            if (inside_a_box_or_outside_the_room(scene, ro)) continue;  // no path ever starts there
+            if (inside_a_box_or_outside_the_room(grouped, ro)) continue;  // no path ever starts there
         }
         const float len = std::sqrt(rd.x * rd.x + rd.y * rd.y + rd.z * rd.z);
         rd = {rd.x / len, rd.y / len, rd.z / len};

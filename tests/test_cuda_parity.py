@@ -346,11 +346,11 @@ def test_accumulation_survives_a_plugin_reload_when_the_host_keeps_it(torch_cuda
     plain.close()
 
 
-@pytest.mark.parametrize("scan", ["generic", "quads", "generic-quads"])
+@pytest.mark.parametrize("scan", ["generic", "boxes", "generic-boxes"])
 def test_every_scan_variant_is_bit_exact(torch_cuda, oracle, scan):
     """QUASI_CUDA_SCAN selects the any-scene kernel (one loop per quad shape instead of the
-    code unrolled for the demo scene) and/or switches the grouping of blocks off. All of
-    them decide the same closest hit."""
+    code unrolled for the demo scene) and/or the grouping of each block's five faces into one
+    slab test. All of them decide the same closest hit."""
     from quasi_b200.headless import headless_host
 
     w, h, frames = 211, 119, 4

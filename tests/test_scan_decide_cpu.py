@@ -6,6 +6,8 @@ blocks' faces, the floor within t_min of a block, directions almost parallel to 
 import subprocess
 from pathlib import Path
 
+import pytest
+
 ROOT = Path(__file__).resolve().parent.parent
 
 
@@ -16,9 +18,11 @@ def build(tmp_path, include_dir, *flags):
     return exe
 
 
-def test_fast_scan_names_the_literal_winner(tmp_path):
+@pytest.mark.parametrize("form", ["quads", "boxes"])
+def test_fast_scan_names_the_literal_winner(tmp_path, form):
+    """Both forms of the scan: every quad on its own (the default) and blocks as slab tests."""
     exe = build(tmp_path, ROOT / "quasi_b200" / "csrc")
-    out = subprocess.run([str(exe), "4000000"], capture_output=True, text=True)
+    out = subprocess.run([str(exe), "4000000", form], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout[-2000:]
     counts = dict(zip(out.stdout.split()[0::2], out.stdout.split()[1::2]))
     assert int(counts["mismatches"]) == 0 and int(counts["decided"]) > 2_000_000
@@ -34,6 +38,22 @@ def test_margins_absorb_an_approximate_reciprocal(tmp_path):
     out = subprocess.run([str(exe), "4000000"], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout[-2000:]
     assert "mismatches 0" in out.stdout
+
+
+def test_the_check_notices_a_missing_grazing_rule(tmp_path):
+    """The speed-scaled edge margin of scan_box (a ray almost in the plane of the face it enters
+    through may be counted as hitting a neighbouring face earlier: one wrong quad in 2e8
+    uniformly aimed rays without it) has rays aimed at it too."""
+    mutated = tmp_path / "mutated_grazing"
+    mutated.mkdir()
+    src = (ROOT / "quasi_b200" / "csrc" / "scan_decide.hpp").read_text()
+    assert "edge < 0.0f" in src and "(maybe ? 0.0f : k_inf)" in src
+    src = src.replace("edge < 0.0f", "outside < -b.delta").replace("(maybe ? 0.0f : k_inf)", "(maybe ? t_entry : k_inf)")
+    (mutated / "scan_decide.hpp").write_text(src)
+    (mutated / "scene_params.hpp").write_text((ROOT / "quasi_b200" / "csrc" / "scene_params.hpp").read_text())
+    exe = build(tmp_path, mutated)
+    out = subprocess.run([str(exe), "12000000"], capture_output=True, text=True)
+    assert out.returncode == 1 and "MISMATCH" in out.stdout
 
 
 def test_the_check_notices_a_missing_rule(tmp_path):
