@@ -42,6 +42,7 @@
 
 #include "device_common.cuh"
 #include "kernels.hpp"
+#include "slab_test.hpp"
 
 #include <cuda_runtime.h>
 
@@ -105,23 +106,10 @@ struct lane_stack {
     __device__ __forceinline__ uint32_t after_node() const { return sp > 0 ? k_pop : k_done; }
 };
 
-/// Slab test against a padded box: `inv` = 1/dir (clamped to +-2^100), `oi` =
-/// origin * inv. Returns the entry distance in t_near. Conservative, not exact
-/// (see the file comment); NaNs cannot occur because inv is finite.
-__device__ __forceinline__ bool box_hit(float4 lo, float4 hi, v3 inv, v3 oi, float closest, float& t_near) {
-    const float t0x = __fmaf_rn(lo.x, inv.x, -oi.x), t1x = __fmaf_rn(hi.x, inv.x, -oi.x);
-    const float t0y = __fmaf_rn(lo.y, inv.y, -oi.y), t1y = __fmaf_rn(hi.y, inv.y, -oi.y);
-    const float t0z = __fmaf_rn(lo.z, inv.z, -oi.z), t1z = __fmaf_rn(hi.z, inv.z, -oi.z);
-    const float tn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.0f));
-    const float tf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), closest));
-    t_near = tn;
-    return tn <= tf;
-}
+using slab::box_hit;  // slab_test.hpp: the pruning arithmetic, shared with the host check
 
-/// 1/x for the slab test: one MUFU.RCP, clamped so that origin * result stays finite.
-__device__ __forceinline__ float slab_reciprocal(float x) {
-    return fminf(fmaxf(rcp_approx(x), -0x1p+100f), 0x1p+100f);
-}
+/// 1/x for the slab test (slab_test.hpp).
+__device__ __forceinline__ float slab_reciprocal(float x) { return slab::reciprocal(x); }
 
 /// Moeller-Trumbore with the operations, their order and the decisions of
 /// oracle/quasi_oracle_mesh.c:qm_intersect, evaluated without branches: every

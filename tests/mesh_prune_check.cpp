@@ -1,0 +1,182 @@
+// Host check of the mesh traversal's pruning (quasi_b200/csrc/slab_test.hpp, the code the
+// CUDA kernel compiles) on the backend's own scene and BVH (mesh_scene.hpp): for every ray
+// the closest hit found THROUGH the tree, skipping what the slab test says can be skipped,
+// must be the closest hit of a brute-force loop over all triangles, with the same
+// Moeller-Trumbore test (operation order of oracle/quasi_oracle_mesh.c:qm_intersect) and
+// the same tie rule. Compiled with -DQUASI_SCAN_CHECK_PERTURB the reciprocal is two ulps
+// off either way, twice what MUFU.RCP may be, and a * b + c is rounded twice.
+// Rays: from points above the terrain in random directions, bounce rays from points on
+// random triangles, directions almost or exactly parallel to an axis (where 1/dir is huge
+// or clamped), origins exactly on box planes of the tree.
+//   usage: mesh_prune_check [grid] [rays]   -> prints counts, exit code 1 on any mismatch
+#include "mesh_scene.hpp"
+#include "slab_test.hpp"
+
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+
+using namespace Q::cuda;
+
+namespace {
+
+struct hit {
+    float t = 1e30f;
+    uint32_t prim = 0xffffffffu;
+};
+
+struct f4 {
+    float x, y, z, w;
+};
+
+void intersect(const mesh::triangle& tri, uint32_t prim, v3 o, v3 d, hit& best) {
+    const v3 e1{tri.e1[0], tri.e1[1], tri.e1[2]}, e2{tri.e2[0], tri.e2[1], tri.e2[2]};
+    const v3 pvec{d.y * e2.z - d.z * e2.y, d.z * e2.x - d.x * e2.z, d.x * e2.y - d.y * e2.x};
+    const float det = e1.x * pvec.x + e1.y * pvec.y + e1.z * pvec.z;
+    if (std::fabs(det) < 1e-12f) return;
+    const float inv_det = 1.0f / det;
+    const v3 tvec{o.x - tri.v0[0], o.y - tri.v0[1], o.z - tri.v0[2]};
+    const float u = (tvec.x * pvec.x + tvec.y * pvec.y + tvec.z * pvec.z) * inv_det;
+    if (u < 0.0f || u > 1.0f) return;
+    const v3 qvec{tvec.y * e1.z - tvec.z * e1.y, tvec.z * e1.x - tvec.x * e1.z, tvec.x * e1.y - tvec.y * e1.x};
+    const float v = (d.x * qvec.x + d.y * qvec.y + d.z * qvec.z) * inv_det;
+    if (v < 0.0f || u + v > 1.0f) return;
+    const float t = (e2.x * qvec.x + e2.y * qvec.y + e2.z * qvec.z) * inv_det;
+    if (t < 0.001f || t > best.t) return;
+    if (t == best.t && best.prim != 0xffffffffu && prim < best.prim) return;
+    best.t = t;
+    best.prim = prim;
+}
+
+hit brute_force(const mesh::scene& s, v3 o, v3 d) {
+    hit best;
+    for (uint32_t t = 0; t < s.triangles.size(); t++) intersect(s.triangles[t], t, o, d, best);
+    return best;
+}
+
+/// The traversal of mesh_trace.cu in one thread: near child first, far child deferred with its
+/// entry distance (kept at the precision of the kernel's stack: upper 16 bits), culled on pop.
+hit through_the_tree(const mesh::scene& s, v3 o, v3 d, uint64_t& boxes) {
+    hit best;
+    const v3 inv{slab::reciprocal(d.x), slab::reciprocal(d.y), slab::reciprocal(d.z)};
+    const v3 oi{o.x * inv.x, o.y * inv.y, o.z * inv.z};
+    auto box = [&](const mesh::node& n, float& tn) {
+        boxes++;
+        return slab::box_hit(f4{n.bmin[0], n.bmin[1], n.bmin[2], 0.0f}, f4{n.bmax[0], n.bmax[1], n.bmax[2], 0.0f}, inv, oi,
+                             best.t, tn);
+    };
+    struct entry {
+        uint32_t node;
+        float t_near;
+    };
+    entry stack[64];
+    int sp = 0;
+    float tn;
+    if (!box(s.nodes[0], tn)) return best;
+    uint32_t cur = 0;
+    for (;;) {
+        const mesh::node& n = s.nodes[cur];
+        bool descended = false;
+        if (n.count == 0) {
+            float tl, tr;
+            const bool hl = box(s.nodes[n.left_first], tl), hr = box(s.nodes[n.left_first + 1], tr);
+            if (hl && hr) {
+                const bool go_left = tl <= tr;
+                uint32_t bits;
+                const float far_t = go_left ? tr : tl;
+                std::memcpy(&bits, &far_t, 4);
+                bits &= 0xffff0000u;  // the kernel keeps the upper 16 bits of the entry distance
+                float kept;
+                std::memcpy(&kept, &bits, 4);
+                stack[sp++] = {go_left ? n.left_first + 1 : n.left_first, kept};
+                cur = go_left ? n.left_first : n.left_first + 1;
+                descended = true;
+            } else if (hl || hr) {
+                cur = hl ? n.left_first : n.left_first + 1;
+                descended = true;
+            }
+        } else {
+            for (uint32_t k = 0; k < n.count; k++) {
+                const uint32_t prim = s.leaf_order[n.left_first + k];
+                intersect(s.triangles[prim], prim, o, d, best);
+            }
+        }
+        if (descended) continue;
+        bool found = false;
+        while (sp > 0) {
+            sp--;
+            if (stack[sp].t_near <= best.t) {
+                cur = stack[sp].node;
+                found = true;
+                break;
+            }
+        }
+        if (!found) break;
+    }
+    return best;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+    const uint32_t grid = argc > 1 ? static_cast<uint32_t>(std::atoi(argv[1])) : 40u;
+    const long rays = argc > 2 ? std::atol(argv[2]) : 200000;
+    mesh::scene s;
+    mesh::generate_triangles(grid, 1, s);
+    mesh::build_bvh(s);
+
+    std::mt19937 rng(11);
+    std::uniform_real_distribution<float> uniform(0.0f, 1.0f);
+    auto coin = [&] { return (rng() & 1u) != 0u; };
+    long mismatches = 0, hits = 0;
+    uint64_t boxes = 0;
+    for (long it = 0; it < rays; it++) {
+        v3 o{}, d{};
+        const int kind = static_cast<int>(it % 4);
+        float len2;
+        do {
+            d = {2.0f * uniform(rng) - 1.0f, 2.0f * uniform(rng) - 1.0f, 2.0f * uniform(rng) - 1.0f};
+            len2 = d.x * d.x + d.y * d.y + d.z * d.z;
+        } while (len2 > 1.0f || len2 < 1e-4f);
+        if (kind == 0) {  // anywhere in the room above the terrain, or the camera's place
+            o = coin() ? v3{0.0f, 1.0f, 3.5f} : v3{1.9f * uniform(rng) - 0.95f, 0.7f + 1.25f * uniform(rng), 1.9f * uniform(rng) - 0.95f};
+            if (o.z > 2.0f) d = {0.6f * (d.x), 0.5f * d.y, -1.0f};
+        } else {  // a bounce: a point of a random triangle, lifted 0.001 along its normal
+            const mesh::triangle& tri = s.triangles[rng() % s.triangles.size()];
+            float a = uniform(rng), b = uniform(rng);
+            if (a + b > 1.0f) a = 1.0f - a, b = 1.0f - b;
+            const v3 n{tri.e1[1] * tri.e2[2] - tri.e1[2] * tri.e2[1], tri.e1[2] * tri.e2[0] - tri.e1[0] * tri.e2[2],
+                       tri.e1[0] * tri.e2[1] - tri.e1[1] * tri.e2[0]};
+            const float nl = std::sqrt(n.x * n.x + n.y * n.y + n.z * n.z);
+            float side = (d.x * n.x + d.y * n.y + d.z * n.z) < 0.0f ? -1.0f : 1.0f;
+            o = {tri.v0[0] + tri.e1[0] * a + tri.e2[0] * b + n.x / nl * 0.001f * side,
+                 tri.v0[1] + tri.e1[1] * a + tri.e2[1] * b + n.y / nl * 0.001f * side,
+                 tri.v0[2] + tri.e1[2] * a + tri.e2[2] * b + n.z / nl * 0.001f * side};
+        }
+        if (kind == 2) {  // almost or exactly parallel to an axis plane: 1/dir huge, infinite (clamped) or denormal
+            float* comp = (rng() % 3u == 0) ? &d.x : (coin() ? &d.y : &d.z);
+            const uint32_t how = rng() % 4u;
+            *comp = how == 0 ? 0.0f : (how == 1 ? -0.0f : (how == 2 ? (uniform(rng) - 0.5f) * 1e-7f : (uniform(rng) - 0.5f) * 1e-38f));
+        }
+        if (kind == 3) {  // an origin exactly in a box plane of the tree
+            const mesh::node& n = s.nodes[rng() % s.nodes.size()];
+            const uint32_t axis = rng() % 3u;
+            (axis == 0 ? o.x : (axis == 1 ? o.y : o.z)) = coin() ? n.bmin[axis] : n.bmax[axis];
+        }
+        const float len = std::sqrt(d.x * d.x + d.y * d.y + d.z * d.z);
+        if (!(len > 0.0f)) continue;
+        d = {d.x / len, d.y / len, d.z / len};
+        const hit want = brute_force(s, o, d);
+        const hit got = through_the_tree(s, o, d, boxes);
+        hits += want.prim != 0xffffffffu;
+        if (got.prim != want.prim || got.t != want.t) {
+            if (mismatches < 10) {
+                std::printf("MISMATCH tree %u (t %.9g) brute force %u (t %.9g) o %.9g %.9g %.9g d %.9g %.9g %.9g\n", got.prim,
+                            got.t, want.prim, want.t, o.x, o.y, o.z, d.x, d.y, d.z);
+            }
+            mismatches++;
+        }
+    }
+    std::printf("rays %ld hits %ld boxes_per_ray %.1f mismatches %ld\n", rays, hits, static_cast<double>(boxes) / rays, mismatches);
+    return mismatches == 0 ? 0 : 1;
+}
