@@ -17,7 +17,7 @@ inline constexpr uint32_t k_mesh_materials = 8;
 
 /// Device view of the mesh scene (mesh_scene.hpp:pack_for_device).
 struct alignas(16) mesh_params {
-    const float4* nodes;    ///< 2 float4 per node: {min.xyz, left_first} {max.xyz, count}
+    const float4* nodes;    ///< 2 float4 per node: {min.xyz, left_first} {max.xyz, count}; wide: 8 per node (wide_bvh.hpp)
     const float4* tri_v0;   ///< leaf order: {v0.xyz, material}
     const float4* tri_e1;   ///< leaf order: {e1.xyz, original index}
     const float4* tri_e2;   ///< leaf order: {e2.xyz, 0}
@@ -25,7 +25,7 @@ struct alignas(16) mesh_params {
     uint32_t n_nodes;
     uint32_t n_triangles;
     uint32_t max_bounces;
-    uint32_t pad;
+    uint32_t wide;          ///< 1: `nodes` is the 4-wide tree and n_nodes counts its nodes
     float materials[k_mesh_materials * 8];  ///< per material: albedo.xyz, 0, emission.xyz, 0
 };
 

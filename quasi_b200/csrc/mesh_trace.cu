@@ -39,10 +39,17 @@
 /// The order in which nodes are visited cannot change the result: boxes only
 /// prune what the ray provably misses, and an equal t is won by the higher
 /// triangle index.
+///
+/// Second form, selected per scene (mesh_params::wide, QUASI_CUDA_MESH_WIDE=1): the same
+/// kernel over the 4-wide tree collapsed from the binary one (wide_bvh.hpp). A visit is
+/// one 128-byte line (7 x LDG.128), four slab tests, the nearest child hit taken and the
+/// others deferred nearest on top; half as many visits, dependent loads and scheduler
+/// iterations per ray.
 
 #include "device_common.cuh"
 #include "kernels.hpp"
 #include "slab_test.hpp"
+#include "wide_bvh.hpp"
 
 #include <cuda_runtime.h>
 
@@ -91,10 +98,19 @@ struct lane_stack {
     uint16_t* dist;
     int sp = 0;
 
-    __device__ __forceinline__ void push(uint2 e) {
-        refs[sp * k_block_threads] = e.x;
-        dist[sp * k_block_threads] = static_cast<uint16_t>(e.y >> 16);
+    __device__ __forceinline__ void push(uint2 e) { push(e.x, e.y); }
+    /// `distance_bits`: the entry distance (>= 0) as the bits of its float.
+    __device__ __forceinline__ void push(uint32_t ref, uint32_t distance_bits) {
+        refs[sp * k_block_threads] = ref;
+        dist[sp * k_block_threads] = static_cast<uint16_t>(distance_bits >> 16);
         sp++;
+    }
+    /// Stores the entry at the top and keeps it only if `keep`: needs one entry of room beyond
+    /// what the stack logically holds (wide_bvh.hpp:collapse_wide is given that limit).
+    __device__ __forceinline__ void push_if(bool keep, uint32_t ref, uint32_t distance_bits) {
+        refs[sp * k_block_threads] = ref;
+        dist[sp * k_block_threads] = static_cast<uint16_t>(distance_bits >> 16);
+        sp += keep ? 1 : 0;
     }
     __device__ __forceinline__ uint32_t pop_one(float closest) {
         sp--;
@@ -165,6 +181,16 @@ __device__ __forceinline__ void interior_step(const float4* __restrict__ nodes, 
     }
 }
 
+/// One visit of a 4-wide node (wide_bvh.hpp): one 128-byte line, four slab tests.
+__device__ __forceinline__ void wide_step(const float4* __restrict__ nodes, lane_stack& stack, v3 inv, v3 oi,
+                                          float closest, uint32_t& cur) {
+    const float4* n = nodes + mesh::k_wide_node_float4 * static_cast<size_t>(cur >> 3);
+    const float4 lx = __ldg(n), ly = __ldg(n + 1), lz = __ldg(n + 2), hx = __ldg(n + 3), hy = __ldg(n + 4),
+                 hz = __ldg(n + 5), refs = __ldg(n + 6);
+    cur = slab::wide_visit(lx, ly, lz, hx, hy, hz, refs, inv, oi, closest, stack);
+}
+
+template <bool Wide>
 __global__ void __launch_bounds__(k_block_threads, k_blocks_per_sm)
 mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_constant__ frame_params frame,
                       float4* __restrict__ beauty, float4* __restrict__ albedo, float4* __restrict__ normal,
@@ -343,10 +369,14 @@ mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_co
             inv = make_v3(slab_reciprocal(rd.x), slab_reciprocal(rd.y), slab_reciprocal(rd.z));
             oi = ro * inv;
             stack.sp = 0;
-            float tn;
-            const float4 lo = __ldg(nodes), hi = __ldg(nodes + 1);
-            nodes_visited++;
-            cur = box_hit(lo, hi, inv, oi, best.t, tn) ? node_ref(lo, hi) : k_done;
+            if constexpr (Wide) {
+                cur = 0u;  // the root of the wide tree; its children's boxes are the first test
+            } else {
+                float tn;
+                const float4 lo = __ldg(nodes), hi = __ldg(nodes + 1);
+                nodes_visited++;
+                cur = box_hit(lo, hi, inv, oi, best.t, tn) ? node_ref(lo, hi) : k_done;
+            }
         }
         const uint32_t m_active = __ballot_sync(0xffffffffu, active);
         if (m_active == 0u) {
@@ -371,8 +401,13 @@ mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_co
                 do {
                     if (cur == k_pop) cur = stack.pop_one(best.t);
                     if ((cur & 7u) == 0u) {
-                        nodes_visited += 2u;
-                        interior_step(nodes, stack, inv, oi, best.t, cur);
+                        if constexpr (Wide) {
+                            nodes_visited += mesh::k_wide;
+                            wide_step(nodes, stack, inv, oi, best.t, cur);
+                        } else {
+                            nodes_visited += 2u;
+                            interior_step(nodes, stack, inv, oi, best.t, cur);
+                        }
                     }
                 } while (__popc(__ballot_sync(0xffffffffu, (cur & 7u) == 0u || cur == k_pop)) > keep);
             } else if ((cur & 7u) - 1u < 4u) {
@@ -409,10 +444,15 @@ cudaError_t launch_mesh_pathtrace(const mesh_params& scene, const frame_params& 
     const uint32_t needed = (n_tiles + k_warps_per_block - 1u) / k_warps_per_block;
     if (needed < blocks) blocks = needed;
     if (blocks == 0) return cudaSuccess;
-    static const cudaError_t attr = cudaFuncSetAttribute(
-        mesh_pathtrace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(k_stack_bytes));
-    if (attr != cudaSuccess) return attr;
-    mesh_pathtrace_kernel<<<blocks, k_block_threads, k_stack_bytes, stream>>>(
+    auto* kernel = scene.wide != 0u ? mesh_pathtrace_kernel<true> : mesh_pathtrace_kernel<false>;
+    static const cudaError_t attr[2] = {
+        cudaFuncSetAttribute(mesh_pathtrace_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(k_stack_bytes)),
+        cudaFuncSetAttribute(mesh_pathtrace_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(k_stack_bytes))};
+    if (attr[0] != cudaSuccess) return attr[0];
+    if (attr[1] != cudaSuccess) return attr[1];
+    kernel<<<blocks, k_block_threads, k_stack_bytes, stream>>>(
         scene, frame, reinterpret_cast<float4*>(layers[0]), reinterpret_cast<float4*>(layers[1]),
         reinterpret_cast<float4*>(layers[2]), reinterpret_cast<float4*>(layers[3]), counters, tile_counters);
     return cudaGetLastError();

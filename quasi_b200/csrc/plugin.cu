@@ -9,6 +9,7 @@
 
 #include "kernels.hpp"
 #include "mesh_scene.hpp"
+#include "wide_bvh.hpp"
 
 #include <quasi_cuda_backend.h>
 
@@ -106,7 +107,8 @@ struct plugin_state {
     bool use_mesh = false;
     Q::cuda::mesh::scene mesh;
     Q::cuda::mesh_params mesh_device{};
-    void* mesh_buffers[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    void* mesh_buffers[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  ///< [5]: the 4-wide tree, if asked for
+    uint32_t wide_nodes = 0;
 
     float* layers[Q_AOV_COUNT] = {nullptr, nullptr, nullptr, nullptr};
     unsigned long long* ray_counter = nullptr;
@@ -227,6 +229,12 @@ void finish_mesh_params(plugin_state* state, uint32_t max_bounces) {
     d.tri_e2 = static_cast<const float4*>(state->mesh_buffers[3]);
     d.tri_shade = static_cast<const float4*>(state->mesh_buffers[4]);
     d.n_nodes = static_cast<uint32_t>(state->mesh.nodes.size());
+    d.wide = 0;
+    if (state->mesh_buffers[5]) {
+        d.nodes = static_cast<const float4*>(state->mesh_buffers[5]);
+        d.n_nodes = state->wide_nodes;
+        d.wide = 1;
+    }
     d.n_triangles = static_cast<uint32_t>(state->mesh.triangles.size());
     d.max_bounces = max_bounces;
     for (uint32_t m = 0; m < mesh::k_material_count; m++) {
@@ -302,6 +310,8 @@ bool build_mesh_on_gpu(plugin_state* state) {
     return cleanup(true);
 }
 
+uint32_t env_u32(const char* name, uint32_t fallback, uint32_t lo, uint32_t hi);
+
 /// Generates the terrain-box scene, builds its BVH (binned SAH on the host by default,
 /// LBVH on the GPU with QUASI_CUDA_MESH_BUILDER=lbvh) and leaves both on the device.
 bool create_mesh(plugin_state* state, uint32_t grid, uint32_t seed, uint32_t max_bounces) {
@@ -328,10 +338,32 @@ bool create_mesh(plugin_state* state, uint32_t grid, uint32_t seed, uint32_t max
         }
         if (!check(state, cudaStreamSynchronize(state->queue), "upload(mesh) sync")) return false;
     }
+    // QUASI_CUDA_MESH_WIDE=1: the kernel walks the 4-wide tree collapsed from the binary one
+    // (wide_bvh.hpp), whichever builder made that; the binary tree stays what
+    // Q_cuda_plugin_mesh_view shows.
+    if (env_u32("QUASI_CUDA_MESH_WIDE", 0, 0, 1) != 0) {
+        // one entry of the stack stays free: the wide visit stores before it knows whether to keep
+        constexpr uint32_t limit = Q::cuda::k_mesh_stack_entries - 1;
+        const mesh::wide_tree wide = mesh::collapse_wide(state->mesh, limit);
+        const size_t bytes = wide.nodes.size() * sizeof(mesh::float4_t);
+        if (wide.node_count == 0 || wide.stack_need > limit) {
+            log_msg(state, "4-wide tree does not fit the traversal stack: using the binary tree");
+        } else if (!check(state, cudaMalloc(&state->mesh_buffers[5], bytes), "cudaMalloc(wide nodes)") ||
+                   !check(state, cudaMemcpy(state->mesh_buffers[5], wide.nodes.data(), bytes, cudaMemcpyHostToDevice),
+                          "upload(wide nodes)")) {
+            return false;
+        } else {
+            state->wide_nodes = wide.node_count;
+            char msg[200];
+            std::snprintf(msg, sizeof msg, "Mesh BVH collapsed to %u 4-wide nodes (%.2f children each), depth %u, stack bound %u",
+                          wide.node_count, static_cast<double>(wide.children) / wide.node_count, wide.depth, wide.stack_need);
+            log_msg(state, msg);
+        }
+    }
     finish_mesh_params(state, max_bounces);
     char buf[160];
     std::snprintf(buf, sizeof buf, "Mesh scene: %u triangles, %u BVH nodes, depth %u", state->mesh_device.n_triangles,
-                  state->mesh_device.n_nodes, state->mesh.depth);
+                  static_cast<uint32_t>(state->mesh.nodes.size()), state->mesh.depth);
     log_msg(state, buf);
     return true;
 }

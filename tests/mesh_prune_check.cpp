@@ -8,13 +8,21 @@
 // Rays: from points above the terrain in random directions, bounce rays from points on
 // random triangles, directions almost or exactly parallel to an axis (where 1/dir is huge
 // or clamped), origins exactly on box planes of the tree.
-//   usage: mesh_prune_check [grid] [rays]   -> prints counts, exit code 1 on any mismatch
+// With a third argument "wide" the same rays go through the 4-wide tree collapsed from the
+// binary one (wide_bvh.hpp: collapse_wide and wide_visit, the code the kernel compiles), after
+// a structural check of that tree: every leaf slot reachable exactly once, every child box
+// the box of a node of the binary tree, the stack bound it reports never exceeded.
+//   usage: mesh_prune_check [grid] [rays] [wide [stack limit]]   -> prints counts, exit code 1 on any mismatch
 #include "mesh_scene.hpp"
 #include "slab_test.hpp"
+#include "wide_bvh.hpp"
 
 #include <cstdio>
 #include <cstdlib>
+#include <map>
 #include <random>
+#include <utility>
+#include <vector>
 
 using namespace Q::cuda;
 
@@ -116,14 +124,155 @@ hit through_the_tree(const mesh::scene& s, v3 o, v3 d, uint64_t& boxes) {
     return best;
 }
 
+/// The stack of mesh_trace.cu as the wide visit sees it: references, and entry distances cut
+/// to their upper 16 bits.
+struct host_stack {
+    struct entry {
+        uint32_t ref;
+        float t_near;
+    };
+    entry entries[96];
+    int sp = 0, high_water = 0;
+    void push_if(bool keep, uint32_t ref, uint32_t distance_bits) {
+        distance_bits &= 0xffff0000u;
+        float kept;
+        std::memcpy(&kept, &distance_bits, 4);
+        entries[sp] = {ref, kept};  // written either way, as in the kernel
+        sp += keep ? 1 : 0;
+        if (sp > high_water) high_water = sp;
+    }
+    static constexpr uint32_t k_pop = 0xfffffffeu, k_done = 0xffffffffu;
+    [[nodiscard]] uint32_t after_node() const { return sp > 0 ? k_pop : k_done; }
+};
+
+/// The wide traversal of mesh_trace.cu in one thread.
+hit through_the_wide_tree(const mesh::scene& s, const mesh::wide_tree& w, v3 o, v3 d, uint64_t& boxes, uint64_t& visits,
+                          int& high_water) {
+    hit best;
+    const v3 inv{slab::reciprocal(d.x), slab::reciprocal(d.y), slab::reciprocal(d.z)};
+    const v3 oi{o.x * inv.x, o.y * inv.y, o.z * inv.z};
+    host_stack stack;
+    uint32_t cur = 0;  // the root, a wide node
+    while (cur != host_stack::k_done) {
+        if (cur == host_stack::k_pop) {
+            stack.sp--;
+            cur = stack.entries[stack.sp].t_near <= best.t ? stack.entries[stack.sp].ref : stack.after_node();
+            continue;
+        }
+        if ((cur & 7u) == 0u) {
+            const mesh::float4_t* n = &w.nodes[static_cast<size_t>(cur >> 3) * mesh::k_wide_node_float4];
+            boxes += 4;
+            visits++;
+            cur = slab::wide_visit(n[0], n[1], n[2], n[3], n[4], n[5], n[6], inv, oi, best.t, stack);
+        } else {
+            const uint32_t first = cur >> 3, count = cur & 7u;
+            for (uint32_t k = 0; k < count; k++) {
+                const uint32_t prim = s.leaf_order[first + k];
+                intersect(s.triangles[prim], prim, o, d, best);
+            }
+            cur = stack.after_node();
+        }
+    }
+    if (stack.high_water > high_water) high_water = stack.high_water;
+    return best;
+}
+
+/// Every leaf slot in exactly one leaf; every child of a wide node covers the slot range of
+/// one node of the binary tree and carries that node's box, bit for bit; every wide node is
+/// referenced once; counts as reported. Returns the number of violations.
+long check_wide_structure(const mesh::scene& s, const mesh::wide_tree& w) {
+    long bad = 0;
+    if (w.nodes.size() != static_cast<size_t>(w.node_count) * mesh::k_wide_node_float4) return 1;
+    // slot range of every binary node -> that node (ranges are unique: both children of an interior node are non-empty)
+    std::map<std::pair<uint32_t, uint32_t>, uint32_t> by_range;
+    {
+        std::vector<std::pair<uint32_t, uint32_t>> range(s.nodes.size());
+        for (size_t i = s.nodes.size(); i-- > 0;) {  // children have higher numbers than their parent
+            const mesh::node& n = s.nodes[i];
+            range[i] = n.count != 0 ? std::make_pair(n.left_first, n.count)
+                                    : std::make_pair(range[n.left_first].first, range[n.left_first].second + range[n.left_first + 1].second);
+            if (n.count == 0 && range[n.left_first].first + range[n.left_first].second != range[n.left_first + 1].first) bad++;
+            by_range[range[i]] = static_cast<uint32_t>(i);
+        }
+    }
+    std::vector<uint8_t> slot_seen(s.triangles.size(), 0);
+    std::vector<uint8_t> node_seen(w.node_count, 0);
+    std::vector<std::pair<uint32_t, uint32_t>> wide_range(w.node_count, {0u, 0u});
+    uint32_t children = 0;
+    // wide nodes are numbered parents first, so walking the numbers downwards sees children before parents
+    for (uint32_t i = w.node_count; i-- > 0;) {
+        const mesh::float4_t* n = &w.nodes[static_cast<size_t>(i) * mesh::k_wide_node_float4];
+        uint32_t first = 0, count = 0;
+        bool gap = false;
+        for (uint32_t c = 0; c < mesh::k_wide; c++) {
+            uint32_t ref;
+            std::memcpy(&ref, &(&n[6].x)[c], 4);
+            const bool empty = (&n[0].x)[c] == mesh::k_nowhere;
+            if (empty) {
+                gap = true;
+                continue;
+            }
+            if (gap) bad++;  // occupied places come first
+            children++;
+            std::pair<uint32_t, uint32_t> r;
+            if ((ref & 7u) != 0u) {
+                r = {ref >> 3, ref & 7u};
+                for (uint32_t k = 0; k < r.second; k++) {
+                    if (r.first + k >= slot_seen.size() || slot_seen[r.first + k]++ != 0) bad++;
+                }
+            } else {
+                const uint32_t child = ref >> 3;
+                if (child <= i || child >= w.node_count || node_seen[child]++ != 0) {
+                    bad++;
+                    continue;
+                }
+                r = wide_range[child];
+            }
+            if (count != 0 && first + count != r.first) bad++;  // children in slot order, contiguous
+            if (count == 0) first = r.first;
+            count += r.second;
+            const auto found = by_range.find(r);
+            if (found == by_range.end()) {
+                bad++;
+                continue;
+            }
+            const mesh::node& b = s.nodes[found->second];
+            for (int a = 0; a < 3; a++) {
+                if ((&n[a].x)[c] != b.bmin[a] || (&n[3 + a].x)[c] != b.bmax[a]) bad++;
+            }
+            if (((ref & 7u) != 0u) != (b.count != 0)) bad++;
+        }
+        wide_range[i] = {first, count};
+    }
+    if (w.node_count != 0 && wide_range[0] != std::make_pair(0u, static_cast<uint32_t>(s.triangles.size()))) bad++;
+    for (uint8_t seen : slot_seen) bad += seen != 1;
+    for (uint32_t i = 1; i < w.node_count; i++) bad += node_seen[i] != 1;
+    if (children != w.children) bad++;
+    return bad;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
     const uint32_t grid = argc > 1 ? static_cast<uint32_t>(std::atoi(argv[1])) : 40u;
     const long rays = argc > 2 ? std::atol(argv[2]) : 200000;
+    const bool wide = argc > 3 && std::strcmp(argv[3], "wide") == 0;
     mesh::scene s;
     mesh::generate_triangles(grid, 1, s);
     mesh::build_bvh(s);
+    mesh::wide_tree w;
+    long structure = 0;
+    uint64_t visits = 0;
+    int high_water = 0;
+    if (wide) {
+        const uint32_t stack_limit = argc > 4 ? static_cast<uint32_t>(std::atoi(argv[4])) : 31u;
+        w = mesh::collapse_wide(s, stack_limit);
+        structure = check_wide_structure(s, w) + (w.stack_need > stack_limit);
+        std::printf("wide tree: %u nodes (binary: %zu, %zu interior), %.2f children per node, depth %u (binary %u), stack bound %u, "
+                    "structure violations %ld\n",
+                    w.node_count, s.nodes.size(), s.nodes.size() / 2, static_cast<double>(w.children) / w.node_count, w.depth,
+                    s.depth, w.stack_need, structure);
+    }
 
     std::mt19937 rng(11);
     std::uniform_real_distribution<float> uniform(0.0f, 1.0f);
@@ -167,7 +316,7 @@ int main(int argc, char** argv) {
         if (!(len > 0.0f)) continue;
         d = {d.x / len, d.y / len, d.z / len};
         const hit want = brute_force(s, o, d);
-        const hit got = through_the_tree(s, o, d, boxes);
+        const hit got = wide ? through_the_wide_tree(s, w, o, d, boxes, visits, high_water) : through_the_tree(s, o, d, boxes);
         hits += want.prim != 0xffffffffu;
         if (got.prim != want.prim || got.t != want.t) {
             if (mismatches < 10) {
@@ -178,5 +327,10 @@ int main(int argc, char** argv) {
         }
     }
     std::printf("rays %ld hits %ld boxes_per_ray %.1f mismatches %ld\n", rays, hits, static_cast<double>(boxes) / rays, mismatches);
-    return mismatches == 0 ? 0 : 1;
+    if (wide) {
+        std::printf("wide visits_per_ray %.1f deepest stack %d (bound %u)\n", static_cast<double>(visits) / rays, high_water,
+                    w.stack_need);
+        if (high_water > static_cast<int>(w.stack_need)) structure++;
+    }
+    return mismatches == 0 && structure == 0 ? 0 : 1;
 }

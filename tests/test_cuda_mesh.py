@@ -1,6 +1,7 @@
 """BASELINE config 3 on the GPU: the mesh path tracer (BVH traversal kernel) through the
 plugin C ABI against oracle/quasi_oracle_mesh.c. Bit-exact, like the quad scene."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -11,16 +12,16 @@ from oracle_lib import MeshOracle, bits
 pytestmark = pytest.mark.gpu
 
 
-def mesh_host(width, height, grid, bounces=4, seed=1, builder="sah"):
+def mesh_host(width, height, grid, bounces=4, seed=1, builder="sah", wide=0):
     from quasi_b200.headless import headless_host
 
     return headless_host(width, height, env={"QUASI_CUDA_SCENE": "mesh", "QUASI_CUDA_MESH_GRID": grid,
                                              "QUASI_CUDA_MESH_SEED": seed, "QUASI_CUDA_MAX_BOUNCES": bounces,
-                                             "QUASI_CUDA_MESH_BUILDER": builder})
+                                             "QUASI_CUDA_MESH_BUILDER": builder, "QUASI_CUDA_MESH_WIDE": wide})
 
 
-def render(width, height, frames, grid, bounces=4, builder="sah"):
-    h = mesh_host(width, height, grid, bounces, builder=builder)
+def render(width, height, frames, grid, bounces=4, builder="sah", wide=0):
+    h = mesh_host(width, height, grid, bounces, builder=builder, wide=wide)
     h.render(frames)
     layers = h.readback_aov()
     stats = h.stats()
@@ -97,6 +98,26 @@ def test_gpu_built_bvh_renders_the_oracle_image(grid, size, frames):
     tree; the closest hit does not depend on the tree, so the image is the same bits."""
     w, h = size
     got, stats = render(w, h, frames, grid, builder="lbvh")
+    want, st = MeshOracle(grid).render_frames(w, h, frames, max_bounces=4, use_bvh=True)
+    assert_bit_exact(got, want)
+    assert stats.rays == st["rays"]
+    assert stats.nodes_visited > 0 and stats.triangles_tested > 0
+
+
+WIDE_VERIFIED_ON_GPU = False  # set once a B200 run of these cases has been seen to pass (DESIGN.md 4.3)
+
+
+@pytest.mark.skipif(not WIDE_VERIFIED_ON_GPU and os.environ.get("QUASI_TEST_WIDE") != "1",
+                    reason="the 4-wide form has only been checked on the host so far; QUASI_TEST_WIDE=1 runs it")
+@pytest.mark.parametrize("grid,size,frames,builder", [(1, (64, 36), 2, "sah"), (3, (64, 36), 2, "sah"),
+                                                      (24, (160, 90), 3, "sah"), (100, (97, 61), 2, "sah"),
+                                                      (100, (97, 61), 2, "lbvh"), (707, (480, 270), 2, "sah")])
+def test_wide_tree_renders_the_oracle_image(grid, size, frames, builder):
+    """QUASI_CUDA_MESH_WIDE=1: the kernel walks the 4-wide tree collapsed from the binary one
+    (wide_bvh.hpp); it prunes what the binary tree prunes, so the image is the same bits, from
+    either builder's tree."""
+    w, h = size
+    got, stats = render(w, h, frames, grid, builder=builder, wide=1)
     want, st = MeshOracle(grid).render_frames(w, h, frames, max_bounces=4, use_bvh=True)
     assert_bit_exact(got, want)
     assert stats.rays == st["rays"]
