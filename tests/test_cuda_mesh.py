@@ -1,7 +1,6 @@
 """BASELINE config 3 on the GPU: the mesh path tracer (BVH traversal kernel) through the
 plugin C ABI against oracle/quasi_oracle_mesh.c. Bit-exact, like the quad scene."""
 import ctypes as C
-import os
 
 import numpy as np
 import pytest
@@ -104,11 +103,6 @@ def test_gpu_built_bvh_renders_the_oracle_image(grid, size, frames):
     assert stats.nodes_visited > 0 and stats.triangles_tested > 0
 
 
-WIDE_VERIFIED_ON_GPU = False  # set once a B200 run of these cases has been seen to pass
-
-
-@pytest.mark.skipif(not WIDE_VERIFIED_ON_GPU and os.environ.get("QUASI_TEST_WIDE") != "1",
-                    reason="the 4-wide form has only been checked on the host so far; QUASI_TEST_WIDE=1 runs it")
 @pytest.mark.parametrize("grid,size,frames,builder", [(1, (64, 36), 2, "sah"), (3, (64, 36), 2, "sah"),
                                                       (24, (160, 90), 3, "sah"), (100, (97, 61), 2, "sah"),
                                                       (100, (97, 61), 2, "lbvh"), (707, (480, 270), 2, "sah")])

@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--json", default=None)
     ap.add_argument("--builder", choices=["sah", "lbvh"], default="sah",
                     help="BVH builder: binned SAH on the host (default) or LBVH on the GPU")
+    ap.add_argument("--wide", type=int, default=0, help="1: the kernel walks the 4-wide tree (QUASI_CUDA_MESH_WIDE); 2: both forms, one after the other")
     ap.add_argument("--plugin", default=None, help="path of a libquasi_cuda.so build to measure")
     args = ap.parse_args()
 
@@ -39,11 +40,20 @@ def main():
 
     import quasi_b200
 
+    results = []
+    for wide in ([0, 1] if args.wide == 2 else [args.wide]):
+        results.append(measure(args, torch, headless_host, quasi_b200, wide))
+        print(json.dumps(results[-1]), flush=True)
+    if args.json:
+        Path(args.json).write_text(json.dumps(results[0] if len(results) == 1 else results, indent=1))
+
+
+def measure(args, torch, headless_host, quasi_b200, wide):
     host = headless_host(args.width, args.height, single_stream=True,
                          plugin_path=args.plugin or quasi_b200.PLUGIN_PATH,
                          env={"QUASI_CUDA_SCENE": "mesh", "QUASI_CUDA_MESH_GRID": args.grid,
                               "QUASI_CUDA_MESH_SEED": 1, "QUASI_CUDA_MAX_BOUNCES": args.bounces,
-                              "QUASI_CUDA_MESH_BUILDER": args.builder})
+                              "QUASI_CUDA_MESH_BUILDER": args.builder, "QUASI_CUDA_MESH_WIDE": wide})
     stream = host.context.frame_stream()
 
     def step():
@@ -76,12 +86,10 @@ def main():
         "nodes_per_ray": round(nodes / rays, 2), "triangles_per_ray": round(tris / rays, 2),
         "algorithmic_bytes_per_ray": round((nodes * 32 + tris * 48) / rays, 1),
         "algorithmic_gbs": round((nodes * 32 + tris * 48) / (ms * 1e-3) / 1e9, 1),
-        "messages": [m for m in host.messages if "esh" in m],
+        "wide": wide, "messages": [m for m in host.messages if "esh" in m],
     }
     host.close()
-    print(json.dumps(out))
-    if args.json:
-        Path(args.json).write_text(json.dumps(out, indent=1))
+    return out
 
 
 if __name__ == "__main__":
