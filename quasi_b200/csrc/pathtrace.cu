@@ -131,19 +131,19 @@ __device__ __forceinline__ void trace_scene(const scene_params& scene, const flo
     if constexpr (Layout::fixed) {
 #pragma unroll
         for (int i = Layout::begin_flat_y; i < Layout::begin_flat_y + Layout::flat_y; i++) {
-            scan_flat<1>(s, scene.quads[i], i, ro, rd);
+            scan_flat<1>(s, QUASI_SCAN_SOURCE(scene, i), i, ro, rd);
         }
 #pragma unroll
         for (int i = Layout::begin_upright; i < Layout::begin_upright + Layout::upright; i++) {
-            scan_upright(s, scene.quads[i], i, ro, rd);
+            scan_upright(s, QUASI_SCAN_SOURCE(scene, i), i, ro, rd);
         }
 #pragma unroll
         for (int i = Layout::begin_flat_x; i < Layout::begin_flat_x + Layout::flat_x; i++) {
-            scan_flat<0>(s, scene.quads[i], i, ro, rd);
+            scan_flat<0>(s, QUASI_SCAN_SOURCE(scene, i), i, ro, rd);
         }
 #pragma unroll
         for (int i = Layout::begin_flat_z; i < Layout::begin_flat_z + Layout::flat_z; i++) {
-            scan_flat<2>(s, scene.quads[i], i, ro, rd);
+            scan_flat<2>(s, QUASI_SCAN_SOURCE(scene, i), i, ro, rd);
         }
 #pragma unroll
         for (int i = Layout::begin_general; i < Layout::begin_general + Layout::general; i++) {
@@ -156,19 +156,19 @@ __device__ __forceinline__ void trace_scene(const scene_params& scene, const flo
         // Trip counts and table offsets are launch-uniform.
 #pragma unroll 1
         for (uint32_t i = scene.shape_begin[k_shape_flat_y]; i < scene.shape_begin[k_shape_flat_y + 1]; i++) {
-            scan_flat<1>(s, scene.quads[i], static_cast<int>(i), ro, rd);
+            scan_flat<1>(s, QUASI_SCAN_SOURCE(scene, i), static_cast<int>(i), ro, rd);
         }
 #pragma unroll 1
         for (uint32_t i = scene.shape_begin[k_shape_upright]; i < scene.shape_begin[k_shape_upright + 1]; i++) {
-            scan_upright(s, scene.quads[i], static_cast<int>(i), ro, rd);
+            scan_upright(s, QUASI_SCAN_SOURCE(scene, i), static_cast<int>(i), ro, rd);
         }
 #pragma unroll 1
         for (uint32_t i = scene.shape_begin[k_shape_flat_x]; i < scene.shape_begin[k_shape_flat_x + 1]; i++) {
-            scan_flat<0>(s, scene.quads[i], static_cast<int>(i), ro, rd);
+            scan_flat<0>(s, QUASI_SCAN_SOURCE(scene, i), static_cast<int>(i), ro, rd);
         }
 #pragma unroll 1
         for (uint32_t i = scene.shape_begin[k_shape_flat_z]; i < scene.shape_begin[k_shape_flat_z + 1]; i++) {
-            scan_flat<2>(s, scene.quads[i], static_cast<int>(i), ro, rd);
+            scan_flat<2>(s, QUASI_SCAN_SOURCE(scene, i), static_cast<int>(i), ro, rd);
         }
 #pragma unroll 1
         for (uint32_t i = scene.shape_begin[k_shape_general]; i < scene.shape_begin[k_shape_general + 1]; i++) {

@@ -85,6 +85,16 @@ QUASI_SCAN_FN void consider(scan_state& s, const quad_params& q, int i, float t_
     s.best_t = better ? t_fast : s.best_t;
     s.best_i = better ? i : s.best_i;
 }
+/// consider() with the two margins given as values (the packed-record forms below).
+QUASI_SCAN_FN void consider(scan_state& s, float half_plus, float half_minus, int i, float t_fast, float m, bool ahead) {
+    const bool maybe = ahead && m <= half_plus;
+    const bool sure = ahead && m < half_minus && t_fast > k_t_min_hi;
+    const bool better = sure && t_fast < s.best_t;
+    const float loser = better ? s.best_t : (maybe ? t_fast : k_inf);
+    s.challenger_t = std::fmin(s.challenger_t, loser);
+    s.best_t = better ? t_fast : s.best_t;
+    s.best_i = better ? i : s.best_i;
+}
 
 QUASI_SCAN_FN float axis(v3 a, int k) { return k == 0 ? a.x : (k == 1 ? a.y : a.z); }
 
@@ -106,6 +116,22 @@ QUASI_SCAN_FN void scan_flat(scan_state& s, const quad_params& q, int i, v3 ro, 
     consider(s, q, i, t_fast, std::fmax(std::fabs(alpha), std::fabs(beta)), ahead);
 }
 
+/// scan_flat<K> reading the packed record of the quad (scene_params.hpp:scan_record): the
+/// same operations on the same values.
+template <int K>
+QUASI_SCAN_FN void scan_flat(scan_state& s, const scan_record& q, int i, v3 ro, v3 rd) {
+    constexpr int I = (K + 1) % 3, J = (K + 2) % 3;
+    const float denom = q.r[0] * axis(rd, K);
+    const float num = q.r[1] - q.r[0] * axis(ro, K);
+    const float t_fast = num * rcp(denom);
+    const bool ahead = std::fabs(denom) >= 1e-8f && t_fast > k_t_min_lo;
+    const float pi = fma_rn(axis(rd, I), t_fast, axis(ro, I)) - q.r[2];
+    const float pj = fma_rn(axis(rd, J), t_fast, axis(ro, J)) - q.r[3];
+    const float alpha = fma_rn(pi, q.r[4], pj * q.r[5]);
+    const float beta = fma_rn(pi, q.r[6], pj * q.r[7]);
+    consider(s, q.r[8], q.r[9], i, t_fast, std::fmax(std::fabs(alpha), std::fabs(beta)), ahead);
+}
+
 /// Quad with a horizontal normal and one vertical edge (the side of a box
 /// standing on the floor): alpha lives in (x, z), beta along y.
 QUASI_SCAN_FN void scan_upright(scan_state& s, const quad_params& q, int i, v3 ro, v3 rd) {
@@ -119,6 +145,20 @@ QUASI_SCAN_FN void scan_upright(scan_state& s, const quad_params& q, int i, v3 r
     const float alpha = fma_rn(px, q.fast_a[0], pz * q.fast_a[2]);
     const float beta = py * q.fast_b[1];
     consider(s, q, i, t_fast, std::fmax(std::fabs(alpha), std::fabs(beta)), ahead);
+}
+
+/// scan_upright reading the packed record of the quad.
+QUASI_SCAN_FN void scan_upright(scan_state& s, const scan_record& q, int i, v3 ro, v3 rd) {
+    const float denom = q.r[0] * rd.x + q.r[1] * rd.z;
+    const float num = q.r[2] - (q.r[0] * ro.x + q.r[1] * ro.z);
+    const float t_fast = num * rcp(denom);
+    const bool ahead = std::fabs(denom) >= 1e-8f && t_fast > k_t_min_lo;
+    const float px = fma_rn(rd.x, t_fast, ro.x) - q.r[3];
+    const float py = fma_rn(rd.y, t_fast, ro.y) - q.r[4];
+    const float pz = fma_rn(rd.z, t_fast, ro.z) - q.r[5];
+    const float alpha = fma_rn(px, q.r[6], pz * q.r[7]);
+    const float beta = py * q.r[8];
+    consider(s, q.r[9], q.r[10], i, t_fast, std::fmax(std::fabs(alpha), std::fabs(beta)), ahead);
 }
 
 QUASI_SCAN_FN void scan_general(scan_state& s, const quad_params& q, int i, v3 ro, v3 rd) {
@@ -218,20 +258,28 @@ QUASI_SCAN_FN void scan_box(scan_state& s, const box_params& b, v3 ro, v3 rd) {
     s.best_i = better ? face : s.best_i;
 }
 
+/// What scan_flat and scan_upright read a quad from: its packed record with
+/// -DQUASI_SCAN_RECORDS=1, the quad_params fields otherwise. Same values either way.
+#if defined(QUASI_SCAN_RECORDS) && QUASI_SCAN_RECORDS
+#define QUASI_SCAN_SOURCE(scene, i) (scene).records[i]
+#else
+#define QUASI_SCAN_SOURCE(scene, i) (scene).quads[i]
+#endif
+
 /// The whole fast scan for any scene (one loop per shape with launch-uniform bounds, then
 /// the boxes). The kernel unrolls the same calls for the demo scene's layout.
 QUASI_SCAN_FN void scan_scene(scan_state& s, const scene_params& scene, v3 ro, v3 rd) {
     for (uint32_t i = scene.shape_begin[k_shape_flat_y]; i < scene.shape_begin[k_shape_flat_y + 1]; i++) {
-        scan_flat<1>(s, scene.quads[i], static_cast<int>(i), ro, rd);
+        scan_flat<1>(s, QUASI_SCAN_SOURCE(scene, i), static_cast<int>(i), ro, rd);
     }
     for (uint32_t i = scene.shape_begin[k_shape_upright]; i < scene.shape_begin[k_shape_upright + 1]; i++) {
-        scan_upright(s, scene.quads[i], static_cast<int>(i), ro, rd);
+        scan_upright(s, QUASI_SCAN_SOURCE(scene, i), static_cast<int>(i), ro, rd);
     }
     for (uint32_t i = scene.shape_begin[k_shape_flat_x]; i < scene.shape_begin[k_shape_flat_x + 1]; i++) {
-        scan_flat<0>(s, scene.quads[i], static_cast<int>(i), ro, rd);
+        scan_flat<0>(s, QUASI_SCAN_SOURCE(scene, i), static_cast<int>(i), ro, rd);
     }
     for (uint32_t i = scene.shape_begin[k_shape_flat_z]; i < scene.shape_begin[k_shape_flat_z + 1]; i++) {
-        scan_flat<2>(s, scene.quads[i], static_cast<int>(i), ro, rd);
+        scan_flat<2>(s, QUASI_SCAN_SOURCE(scene, i), static_cast<int>(i), ro, rd);
     }
     for (uint32_t i = scene.shape_begin[k_shape_general]; i < scene.shape_begin[k_shape_general + 1]; i++) {
         scan_general(s, scene.quads[i], static_cast<int>(i), ro, rd);

@@ -86,6 +86,20 @@ static_assert(sizeof(quad_params) == 224);
 inline constexpr uint32_t k_shade_offset = 32;  ///< first float of the shading group
 inline constexpr uint32_t k_shade_floats = 24;
 
+/// What the fast scan reads of one flat or upright quad, packed in the order it is used so
+/// that the constant bank is read with three 16-byte loads per quad instead of eight loads
+/// of 4 and 8 bytes (sm_100 has no constant operands for FP32 instructions: every constant
+/// costs an LDCU issue slot, and the scan of the demo scene is 126 of them per ray).
+/// The values are copies of quad_params fields, bit for bit (fill_scan_records):
+///   flat<K> (I, J the other two axes):
+///     {normal[K], plane_d, center[I], center[J]} {fast_a[I], fast_a[J], fast_b[I], fast_b[J]} {half_plus, half_minus}
+///   upright:
+///     {normal[0], normal[2], plane_d, center[0]} {center[1], center[2], fast_a[0], fast_a[2]} {fast_b[1], half_plus, half_minus}
+/// General quads are scanned from quad_params.
+struct alignas(16) scan_record {
+    float r[12];
+};
+
 inline constexpr uint32_t k_shape_count = 5;  ///< shapes the scan walks quad by quad (boxed faces are not among them)
 inline constexpr uint32_t k_max_boxes = 4;
 
@@ -131,6 +145,9 @@ struct alignas(16) scene_params {
     float corner_radius;    ///< farthest quad corner from the world origin
     uint32_t box_count;
     box_params boxes[k_max_boxes];
+#if defined(QUASI_SCAN_RECORDS) && QUASI_SCAN_RECORDS
+    scan_record records[k_max_quads];        ///< per position in `quads` (fill_scan_records); build-time option
+#endif
 };
 
 /// Per-call camera and sample bookkeeping.
@@ -465,6 +482,31 @@ inline void prepare_scene(const scene_desc& desc, uint32_t max_bounces, scene_pa
     }
 }
 
+/// @brief Copies what the scan reads of every flat and upright quad into scene.records.
+inline void fill_scan_records([[maybe_unused]] scene_params& scene) {
+#if defined(QUASI_SCAN_RECORDS) && QUASI_SCAN_RECORDS
+    for (uint32_t i = 0; i < scene.quad_count; i++) {
+        const quad_params& g = scene.quads[i];
+        float* r = scene.records[i].r;
+        for (int k = 0; k < 12; k++) r[k] = 0.0f;
+        int axis = -1;
+        if (g.shape == k_shape_flat_x) axis = 0;
+        if (g.shape == k_shape_flat_y) axis = 1;
+        if (g.shape == k_shape_flat_z) axis = 2;
+        if (axis >= 0) {
+            const int a = (axis + 1) % 3, b = (axis + 2) % 3;
+            const float packed[10] = {g.normal[axis], g.plane_d, g.center[a], g.center[b], g.fast_a[a],
+                                      g.fast_a[b],    g.fast_b[a], g.fast_b[b], g.half_plus, g.half_minus};
+            for (int k = 0; k < 10; k++) r[k] = packed[k];
+        } else if (g.shape == k_shape_upright || g.shape == k_shape_boxed) {
+            const float packed[11] = {g.normal[0], g.normal[2], g.plane_d,   g.center[0], g.center[1],  g.center[2],
+                                      g.fast_a[0], g.fast_a[2], g.fast_b[1], g.half_plus, g.half_minus};
+            for (int k = 0; k < 11; k++) r[k] = packed[k];
+        }
+    }
+#endif
+}
+
 /// @brief Sets the per-quad decision margin of the fast scan for a camera position.
 ///
 /// The fast scan decides "is the plane hit inside the quad" from
@@ -496,6 +538,7 @@ inline void set_decision_margins(scene_params& scene, const float camera_positio
         for (uint32_t f : faces) widest = std::fmax(widest, scene.quads[f].half_plus - 0.5f);
         b.delta = widest * b.edge_scale;
     }
+    fill_scan_records(scene);
 }
 
 /// @brief Camera block for one render call: plugin.mm:648-674 (host) followed by

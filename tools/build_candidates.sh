@@ -1,0 +1,10 @@
+#!/bin/bash
+# Builds the candidate libraries that have been checked on the host and by their SASS but not yet
+# timed on a GPU; `gpurun -- 'bash tools/gpu_quad_variants.sh'` then runs the
+# parity tests and the headline bench on each of them.
+set -e
+cd "$(dirname "$0")/.."
+bash tools/build_variant.sh scanrec -DQUASI_SCAN_RECORDS=1
+bash tools/build_variant.sh sincostab -DQUASI_SINCOS_TABLE=1
+bash tools/build_variant.sh scanrec_sincostab -DQUASI_SCAN_RECORDS=1 -DQUASI_SINCOS_TABLE=1
+ls -la quasi_b200/lib/variants/
