@@ -6,6 +6,9 @@
 #include "scene_params.hpp"
 
 #include <cuda_runtime_api.h>
+#if defined(QUASI_PDL) && QUASI_PDL
+#include <cuda_runtime.h>
+#endif
 
 #include <cstdint>
 
@@ -28,6 +31,26 @@ struct alignas(16) mesh_params {
     uint32_t wide;          ///< 1: `nodes` is the 4-wide tree and n_nodes counts its nodes
     float materials[k_mesh_materials * 8];  ///< per material: albedo.xyz, 0, emission.xyz, 0
 };
+
+/// Build-time option QUASI_PDL: launches `kernel` on `stream` as a programmatic dependent of
+/// the kernel before it on that stream (device_common.cuh:pdl_wait).
+#if defined(QUASI_PDL) && QUASI_PDL
+template <class... Params, class... Args>
+cudaError_t launch_persistent(void (*kernel)(Params...), uint32_t blocks, uint32_t threads, size_t dynamic_smem,
+                              cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t config{};
+    config.gridDim = dim3(blocks);
+    config.blockDim = dim3(threads);
+    config.dynamicSmemBytes = dynamic_smem;
+    config.stream = stream;
+    cudaLaunchAttribute attribute{};
+    attribute.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attribute.val.programmaticStreamSerializationAllowed = 1;
+    config.attrs = &attribute;
+    config.numAttrs = 1;
+    return cudaLaunchKernelEx(&config, kernel, Params(args)...);
+}
+#endif
 
 /// @brief One new sample per pixel, folded into the four accumulated layers in place.
 /// @param layers Device pointers to beauty, albedo, normal, depth (RGBA32F, row 0 = top).

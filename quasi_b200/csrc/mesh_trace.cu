@@ -196,12 +196,14 @@ mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_co
                       float4* __restrict__ beauty, float4* __restrict__ albedo, float4* __restrict__ normal,
                       float4* __restrict__ depth, unsigned long long* __restrict__ counters,
                       unsigned int* __restrict__ tile_counters) {
+    pdl_launch_dependents();
     extern __shared__ uint32_t s_refs[];  // [k_mesh_stack_entries][k_block_threads], then the uint16 distances
     __shared__ float s_material[k_mesh_materials * 8];
     for (int i = threadIdx.x; i < static_cast<int>(k_mesh_materials) * 8; i += k_block_threads) {
         s_material[i] = scene.materials[i];
     }
     __syncthreads();
+    pdl_wait();  // layers, tile queue and counters belong to the previous launch until here
     lane_stack stack;
     stack.refs = s_refs + threadIdx.x;
     stack.dist = reinterpret_cast<uint16_t*>(s_refs + k_mesh_stack_entries * k_block_threads) + threadIdx.x;
@@ -452,6 +454,12 @@ cudaError_t launch_mesh_pathtrace(const mesh_params& scene, const frame_params& 
                              static_cast<int>(k_stack_bytes))};
     if (attr[0] != cudaSuccess) return attr[0];
     if (attr[1] != cudaSuccess) return attr[1];
+#if defined(QUASI_PDL) && QUASI_PDL
+    return launch_persistent(kernel, blocks, k_block_threads, k_stack_bytes, stream, scene, frame,
+                             reinterpret_cast<float4*>(layers[0]), reinterpret_cast<float4*>(layers[1]),
+                             reinterpret_cast<float4*>(layers[2]), reinterpret_cast<float4*>(layers[3]), counters,
+                             tile_counters);
+#endif
     kernel<<<blocks, k_block_threads, k_stack_bytes, stream>>>(
         scene, frame, reinterpret_cast<float4*>(layers[0]), reinterpret_cast<float4*>(layers[1]),
         reinterpret_cast<float4*>(layers[2]), reinterpret_cast<float4*>(layers[3]), counters, tile_counters);

@@ -210,6 +210,7 @@ pathtrace_accumulate_kernel(const __grid_constant__ scene_params scene,
                             float4* __restrict__ albedo, float4* __restrict__ normal,
                             float4* __restrict__ depth, unsigned long long* __restrict__ ray_counter,
                             unsigned int* __restrict__ tile_counters) {
+    pdl_launch_dependents();
     __shared__ float s_shade[NQ * k_shade_stride];
     for (int idx = threadIdx.x; idx < NQ * static_cast<int>(k_shade_floats); idx += k_block_threads) {
         const int qi = idx / static_cast<int>(k_shade_floats);
@@ -218,6 +219,7 @@ pathtrace_accumulate_kernel(const __grid_constant__ scene_params scene,
             reinterpret_cast<const float*>(&scene.quads[qi])[k_shade_offset + k];
     }
     __syncthreads();
+    pdl_wait();  // layers, tile queue and counters belong to the previous launch until here
 
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lanes_below = (1u << lane) - 1u;
@@ -415,6 +417,18 @@ cudaError_t launch_pathtrace_accumulate(const scene_params& scene, const frame_p
     auto* a = reinterpret_cast<float4*>(layers[1]);
     auto* n = reinterpret_cast<float4*>(layers[2]);
     auto* d = reinterpret_cast<float4*>(layers[3]);
+#if defined(QUASI_PDL) && QUASI_PDL
+    if (!generic_scan && cornell_layout::matches(scene)) {
+        return launch_persistent(pathtrace_accumulate_kernel<16, cornell_layout>, blocks, k_block_threads, 0, stream, scene,
+                                 frame, b, a, n, d, ray_counter, tile_counters);
+    }
+    if (!generic_scan && cornell_quads_layout::matches(scene)) {
+        return launch_persistent(pathtrace_accumulate_kernel<16, cornell_quads_layout>, blocks, k_block_threads, 0, stream,
+                                 scene, frame, b, a, n, d, ray_counter, tile_counters);
+    }
+    return launch_persistent(pathtrace_accumulate_kernel<32, dynamic_layout>, blocks, k_block_threads, 0, stream, scene, frame,
+                             b, a, n, d, ray_counter, tile_counters);
+#endif
     if (!generic_scan && cornell_layout::matches(scene)) {
         pathtrace_accumulate_kernel<16, cornell_layout>
             <<<blocks, k_block_threads, 0, stream>>>(scene, frame, b, a, n, d, ray_counter, tile_counters);

@@ -114,6 +114,10 @@ struct plugin_state {
     unsigned long long* ray_counter = nullptr;
     cudaEvent_t last_render = nullptr;
     bool render_pending = false;
+#if defined(QUASI_PDL) && QUASI_PDL
+    cudaStream_t last_stream = nullptr;  ///< where the most recent render was enqueued
+    bool event_recorded = false;         ///< last_render has been recorded behind it
+#endif
 
     uint32_t frame_count = 0;
     uint32_t last_width = 0;
@@ -147,11 +151,28 @@ void free_layers(plugin_state* state) {
     for (auto& l : state->layers) l = nullptr;
 }
 
+#if defined(QUASI_PDL) && QUASI_PDL
+/// Build-time option QUASI_PDL (programmatic dependent launch, kernels.hpp): consecutive render
+/// kernels on one stream are launched so that the next one's CTAs may start their prologue
+/// while the previous one drains, which only works if no other stream operation sits between
+/// them. So the event that marks the end of a render is recorded when somebody needs it.
+void ensure_render_event(plugin_state* state) {
+    if (state->render_pending && !state->event_recorded) {
+        cudaEventRecord(state->last_render, state->last_stream);
+        state->event_recorded = true;
+    }
+}
+#define QUASI_RENDER_EVENT(state) ensure_render_event(state)
+#else
+#define QUASI_RENDER_EVENT(state) ((void)0)
+#endif
+
 /// Counterpart of create_textures (plugin.mm:491-535): four RGBA32F layers,
 /// accumulated in place, so one allocation of 64 B/px instead of twelve textures
 /// of 16 B/px. The layers are contiguous (beauty, albedo, normal, depth) so a
 /// multi-GPU host can reduce all four with a single collective.
 bool create_layers(plugin_state* state, uint32_t width, uint32_t height) {
+    QUASI_RENDER_EVENT(state);
     if (state->render_pending) cudaEventSynchronize(state->last_render);
     free_layers(state);
     size_t floats = static_cast<size_t>(width) * height * 4;
@@ -398,6 +419,10 @@ Q_aov_buffer download_layer(plugin_state* state, int layer) {
 
 /// Orders `stream` after the most recent render without blocking the host.
 void order_after_render(plugin_state* state, cudaStream_t stream) {
+#if defined(QUASI_PDL) && QUASI_PDL
+    if (state->render_pending && stream == state->last_stream) return;  // stream order does it
+    ensure_render_event(state);
+#endif
     if (state->render_pending) cudaStreamWaitEvent(stream, state->last_render, 0);
 }
 
@@ -504,6 +529,7 @@ Q_PLUGIN_EXPORT void Q_plugin_destroy(Q_plugin_handle* handle) {
     log_msg(state, "Path tracer destroyed");
 
     cudaSetDevice(state->device);
+    QUASI_RENDER_EVENT(state);
     if (state->render_pending) cudaEventSynchronize(state->last_render);
     cudaStreamSynchronize(state->queue);
     free_mesh(state);
@@ -584,7 +610,12 @@ Q_PLUGIN_EXPORT void Q_plugin_render(Q_plugin_handle* handle, Q_render_frame* fr
         }
     }
 
+#if defined(QUASI_PDL) && QUASI_PDL
+    state->last_stream = stream;
+    state->event_recorded = false;
+#else
     cudaEventRecord(state->last_render, stream);
+#endif
     state->render_pending = true;
 
     state->paths += static_cast<uint64_t>(width) * height;
@@ -658,6 +689,7 @@ Q_PLUGIN_EXPORT int Q_cuda_plugin_stats(Q_plugin_handle* handle, Q_cuda_stats* o
     if (!handle || !out) return -1;
     auto* state = reinterpret_cast<plugin_state*>(handle);
     if (cudaSetDevice(state->device) != cudaSuccess) return -1;
+    QUASI_RENDER_EVENT(state);
     if (state->render_pending) cudaEventSynchronize(state->last_render);
     unsigned long long counters[3] = {0, 0, 0};
     order_after_render(state, state->queue);
