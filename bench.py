@@ -235,7 +235,8 @@ def run_ours(args):
     ms_total = ev0.elapsed_time(ev1)
     s1 = host.stats()
     rays_local = s1.rays - s0.rays
-    launches_local = s1.kernel_launches - s0.kernel_launches + (reducer.launches - reducer_launches0 if reducer else 0)
+    render_launches_local = s1.kernel_launches - s0.kernel_launches
+    launches_local = render_launches_local + (reducer.launches - reducer_launches0 if reducer else 0)
 
     # ---- end to end through the public API with host buffers (e2e) ----
     def e2e_step():
@@ -276,7 +277,9 @@ def run_ours(args):
         value = rays_step / (ms_step * 1e-3) / 1e6
         e2e_value = rays_step / (e2e_s / args.steps) / 1e6
         peak, peak_src = measured_peaks()
-        kernel_ms = ms_step / SPP  # the step is SPP back-to-back launches of the one kernel (N=1)
+        # the step is back-to-back launches of the one kernel: SPP of them, or SPP / k under QUASI_CUDA_BATCH=k
+        launches_per_step = max(1.0, render_launches_local / args.steps)
+        kernel_ms = ms_step / launches_per_step
         achieved = ALGORITHMIC_BYTES_PER_PIXEL_PER_CALL * n_px / (kernel_ms * 1e-3) / 1e9
         traffic, issue_util = None, None
         summary = ROOT / "profiles" / "ncu_summary.json"
@@ -286,7 +289,7 @@ def run_ours(args):
                 traffic, issue_util = k.get("dram_bytes_per_launch"), k.get("issue_slot_utilization")
             except Exception:
                 traffic = None
-        param_bytes = SPP * (7856 + 80)  # sizeof(scene_params) + sizeof(frame_params) per launch
+        param_bytes = int(launches_per_step) * (7856 + 80)  # sizeof(scene_params) + sizeof(frame_params) per launch
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": "Mrays/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4),
@@ -296,6 +299,7 @@ def run_ours(args):
                 "workload": f"demo scene {WIDTH}x{HEIGHT}, {SPP} spp per GPU per frame "
                             f"({SPP * world} spp total), 5 bounces, 4 AOV layers, plugin C ABI",
                 "spp_per_gpu": SPP, "spp_total": SPP * world, "render_calls_per_step": SPP,
+                "launches_per_step": launches_per_step,
                 "parallelism": f"sample-sharded x{world}" + (
                     f", 1 {args.reduce} combine/frame (sum over ranks, 1/N scale, result on rank 0)"
                     if world > 1 else ""),

@@ -203,7 +203,12 @@ constexpr int k_block_threads = QUASI_QUAD_BLOCK_THREADS;
 constexpr int k_blocks_per_sm = QUASI_QUAD_BLOCKS_PER_SM;
 constexpr int k_warps_per_block = k_block_threads / 32;
 
-template <int NQ, class Layout>
+/// `Batch` (QUASI_CUDA_BATCH, plugin.cu): one launch gives every pixel frame.batch_samples
+/// consecutive samples instead of one. A lane that ends a path starts the next sample of the
+/// SAME pixel, so the samples of a pixel are accumulated in order by one thread (the running
+/// mean of plugin.mm:326 depends on the order) and its 64 bytes of history stay in L1/L2
+/// between them; launch ramp and drain are paid once per batch instead of once per sample.
+template <int NQ, class Layout, bool Batch = false>
 __global__ void __launch_bounds__(k_block_threads, k_blocks_per_sm)
 pathtrace_accumulate_kernel(const __grid_constant__ scene_params scene,
                             const __grid_constant__ frame_params frame, float4* __restrict__ beauty,
@@ -242,11 +247,77 @@ pathtrace_accumulate_kernel(const __grid_constant__ scene_params scene,
     // Where a continuing path scatters from: the quad it hit, complemented when it was hit
     // from behind. Set by the shading step, consumed at the top of the next iteration.
     int scatter = 0;
+    // Batch only: which sample of the launch this lane's path is, its pixel, and that sample's
+    // accumulation constants (first_sample / weight are per launch otherwise).
+    [[maybe_unused]] uint32_t sample_of_item = 0, pixel_xy = 0xffffffffu;
+    [[maybe_unused]] bool lane_first = first_sample;
+    [[maybe_unused]] float lane_weight = weight;
+    [[maybe_unused]] const uint32_t batch = frame.batch_samples > 1u ? frame.batch_samples : 1u;
 
     while (true) {
         // Regeneration: idle lanes take the warp's next pixels, compacted.
         bool fresh = false;
         float uv_x = 0.0f, uv_y = 0.0f;
+        if constexpr (Batch) {
+            // A lane whose path has ended goes on with the next sample of its pixel; only a lane
+            // that has given its pixel all its samples takes a new pixel from the queue.
+            bool start = false;
+            uint32_t px = 0, py = 0;
+            if (!active && pixel_xy != 0xffffffffu) {
+                if (sample_of_item + 1u < batch) {
+                    sample_of_item++;
+                    px = pixel_xy & 0xffffu;
+                    py = pixel_xy >> 16;
+                    start = true;
+                } else {
+                    pixel_xy = 0xffffffffu;
+                }
+            }
+            const uint32_t idle = __ballot_sync(0xffffffffu, !active && !start);
+            if (idle != 0u) {
+                feed.open(next_item, next_item + __popc(idle) - 1u);
+                if (!active && !start) {
+                    const uint32_t item = next_item + __popc(idle & lanes_below);
+                    const uint32_t tile = feed.tile_of(item);
+                    if (tile < n_tiles) {
+                        uint32_t tile_y = __umulhi(tile, frame.tiles_x_magic);
+                        uint32_t tile_x = tile - tile_y * tiles_x;
+                        if (tile_x >= tiles_x) {
+                            tile_x -= tiles_x;
+                            tile_y++;
+                        }
+                        px = tile_x * 8u + (item & 7u);
+                        py = tile_y * 4u + ((item >> 3) & 3u);
+                        if (px < frame.width && py < frame.height) {
+                            pixel_xy = px | (py << 16);  // the ABI's sizes are far below 65536
+                            sample_of_item = 0;
+                            start = true;
+                            pixel = static_cast<size_t>(py) * frame.width + px;
+                            if (!first_sample) {
+                                prefetch_l2(beauty + pixel);
+                                prefetch_l2(albedo + pixel);
+                                prefetch_l2(normal + pixel);
+                                prefetch_l2(depth + pixel);
+                            }
+                        }
+                    }
+                }
+                next_item += __popc(idle);
+            }
+            if (start) {
+                const uint32_t sample_index = frame.sample_index + sample_of_item;
+                uv_x = (static_cast<float>(px) + 0.5f) / static_cast<float>(frame.width);
+                uv_y = 1.0f - (static_cast<float>(py) + 0.5f) / static_cast<float>(frame.height);
+                rng = pcg_hash(px + py * 1920u + (frame.frame_index + sample_of_item * frame.frame_stride) * 1920u * 1080u);
+                fresh = true;
+                throughput = make_v3(1.0f, 1.0f, 1.0f);
+                color = make_v3(0.0f, 0.0f, 0.0f);
+                bounce = 0;
+                active = true;
+                lane_first = sample_index == 0u;
+                lane_weight = 1.0f / static_cast<float>(sample_index + 1u);  // scene_params.hpp:prepare_frame
+            }
+        } else {
         const uint32_t idle = __ballot_sync(0xffffffffu, !active);
         if (idle != 0u) {
             feed.open(next_item, next_item + __popc(idle) - 1u);
@@ -289,6 +360,7 @@ pathtrace_accumulate_kernel(const __grid_constant__ scene_params scene,
             }
             next_item += __popc(idle);
         }
+        }  // !Batch
         if (!__any_sync(0xffffffffu, active)) {
             if (feed.exhausted(next_item)) break;
             continue;  // only off-image pixels of an edge tile were handed out
@@ -348,9 +420,12 @@ pathtrace_accumulate_kernel(const __grid_constant__ scene_params scene,
                     first_t = hit.t;
                 }
                 const float nd = fminf(fmaxf((first_t - 1.0f) / 4.0f, 0.0f), 1.0f);
-                accumulate_pixel(albedo, pixel, make_float4(a.x, a.y, a.z, 1.0f), first_sample, weight);
-                accumulate_pixel(normal, pixel, make_float4(nn.x, nn.y, nn.z, 1.0f), first_sample, weight);
-                accumulate_pixel(depth, pixel, make_float4(nd, nd, nd, 1.0f), first_sample, weight);
+                accumulate_pixel(albedo, pixel, make_float4(a.x, a.y, a.z, 1.0f), Batch ? lane_first : first_sample,
+                                 Batch ? lane_weight : weight);
+                accumulate_pixel(normal, pixel, make_float4(nn.x, nn.y, nn.z, 1.0f), Batch ? lane_first : first_sample,
+                                 Batch ? lane_weight : weight);
+                accumulate_pixel(depth, pixel, make_float4(nd, nd, nd, 1.0f), Batch ? lane_first : first_sample,
+                                 Batch ? lane_weight : weight);
             }
 
             bool done = !is_hit;
@@ -377,7 +452,7 @@ pathtrace_accumulate_kernel(const __grid_constant__ scene_params scene,
                 scatter = hit.front ? hit.index : ~hit.index;  // the direction is drawn at the top
             } else {
                 accumulate_pixel(beauty, pixel, make_float4(color.x, color.y, color.z, 1.0f),
-                                 first_sample, weight);
+                                 Batch ? lane_first : first_sample, Batch ? lane_weight : weight);
                 active = false;
             }
         }
@@ -429,6 +504,19 @@ cudaError_t launch_pathtrace_accumulate(const scene_params& scene, const frame_p
     return launch_persistent(pathtrace_accumulate_kernel<32, dynamic_layout>, blocks, k_block_threads, 0, stream, scene, frame,
                              b, a, n, d, ray_counter, tile_counters);
 #endif
+    if (frame.batch_samples > 1u) {  // QUASI_CUDA_BATCH: several samples per pixel in one launch
+        if (!generic_scan && cornell_layout::matches(scene)) {
+            pathtrace_accumulate_kernel<16, cornell_layout, true>
+                <<<blocks, k_block_threads, 0, stream>>>(scene, frame, b, a, n, d, ray_counter, tile_counters);
+        } else if (!generic_scan && cornell_quads_layout::matches(scene)) {
+            pathtrace_accumulate_kernel<16, cornell_quads_layout, true>
+                <<<blocks, k_block_threads, 0, stream>>>(scene, frame, b, a, n, d, ray_counter, tile_counters);
+        } else {
+            pathtrace_accumulate_kernel<32, dynamic_layout, true>
+                <<<blocks, k_block_threads, 0, stream>>>(scene, frame, b, a, n, d, ray_counter, tile_counters);
+        }
+        return cudaGetLastError();
+    }
     if (!generic_scan && cornell_layout::matches(scene)) {
         pathtrace_accumulate_kernel<16, cornell_layout>
             <<<blocks, k_block_threads, 0, stream>>>(scene, frame, b, a, n, d, ray_counter, tile_counters);

@@ -127,6 +127,15 @@ struct plugin_state {
     uint64_t kernel_launches = 0;
 
     bool generic_scan = false;  ///< QUASI_CUDA_SCAN=generic: the any-scene kernel
+
+    // QUASI_CUDA_BATCH=k (k > 1, demo scene, headless): render calls are collected and every k of
+    // them become ONE launch that gives each pixel k consecutive samples (pathtrace.cu, Batch).
+    // Anything that looks at the layers, and any call with another camera, size or stream,
+    // launches what has been collected first, so the only observable difference is time.
+    uint32_t batch = 1;
+    uint32_t pending = 0;              ///< render calls collected and not yet launched
+    uint32_t pending_first_sample = 0; ///< frame_count of the first of them
+    Q_render_frame pending_frame{};    ///< that call's frame (camera, size, stream)
     Q_cuda_persistent_state* persistent = nullptr;  ///< host-owned, Q_gpu_context::layer (may be null)
     uint32_t scene_tag = 0;
 };
@@ -426,6 +435,62 @@ void order_after_render(plugin_state* state, cudaStream_t stream) {
     if (state->render_pending) cudaStreamWaitEvent(stream, state->last_render, 0);
 }
 
+
+/// Launches the render calls collected under QUASI_CUDA_BATCH as one kernel. The arguments are
+/// the ones Q_plugin_render computes for a single call, for the first collected call; sample s of
+/// the launch is what the (s+1)-th collected call would have rendered.
+void flush_pending(plugin_state* state) {
+    if (state->pending == 0) return;
+    const Q_render_frame& f = state->pending_frame;
+    auto stream = static_cast<cudaStream_t>(f.command_buffer);
+    frame_params fp;
+    const uint32_t frame_index = state->shard_index + state->pending_first_sample * state->shard_count;
+    Q::cuda::prepare_frame(f.camera.position, f.camera.target, f.camera.up, f.camera.fov, f.width, f.height, frame_index,
+                           state->pending_first_sample, fp);
+    fp.batch_samples = state->pending;
+    fp.frame_stride = state->shard_count;
+    state->pending = 0;
+    Q::cuda::set_decision_margins(state->scene, f.camera.position);
+    order_after_render(state, stream);
+    auto* tile_counters = reinterpret_cast<unsigned int*>(state->ray_counter + 3);
+    if (!check(state, Q::cuda::launch_pathtrace_accumulate(state->scene, fp, state->layers, state->ray_counter, tile_counters,
+                                                          state->sm_count, stream, state->generic_scan),
+               "pathtrace_accumulate (batch)")) {
+        return;
+    }
+    state->kernel_launches++;
+#if defined(QUASI_PDL) && QUASI_PDL
+    state->last_stream = stream;
+    state->event_recorded = false;
+#else
+    cudaEventRecord(state->last_render, stream);
+#endif
+    state->render_pending = true;
+}
+
+/// Q_plugin_render under QUASI_CUDA_BATCH: the bookkeeping of one call (plugin.mm:637-646, 791),
+/// the launch deferred until `batch` calls with the same camera, size and stream have come in.
+void render_batched(plugin_state* state, const Q_render_frame* frame) {
+    const bool same_view = state->pending != 0 && frame->width == state->pending_frame.width &&
+                           frame->height == state->pending_frame.height &&
+                           frame->command_buffer == state->pending_frame.command_buffer && frame->camera_dirty == 0 &&
+                           std::memcmp(&frame->camera, &state->pending_frame.camera, sizeof frame->camera) == 0;
+    if (!same_view) flush_pending(state);
+    if (frame->width != state->last_width || frame->height != state->last_height) {
+        if (!create_layers(state, frame->width, frame->height)) return;
+    }
+    if (frame->width == 0 || frame->height == 0) return;
+    if (frame->camera_dirty) state->frame_count = 0;
+    if (state->pending == 0) {
+        state->pending_frame = *frame;
+        state->pending_first_sample = state->frame_count;
+    }
+    state->pending++;
+    state->paths += static_cast<uint64_t>(frame->width) * frame->height;
+    state->frame_count++;
+    if (state->pending >= state->batch) flush_pending(state);
+}
+
 }  // namespace
 
 extern "C" {
@@ -489,6 +554,7 @@ Q_PLUGIN_EXPORT Q_plugin_handle* Q_plugin_create(Q_plugin_context* ctx) {
         state->generic_scan = scan && std::strncmp(scan, "generic", 7) == 0;
         const bool group_boxes = scan && std::strstr(scan, "boxes") != nullptr;
         Q::cuda::prepare_scene(state->scene_desc, bounces, state->scene, group_boxes);
+        state->batch = env_u32("QUASI_CUDA_BATCH", 1, 1, 1024);
         const char* scene_name = std::getenv("QUASI_CUDA_SCENE");
         if (scene_name && std::strcmp(scene_name, "mesh") == 0) {
             state->use_mesh = true;
@@ -529,6 +595,7 @@ Q_PLUGIN_EXPORT void Q_plugin_destroy(Q_plugin_handle* handle) {
     log_msg(state, "Path tracer destroyed");
 
     cudaSetDevice(state->device);
+    flush_pending(state);
     QUASI_RENDER_EVENT(state);
     if (state->render_pending) cudaEventSynchronize(state->last_render);
     cudaStreamSynchronize(state->queue);
@@ -565,6 +632,12 @@ Q_PLUGIN_EXPORT void Q_plugin_render(Q_plugin_handle* handle, Q_render_frame* fr
     const auto* drawable = static_cast<const Q_cuda_drawable*>(frame->drawable);
 
     if (cudaSetDevice(state->device) != cudaSuccess) return;
+
+    if (state->batch > 1 && !state->use_mesh && !(drawable && drawable->pixels)) {
+        render_batched(state, frame);
+        return;
+    }
+    flush_pending(state);  // a call that presents, after headless ones that were being collected
 
     const uint32_t width = frame->width;
     const uint32_t height = frame->height;
@@ -628,6 +701,7 @@ Q_PLUGIN_EXPORT Q_readback_result Q_plugin_readback(Q_plugin_handle* handle) {
     if (!handle) return result;
     auto* state = reinterpret_cast<plugin_state*>(handle);
     if (cudaSetDevice(state->device) != cudaSuccess) return result;
+    flush_pending(state);
 
     order_after_render(state, state->queue);
     Q_aov_buffer buf = download_layer(state, Q_AOV_BEAUTY);
@@ -658,6 +732,7 @@ Q_PLUGIN_EXPORT Q_readback_aov_result Q_plugin_readback_aov(Q_plugin_handle* han
     if (!handle) return result;
     auto* state = reinterpret_cast<plugin_state*>(handle);
     if (cudaSetDevice(state->device) != cudaSuccess) return result;
+    flush_pending(state);
 
     order_after_render(state, state->queue);
     for (int i = 0; i < Q_AOV_COUNT; i++) result.buffers[i] = download_layer(state, i);
@@ -689,6 +764,7 @@ Q_PLUGIN_EXPORT int Q_cuda_plugin_stats(Q_plugin_handle* handle, Q_cuda_stats* o
     if (!handle || !out) return -1;
     auto* state = reinterpret_cast<plugin_state*>(handle);
     if (cudaSetDevice(state->device) != cudaSuccess) return -1;
+    flush_pending(state);
     QUASI_RENDER_EVENT(state);
     if (state->render_pending) cudaEventSynchronize(state->last_render);
     unsigned long long counters[3] = {0, 0, 0};
@@ -715,6 +791,7 @@ Q_PLUGIN_EXPORT int Q_cuda_plugin_layers(Q_plugin_handle* handle, void* stream,
     if (!handle || !out) return -1;
     auto* state = reinterpret_cast<plugin_state*>(handle);
     if (cudaSetDevice(state->device) != cudaSuccess) return -1;
+    flush_pending(state);
     order_after_render(state, static_cast<cudaStream_t>(stream));
     std::memset(out, 0, sizeof *out);
     for (int i = 0; i < Q_AOV_COUNT; i++) out->device_ptr[i] = state->layers[i];

@@ -162,7 +162,8 @@ struct alignas(16) frame_params {
     uint32_t frame_index;  ///< RNG frame index                   (plugin.mm:295)
     uint32_t sample_index; ///< render calls since the last restart
     uint32_t tiles_x_magic; ///< floor(2^32 / ceil(width / 8)), for the kernel's tile -> (x, y)
-    uint32_t pad[2];
+    uint32_t batch_samples; ///< samples per pixel in this launch (0 or 1: one; QUASI_CUDA_BATCH)
+    uint32_t frame_stride;  ///< RNG frame index of sample s of the launch: frame_index + s * frame_stride
 };
 
 /// The scene as the host describes it: the same 12+8 floats per quad the Metal

@@ -362,3 +362,33 @@ def test_every_scan_variant_is_bit_exact(torch_cuda, oracle, scan):
     for name, g, wv in zip(LAYERS, got, want):
         assert np.array_equal(bits(g), bits(wv)), f"{scan}: {name}"
     assert stats.rays == rays
+
+
+@pytest.mark.skipif(__import__("os").environ.get("QUASI_TEST_BATCH") != "1",
+                    reason="QUASI_CUDA_BATCH has not run on a GPU yet (DESIGN.md section 9); QUASI_TEST_BATCH=1 runs it")
+@pytest.mark.parametrize("batch,frames,scan", [(4, 10, ""), (64, 64, ""), (3, 7, "boxes"), (8, 8, "generic")])
+def test_batched_launches_render_the_same_bits(torch_cuda, oracle, batch, frames, scan):
+    """QUASI_CUDA_BATCH=k collects render calls and gives every pixel k consecutive samples in one
+    launch (pathtrace.cu, Batch): full batches, a partial one flushed by the readback, and a
+    camera_dirty restart in the middle of a batch must all give the bits of call-by-call launches."""
+    from quasi_b200.headless import headless_host
+
+    w, h = 211, 119
+    host = headless_host(w, h, env={"QUASI_CUDA_BATCH": batch, "QUASI_CUDA_SCAN": scan})
+    host.render(frames)
+    got, stats = host.readback_aov(), host.stats()
+    want, rays = oracle.render_frames(oracle.scene(w, h), w, h, frames)
+    for name, g, wv in zip(LAYERS, got, want):
+        assert np.array_equal(bits(g), bits(wv)), f"batch {batch}: {name}"
+    assert stats.rays == rays
+    assert stats.kernel_launches == -(-frames // batch)
+    # restart in the middle of a batch: two calls, then a dirty camera, then three more
+    host.render_frame(camera_dirty=True)
+    host.render_frame(camera_dirty=False)
+    host.render_frame(camera_dirty=True)
+    host.render(2)
+    got = host.readback_aov()
+    host.close()
+    want3, _ = oracle.render_frames(oracle.scene(w, h), w, h, 3)
+    for name, g, wv in zip(LAYERS, got, want3):
+        assert np.array_equal(bits(g), bits(wv)), f"after restart: {name}"
