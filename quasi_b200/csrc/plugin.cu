@@ -130,8 +130,8 @@ struct plugin_state {
 
     // QUASI_CUDA_BATCH=k (k > 1, demo scene, headless): render calls are collected and every k of
     // them become ONE launch that gives each pixel k consecutive samples (pathtrace.cu, Batch).
-    // Anything that looks at the layers, and any call with another camera, size or stream,
-    // launches what has been collected first, so the only observable difference is time.
+    // Anything that looks at the layers, and any call with another camera or size, launches
+    // what has been collected first, so the only observable difference is time.
     uint32_t batch = 1;
     uint32_t pending = 0;              ///< render calls collected and not yet launched
     uint32_t pending_first_sample = 0; ///< frame_count of the first of them
@@ -471,9 +471,11 @@ void flush_pending(plugin_state* state) {
 /// Q_plugin_render under QUASI_CUDA_BATCH: the bookkeeping of one call (plugin.mm:637-646, 791),
 /// the launch deferred until `batch` calls with the same camera, size and stream have come in.
 void render_batched(plugin_state* state, const Q_render_frame* frame) {
+    // The stream may differ from call to call (a host with several frames in flight hands out one
+    // per frame): the launch goes to the stream of the last collected call, ordered after the
+    // previous launch by order_after_render like any call on a new stream.
     const bool same_view = state->pending != 0 && frame->width == state->pending_frame.width &&
-                           frame->height == state->pending_frame.height &&
-                           frame->command_buffer == state->pending_frame.command_buffer && frame->camera_dirty == 0 &&
+                           frame->height == state->pending_frame.height && frame->camera_dirty == 0 &&
                            std::memcmp(&frame->camera, &state->pending_frame.camera, sizeof frame->camera) == 0;
     if (!same_view) flush_pending(state);
     if (frame->width != state->last_width || frame->height != state->last_height) {
@@ -485,6 +487,7 @@ void render_batched(plugin_state* state, const Q_render_frame* frame) {
         state->pending_frame = *frame;
         state->pending_first_sample = state->frame_count;
     }
+    state->pending_frame.command_buffer = frame->command_buffer;
     state->pending++;
     state->paths += static_cast<uint64_t>(frame->width) * frame->height;
     state->frame_count++;
