@@ -636,7 +636,8 @@ Q_PLUGIN_EXPORT void Q_plugin_render(Q_plugin_handle* handle, Q_render_frame* fr
 
     if (cudaSetDevice(state->device) != cudaSuccess) return;
 
-    if (state->batch > 1 && !state->use_mesh && !(drawable && drawable->pixels)) {
+    if (state->batch > 1 && !state->use_mesh && !(drawable && drawable->pixels) && frame->width < 65536u &&
+        frame->height < 65536u) {  // the batched kernel keeps a lane's pixel as two 16-bit coordinates
         render_batched(state, frame);
         return;
     }
