@@ -1,5 +1,12 @@
 /// @file async.hpp
 /// @brief Umbrella header for the coroutine runtime.
+///
+/// Same role and names as /root/reference/src/quasi/async/async.hpp: lazy tasks (task.hpp), the
+/// single-threaded cooperative scheduler that the headless host ticks (scheduler.hpp), the
+/// awaitables (awaitables.hpp) and the polling file watcher behind hot reload
+/// (file_watcher.hpp). What waits for the GPU in this tree (gpu/cuda/context.hpp: a frame slot
+/// becoming free, wait_idle) is built on the same awaitables and polls cudaEventQuery, so a
+/// tick never blocks on the device.
 
 #pragma once
 
@@ -10,8 +17,7 @@
 
 namespace Q::async {
 
-inline constexpr int k_version_major = 0;
-inline constexpr int k_version_minor = 1;
-inline constexpr int k_version_patch = 0;
+// version of the coroutine module, as the reference numbers it
+inline constexpr int k_version_major = 0, k_version_minor = 1, k_version_patch = 0;
 
 }  // namespace Q::async
