@@ -464,6 +464,7 @@ pathtrace_accumulate_kernel(const __grid_constant__ scene_params scene,
     if (lane == 0 && rays != 0) atomicAdd(ray_counter, static_cast<unsigned long long>(rays));
 }
 
+#if !defined(QUASI_HOST_EMULATION)  // tests/cuda_emulation runs the kernel above on the host and has its own launcher
 __global__ void sincos_probe_kernel(const float* __restrict__ phi, float* __restrict__ sin_out,
                                     float* __restrict__ cos_out, uint64_t n) {
     const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -531,3 +532,7 @@ cudaError_t launch_pathtrace_accumulate(const scene_params& scene, const frame_p
 }
 
 }  // namespace Q::cuda
+#else
+}  // namespace
+}  // namespace Q::cuda
+#endif  // !QUASI_HOST_EMULATION

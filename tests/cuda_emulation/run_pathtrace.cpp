@@ -1,0 +1,74 @@
+// Runs the SOURCE of the quad path-tracing kernel (quasi_b200/csrc/pathtrace.cu) on the host under
+// tests/cuda_emulation/cuda_on_host.hpp and writes the four accumulated layers as raw binary32.
+//   usage: run_pathtrace WIDTH HEIGHT FRAMES BATCH SCAN OUT.bin
+//     BATCH  samples per launch (1 = one launch per frame, the default of the backend)
+//     SCAN   "quads" (kernel unrolled for the demo scene), "boxes" (blocks as slab tests), "generic"
+//   prints "rays N launches M"
+#define QUASI_HOST_EMULATION 1
+#include "cuda_on_host.hpp"
+
+#include "../../quasi_b200/csrc/pathtrace.cu"
+
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+
+using namespace Q::cuda;
+
+int main(int argc, char** argv) {
+    if (argc < 7) return 2;
+    const uint32_t width = static_cast<uint32_t>(std::atoi(argv[1])), height = static_cast<uint32_t>(std::atoi(argv[2]));
+    const uint32_t frames = static_cast<uint32_t>(std::atoi(argv[3])), batch = static_cast<uint32_t>(std::atoi(argv[4]));
+    const std::string scan = argv[5];
+
+    scene_desc desc = make_cornell_box();
+    static scene_params scene;
+    prepare_scene(desc, k_max_bounces, scene, scan == "boxes");
+    // the camera of the headless hosts (quasi_b200/cuda_context.py:orbit_camera, host/src/main.cpp)
+    const float position[3] = {0.0f, 1.0f, 3.5f}, target[3] = {0.0f, 1.0f, 0.0f}, up[3] = {0.0f, 1.0f, 0.0f};
+    set_decision_margins(scene, position);
+
+    const size_t n = static_cast<size_t>(width) * height;
+    std::vector<float4> layers[4];
+    for (auto& l : layers) l.assign(n, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+    unsigned long long rays = 0;
+    unsigned int tile_counters[2] = {0, 0};
+
+    const uint32_t n_tiles = ((width + 7u) / 8u) * ((height + 3u) / 4u);
+    const uint32_t needed = (n_tiles + k_warps_per_block - 1u) / k_warps_per_block;
+    const uint32_t grid = needed < 3u ? needed : 3u;  // a persistent grid smaller than the work, as on the device
+    uint32_t launches = 0;
+    for (uint32_t first = 0; first < frames; first += batch) {
+        frame_params frame;
+        prepare_frame(position, target, up, 40.0f, width, height, /*frame_index*/ first, /*sample_index*/ first, frame);
+        frame.batch_samples = std::min(batch, frames - first);
+        frame.frame_stride = 1;
+        auto run = [&](auto kernel) {
+            emu::launch(kernel, grid, k_block_threads, /*concurrent CTAs*/ 1u, scene, frame, layers[0].data(), layers[1].data(),
+                        layers[2].data(), layers[3].data(), &rays, tile_counters);
+        };
+        const bool batched = frame.batch_samples > 1u;
+        if (scan == "generic") {
+            batched ? run(pathtrace_accumulate_kernel<32, dynamic_layout, true>) : run(pathtrace_accumulate_kernel<32, dynamic_layout, false>);
+        } else if (scan == "boxes" && cornell_layout::matches(scene)) {
+            batched ? run(pathtrace_accumulate_kernel<16, cornell_layout, true>) : run(pathtrace_accumulate_kernel<16, cornell_layout, false>);
+        } else if (scan == "quads" && cornell_quads_layout::matches(scene)) {
+            batched ? run(pathtrace_accumulate_kernel<16, cornell_quads_layout, true>)
+                    : run(pathtrace_accumulate_kernel<16, cornell_quads_layout, false>);
+        } else {
+            std::fprintf(stderr, "scene does not match the layout of scan form %s\n", scan.c_str());
+            return 3;
+        }
+        launches++;
+        if (tile_counters[0] != 0u || tile_counters[1] != 0u) {
+            std::fprintf(stderr, "tile queue not reset after launch %u\n", launches);
+            return 4;
+        }
+    }
+    FILE* out = std::fopen(argv[6], "wb");
+    if (!out) return 5;
+    for (auto& l : layers) std::fwrite(l.data(), sizeof(float4), n, out);
+    std::fclose(out);
+    std::printf("rays %llu launches %u\n", rays, launches);
+    return 0;
+}

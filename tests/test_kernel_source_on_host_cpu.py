@@ -1,0 +1,74 @@
+"""The SOURCE of the quad path-tracing kernel (quasi_b200/csrc/pathtrace.cu with device_common.cuh,
+scan_decide.hpp, sincos_table.hpp) compiled by g++ and run on the host under a small warp/CTA
+emulator (tests/cuda_emulation/cuda_on_host.hpp: one std::thread per CUDA thread, barriers for
+__syncthreads and the warp collectives), against the CPU oracle, bit for bit.
+
+What this pins without a GPU: the control flow of the persistent kernel (device-wide tile queue,
+ballot/popc path regeneration, ragged edge tiles, the batched form in which a lane gives its pixel
+several consecutive samples) and the arithmetic of every build-time option, as written in the
+source. What it cannot say is what nvcc and ptxas make of that source; tests/test_cuda_parity.py
+does, on the device. The product never runs this way: the emulator lives under tests/."""
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT / "tests"))
+
+from oracle_lib import Oracle, bits  # noqa: E402
+
+LAYERS = ("beauty", "albedo", "normal", "depth")
+
+
+def build(tmp_path, flags):
+    exe = tmp_path / "run_pathtrace"
+    subprocess.run(["g++", "-std=c++20", "-O2", "-ffp-contract=off", "-pthread", "-I/usr/local/cuda/include",
+                    f"-I{ROOT / 'quasi_b200' / 'csrc'}", f"-I{ROOT / 'include'}", *flags,
+                    str(ROOT / "tests" / "cuda_emulation" / "run_pathtrace.cpp"), "-o", str(exe)], check=True)
+    return exe
+
+
+def check(exe, tmp_path, oracle, width, height, frames, batch, scan):
+    out = tmp_path / "layers.bin"
+    run = subprocess.run([str(exe), str(width), str(height), str(frames), str(batch), scan, str(out)],
+                         capture_output=True, text=True, timeout=600)
+    assert run.returncode == 0, run.stdout + run.stderr
+    words = run.stdout.split()
+    want, rays = oracle.render_frames(oracle.scene(width, height), width, height, frames)
+    got = np.fromfile(out, dtype=np.float32).reshape(4, height, width, 4)
+    for name, g, w in zip(LAYERS, got, want):
+        bad = int((bits(g) != bits(w)).any(axis=-1).sum())
+        assert bad == 0, f"{name}: {bad} pixels differ ({width}x{height}, {frames} frames, batch {batch}, {scan})"
+    assert int(words[words.index("rays") + 1]) == rays
+    assert int(words[words.index("launches") + 1]) == -(-frames // batch)
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    return Oracle()
+
+
+CASES = [(64, 36, 3, 1, "quads"), (61, 35, 5, 1, "boxes"), (97, 61, 2, 1, "generic"),     # one launch per frame
+         (64, 36, 7, 3, "quads"), (64, 36, 8, 8, "quads"), (61, 35, 5, 2, "boxes"),        # QUASI_CUDA_BATCH
+         (61, 35, 5, 4, "generic"), (9, 5, 6, 4, "quads")]
+
+
+def test_kernel_source_renders_the_oracle_image(tmp_path, oracle):
+    """The default build: every scan form, ragged sizes, and the batched form (full batches, a
+    partial last one, a batch as long as the run, an image smaller than two tiles)."""
+    exe = build(tmp_path, [])
+    for case in CASES:
+        check(exe, tmp_path, oracle, *case)
+
+
+@pytest.mark.parametrize("flags", [["-DQUASI_SCAN_RECORDS=1"], ["-DQUASI_SINCOS_LOOKUP=1"], ["-DQUASI_SINCOS_TABLE=1"],
+                                   ["-DQUASI_SCAN_RECORDS=1", "-DQUASI_SINCOS_LOOKUP=1"]],
+                         ids=["scan-records", "sincos-lookup", "sincos-table", "records+lookup"])
+def test_build_time_options_render_the_oracle_image(tmp_path, oracle, flags):
+    """The candidates of DESIGN.md section 9, each against the oracle in the plain and the batched form."""
+    exe = build(tmp_path, flags)
+    for case in [(64, 36, 4, 1, "quads"), (61, 35, 6, 4, "quads"), (61, 35, 3, 1, "generic"), (61, 35, 3, 1, "boxes")]:
+        check(exe, tmp_path, oracle, *case)
