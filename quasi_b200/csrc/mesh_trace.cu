@@ -197,7 +197,11 @@ mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_co
                       float4* __restrict__ depth, unsigned long long* __restrict__ counters,
                       unsigned int* __restrict__ tile_counters) {
     pdl_launch_dependents();
+#if defined(QUASI_HOST_EMULATION)  // tests/cuda_emulation: the dynamic shared memory of this CTA
+    uint32_t* s_refs = static_cast<uint32_t*>(emu::dynamic_shared());
+#else
     extern __shared__ uint32_t s_refs[];  // [k_mesh_stack_entries][k_block_threads], then the uint16 distances
+#endif
     __shared__ float s_material[k_mesh_materials * 8];
     for (int i = threadIdx.x; i < static_cast<int>(k_mesh_materials) * 8; i += k_block_threads) {
         s_material[i] = scene.materials[i];
@@ -438,6 +442,7 @@ mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_co
 
 }  // namespace
 
+#if !defined(QUASI_HOST_EMULATION)  // tests/cuda_emulation has its own launcher
 cudaError_t launch_mesh_pathtrace(const mesh_params& scene, const frame_params& frame, float* const layers[4],
                                   unsigned long long* counters, unsigned int* tile_counters, int sm_count,
                                   cudaStream_t stream) {
@@ -465,5 +470,7 @@ cudaError_t launch_mesh_pathtrace(const mesh_params& scene, const frame_params& 
         reinterpret_cast<float4*>(layers[2]), reinterpret_cast<float4*>(layers[3]), counters, tile_counters);
     return cudaGetLastError();
 }
+
+#endif  // !QUASI_HOST_EMULATION
 
 }  // namespace Q::cuda

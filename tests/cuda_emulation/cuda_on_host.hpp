@@ -28,9 +28,11 @@ struct warp_shared {
 };
 
 struct block_shared {
-    explicit block_shared(unsigned threads) : gate(threads), warps((threads + k_warp - 1) / k_warp) {}
+    explicit block_shared(unsigned threads, size_t dynamic_bytes = 0)
+        : gate(threads), warps((threads + k_warp - 1) / k_warp), dynamic((dynamic_bytes + 15) / 16 * 2, 0) {}
     std::barrier<> gate;
     std::vector<warp_shared> warps;
+    std::vector<uint64_t> dynamic;  ///< the CTA's dynamic shared memory
 };
 
 struct thread_context {
@@ -40,6 +42,7 @@ struct thread_context {
 };
 inline thread_local thread_context tls;
 
+inline void* dynamic_shared() { return tls.block->dynamic.data(); }
 inline warp_shared& my_warp() { return tls.block->warps[tls.thread_idx.x / k_warp]; }
 inline unsigned my_lane() { return tls.thread_idx.x % k_warp; }
 
@@ -56,12 +59,13 @@ inline auto exchange(uint32_t mine, F&& reduce) {
 
 /// Runs `kernel(args...)` as grid x block threads, `concurrent_blocks` CTAs at a time.
 template <class Kernel, class... Args>
-void launch(Kernel kernel, unsigned grid, unsigned block, unsigned concurrent_blocks, Args... args) {
+void launch_with_shared(Kernel kernel, unsigned grid, unsigned block, unsigned concurrent_blocks, size_t dynamic_bytes,
+                        Args... args) {
     for (unsigned first = 0; first < grid; first += concurrent_blocks) {
         const unsigned n_blocks = std::min(concurrent_blocks, grid - first);
         std::vector<std::unique_ptr<block_shared>> shared;
         std::vector<std::thread> threads;
-        for (unsigned b = 0; b < n_blocks; b++) shared.push_back(std::make_unique<block_shared>(block));
+        for (unsigned b = 0; b < n_blocks; b++) shared.push_back(std::make_unique<block_shared>(block, dynamic_bytes));
         for (unsigned b = 0; b < n_blocks; b++) {
             for (unsigned t = 0; t < block; t++) {
                 threads.emplace_back([=, &shared] {
@@ -76,6 +80,11 @@ void launch(Kernel kernel, unsigned grid, unsigned block, unsigned concurrent_bl
         }
         for (auto& th : threads) th.join();
     }
+}
+
+template <class Kernel, class... Args>
+void launch(Kernel kernel, unsigned grid, unsigned block, unsigned concurrent_blocks, Args... args) {
+    launch_with_shared(kernel, grid, block, concurrent_blocks, size_t{0}, args...);
 }
 
 }  // namespace emu
@@ -116,10 +125,22 @@ inline uint32_t __reduce_add_sync(unsigned, uint32_t value) {
     });
 }
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
+inline int max(int a, int b) { return a > b ? a : b; }
+inline int min(int a, int b) { return a < b ? a : b; }
 inline unsigned __umulhi(unsigned a, unsigned b) { return static_cast<unsigned>((static_cast<uint64_t>(a) * b) >> 32); }
 inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
 inline float __fmul_rn(float a, float b) { return a * b; }
 inline float __uint2float_rn(unsigned x) { return static_cast<float>(x); }
+inline unsigned __float_as_uint(float x) {
+    unsigned u;
+    std::memcpy(&u, &x, sizeof u);
+    return u;
+}
+inline float __uint_as_float(unsigned u) {
+    float x;
+    std::memcpy(&x, &u, sizeof x);
+    return x;
+}
 template <class T>
 inline T __ldg(const T* p) { return *p; }
 inline unsigned atomicAdd(unsigned* p, unsigned v) { return std::atomic_ref<unsigned>(*p).fetch_add(v); }

@@ -18,16 +18,16 @@ import pytest
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT / "tests"))
 
-from oracle_lib import Oracle, bits  # noqa: E402
+from oracle_lib import MeshOracle, Oracle, bits  # noqa: E402
 
 LAYERS = ("beauty", "albedo", "normal", "depth")
 
 
-def build(tmp_path, flags):
-    exe = tmp_path / "run_pathtrace"
+def build(tmp_path, flags, harness="run_pathtrace"):
+    exe = tmp_path / harness
     subprocess.run(["g++", "-std=c++20", "-O2", "-ffp-contract=off", "-pthread", "-I/usr/local/cuda/include",
                     f"-I{ROOT / 'quasi_b200' / 'csrc'}", f"-I{ROOT / 'include'}", *flags,
-                    str(ROOT / "tests" / "cuda_emulation" / "run_pathtrace.cpp"), "-o", str(exe)], check=True)
+                    str(ROOT / "tests" / "cuda_emulation" / f"{harness}.cpp"), "-o", str(exe)], check=True)
     return exe
 
 
@@ -72,3 +72,23 @@ def test_build_time_options_render_the_oracle_image(tmp_path, oracle, flags):
     exe = build(tmp_path, flags)
     for case in [(64, 36, 4, 1, "quads"), (61, 35, 6, 4, "quads"), (61, 35, 3, 1, "generic"), (61, 35, 3, 1, "boxes")]:
         check(exe, tmp_path, oracle, *case)
+
+
+def test_mesh_kernel_source_renders_the_mesh_oracle_image(tmp_path):
+    """mesh_trace.cu the same way (per-lane state machines, shared-memory stacks, descent runs and
+    triangle batches voted by the warp), on the binary tree and on the 4-wide tree collapsed from it,
+    against oracle/quasi_oracle_mesh.c."""
+    exe = build(tmp_path, [], harness="run_mesh")
+    for grid, width, height, frames in ((3, 64, 36, 2), (24, 80, 45, 2)):
+        want, stats = MeshOracle(grid).render_frames(width, height, frames, max_bounces=4, use_bvh=True)
+        for wide in (0, 1):
+            out = tmp_path / "layers.bin"
+            run = subprocess.run([str(exe), str(grid), str(width), str(height), str(frames), str(wide), str(out)],
+                                 capture_output=True, text=True, timeout=900)
+            assert run.returncode == 0, run.stdout + run.stderr
+            got = np.fromfile(out, dtype=np.float32).reshape(4, height, width, 4)
+            for name, g, w in zip(LAYERS, got, want):
+                bad = int((bits(g) != bits(w)).any(axis=-1).sum())
+                assert bad == 0, f"{name}: {bad} pixels differ (grid {grid}, wide {wide})"
+            words = run.stdout.split()
+            assert int(words[words.index("rays") + 1]) == stats["rays"]
