@@ -128,7 +128,7 @@ struct plugin_state {
 
     bool generic_scan = false;  ///< QUASI_CUDA_SCAN=generic: the any-scene kernel
 
-    // QUASI_CUDA_BATCH=k (k > 1, demo scene, headless): render calls are collected and every k of
+    // QUASI_CUDA_BATCH=k (k > 1, headless): render calls are collected and every k of
     // them become ONE launch that gives each pixel k consecutive samples (pathtrace.cu, Batch).
     // Anything that looks at the layers, and any call with another camera or size, launches
     // what has been collected first, so the only observable difference is time.
@@ -453,11 +453,12 @@ void flush_pending(plugin_state* state) {
     Q::cuda::set_decision_margins(state->scene, f.camera.position);
     order_after_render(state, stream);
     auto* tile_counters = reinterpret_cast<unsigned int*>(state->ray_counter + 3);
-    if (!check(state, Q::cuda::launch_pathtrace_accumulate(state->scene, fp, state->layers, state->ray_counter, tile_counters,
-                                                          state->sm_count, stream, state->generic_scan),
-               "pathtrace_accumulate (batch)")) {
-        return;
-    }
+    const cudaError_t launched =
+        state->use_mesh ? Q::cuda::launch_mesh_pathtrace(state->mesh_device, fp, state->layers, state->ray_counter,
+                                                         tile_counters, state->sm_count, stream)
+                        : Q::cuda::launch_pathtrace_accumulate(state->scene, fp, state->layers, state->ray_counter,
+                                                               tile_counters, state->sm_count, stream, state->generic_scan);
+    if (!check(state, launched, "pathtrace_accumulate (batch)")) return;
     state->kernel_launches++;
 #if defined(QUASI_PDL) && QUASI_PDL
     state->last_stream = stream;
@@ -636,7 +637,7 @@ Q_PLUGIN_EXPORT void Q_plugin_render(Q_plugin_handle* handle, Q_render_frame* fr
 
     if (cudaSetDevice(state->device) != cudaSuccess) return;
 
-    if (state->batch > 1 && !state->use_mesh && !(drawable && drawable->pixels) && frame->width < 65536u &&
+    if (state->batch > 1 && !(drawable && drawable->pixels) && frame->width < 65536u &&
         frame->height < 65536u) {  // the batched kernel keeps a lane's pixel as two 16-bit coordinates
         render_batched(state, frame);
         return;

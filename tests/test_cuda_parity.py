@@ -392,3 +392,22 @@ def test_batched_launches_render_the_same_bits(torch_cuda, oracle, batch, frames
     want3, _ = oracle.render_frames(oracle.scene(w, h), w, h, 3)
     for name, g, wv in zip(LAYERS, got, want3):
         assert np.array_equal(bits(g), bits(wv)), f"after restart: {name}"
+
+
+@pytest.mark.skipif(__import__("os").environ.get("QUASI_TEST_BATCH") != "1",
+                    reason="QUASI_CUDA_BATCH has not run on a GPU yet (DESIGN.md section 9); QUASI_TEST_BATCH=1 runs it")
+@pytest.mark.parametrize("wide", [0, 1])
+def test_batched_launches_of_the_mesh_scene_render_the_same_bits(torch_cuda, wide):
+    from oracle_lib import MeshOracle
+    from quasi_b200.headless import headless_host
+
+    grid, w, h, frames = 24, 160, 90, 7
+    host = headless_host(w, h, env={"QUASI_CUDA_SCENE": "mesh", "QUASI_CUDA_MESH_GRID": grid, "QUASI_CUDA_MESH_SEED": 1,
+                                    "QUASI_CUDA_MAX_BOUNCES": 4, "QUASI_CUDA_MESH_WIDE": wide, "QUASI_CUDA_BATCH": 3})
+    host.render(frames)
+    got, stats = host.readback_aov(), host.stats()
+    host.close()
+    want, st = MeshOracle(grid).render_frames(w, h, frames, max_bounces=4, use_bvh=True)
+    for name, g, wv in zip(LAYERS, got, want):
+        assert np.array_equal(bits(g), bits(wv)), f"mesh batch: {name}"
+    assert stats.rays == st["rays"] and stats.kernel_launches == 3

@@ -77,13 +77,13 @@ def test_build_time_options_render_the_oracle_image(tmp_path, oracle, flags):
 def test_mesh_kernel_source_renders_the_mesh_oracle_image(tmp_path):
     """mesh_trace.cu the same way (per-lane state machines, shared-memory stacks, descent runs and
     triangle batches voted by the warp), on the binary tree and on the 4-wide tree collapsed from it,
-    against oracle/quasi_oracle_mesh.c."""
+    launch by launch and in the batched form, against oracle/quasi_oracle_mesh.c."""
     exe = build(tmp_path, [], harness="run_mesh")
-    for grid, width, height, frames in ((3, 64, 36, 2), (24, 80, 45, 2)):
+    for grid, width, height, frames, batch in ((3, 64, 36, 2, 1), (24, 80, 45, 2, 1), (3, 61, 35, 5, 2), (24, 48, 27, 4, 4)):
         want, stats = MeshOracle(grid).render_frames(width, height, frames, max_bounces=4, use_bvh=True)
         for wide in (0, 1):
             out = tmp_path / "layers.bin"
-            run = subprocess.run([str(exe), str(grid), str(width), str(height), str(frames), str(wide), str(out)],
+            run = subprocess.run([str(exe), str(grid), str(width), str(height), str(frames), str(wide), str(out), str(batch)],
                                  capture_output=True, text=True, timeout=900)
             assert run.returncode == 0, run.stdout + run.stderr
             got = np.fromfile(out, dtype=np.float32).reshape(4, height, width, 4)
