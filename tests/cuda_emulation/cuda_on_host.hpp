@@ -87,6 +87,16 @@ void launch(Kernel kernel, unsigned grid, unsigned block, unsigned concurrent_bl
     launch_with_shared(kernel, grid, block, concurrent_blocks, size_t{0}, args...);
 }
 
+/// Phase statistics (QUASI_EMU_STATS): warp-level passes per phase and the lanes working in them.
+inline constexpr int k_phases = 8;
+inline std::atomic<uint64_t> g_phase_passes[k_phases], g_phase_lanes[k_phases];
+inline void phase_pass(int phase, unsigned mask) {
+    if (my_lane() == 0 && mask != 0u) {
+        g_phase_passes[phase] += 1;
+        g_phase_lanes[phase] += static_cast<uint64_t>(__builtin_popcount(mask));
+    }
+}
+
 }  // namespace emu
 
 // ---- what the kernel source sees -------------------------------------------------------------

@@ -77,5 +77,13 @@ int main(int argc, char** argv) {
     for (auto& l : layers) std::fwrite(l.data(), sizeof(float4), n, out);
     std::fclose(out);
     std::printf("rays %llu nodes %llu triangles %llu\n", counters[0], counters[1], counters[2]);
+#if defined(QUASI_EMU_STATS)
+    const char* names[5] = {"shading", "new_rays", "scheduler", "descent", "triangle"};
+    for (int p = 0; p < 5; p++) {
+        const double passes = static_cast<double>(emu::g_phase_passes[p]), lanes = static_cast<double>(emu::g_phase_lanes[p]);
+        std::printf("phase %-9s passes_per_ray %.3f lanes_per_pass %.2f\n", names[p], passes / static_cast<double>(counters[0]),
+                    passes > 0 ? lanes / passes : 0.0);
+    }
+#endif
     return 0;
 }
