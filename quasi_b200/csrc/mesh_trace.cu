@@ -56,9 +56,9 @@
 // tests/cuda_emulation/run_mesh.cpp with -DQUASI_EMU_STATS: how many warp-level passes each phase
 // of the kernel makes and how many lanes work in them (emu::phase_pass). Nothing on the device.
 #if defined(QUASI_HOST_EMULATION) && defined(QUASI_EMU_STATS)
-#define QUASI_EMU_PASS(phase, lane_works) emu::phase_pass(phase, __ballot_sync(0xffffffffu, lane_works))
+#define QUASI_EMU_PASS(phase, lane_works) emu::phase_pass(phase, __ballot_sync(0xffffffffu, lane_works));
 #else
-#define QUASI_EMU_PASS(phase, lane_works) ((void)0)
+#define QUASI_EMU_PASS(phase, lane_works)  // nothing at all: the device build must see the tokens it saw without this
 #endif
 
 namespace Q::cuda {
@@ -256,7 +256,7 @@ mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_co
         bool new_ray = false, fresh = false;
         v3 fu = make_v3(0.0f, 0.0f, 0.0f), fv = fu, fw = fu;  // scattering frame of a continuing path
         float uv_x = 0.0f, uv_y = 0.0f;                        // pixel centre of a new path
-        QUASI_EMU_PASS(0, active && cur == k_done);  // service: shading
+        QUASI_EMU_PASS(0, active && cur == k_done)  // service: shading
         if (active && cur == k_done) {
             // One bounce of path_trace (plugin.mm:232-273) around the finished query.
             const bool is_hit = best.prim != k_miss;
@@ -429,7 +429,7 @@ mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_co
         // path; cosine_sample_hemisphere, plugin.mm:111-125, with the per-triangle frame for a
         // continuing one: two draws and a normalisation either way, issued once for both kinds),
         // then the root test and the start of the query.
-        QUASI_EMU_PASS(1, new_ray);  // new rays
+        QUASI_EMU_PASS(1, new_ray)  // new rays
         if (new_ray) {
             const float draw_a = random_float(rng);
             const float draw_b = random_float(rng);
@@ -479,17 +479,19 @@ mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_co
             const uint32_t m_tracing = m_descending | m_leaf;
             // enough finished queries to make shading worth issuing, or nothing to traverse
             if (m_tracing == 0u || __popc(m_active & ~m_tracing) >= k_min_waiting) break;
-            QUASI_EMU_PASS(2, m_tracing != 0u);  // scheduler iterations
+            QUASI_EMU_PASS(2, m_tracing != 0u)  // scheduler iterations
+#if defined(QUASI_HOST_EMULATION) && defined(QUASI_EMU_STATS)
             if (!(m_descending != 0u && __popc(m_leaf) < k_leaf_batch)) {
-                for (uint32_t k = 0; k < 4u; k++) QUASI_EMU_PASS(4, (cur & 7u) - 1u < 4u && (cur & 7u) > k);  // triangle passes
+                for (uint32_t k = 0; k < 4u; k++) QUASI_EMU_PASS(4, (cur & 7u) - 1u < 4u && (cur & 7u) > k)  // triangle passes
             }
+#endif
             if (m_descending != 0u && __popc(m_leaf) < k_leaf_batch) {
                 // Descent run: one level per iteration for every lane that is not holding a
                 // leaf, until k_run_exit of them have reached a leaf or finished. Leaf
                 // holders sit this out; they are served once k_leaf_batch have gathered.
                 const int keep = max(__popc(m_descending) - k_run_exit, 0);
                 do {
-                    QUASI_EMU_PASS(3, (cur & 7u) == 0u || cur == k_pop);  // descent passes
+                    QUASI_EMU_PASS(3, (cur & 7u) == 0u || cur == k_pop)  // descent passes
                     if (cur == k_pop) cur = stack.pop_one(best.t);
                     if ((cur & 7u) == 0u) {
                         if constexpr (Wide) {
