@@ -64,6 +64,11 @@ cudaError_t launch_pathtrace_accumulate(const scene_params& scene, const frame_p
                                         unsigned int* tile_counters, int sm_count, cudaStream_t stream,
                                         bool generic_scan = false);
 
+/// @brief Where the batched demo-scene kernels also store every pixel's value after the last sample
+/// of a launch (pathtrace.cu:g_mirror): four pinned host buffers, or null for nowhere. Ordered on
+/// `stream` before the launches that follow on it. One table per device: for one plugin instance.
+cudaError_t set_pathtrace_mirror(float* const mirror[4], cudaStream_t stream);
+
 /// @brief The mesh-scene form of launch_pathtrace_accumulate (BASELINE config 3).
 /// @param counters Device array of 3: rays, BVH nodes visited (box tests), triangles tested.
 cudaError_t launch_mesh_pathtrace(const mesh_params& scene, const frame_params& frame, float* const layers[4],

@@ -203,6 +203,17 @@ constexpr int k_block_threads = QUASI_QUAD_BLOCK_THREADS;
 constexpr int k_blocks_per_sm = QUASI_QUAD_BLOCKS_PER_SM;
 constexpr int k_warps_per_block = k_block_threads / 32;
 
+/// Batched launches only (QUASI_CUDA_MIRROR, plugin.cu): pinned host buffers, one per layer, that
+/// receive every pixel's value after the LAST sample of the launch, written by the lane that
+/// computed it, so that the device-to-host transfer of a frame is spread over the launch that
+/// renders it instead of following it. Null entries: nothing is mirrored.
+__device__ float4* g_mirror[4];
+
+__device__ __forceinline__ void mirror_pixel(int layer, size_t pixel, float4 value) {
+    float4* to = g_mirror[layer];
+    if (to != nullptr) to[pixel] = value;
+}
+
 /// `Batch` (QUASI_CUDA_BATCH, plugin.cu): one launch gives every pixel frame.batch_samples
 /// consecutive samples instead of one. A lane that ends a path starts the next sample of the
 /// SAME pixel, so the samples of a pixel are accumulated in order by one thread (the running
@@ -420,12 +431,20 @@ pathtrace_accumulate_kernel(const __grid_constant__ scene_params scene,
                     first_t = hit.t;
                 }
                 const float nd = fminf(fmaxf((first_t - 1.0f) / 4.0f, 0.0f), 1.0f);
-                accumulate_pixel(albedo, pixel, make_float4(a.x, a.y, a.z, 1.0f), Batch ? lane_first : first_sample,
-                                 Batch ? lane_weight : weight);
-                accumulate_pixel(normal, pixel, make_float4(nn.x, nn.y, nn.z, 1.0f), Batch ? lane_first : first_sample,
-                                 Batch ? lane_weight : weight);
-                accumulate_pixel(depth, pixel, make_float4(nd, nd, nd, 1.0f), Batch ? lane_first : first_sample,
-                                 Batch ? lane_weight : weight);
+                if constexpr (Batch) {
+                    const float4 va = accumulate_pixel_value(albedo, pixel, make_float4(a.x, a.y, a.z, 1.0f), lane_first, lane_weight);
+                    const float4 vn = accumulate_pixel_value(normal, pixel, make_float4(nn.x, nn.y, nn.z, 1.0f), lane_first, lane_weight);
+                    const float4 vd = accumulate_pixel_value(depth, pixel, make_float4(nd, nd, nd, 1.0f), lane_first, lane_weight);
+                    if (sample_of_item + 1u == batch) {  // the pixel's last sample of this launch
+                        mirror_pixel(1, pixel, va);
+                        mirror_pixel(2, pixel, vn);
+                        mirror_pixel(3, pixel, vd);
+                    }
+                } else {
+                accumulate_pixel(albedo, pixel, make_float4(a.x, a.y, a.z, 1.0f), first_sample, weight);
+                accumulate_pixel(normal, pixel, make_float4(nn.x, nn.y, nn.z, 1.0f), first_sample, weight);
+                accumulate_pixel(depth, pixel, make_float4(nd, nd, nd, 1.0f), first_sample, weight);
+                }
             }
 
             bool done = !is_hit;
@@ -451,8 +470,14 @@ pathtrace_accumulate_kernel(const __grid_constant__ scene_params scene,
                 ro = hit.point + n * 0.001f;
                 scatter = hit.front ? hit.index : ~hit.index;  // the direction is drawn at the top
             } else {
+                if constexpr (Batch) {
+                    const float4 vb = accumulate_pixel_value(beauty, pixel, make_float4(color.x, color.y, color.z, 1.0f),
+                                                             lane_first, lane_weight);
+                    if (sample_of_item + 1u == batch) mirror_pixel(0, pixel, vb);
+                } else {
                 accumulate_pixel(beauty, pixel, make_float4(color.x, color.y, color.z, 1.0f),
-                                 Batch ? lane_first : first_sample, Batch ? lane_weight : weight);
+                                 first_sample, weight);
+                }
                 active = false;
             }
         }
@@ -478,6 +503,12 @@ cudaError_t launch_sincos_probe(const float* phi, float* sin_out, float* cos_out
     if (n == 0) return cudaSuccess;
     sincos_probe_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(phi, sin_out, cos_out, n);
     return cudaGetLastError();
+}
+
+cudaError_t set_pathtrace_mirror(float* const mirror[4], cudaStream_t stream) {
+    float4* table[4];
+    for (int i = 0; i < 4; i++) table[i] = mirror ? reinterpret_cast<float4*>(mirror[i]) : nullptr;
+    return cudaMemcpyToSymbolAsync(g_mirror, table, sizeof table, 0, cudaMemcpyHostToDevice, stream);
 }
 
 cudaError_t launch_pathtrace_accumulate(const scene_params& scene, const frame_params& frame,

@@ -133,6 +133,12 @@ struct plugin_state {
     // Anything that looks at the layers, and any call with another camera or size, launches
     // what has been collected first, so the only observable difference is time.
     uint32_t batch = 1;
+    // QUASI_CUDA_MIRROR=1 (with a batch, demo scene): the batched launch also writes every pixel's
+    // final value of the launch into pinned host buffers, so a readback that follows finds the
+    // frame already on the host: the transfer is spread over the launch instead of following it.
+    bool mirror_enabled = false;
+    bool mirror_valid = false;         ///< the buffers hold what the layers hold
+    float* mirror[Q_AOV_COUNT] = {nullptr, nullptr, nullptr, nullptr};
     uint32_t pending = 0;              ///< render calls collected and not yet launched
     uint32_t pending_first_sample = 0; ///< frame_count of the first of them
     Q_render_frame pending_frame{};    ///< that call's frame (camera, size, stream)
@@ -176,6 +182,8 @@ void ensure_render_event(plugin_state* state) {
 #define QUASI_RENDER_EVENT(state) ((void)0)
 #endif
 
+void drop_mirror(plugin_state* state);
+
 /// Counterpart of create_textures (plugin.mm:491-535): four RGBA32F layers,
 /// accumulated in place, so one allocation of 64 B/px instead of twelve textures
 /// of 16 B/px. The layers are contiguous (beauty, albedo, normal, depth) so a
@@ -184,6 +192,7 @@ bool create_layers(plugin_state* state, uint32_t width, uint32_t height) {
     QUASI_RENDER_EVENT(state);
     if (state->render_pending) cudaEventSynchronize(state->last_render);
     free_layers(state);
+    drop_mirror(state);
     size_t floats = static_cast<size_t>(width) * height * 4;
     if (floats != 0) {
         float* block = nullptr;
@@ -436,6 +445,14 @@ void order_after_render(plugin_state* state, cudaStream_t stream) {
 }
 
 
+void drop_mirror(plugin_state* state) {
+    for (auto& m : state->mirror) {
+        if (m) g_pool.release(m);
+        m = nullptr;
+    }
+    state->mirror_valid = false;
+}
+
 /// Launches the render calls collected under QUASI_CUDA_BATCH as one kernel. The arguments are
 /// the ones Q_plugin_render computes for a single call, for the first collected call; sample s of
 /// the launch is what the (s+1)-th collected call would have rendered.
@@ -449,16 +466,32 @@ void flush_pending(plugin_state* state) {
                            state->pending_first_sample, fp);
     fp.batch_samples = state->pending;
     fp.frame_stride = state->shard_count;
+    const bool mirror = state->mirror_enabled && !state->use_mesh && fp.batch_samples > 1u;
     state->pending = 0;
     Q::cuda::set_decision_margins(state->scene, f.camera.position);
     order_after_render(state, stream);
+    state->mirror_valid = false;
+    if (state->mirror_enabled && !state->use_mesh) {
+        const size_t bytes = static_cast<size_t>(f.width) * f.height * 4 * sizeof(float);
+        bool have = mirror;
+        for (int i = 0; i < Q_AOV_COUNT && have; i++) {
+            if (!state->mirror[i]) state->mirror[i] = g_pool.acquire(bytes);
+            have = state->mirror[i] != nullptr;
+        }
+        // the table is set before every batched launch: buffers handed to a caller must never be written again
+        if (!check(state, Q::cuda::set_pathtrace_mirror(have ? state->mirror : nullptr, stream), "set_pathtrace_mirror")) return;
+        state->mirror_valid = have;
+    }
     auto* tile_counters = reinterpret_cast<unsigned int*>(state->ray_counter + 3);
     const cudaError_t launched =
         state->use_mesh ? Q::cuda::launch_mesh_pathtrace(state->mesh_device, fp, state->layers, state->ray_counter,
                                                          tile_counters, state->sm_count, stream)
                         : Q::cuda::launch_pathtrace_accumulate(state->scene, fp, state->layers, state->ray_counter,
                                                                tile_counters, state->sm_count, stream, state->generic_scan);
-    if (!check(state, launched, "pathtrace_accumulate (batch)")) return;
+    if (!check(state, launched, "pathtrace_accumulate (batch)")) {
+        state->mirror_valid = false;
+        return;
+    }
     state->kernel_launches++;
 #if defined(QUASI_PDL) && QUASI_PDL
     state->last_stream = stream;
@@ -559,6 +592,7 @@ Q_PLUGIN_EXPORT Q_plugin_handle* Q_plugin_create(Q_plugin_context* ctx) {
         const bool group_boxes = scan && std::strstr(scan, "boxes") != nullptr;
         Q::cuda::prepare_scene(state->scene_desc, bounces, state->scene, group_boxes);
         state->batch = env_u32("QUASI_CUDA_BATCH", 1, 1, 1024);
+        state->mirror_enabled = state->batch > 1 && env_u32("QUASI_CUDA_MIRROR", 0, 0, 1) != 0;
         const char* scene_name = std::getenv("QUASI_CUDA_SCENE");
         if (scene_name && std::strcmp(scene_name, "mesh") == 0) {
             state->use_mesh = true;
@@ -605,6 +639,7 @@ Q_PLUGIN_EXPORT void Q_plugin_destroy(Q_plugin_handle* handle) {
     cudaStreamSynchronize(state->queue);
     free_mesh(state);
     if (!leave_layers_with_host(state)) free_layers(state);
+    drop_mirror(state);
     if (state->ray_counter) cudaFree(state->ray_counter);
     if (state->last_render) cudaEventDestroy(state->last_render);
     delete state;
@@ -643,6 +678,7 @@ Q_PLUGIN_EXPORT void Q_plugin_render(Q_plugin_handle* handle, Q_render_frame* fr
         return;
     }
     flush_pending(state);  // a call that presents, after headless ones that were being collected
+    state->mirror_valid = false;
 
     const uint32_t width = frame->width;
     const uint32_t height = frame->height;
@@ -738,6 +774,21 @@ Q_PLUGIN_EXPORT Q_readback_aov_result Q_plugin_readback_aov(Q_plugin_handle* han
     auto* state = reinterpret_cast<plugin_state*>(handle);
     if (cudaSetDevice(state->device) != cudaSuccess) return result;
     flush_pending(state);
+
+    if (state->mirror_valid) {
+        // the batched launch has put the frame into pinned host buffers itself: wait for it, hand them over
+        QUASI_RENDER_EVENT(state);
+        if (state->render_pending && check(state, cudaEventSynchronize(state->last_render), "readback sync (mirror)")) {
+            for (int i = 0; i < Q_AOV_COUNT; i++) {
+                result.buffers[i] = Q_aov_buffer{state->mirror[i], state->last_width, state->last_height, 4};
+                state->mirror[i] = nullptr;  // the caller's now; the next batch gets fresh ones
+            }
+            state->mirror_valid = false;
+            log_msg(state, "AOV readback complete (mirrored during the render)");
+            return result;
+        }
+        state->mirror_valid = false;
+    }
 
     order_after_render(state, state->queue);
     for (int i = 0; i < Q_AOV_COUNT; i++) result.buffers[i] = download_layer(state, i);
