@@ -218,7 +218,8 @@ __device__ __forceinline__ void mirror_pixel(int layer, size_t pixel, float4 val
 /// consecutive samples instead of one. A lane that ends a path starts the next sample of the
 /// SAME pixel, so the samples of a pixel are accumulated in order by one thread (the running
 /// mean of plugin.mm:326 depends on the order) and its 64 bytes of history stay in L1/L2
-/// between them; launch ramp and drain are paid once per batch instead of once per sample.
+/// between them; what lies between two launches is paid once per batch instead of once per
+/// sample (the drain inside a launch scales with the item, which is k samples long now).
 template <int NQ, class Layout, bool Batch = false>
 __global__ void __launch_bounds__(k_block_threads, k_blocks_per_sm)
 pathtrace_accumulate_kernel(const __grid_constant__ scene_params scene,
