@@ -152,3 +152,15 @@ static_assert(int(::Q_AOV_DEPTH) == int(ours::Q_AOV_DEPTH) && int(ours::Q_GPU_BA
 int main() { return 0; }''')
     subprocess.run(["g++", "-std=c++20", "-fsyntax-only", "-I/root/reference/src", f"-I{ROOT / 'include'}", str(src)],
                    check=True)
+
+
+def test_every_environment_option_of_the_plugin_is_documented():
+    """The ABI has no slot for options, so the plugin reads QUASI_CUDA_* from the environment
+    (SURVEY.md 8b); INTEGRATION.md is where a maintainer finds them."""
+    import re
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    read = set(re.findall(r'"(QUASI_CUDA_[A-Z_]+)"', (root / "quasi_b200" / "csrc" / "plugin.cu").read_text()))
+    doc = (root / "INTEGRATION.md").read_text()
+    assert read and not [name for name in sorted(read) if name not in doc]
