@@ -62,7 +62,12 @@ cudaError_t launch_persistent(void (*kernel)(Params...), uint32_t blocks, uint32
 cudaError_t launch_pathtrace_accumulate(const scene_params& scene, const frame_params& frame,
                                         float* const layers[4], unsigned long long* ray_counter,
                                         unsigned int* tile_counters, int sm_count, cudaStream_t stream,
-                                        bool generic_scan = false);
+                                        bool generic_scan = false, bool sample_major = false);
+
+/// @brief For sample-major batched launches (`sample_major`, frame.batch_samples > 1): one zeroed
+/// word per 8x4 tile, ordered on `stream` before the launches that follow; the host zeroes the
+/// words before every such launch. Needs scene.max_bounces <= 7 (eight completion counters per warp).
+cudaError_t set_pathtrace_tile_epochs(unsigned int* epochs, cudaStream_t stream);
 
 /// @brief Where the batched demo-scene kernels also store every pixel's value after the last sample
 /// of a launch (pathtrace.cu:g_mirror): four pinned host buffers, or null for nowhere. Ordered on

@@ -214,13 +214,115 @@ __device__ __forceinline__ void mirror_pixel(int layer, size_t pixel, float4 val
     if (to != nullptr) to[pixel] = value;
 }
 
+/// Sample-major batched launches only: one word per tile, the number of samples of THIS launch
+/// that every pixel of the tile has received (zeroed by the host before the launch).
+__device__ unsigned int* g_tile_epochs;
+
+__device__ __forceinline__ unsigned int load_acquire_gpu(const unsigned int* p) {
+#if defined(QUASI_HOST_EMULATION)
+    return std::atomic_ref<const unsigned int>(*p).load(std::memory_order_acquire);
+#else
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+#endif
+}
+__device__ __forceinline__ void store_release_gpu(unsigned int* p, unsigned int v) {
+#if defined(QUASI_HOST_EMULATION)
+    std::atomic_ref<unsigned int>(*p).store(v, std::memory_order_release);
+#else
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#endif
+}
+
+/// The work queue of a sample-major launch: entry q of n_tiles * k is tile q % n_tiles at sample
+/// q / n_tiles, so all tiles get sample 0, then all get sample 1, ...; otherwise tile_feed
+/// (device_common.cuh). An entry with sample s > 0 is READY once the tile's epoch says sample
+/// s - 1 is complete. Entries are handed out in order, so that sample was handed out n_tiles
+/// entries ago and is all but always complete; when it is not, the warp hands out no pixel of the
+/// entry and looks again on its next iteration, never spinning while it holds paths itself (on a
+/// small image the unfinished sample may be in this very warp). It is what lets ONE launch hold k
+/// samples per pixel without a lane being tied to a pixel: the launch ends when the last paths of
+/// the last sample end, the same few iterations that end a one-sample launch, once instead of k times.
+struct sample_major_feed {
+    static constexpr uint32_t k_unfetched = 0xffffffffu;
+    unsigned int* counters;
+    uint32_t n_tiles, n_entries;
+    uint32_t slot0 = 0;
+    uint32_t entry0 = k_unfetched, entry1 = k_unfetched;  ///< queue entries of positions slot0, slot0 + 1
+    uint32_t tile0 = 0, tile1 = 0, sample0 = 0, sample1 = 0;
+    bool ready0 = false, ready1 = false;
+    bool dry = false;
+
+    /// Warp-uniform (every lane looks, the warp takes the answer all lanes agree on: the feed's
+    /// state must be the same in every lane).
+    __device__ __forceinline__ bool is_ready(uint32_t tile, uint32_t sample) const {
+        if (sample == 0u) return true;
+        return __ballot_sync(0xffffffffu, load_acquire_gpu(g_tile_epochs + tile) >= sample) == 0xffffffffu;
+    }
+    __device__ __forceinline__ void fetch(uint32_t& entry, uint32_t& tile, uint32_t& sample, bool& ready) {
+        uint32_t q = 0;
+        if ((threadIdx.x & 31u) == 0u) q = atomicAdd(counters, 1u);
+        q = __shfl_sync(0xffffffffu, q, 0);
+        dry = q >= n_entries;
+        entry = q;
+        ready = false;
+        if (dry) return;
+        sample = q / n_tiles;
+        tile = q - sample * n_tiles;
+        ready = is_ready(tile, sample);
+    }
+    /// Warp-uniform: makes the entries of items [first, last] available and looks again at the
+    /// epochs of those that were not ready.
+    __device__ __forceinline__ void open(uint32_t first, uint32_t last) {
+        if (slot0 < (first >> 5)) {
+            slot0 = first >> 5;
+            entry0 = entry1, tile0 = tile1, sample0 = sample1, ready0 = ready1;
+            entry1 = k_unfetched;
+            ready1 = false;
+        }
+        if (entry0 == k_unfetched && !dry) fetch(entry0, tile0, sample0, ready0);
+        if (entry0 < n_entries && !ready0) ready0 = is_ready(tile0, sample0);
+        if (!dry && (last >> 5) > slot0 && entry1 == k_unfetched) fetch(entry1, tile1, sample1, ready1);
+        if (entry1 < n_entries && !ready1) ready1 = is_ready(tile1, sample1);
+    }
+    __device__ __forceinline__ bool has(uint32_t item) const { return ((item >> 5) == slot0 ? entry0 : entry1) < n_entries; }
+    __device__ __forceinline__ uint32_t tile_of(uint32_t item) const { return (item >> 5) == slot0 ? tile0 : tile1; }
+    __device__ __forceinline__ uint32_t sample_of(uint32_t item) const { return (item >> 5) == slot0 ? sample0 : sample1; }
+    /// How many of the `wanted` items starting at `first` may be handed out now: up to the first
+    /// one that belongs to an entry that is not ready (an entry past the end of the queue counts as
+    /// ready: its items are skipped).
+    __device__ __forceinline__ uint32_t grantable(uint32_t first, uint32_t wanted) const {
+        const bool ok0 = ready0 || entry0 >= n_entries;
+        const bool ok1 = ready1 || entry1 >= n_entries;
+        if (!ok0) return 0u;
+        const uint32_t in_entry0 = 32u - (first & 31u);
+        return (wanted <= in_entry0 || ok1) ? wanted : in_entry0;
+    }
+    /// Warp-uniform: the queue has run out at item `next` (false while an entry is only not ready).
+    __device__ __forceinline__ bool exhausted(uint32_t next) {
+        open(next, next);
+        return dry && entry0 >= n_entries;  // (an entry never fetched because the queue had run out counts as past its end)
+    }
+    __device__ __forceinline__ void finish(uint32_t n_warps) {
+        if ((threadIdx.x & 31u) == 0u) {
+            if (atomicAdd(counters + 1, 1u) == n_warps - 1u) {
+                counters[0] = 0u;
+                counters[1] = 0u;
+            }
+        }
+    }
+};
+
 /// `Batch` (QUASI_CUDA_BATCH, plugin.cu): one launch gives every pixel frame.batch_samples
 /// consecutive samples instead of one. A lane that ends a path starts the next sample of the
 /// SAME pixel, so the samples of a pixel are accumulated in order by one thread (the running
 /// mean of plugin.mm:326 depends on the order) and its 64 bytes of history stay in L1/L2
 /// between them; what lies between two launches is paid once per batch instead of once per
 /// sample (the drain inside a launch scales with the item, which is k samples long now).
-template <int NQ, class Layout, bool Batch = false>
+/// `SampleMajor` (with Batch): the k samples are k passes over the image inside the one launch
+/// (sample_major_feed) instead of k consecutive samples per lane and pixel.
+template <int NQ, class Layout, bool Batch = false, bool SampleMajor = false>
 __global__ void __launch_bounds__(k_block_threads, k_blocks_per_sm)
 pathtrace_accumulate_kernel(const __grid_constant__ scene_params scene,
                             const __grid_constant__ frame_params frame, float4* __restrict__ beauty,
@@ -265,12 +367,77 @@ pathtrace_accumulate_kernel(const __grid_constant__ scene_params scene,
     [[maybe_unused]] bool lane_first = first_sample;
     [[maybe_unused]] float lane_weight = weight;
     [[maybe_unused]] const uint32_t batch = frame.batch_samples > 1u ? frame.batch_samples : 1u;
+    // SampleMajor only: the queue, this warp's eight completion counters (dynamic shared memory,
+    // zeroed here), and per lane tile << 9 | pixels of the tile inside the image << 3 | counter
+    [[maybe_unused]] sample_major_feed sfeed{tile_counters, n_tiles, n_tiles * batch};
+    [[maybe_unused]] unsigned int* tile_done = nullptr;
+    [[maybe_unused]] uint32_t item_tag = 0;
+    if constexpr (SampleMajor) {
+#if defined(QUASI_HOST_EMULATION)
+        unsigned int* s_done = static_cast<unsigned int*>(emu::dynamic_shared());
+#else
+        extern __shared__ unsigned int s_done[];
+#endif
+        tile_done = s_done + (threadIdx.x >> 5) * 8u;
+        if (lane < 8u) tile_done[lane] = 0u;
+        __syncthreads();
+    }
 
     while (true) {
         // Regeneration: idle lanes take the warp's next pixels, compacted.
         bool fresh = false;
         float uv_x = 0.0f, uv_y = 0.0f;
-        if constexpr (Batch) {
+        if constexpr (Batch && SampleMajor) {
+            bool start = false;
+            uint32_t px = 0, py = 0;
+            const uint32_t idle = __ballot_sync(0xffffffffu, !active);
+            if (idle != 0u) {
+                sfeed.open(next_item, next_item + __popc(idle) - 1u);
+                const uint32_t granted = sfeed.grantable(next_item, __popc(idle));
+                if (!active) {
+                    const uint32_t item = next_item + __popc(idle & lanes_below);
+                    if (item < next_item + granted && sfeed.has(item)) {
+                        const uint32_t tile = sfeed.tile_of(item);
+                        uint32_t tile_y = __umulhi(tile, frame.tiles_x_magic);
+                        uint32_t tile_x = tile - tile_y * tiles_x;
+                        if (tile_x >= tiles_x) {
+                            tile_x -= tiles_x;
+                            tile_y++;
+                        }
+                        px = tile_x * 8u + (item & 7u);
+                        py = tile_y * 4u + ((item >> 3) & 3u);
+                        if (px < frame.width && py < frame.height) {
+                            const uint32_t in_x = frame.width - tile_x * 8u, in_y = frame.height - tile_y * 4u;
+                            const uint32_t valid = (in_x < 8u ? in_x : 8u) * (in_y < 4u ? in_y : 4u);
+                            sample_of_item = sfeed.sample_of(item);
+                            item_tag = (tile << 9) | (valid << 3) | ((item >> 5) & 7u);
+                            start = true;
+                            pixel = static_cast<size_t>(py) * frame.width + px;
+                            if (!(first_sample && sample_of_item == 0u)) {
+                                prefetch_l2(beauty + pixel);
+                                prefetch_l2(albedo + pixel);
+                                prefetch_l2(normal + pixel);
+                                prefetch_l2(depth + pixel);
+                            }
+                        }
+                    }
+                }
+                next_item += granted;
+            }
+            if (start) {
+                const uint32_t sample_index = frame.sample_index + sample_of_item;
+                uv_x = (static_cast<float>(px) + 0.5f) / static_cast<float>(frame.width);
+                uv_y = 1.0f - (static_cast<float>(py) + 0.5f) / static_cast<float>(frame.height);
+                rng = pcg_hash(px + py * 1920u + (frame.frame_index + sample_of_item * frame.frame_stride) * 1920u * 1080u);
+                fresh = true;
+                throughput = make_v3(1.0f, 1.0f, 1.0f);
+                color = make_v3(0.0f, 0.0f, 0.0f);
+                bounce = 0;
+                active = true;
+                lane_first = sample_index == 0u;
+                lane_weight = 1.0f / static_cast<float>(sample_index + 1u);
+            }
+        } else if constexpr (Batch) {
             // A lane whose path has ended goes on with the next sample of its pixel; only a lane
             // that has given its pixel all its samples takes a new pixel from the queue.
             bool start = false;
@@ -374,7 +541,11 @@ pathtrace_accumulate_kernel(const __grid_constant__ scene_params scene,
         }
         }  // !Batch
         if (!__any_sync(0xffffffffu, active)) {
-            if (feed.exhausted(next_item)) break;
+            if constexpr (SampleMajor) {
+                if (sfeed.exhausted(next_item)) break;
+            } else {
+                if (feed.exhausted(next_item)) break;
+            }
             continue;  // only off-image pixels of an edge tile were handed out
         }
 
@@ -433,9 +604,10 @@ pathtrace_accumulate_kernel(const __grid_constant__ scene_params scene,
                 }
                 const float nd = fminf(fmaxf((first_t - 1.0f) / 4.0f, 0.0f), 1.0f);
                 if constexpr (Batch) {
-                    const float4 va = accumulate_pixel_value(albedo, pixel, make_float4(a.x, a.y, a.z, 1.0f), lane_first, lane_weight);
-                    const float4 vn = accumulate_pixel_value(normal, pixel, make_float4(nn.x, nn.y, nn.z, 1.0f), lane_first, lane_weight);
-                    const float4 vd = accumulate_pixel_value(depth, pixel, make_float4(nd, nd, nd, 1.0f), lane_first, lane_weight);
+                    constexpr auto accumulate = SampleMajor ? accumulate_pixel_value_cg : accumulate_pixel_value;
+                    const float4 va = accumulate(albedo, pixel, make_float4(a.x, a.y, a.z, 1.0f), lane_first, lane_weight);
+                    const float4 vn = accumulate(normal, pixel, make_float4(nn.x, nn.y, nn.z, 1.0f), lane_first, lane_weight);
+                    const float4 vd = accumulate(depth, pixel, make_float4(nd, nd, nd, 1.0f), lane_first, lane_weight);
                     if (sample_of_item + 1u == batch) {  // the pixel's last sample of this launch
                         mirror_pixel(1, pixel, va);
                         mirror_pixel(2, pixel, vn);
@@ -472,9 +644,19 @@ pathtrace_accumulate_kernel(const __grid_constant__ scene_params scene,
                 scatter = hit.front ? hit.index : ~hit.index;  // the direction is drawn at the top
             } else {
                 if constexpr (Batch) {
-                    const float4 vb = accumulate_pixel_value(beauty, pixel, make_float4(color.x, color.y, color.z, 1.0f),
-                                                             lane_first, lane_weight);
+                    constexpr auto accumulate = SampleMajor ? accumulate_pixel_value_cg : accumulate_pixel_value;
+                    const float4 vb = accumulate(beauty, pixel, make_float4(color.x, color.y, color.z, 1.0f), lane_first, lane_weight);
                     if (sample_of_item + 1u == batch) mirror_pixel(0, pixel, vb);
+                    if constexpr (SampleMajor) {
+                        // this pixel has its sample; the lane that completes the tile publishes the tile's epoch
+                        __threadfence_block();
+                        const uint32_t counter = item_tag & 7u, valid = (item_tag >> 3) & 63u;
+                        if (atomicAdd(tile_done + counter, 1u) + 1u == valid) {
+                            tile_done[counter] = 0u;
+                            __threadfence();
+                            store_release_gpu(g_tile_epochs + (item_tag >> 9), sample_of_item + 1u);
+                        }
+                    }
                 } else {
                 accumulate_pixel(beauty, pixel, make_float4(color.x, color.y, color.z, 1.0f),
                                  first_sample, weight);
@@ -484,7 +666,11 @@ pathtrace_accumulate_kernel(const __grid_constant__ scene_params scene,
         }
     }
 
-    feed.finish(gridDim.x * k_warps_per_block);
+    if constexpr (SampleMajor) {
+        sfeed.finish(gridDim.x * k_warps_per_block);
+    } else {
+        feed.finish(gridDim.x * k_warps_per_block);
+    }
     // One atomic per warp for the ray statistic (SURVEY.md 8d "Ray counting").
     rays = __reduce_add_sync(0xffffffffu, rays);
     if (lane == 0 && rays != 0) atomicAdd(ray_counter, static_cast<unsigned long long>(rays));
@@ -512,10 +698,14 @@ cudaError_t set_pathtrace_mirror(float* const mirror[4], cudaStream_t stream) {
     return cudaMemcpyToSymbolAsync(g_mirror, table, sizeof table, 0, cudaMemcpyHostToDevice, stream);
 }
 
+cudaError_t set_pathtrace_tile_epochs(unsigned int* epochs, cudaStream_t stream) {
+    return cudaMemcpyToSymbolAsync(g_tile_epochs, &epochs, sizeof epochs, 0, cudaMemcpyHostToDevice, stream);
+}
+
 cudaError_t launch_pathtrace_accumulate(const scene_params& scene, const frame_params& frame,
                                         float* const layers[4], unsigned long long* ray_counter,
                                         unsigned int* tile_counters, int sm_count, cudaStream_t stream,
-                                        bool generic_scan) {
+                                        bool generic_scan, bool sample_major) {
     const uint32_t n_tiles = ((frame.width + 7u) / 8u) * ((frame.height + 3u) / 4u);
     uint32_t blocks = static_cast<uint32_t>(sm_count) * k_blocks_per_sm;
     const uint32_t needed = (n_tiles + k_warps_per_block - 1u) / k_warps_per_block;
@@ -537,6 +727,20 @@ cudaError_t launch_pathtrace_accumulate(const scene_params& scene, const frame_p
     return launch_persistent(pathtrace_accumulate_kernel<32, dynamic_layout>, blocks, k_block_threads, 0, stream, scene, frame,
                              b, a, n, d, ray_counter, tile_counters);
 #endif
+    if (frame.batch_samples > 1u && sample_major) {  // QUASI_CUDA_BATCH_ORDER=sample: k passes over the image in one launch
+        constexpr size_t smem = k_warps_per_block * 8 * sizeof(unsigned int);  // completion counters, eight per warp
+        if (!generic_scan && cornell_layout::matches(scene)) {
+            pathtrace_accumulate_kernel<16, cornell_layout, true, true>
+                <<<blocks, k_block_threads, smem, stream>>>(scene, frame, b, a, n, d, ray_counter, tile_counters);
+        } else if (!generic_scan && cornell_quads_layout::matches(scene)) {
+            pathtrace_accumulate_kernel<16, cornell_quads_layout, true, true>
+                <<<blocks, k_block_threads, smem, stream>>>(scene, frame, b, a, n, d, ray_counter, tile_counters);
+        } else {
+            pathtrace_accumulate_kernel<32, dynamic_layout, true, true>
+                <<<blocks, k_block_threads, smem, stream>>>(scene, frame, b, a, n, d, ray_counter, tile_counters);
+        }
+        return cudaGetLastError();
+    }
     if (frame.batch_samples > 1u) {  // QUASI_CUDA_BATCH: several samples per pixel in one launch
         if (!generic_scan && cornell_layout::matches(scene)) {
             pathtrace_accumulate_kernel<16, cornell_layout, true>

@@ -136,6 +136,12 @@ struct plugin_state {
     // QUASI_CUDA_MIRROR=1 (with a batch, demo scene): the batched launch also writes every pixel's
     // final value of the launch into pinned host buffers, so a readback that follows finds the
     // frame already on the host: the transfer is spread over the launch instead of following it.
+    // QUASI_CUDA_BATCH_ORDER=sample (demo scene, at most 7 bounces): the batched launch makes k passes
+    // over the image (pathtrace.cu:sample_major_feed) instead of giving each lane k samples of a pixel;
+    // one word per tile orders a pass after the previous one.
+    bool sample_major = false;
+    unsigned int* tile_epochs = nullptr;
+    size_t tile_epoch_words = 0;
     bool mirror_enabled = false;
     bool mirror_valid = false;         ///< the buffers hold what the layers hold
     float* mirror[Q_AOV_COUNT] = {nullptr, nullptr, nullptr, nullptr};
@@ -467,6 +473,21 @@ void flush_pending(plugin_state* state) {
     fp.batch_samples = state->pending;
     fp.frame_stride = state->shard_count;
     const bool mirror = state->mirror_enabled && !state->use_mesh && fp.batch_samples > 1u;
+    bool sample_major = state->sample_major && !state->use_mesh && fp.batch_samples > 1u && state->scene.max_bounces <= 7u;
+    if (sample_major) {
+        const size_t words = static_cast<size_t>((f.width + 7u) / 8u) * ((f.height + 3u) / 4u);
+        if (state->tile_epoch_words != words) {
+            if (state->tile_epochs) cudaFree(state->tile_epochs);
+            state->tile_epochs = nullptr;
+            state->tile_epoch_words = 0;
+            if (cudaMalloc(reinterpret_cast<void**>(&state->tile_epochs), words * sizeof(unsigned int)) == cudaSuccess) {
+                state->tile_epoch_words = words;
+            } else {
+                (void)cudaGetLastError();
+                sample_major = false;  // the other order needs nothing
+            }
+        }
+    }
     state->pending = 0;
     Q::cuda::set_decision_margins(state->scene, f.camera.position);
     order_after_render(state, stream);
@@ -482,12 +503,19 @@ void flush_pending(plugin_state* state) {
         if (!check(state, Q::cuda::set_pathtrace_mirror(have ? state->mirror : nullptr, stream), "set_pathtrace_mirror")) return;
         state->mirror_valid = have;
     }
+    if (sample_major &&
+        (!check(state, cudaMemsetAsync(state->tile_epochs, 0, state->tile_epoch_words * sizeof(unsigned int), stream),
+                "memset(tile epochs)") ||
+         !check(state, Q::cuda::set_pathtrace_tile_epochs(state->tile_epochs, stream), "set_pathtrace_tile_epochs"))) {
+        return;
+    }
     auto* tile_counters = reinterpret_cast<unsigned int*>(state->ray_counter + 3);
     const cudaError_t launched =
         state->use_mesh ? Q::cuda::launch_mesh_pathtrace(state->mesh_device, fp, state->layers, state->ray_counter,
                                                          tile_counters, state->sm_count, stream)
                         : Q::cuda::launch_pathtrace_accumulate(state->scene, fp, state->layers, state->ray_counter,
-                                                               tile_counters, state->sm_count, stream, state->generic_scan);
+                                                               tile_counters, state->sm_count, stream, state->generic_scan,
+                                                               sample_major);
     if (!check(state, launched, "pathtrace_accumulate (batch)")) {
         state->mirror_valid = false;
         return;
@@ -593,6 +621,8 @@ Q_PLUGIN_EXPORT Q_plugin_handle* Q_plugin_create(Q_plugin_context* ctx) {
         Q::cuda::prepare_scene(state->scene_desc, bounces, state->scene, group_boxes);
         state->batch = env_u32("QUASI_CUDA_BATCH", 1, 1, 1024);
         state->mirror_enabled = state->batch > 1 && env_u32("QUASI_CUDA_MIRROR", 0, 0, 1) != 0;
+        const char* order = std::getenv("QUASI_CUDA_BATCH_ORDER");
+        state->sample_major = state->batch > 1 && order && std::strcmp(order, "sample") == 0;
         const char* scene_name = std::getenv("QUASI_CUDA_SCENE");
         if (scene_name && std::strcmp(scene_name, "mesh") == 0) {
             state->use_mesh = true;
@@ -640,6 +670,7 @@ Q_PLUGIN_EXPORT void Q_plugin_destroy(Q_plugin_handle* handle) {
     free_mesh(state);
     if (!leave_layers_with_host(state)) free_layers(state);
     drop_mirror(state);
+    if (state->tile_epochs) cudaFree(state->tile_epochs);
     if (state->ray_counter) cudaFree(state->ray_counter);
     if (state->last_render) cudaEventDestroy(state->last_render);
     delete state;

@@ -1,7 +1,8 @@
 // Runs the SOURCE of the quad path-tracing kernel (quasi_b200/csrc/pathtrace.cu) on the host under
 // tests/cuda_emulation/cuda_on_host.hpp and writes the four accumulated layers as raw binary32.
 //   usage: run_pathtrace WIDTH HEIGHT FRAMES BATCH SCAN OUT.bin
-//     BATCH  samples per launch (1 = one launch per frame, the default of the backend)
+//     BATCH  samples per launch (1 = one launch per frame, the default of the backend); with an "s"
+//            appended, the sample-major form (k passes over the image inside the launch)
 //     SCAN   "quads" (kernel unrolled for the demo scene), "boxes" (blocks as slab tests), "generic"
 //   prints "rays N launches M"
 #define QUASI_HOST_EMULATION 1
@@ -20,6 +21,7 @@ int main(int argc, char** argv) {
     const uint32_t width = static_cast<uint32_t>(std::atoi(argv[1])), height = static_cast<uint32_t>(std::atoi(argv[2]));
     const uint32_t frames = static_cast<uint32_t>(std::atoi(argv[3])), batch = static_cast<uint32_t>(std::atoi(argv[4]));
     const std::string scan = argv[5];
+    const bool sample_major = std::string(argv[4]).find('s') != std::string::npos;
 
     scene_desc desc = make_cornell_box();
     static scene_params scene;
@@ -44,17 +46,32 @@ int main(int argc, char** argv) {
     const uint32_t needed = (n_tiles + k_warps_per_block - 1u) / k_warps_per_block;
     const uint32_t grid = needed < 3u ? needed : 3u;  // a persistent grid smaller than the work, as on the device
     uint32_t launches = 0;
+    std::vector<unsigned int> epochs(n_tiles, 0u);
+    g_tile_epochs = epochs.data();
     for (uint32_t first = 0; first < frames; first += batch) {
+        std::fill(epochs.begin(), epochs.end(), 0u);
         frame_params frame;
         prepare_frame(position, target, up, 40.0f, width, height, /*frame_index*/ first, /*sample_index*/ first, frame);
         frame.batch_samples = std::min(batch, frames - first);
         frame.frame_stride = 1;
         auto run = [&](auto kernel) {
-            emu::launch(kernel, grid, k_block_threads, /*concurrent CTAs*/ 1u, scene, frame, layers[0].data(), layers[1].data(),
-                        layers[2].data(), layers[3].data(), &rays, tile_counters);
+            // sample-major: a CTA may wait for a tile another CTA is finishing, so all of them run at once, as on the device
+            emu::launch_with_shared(kernel, grid, k_block_threads, /*concurrent CTAs*/ sample_major ? grid : 1u,
+                                    k_warps_per_block * 8 * sizeof(unsigned int), scene, frame, layers[0].data(), layers[1].data(),
+                                    layers[2].data(), layers[3].data(), &rays, tile_counters);
         };
         const bool batched = frame.batch_samples > 1u;
-        if (scan == "generic") {
+        if (batched && sample_major) {
+            if (scan == "generic") {
+                run(pathtrace_accumulate_kernel<32, dynamic_layout, true, true>);
+            } else if (scan == "boxes" && cornell_layout::matches(scene)) {
+                run(pathtrace_accumulate_kernel<16, cornell_layout, true, true>);
+            } else if (scan == "quads" && cornell_quads_layout::matches(scene)) {
+                run(pathtrace_accumulate_kernel<16, cornell_quads_layout, true, true>);
+            } else {
+                return 3;
+            }
+        } else if (scan == "generic") {
             batched ? run(pathtrace_accumulate_kernel<32, dynamic_layout, true>) : run(pathtrace_accumulate_kernel<32, dynamic_layout, false>);
         } else if (scan == "boxes" && cornell_layout::matches(scene)) {
             batched ? run(pathtrace_accumulate_kernel<16, cornell_layout, true>) : run(pathtrace_accumulate_kernel<16, cornell_layout, false>);

@@ -366,9 +366,10 @@ def test_every_scan_variant_is_bit_exact(torch_cuda, oracle, scan):
 
 @pytest.mark.skipif(__import__("os").environ.get("QUASI_TEST_BATCH") != "1",
                     reason="QUASI_CUDA_BATCH has not run on a GPU yet (DESIGN.md section 9); QUASI_TEST_BATCH=1 runs it")
+@pytest.mark.parametrize("order", ["pixel", "sample"])
 @pytest.mark.parametrize("mirror", [0, 1], ids=["copy-after", "mirrored-during"])
 @pytest.mark.parametrize("batch,frames,scan", [(4, 10, ""), (64, 64, ""), (3, 7, "boxes"), (8, 8, "generic")])
-def test_batched_launches_render_the_same_bits(torch_cuda, oracle, batch, frames, scan, mirror):
+def test_batched_launches_render_the_same_bits(torch_cuda, oracle, batch, frames, scan, mirror, order):
     """QUASI_CUDA_BATCH=k collects render calls and gives every pixel k consecutive samples in one
     launch (pathtrace.cu, Batch): full batches, a partial one flushed by the readback, and a
     camera_dirty restart in the middle of a batch must all give the bits of call-by-call launches.
@@ -377,7 +378,8 @@ def test_batched_launches_render_the_same_bits(torch_cuda, oracle, batch, frames
     from quasi_b200.headless import headless_host
 
     w, h = 211, 119
-    host = headless_host(w, h, env={"QUASI_CUDA_BATCH": batch, "QUASI_CUDA_SCAN": scan, "QUASI_CUDA_MIRROR": mirror})
+    host = headless_host(w, h, env={"QUASI_CUDA_BATCH": batch, "QUASI_CUDA_SCAN": scan, "QUASI_CUDA_MIRROR": mirror,
+                                    "QUASI_CUDA_BATCH_ORDER": order})
     host.render(frames)
     got, stats = host.readback_aov(), host.stats()
     if mirror and frames % batch != 1:

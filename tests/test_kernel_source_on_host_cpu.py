@@ -5,8 +5,9 @@ __syncthreads and the warp collectives), against the CPU oracle, bit for bit.
 
 What this pins without a GPU: the control flow of the persistent kernel (device-wide tile queue,
 ballot/popc path regeneration, ragged edge tiles, the batched form in which a lane gives its pixel
-several consecutive samples) and the arithmetic of every build-time option, as written in the
-source. What it cannot say is what nvcc and ptxas make of that source; tests/test_cuda_parity.py
+several consecutive samples, and the sample-major one with its per-tile epochs, where running the
+source this way found a self-deadlock and a lane-dependent readiness test before any GPU saw them)
+and the arithmetic of every build-time option, as written in the source. What it cannot say is what nvcc and ptxas make of that source; tests/test_cuda_parity.py
 does, on the device. The product never runs this way: the emulator lives under tests/."""
 import subprocess
 import sys
@@ -31,9 +32,10 @@ def build(tmp_path, flags, harness="run_pathtrace"):
     return exe
 
 
-def check(exe, tmp_path, oracle, width, height, frames, batch, scan):
+def check(exe, tmp_path, oracle, width, height, frames, batch, scan, order=""):
+    """`order` "s": the sample-major form of the batched launch."""
     out = tmp_path / "layers.bin"
-    run = subprocess.run([str(exe), str(width), str(height), str(frames), str(batch), scan, str(out)],
+    run = subprocess.run([str(exe), str(width), str(height), str(frames), f"{batch}{order}", scan, str(out)],
                          capture_output=True, text=True, timeout=600)
     assert run.returncode == 0, run.stdout + run.stderr
     words = run.stdout.split()
@@ -53,7 +55,10 @@ def oracle():
 
 CASES = [(64, 36, 3, 1, "quads"), (61, 35, 5, 1, "boxes"), (97, 61, 2, 1, "generic"),     # one launch per frame
          (64, 36, 7, 3, "quads"), (64, 36, 8, 8, "quads"), (61, 35, 5, 2, "boxes"),        # QUASI_CUDA_BATCH
-         (61, 35, 5, 4, "generic"), (9, 5, 6, 4, "quads")]
+         (61, 35, 5, 4, "generic"), (9, 5, 6, 4, "quads"),
+         # QUASI_CUDA_BATCH_ORDER=sample; on the small images a warp meets its own unfinished tile again
+         (64, 36, 8, 8, "quads", "s"), (61, 35, 6, 3, "boxes", "s"), (61, 35, 5, 2, "generic", "s"),
+         (97, 61, 4, 4, "quads", "s"), (9, 5, 6, 4, "quads", "s"), (8, 4, 5, 5, "quads", "s")]
 
 
 def test_kernel_source_renders_the_oracle_image(tmp_path, oracle):
@@ -70,7 +75,8 @@ def test_kernel_source_renders_the_oracle_image(tmp_path, oracle):
 def test_build_time_options_render_the_oracle_image(tmp_path, oracle, flags):
     """The candidates of DESIGN.md section 9, each against the oracle in the plain and the batched form."""
     exe = build(tmp_path, flags)
-    for case in [(64, 36, 4, 1, "quads"), (61, 35, 6, 4, "quads"), (61, 35, 3, 1, "generic"), (61, 35, 3, 1, "boxes")]:
+    for case in [(64, 36, 4, 1, "quads"), (61, 35, 6, 4, "quads"), (61, 35, 3, 1, "generic"), (61, 35, 3, 1, "boxes"),
+                 (61, 35, 6, 3, "quads", "s")]:
         check(exe, tmp_path, oracle, *case)
 
 
