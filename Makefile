@@ -76,8 +76,13 @@ $(TESTDIR)/exr_write_tool: $(HOST)/test/exr_write_tool.cpp $(HOST)/src/exr_write
 	mkdir -p $(TESTDIR)
 	$(CXX) $(TEST_CXXFLAGS) -o $@ $(HOST)/test/exr_write_tool.cpp $(HOST)/src/exr_writer.cpp -lz
 
+# ref_loader_host: tests/ref_loader_host.cpp against the REFERENCE's own loader / manager headers
+# (-I$(REFERENCE)/src, none of this repository's host headers): the drop-in proof.
 reference-tests:
 	mkdir -p $(TESTDIR)
+	$(CXX) -std=c++23 -O1 -Wall -Wextra -Wpedantic -fcoroutines -pthread -I$(REFERENCE)/src -Iinclude \
+		-I/usr/local/cuda/include -o $(TESTDIR)/ref_loader_host tests/ref_loader_host.cpp \
+		-L/usr/local/cuda/lib64 -lcudart -ldl
 	for t in async_test plugin_test exr_writer_test; do \
 		$(CXX) $(TEST_CXXFLAGS) -o $(TESTDIR)/ref_$$t $(REFERENCE)/test/$$t.cpp $(HOST)/test/catch2_main.cpp \
 			$(HOST)/src/exr_writer.cpp -lz -ldl || exit 1; \

@@ -20,7 +20,23 @@
 #ifndef QUASI_CUDA_BACKEND_H
 #define QUASI_CUDA_BACKEND_H
 
+/* A host built inside the Quasi tree already has the ABI types from the reference's own
+ * <quasi/plugin/plugin_interface.hpp> (layout-identical to quasi_plugin_abi.h, checked in
+ * tests/test_abi_cpu.py). It defines QUASI_HOST_HAS_REFERENCE_HEADERS before including this file
+ * and gets only the CUDA additions from here (tests/ref_loader_host.cpp does exactly that). */
+#if defined(QUASI_HOST_HAS_REFERENCE_HEADERS)
+#include <quasi/plugin/plugin_interface.hpp>
+#ifndef Q_PLUGIN_EXPORT
+#define Q_PLUGIN_EXPORT
+#endif
+#ifndef Q_GPU_BACKEND_CUDA_DEFINED
+#define Q_GPU_BACKEND_CUDA_DEFINED
+/* appended to the reference's enum (types.hpp:14-19) until the tree carries it */
+static const Q_gpu_backend Q_GPU_BACKEND_CUDA = (Q_gpu_backend)4;
+#endif
+#else
 #include "quasi_plugin_abi.h"
+#endif
 
 #ifdef __cplusplus
 extern "C" {

@@ -279,16 +279,24 @@ emit_kernel(build_arrays a, float4* nodes, uint32_t n) {
 __global__ void __launch_bounds__(k_threads)
 depth_and_order_kernel(build_arrays a, uint32_t* leaf_order, uint32_t* depth, uint32_t n) {
     const uint32_t k = blockIdx.x * k_threads + threadIdx.x;
-    if (k >= n) return;
-    leaf_order[k] = static_cast<uint32_t>(a.keys[k]);
-    uint32_t node = a.parent[(n - 1) + k], levels = 1u;  // the leaf node itself
-    for (;;) {
-        if (!collapses(a, node)) levels++;  // an interior node of the emitted tree
-        if (node == 0u) break;
-        node = a.parent[node];
+    // Every lane of the warp reaches the reduction below (no early return): the mask is explicit
+    // and lanes past the end contribute zero, so the depth that guards the traversal stack
+    // (plugin.cu: mesh.depth > k_mesh_stack_entries) never depends on where the warp reconverges
+    // after the walks of different length.
+    uint32_t levels = 0u;
+    if (k < n) {
+        leaf_order[k] = static_cast<uint32_t>(a.keys[k]);
+        uint32_t node = a.parent[(n - 1) + k];
+        levels = 1u;  // the leaf node itself
+        for (;;) {
+            if (!collapses(a, node)) levels++;  // an interior node of the emitted tree
+            if (node == 0u) break;
+            node = a.parent[node];
+        }
     }
-    levels = __reduce_max_sync(__activemask(), levels);
-    if ((threadIdx.x & 31) == 0 || k == n - 1) atomicMax(depth, levels);
+    __syncwarp();
+    levels = __reduce_max_sync(0xffffffffu, levels);
+    if ((threadIdx.x & 31) == 0 && levels != 0u) atomicMax(depth, levels);
 }
 
 __global__ void __launch_bounds__(k_threads)

@@ -122,8 +122,8 @@ using cornell_layout = fixed_layout<0, 2, 3, 1, 0, 2>;
 /// as trace_scene_exact. `shade` is the shared-memory copy of the quads' shading
 /// records; the winner's plane is re-read from it for the literal finalisation.
 ///
-/// plugin.mm:174 (|denom| < 1e-8) is decided exactly in every form; plugin.mm:177
-/// (t < t_min) and plugin.mm:186 (alpha, beta in [0,1]) with margins.
+/// plugin.mm:177 (t < t_min) and plugin.mm:186 (alpha, beta in [0,1]) are decided with margins;
+/// plugin.mm:174 (|denom| < 1e-8) exactly, on the winner (scan_decide.hpp:accept_winner).
 template <class Layout>
 __device__ __forceinline__ void trace_scene(const scene_params& scene, const float* shade, v3 ro,
                                             v3 rd, hit_record& hit) {
@@ -188,6 +188,10 @@ __device__ __forceinline__ void trace_scene(const scene_params& scene, const flo
     const float* sh = shade + s.best_i * k_shade_stride;
     const v3 normal = load_v3(sh + k_sh_normal);
     const float denom = dot(normal, rd);
+    if (!accept_winner(denom)) {  // plugin.mm:174, taken once per ray instead of once per quad
+        trace_scene_exact(scene, ro, rd, hit);
+        return;
+    }
     hit.front = denom < 0.0f;
     hit.t = (sh[k_sh_plane_d] - dot(normal, ro)) / denom;
     hit.point = ro + rd * hit.t;

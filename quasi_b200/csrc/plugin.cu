@@ -462,10 +462,21 @@ void drop_mirror(plugin_state* state) {
 /// Launches the render calls collected under QUASI_CUDA_BATCH as one kernel. The arguments are
 /// the ones Q_plugin_render computes for a single call, for the first collected call; sample s of
 /// the launch is what the (s+1)-th collected call would have rendered.
-void flush_pending(plugin_state* state) {
+/// `stream`: the stream of the render call that triggers the launch; null when something else does (a readback, the
+/// statistics, destroy): then the launch goes to the plugin's own queue, because the stream of an earlier render
+/// call may no longer exist (a host may create one per frame). Either way it is ordered after the previous launch.
+/// If the launch cannot be made, the collected calls are taken back (frame_count and the path statistic), so that
+/// the samples that follow carry the weights of what is really in the layers.
+void flush_pending(plugin_state* state, cudaStream_t stream = nullptr) {
     if (state->pending == 0) return;
     const Q_render_frame& f = state->pending_frame;
-    auto stream = static_cast<cudaStream_t>(f.command_buffer);
+    if (stream == nullptr) stream = state->queue;
+    const uint32_t collected = state->pending;
+    auto take_back = [state, collected, &f]() {
+        state->frame_count -= collected < state->frame_count ? collected : state->frame_count;
+        state->paths -= static_cast<uint64_t>(collected) * f.width * f.height;
+        state->mirror_valid = false;
+    };
     frame_params fp;
     const uint32_t frame_index = state->shard_index + state->pending_first_sample * state->shard_count;
     Q::cuda::prepare_frame(f.camera.position, f.camera.target, f.camera.up, f.camera.fov, f.width, f.height, frame_index,
@@ -500,13 +511,17 @@ void flush_pending(plugin_state* state) {
             have = state->mirror[i] != nullptr;
         }
         // the table is set before every batched launch: buffers handed to a caller must never be written again
-        if (!check(state, Q::cuda::set_pathtrace_mirror(have ? state->mirror : nullptr, stream), "set_pathtrace_mirror")) return;
+        if (!check(state, Q::cuda::set_pathtrace_mirror(have ? state->mirror : nullptr, stream), "set_pathtrace_mirror")) {
+            take_back();
+            return;
+        }
         state->mirror_valid = have;
     }
     if (sample_major &&
         (!check(state, cudaMemsetAsync(state->tile_epochs, 0, state->tile_epoch_words * sizeof(unsigned int), stream),
                 "memset(tile epochs)") ||
          !check(state, Q::cuda::set_pathtrace_tile_epochs(state->tile_epochs, stream), "set_pathtrace_tile_epochs"))) {
+        take_back();
         return;
     }
     auto* tile_counters = reinterpret_cast<unsigned int*>(state->ray_counter + 3);
@@ -517,7 +532,7 @@ void flush_pending(plugin_state* state) {
                                                                tile_counters, state->sm_count, stream, state->generic_scan,
                                                                sample_major);
     if (!check(state, launched, "pathtrace_accumulate (batch)")) {
-        state->mirror_valid = false;
+        take_back();
         return;
     }
     state->kernel_launches++;
@@ -539,7 +554,8 @@ void render_batched(plugin_state* state, const Q_render_frame* frame) {
     const bool same_view = state->pending != 0 && frame->width == state->pending_frame.width &&
                            frame->height == state->pending_frame.height && frame->camera_dirty == 0 &&
                            std::memcmp(&frame->camera, &state->pending_frame.camera, sizeof frame->camera) == 0;
-    if (!same_view) flush_pending(state);
+    auto stream = static_cast<cudaStream_t>(frame->command_buffer);
+    if (!same_view) flush_pending(state, stream);
     if (frame->width != state->last_width || frame->height != state->last_height) {
         if (!create_layers(state, frame->width, frame->height)) return;
     }
@@ -553,7 +569,7 @@ void render_batched(plugin_state* state, const Q_render_frame* frame) {
     state->pending++;
     state->paths += static_cast<uint64_t>(frame->width) * frame->height;
     state->frame_count++;
-    if (state->pending >= state->batch) flush_pending(state);
+    if (state->pending >= state->batch) flush_pending(state, stream);
 }
 
 }  // namespace
@@ -708,7 +724,7 @@ Q_PLUGIN_EXPORT void Q_plugin_render(Q_plugin_handle* handle, Q_render_frame* fr
         render_batched(state, frame);
         return;
     }
-    flush_pending(state);  // a call that presents, after headless ones that were being collected
+    flush_pending(state, stream);  // a call that presents, after headless ones that were being collected
     state->mirror_valid = false;
 
     const uint32_t width = frame->width;

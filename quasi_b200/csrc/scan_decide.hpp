@@ -69,15 +69,26 @@ struct scan_state {
 
 /// Files one plane hit. `m` = max(|alpha' - 1/2|, |beta' - 1/2|): the point is
 /// surely outside the quad beyond half_plus and surely inside within half_minus.
-/// `ahead`: the plane is hit at all (|denom| >= 1e-8, decided exactly) and not surely
-/// behind t_min. The scan evaluates every quad for every lane without a branch: the
-/// inside test is 20 instructions, a divergent branch around it costs 3 and nearly
-/// always has a lane that takes it. What a lane computes past a failed `ahead` (possibly
-/// from an infinite t') is discarded here.
+/// `ahead`: the plane is not surely behind t_min. The scan evaluates every quad for every
+/// lane without a branch: the inside test is 20 instructions, a divergent branch around it
+/// costs 3 and nearly always has a lane that takes it. What a lane computes past a failed
+/// `ahead` is discarded here.
+///
+/// Two of the shader's rejections are NOT taken per quad but once per ray, on the winner
+/// (accept_winner below): |denom| < 1e-8 (plugin.mm:174) and t < t_min inside the band
+/// (k_t_min_lo, k_t_min_hi] (plugin.mm:177). Per quad they cost two comparisons each, sixteen
+/// times per ray, and they all but never fire. That is sound because a quad the shader rejects
+/// for one of them can only be filed here as a candidate it is not, never the other way round:
+/// if such a quad is the closest "sure" one, accept_winner sees its t' or its denominator and
+/// hands the ray to the literal loop; if it is not, it is a challenger like any other (literal
+/// loop when it is in front of, or ties with, the winner; irrelevant when it is behind).
+/// With denom == 0 the reciprocal is infinite and t' is +-inf or NaN: the point, alpha', beta'
+/// and m are then infinite or NaN, never finite, so neither `maybe` nor `sure` holds
+/// (comparisons with NaN are false; fmax(|a|, |b|) is NaN only if both are).
 QUASI_SCAN_FN void consider(scan_state& s, const quad_params& q, int i, float t_fast,
                                          float m, bool ahead) {
     const bool maybe = ahead && m <= q.half_plus;
-    const bool sure = ahead && m < q.half_minus && t_fast > k_t_min_hi;
+    const bool sure = ahead && m < q.half_minus;  // t_min_hi and |denom|: once per ray, accept_winner()
     const bool better = sure && t_fast < s.best_t;
     // Whoever does not become the winner challenges it.
     const float loser = better ? s.best_t : (maybe ? t_fast : k_inf);
@@ -88,7 +99,7 @@ QUASI_SCAN_FN void consider(scan_state& s, const quad_params& q, int i, float t_
 /// consider() with the two margins given as values (the packed-record forms below).
 QUASI_SCAN_FN void consider(scan_state& s, float half_plus, float half_minus, int i, float t_fast, float m, bool ahead) {
     const bool maybe = ahead && m <= half_plus;
-    const bool sure = ahead && m < half_minus && t_fast > k_t_min_hi;
+    const bool sure = ahead && m < half_minus;
     const bool better = sure && t_fast < s.best_t;
     const float loser = better ? s.best_t : (maybe ? t_fast : k_inf);
     s.challenger_t = std::fmin(s.challenger_t, loser);
@@ -107,7 +118,7 @@ QUASI_SCAN_FN void scan_flat(scan_state& s, const quad_params& q, int i, v3 ro, 
     const float denom = q.normal[K] * axis(rd, K);
     const float num = q.plane_d - q.normal[K] * axis(ro, K);
     const float t_fast = num * rcp(denom);
-    const bool ahead = std::fabs(denom) >= 1e-8f && t_fast > k_t_min_lo;
+    const bool ahead = t_fast > k_t_min_lo;
     // p', alpha', beta' only feed margin decisions: contracted (FFMA), unlike num and denom
     const float pi = fma_rn(axis(rd, I), t_fast, axis(ro, I)) - q.center[I];
     const float pj = fma_rn(axis(rd, J), t_fast, axis(ro, J)) - q.center[J];
@@ -124,7 +135,7 @@ QUASI_SCAN_FN void scan_flat(scan_state& s, const scan_record& q, int i, v3 ro, 
     const float denom = q.r[0] * axis(rd, K);
     const float num = q.r[1] - q.r[0] * axis(ro, K);
     const float t_fast = num * rcp(denom);
-    const bool ahead = std::fabs(denom) >= 1e-8f && t_fast > k_t_min_lo;
+    const bool ahead = t_fast > k_t_min_lo;
     const float pi = fma_rn(axis(rd, I), t_fast, axis(ro, I)) - q.r[2];
     const float pj = fma_rn(axis(rd, J), t_fast, axis(ro, J)) - q.r[3];
     const float alpha = fma_rn(pi, q.r[4], pj * q.r[5]);
@@ -138,7 +149,7 @@ QUASI_SCAN_FN void scan_upright(scan_state& s, const quad_params& q, int i, v3 r
     const float denom = q.normal[0] * rd.x + q.normal[2] * rd.z;
     const float num = q.plane_d - (q.normal[0] * ro.x + q.normal[2] * ro.z);
     const float t_fast = num * rcp(denom);
-    const bool ahead = std::fabs(denom) >= 1e-8f && t_fast > k_t_min_lo;
+    const bool ahead = t_fast > k_t_min_lo;
     const float px = fma_rn(rd.x, t_fast, ro.x) - q.center[0];
     const float py = fma_rn(rd.y, t_fast, ro.y) - q.center[1];
     const float pz = fma_rn(rd.z, t_fast, ro.z) - q.center[2];
@@ -152,7 +163,7 @@ QUASI_SCAN_FN void scan_upright(scan_state& s, const scan_record& q, int i, v3 r
     const float denom = q.r[0] * rd.x + q.r[1] * rd.z;
     const float num = q.r[2] - (q.r[0] * ro.x + q.r[1] * ro.z);
     const float t_fast = num * rcp(denom);
-    const bool ahead = std::fabs(denom) >= 1e-8f && t_fast > k_t_min_lo;
+    const bool ahead = t_fast > k_t_min_lo;
     const float px = fma_rn(rd.x, t_fast, ro.x) - q.r[3];
     const float py = fma_rn(rd.y, t_fast, ro.y) - q.r[4];
     const float pz = fma_rn(rd.z, t_fast, ro.z) - q.r[5];
@@ -166,7 +177,7 @@ QUASI_SCAN_FN void scan_general(scan_state& s, const quad_params& q, int i, v3 r
     const float denom = q.normal[0] * rd.x + q.normal[1] * rd.y + q.normal[2] * rd.z;
     const float num = q.plane_d - (q.normal[0] * ro.x + q.normal[1] * ro.y + q.normal[2] * ro.z);
     const float t_fast = num * rcp(denom);
-    const bool ahead = std::fabs(denom) >= 1e-8f && t_fast > k_t_min_lo;
+    const bool ahead = t_fast > k_t_min_lo;
     {
         const v3 planar{fma_rn(rd.x, t_fast, ro.x) - q.center[0], fma_rn(rd.y, t_fast, ro.y) - q.center[1],
                         fma_rn(rd.z, t_fast, ro.z) - q.center[2]};
@@ -291,7 +302,13 @@ QUASI_SCAN_FN void scan_scene(scan_state& s, const scene_params& scene, v3 ro, v
 QUASI_SCAN_FN bool needs_literal_scan(const scan_state& s) {
     // A challenger matters only if it could be in front of, or tie with, the sure
     // winner. With no sure winner (best_t == inf) any challenger matters.
-    return s.challenger_t < k_inf && s.challenger_t <= s.best_t * k_tie;
+    // A winner inside the t_min band may be one the shader rejects (plugin.mm:177).
+    return (s.challenger_t < k_inf && s.challenger_t <= s.best_t * k_tie) || s.best_t <= k_t_min_hi;
 }
+
+/// Second half of the per-ray acceptance, for a scan that named a winner: `denom` is the
+/// shader's dot(normal, rd) of that quad (the caller computes it anyway, for the literal t).
+/// plugin.mm:174 rejects the quad below 1e-8; the literal loop then decides the ray.
+QUASI_SCAN_FN bool accept_winner(float denom) { return std::fabs(denom) >= 1e-8f; }
 
 }  // namespace Q::cuda::scan

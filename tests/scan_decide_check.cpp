@@ -101,8 +101,44 @@ int main(int argc, char** argv) {
     long tested = 0, decided = 0, literal = 0, mismatches = 0;
     for (long it = 0; it < rays; it++) {
         v3 ro{}, rd{};
-        const int kind = static_cast<int>(it % 4);
-        if (kind == 0 && coin()) {  // camera rays of the default camera
+        const int kind = static_cast<int>(it % 5);
+        if (kind == 4 && coin()) {
+            // A ray that meets a quad at t = t_min give or take 1e-5 of it: the band (k_t_min_lo, k_t_min_hi] in
+            // which t' cannot tell which side of plugin.mm:177 the shader's t falls on (once per ray, on the winner).
+            const quad_params& q = scene.quads[rng() % scene.quad_count];
+            const float a = 0.05f + 0.9f * uniform(rng), b = 0.05f + 0.9f * uniform(rng);
+            const v3 target{q.origin[0] + q.u[0] * a + q.v[0] * b, q.origin[1] + q.u[1] * a + q.v[1] * b,
+                            q.origin[2] + q.u[2] * a + q.v[2] * b};
+            float len2;
+            do {
+                rd = {2.0f * uniform(rng) - 1.0f, 2.0f * uniform(rng) - 1.0f, 2.0f * uniform(rng) - 1.0f};
+                len2 = rd.x * rd.x + rd.y * rd.y + rd.z * rd.z;
+            } while (len2 > 1.0f || len2 < 1e-2f);
+            const float len = std::sqrt(len2);
+            rd = {rd.x / len, rd.y / len, rd.z / len};
+            const float t0 = 0.001f * (1.0f + (uniform(rng) - 0.5f) * (coin() ? 2e-5f : 1e-6f));
+            ro = {target.x - rd.x * t0, target.y - rd.y * t0, target.z - rd.z * t0};
+            if (inside_a_box_or_outside_the_room(grouped, ro)) continue;
+        } else if (kind == 4) {
+            // A ray almost IN the plane of a quad, starting within a few 1e-8 of that plane and aimed at a
+            // point of the quad: its |denom| straddles the shader's 1e-8 rejection (plugin.mm:174) while
+            // t' = num / denom is an ordinary distance. The scan takes that rejection once per ray, on the winner.
+            const quad_params& q = scene.quads[rng() % scene.quad_count];
+            const float a = 0.05f + 0.9f * uniform(rng), b = 0.05f + 0.9f * uniform(rng);
+            const v3 target{q.origin[0] + q.u[0] * a + q.v[0] * b, q.origin[1] + q.u[1] * a + q.v[1] * b,
+                            q.origin[2] + q.u[2] * a + q.v[2] * b};
+            const float angle = 6.2831853f * uniform(rng), reach = 0.05f + 1.5f * uniform(rng);
+            const float ulen = std::sqrt(q.u[0] * q.u[0] + q.u[1] * q.u[1] + q.u[2] * q.u[2]);
+            const float vlen = std::sqrt(q.v[0] * q.v[0] + q.v[1] * q.v[1] + q.v[2] * q.v[2]);
+            const float cu = std::cos(angle) * reach / ulen, cv = std::sin(angle) * reach / vlen;
+            const float slope = (coin() ? 1.0f : -1.0f) * std::pow(10.0f, -9.5f + 3.0f * uniform(rng));  // 3e-10 .. 3e-7
+            const float lift = slope * reach;  // so that the ray comes down to the plane at the target
+            ro = {target.x - q.u[0] * cu - q.v[0] * cv + q.normal[0] * lift,
+                  target.y - q.u[1] * cu - q.v[1] * cv + q.normal[1] * lift,
+                  target.z - q.u[2] * cu - q.v[2] * cv + q.normal[2] * lift};
+            rd = {target.x - ro.x, target.y - ro.y, target.z - ro.z};
+            if (inside_a_box_or_outside_the_room(grouped, ro)) continue;
+        } else if (kind == 0 && coin()) {  // camera rays of the default camera
             ro = {0.0f, 1.0f, 3.5f};
             rd = {-0.6f + 1.2f * uniform(rng), -0.5f + uniform(rng), -1.0f};
         } else if (kind == 0) {  // a camera anywhere around the room, looking at a point in or near it
@@ -189,7 +225,11 @@ int main(int argc, char** argv) {
             }
         }
 #endif
-        if (scan::needs_literal_scan(state)) {
+        bool to_literal = scan::needs_literal_scan(state);
+        if (!to_literal && state.best_i >= 0) {  // the kernel's finalisation: the winner's own denominator
+            to_literal = !scan::accept_winner(dot3(scene.quads[state.best_i].normal, rd));
+        }
+        if (to_literal) {
             literal++;
             continue;
         }

@@ -186,3 +186,33 @@ def test_headless_host_keeps_the_accumulation_across_a_reload(host_built, tmp_pa
     assert stats["reloads"] == 1 and stats["reload_failures"] == 0
     assert out.count("Accumulation adopted from the host's persistent state") == 1
     assert out.index("Path tracer destroyed") < out.index("Accumulation adopted")
+
+
+@pytest.mark.gpu
+def test_backend_under_the_references_own_loader_and_manager(oracle, tmp_path):
+    """Drop-in proof: tests/ref_loader_host.cpp is compiled against the reference's
+    UNMODIFIED dynamic_library.hpp, loader.hpp (:65-137) and manager.hpp (:122-135, :209-268) and
+    none of this repository's host headers. Loaded by them, libquasi_cuda.so renders the oracle's
+    image bit for bit and survives a reload driven by the reference's manager. The binary is built
+    where /root/reference exists (`make reference-tests`) and travels with the tree."""
+    import quasi_b200
+
+    exe = TESTS / "ref_loader_host"
+    if not exe.exists():
+        if not Path("/root/reference/src").exists():
+            pytest.skip("ref_loader_host was not built and the reference tree is not present")
+        subprocess.run(["make", "-s", "-C", str(ROOT), "reference-tests"], check=True)
+    w, h, n = 200, 113, 4
+    out = tmp_path / "layers.bin"
+    run = subprocess.run([str(exe), str(quasi_b200.PLUGIN_PATH), str(w), str(h), str(n), str(out)],
+                         capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0, run.stdout[-3000:] + run.stderr[-3000:]
+    assert "[Host] Loaded plugin: CUDA Path Tracer v1.0.0 (ABI 3)" in run.stdout
+    assert "[Host] manager path: reloads 1 ok 1 failed 0 errors 0" in run.stdout
+    # loader instance + two manager instances were created, and each was destroyed
+    assert run.stdout.count("Cornell Box path tracer initialized (CUDA)") == 3
+    assert run.stdout.count("Path tracer destroyed") >= 2
+    got = np.fromfile(out, dtype=np.float32).reshape(4, h, w, 4)
+    want, _ = oracle.render_frames(oracle.scene(w, h), w, h, n)
+    for name, g, wv in zip(LAYERS, got, want):
+        assert np.array_equal(g.view(np.uint32), wv.view(np.uint32)), name

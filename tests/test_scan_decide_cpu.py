@@ -81,3 +81,23 @@ def test_the_check_notices_a_missing_rule(tmp_path):
     exe = build(tmp_path, mutated)
     out = subprocess.run([str(exe), "3000000"], capture_output=True, text=True)
     assert out.returncode == 1 and "MISMATCH" in out.stdout
+
+
+def test_the_check_notices_a_missing_per_ray_rule(tmp_path):
+    """The shader's |denom| < 1e-8 rejection (plugin.mm:174) and its t < t_min rejection inside the
+    band t' cannot resolve (plugin.mm:177) are taken once per ray, on the winner
+    (scan_decide.hpp:needs_literal_scan / accept_winner), not once per quad. The check aims rays
+    at both: grazing rays that start within 1e-8 of a quad's plane, and rays that meet a quad at
+    t_min give or take 1e-5 of it. Without either rule the scan names quads the shader rejects."""
+    csrc = ROOT / "quasi_b200" / "csrc"
+    src = (csrc / "scan_decide.hpp").read_text()
+    assert "|| s.best_t <= k_t_min_hi;" in src and "return std::fabs(denom) >= 1e-8f; }" in src
+    for name, old, new in (("band", "|| s.best_t <= k_t_min_hi;", ";"),
+                           ("denom", "return std::fabs(denom) >= 1e-8f; }", "return denom == denom; }")):
+        mutated = tmp_path / f"mutated_{name}"
+        mutated.mkdir()
+        (mutated / "scan_decide.hpp").write_text(src.replace(old, new))
+        (mutated / "scene_params.hpp").write_text((csrc / "scene_params.hpp").read_text())
+        exe = build(tmp_path, mutated, f"-DMUTATION_{name}")
+        out = subprocess.run([str(exe), "3000000", "quads"], capture_output=True, text=True)
+        assert out.returncode == 1 and "MISMATCH" in out.stdout, name
