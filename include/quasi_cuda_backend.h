@@ -136,6 +136,39 @@ typedef struct Q_cuda_layers {
     uint32_t reserved;
 } Q_cuda_layers;
 
+/* Where batched launches (QUASI_CUDA_BATCH, the default) send every 8x4 tile of the four layers as soon
+ * as it has received the last sample of the launch, rows of 8 pixels (128 bytes) at a time, while the
+ * rest of the image is still being rendered. The contiguous layer block (4 * width * height float4:
+ * beauty, albedo, normal, depth) is cut into `slices` pieces of `float4_per_slice` float4 (the last
+ * one may be shorter); float4 i of the block is stored at base[i / float4_per_slice] +
+ * (i % float4_per_slice). A multi-GPU host points base[g] into GPU g's staging memory (peer-mapped,
+ * Q_cuda_ipc_open): every rank pushes each slice of its layers to the slice's owner over NVLink as
+ * part of the render, and the exchange that follows the frame is a local sum (Q_cuda_reduce_slices).
+ * Pinned host memory works as well (that is what the plugin's own readback mirror is). */
+#define Q_CUDA_MAX_EXPORT_SLICES 16u
+typedef struct Q_cuda_export_table {
+    uint32_t struct_size;       /* sizeof(Q_cuda_export_table) */
+    uint32_t slices;            /* 1 .. Q_CUDA_MAX_EXPORT_SLICES */
+    uint32_t float4_per_slice;  /* > 0 */
+    uint32_t reserved;
+    void* base[Q_CUDA_MAX_EXPORT_SLICES];
+} Q_cuda_export_table;
+
+/* Sets (table != NULL) or clears the export target of the launches that follow; render calls already
+ * collected are launched first, with the previous target. While a table is set the plugin's own
+ * readback mirror is off (Q_plugin_readback* copy from the device as usual). Returns 0, or -1 for a
+ * malformed table. The memory behind base[] must stay valid until the launches have completed. */
+Q_PLUGIN_EXPORT int Q_cuda_plugin_set_export(Q_plugin_handle* handle, const Q_cuda_export_table* table);
+
+/* Launches the render calls the plugin has collected (QUASI_CUDA_BATCH) on `stream` (NULL: the
+ * plugin's own queue) without waiting for them. A host that keeps the device pointers of
+ * Q_cuda_plugin_layers across frames calls this before it reads the layers on the device; every
+ * Q_plugin_* and Q_cuda_plugin_* call that looks at the layers does it by itself.
+ * Returns 1 if the most recent launch exported the whole frame to the export target (a batched
+ * launch with a table set, or the readback mirror), 0 if not (a launch of a single sample exports
+ * nothing: a multi-GPU host then sends the layers with Q_cuda_push_slices), -1 on a NULL handle. */
+Q_PLUGIN_EXPORT int Q_cuda_plugin_flush(Q_plugin_handle* handle, void* stream);
+
 /* Blocking: waits for enqueued renders so that the counters are final. */
 Q_PLUGIN_EXPORT int Q_cuda_plugin_stats(Q_plugin_handle* handle, Q_cuda_stats* out);
 
@@ -187,20 +220,37 @@ Q_PLUGIN_EXPORT int Q_cuda_ipc_export(void* device_ptr, Q_cuda_ipc_handle* out);
 Q_PLUGIN_EXPORT int Q_cuda_ipc_open(const Q_cuda_ipc_handle* handle, void** out_device_ptr);
 Q_PLUGIN_EXPORT int Q_cuda_ipc_close(void* device_ptr);
 
-/* Q_cuda_combine_shards with the cross-GPU synchronisation INSIDE the kernel, so
- * the exchange of a frame is one launch per GPU and no host barrier: rank `rank`
- * of n_shards passes its slice of every rank's layer block (shards[g]), every
- * rank's flag block (flags[g]: Q_CUDA_SYNC_WORDS uint32, zeroed once with
- * Q_cuda_memset_async, mapped with the IPC calls above) and the frame's epoch
- * (1, 2, 3, ... identical on all ranks). The kernel waits until every rank's
- * render of this epoch has finished, combines, and returns only when every
- * rank's slice has landed in `out`'s owner and nobody still reads this rank's
- * layers. Every rank must launch it for every epoch (n_pixels may be 0). */
+/* ---- the multi-GPU exchange, push-based -----------------------------------------
+ * The layer block of 4 * width * height float4 is cut into G slices of P float4; rank s owns slice s
+ * and holds a staging area of G * P float4 (device memory, exported with Q_cuda_ipc_export) in which
+ * slot g receives rank g's copy of slice s. Every rank sends slice s of its own layers to
+ * staging_s + g * P (Q_cuda_plugin_set_export: the batched render kernel does it tile by tile while it
+ * renders; or Q_cuda_push_slices afterwards), then runs Q_cuda_reduce_slices_sync on its own slice.
+ * The summation order is the rank order, so the result is bit-identical to
+ * oracle/quasi_oracle.c:qo_combine_shards whatever the timing. */
+
+/* block[i] -> table->base[i / P][i % P] for i < n_float4, enqueued on `stream`. */
+Q_PLUGIN_EXPORT int Q_cuda_push_slices(const float* block, uint64_t n_float4, const Q_cuda_export_table* table,
+                                       void* stream);
+
+/* One launch, enqueue only. Device-side flags replace host barriers: the kernel stores `epoch` into
+ * flags[g][rank] of every rank g (its frame, and everything it pushed, is complete: the launch follows the
+ * render in stream order), waits until flags[rank][g] >= epoch for every g, then
+ * out[i] = (staging[i] + staging[P + i] + ... + staging[(G-1) P + i]) * scale for i < n_float4
+ * (scale 0 = 1/G). `out` may be pinned host memory (Q_cuda_host_register): every GPU then sends its
+ * slice of the finished frame to the host over its own PCIe link. `flags[g]`: rank g's flag block
+ * (Q_CUDA_SYNC_WORDS zeroed uint32, Q_cuda_alloc + Q_cuda_ipc_export); `epoch` counts frames from 1 and
+ * is the same on every rank. The staging area must be double-buffered by frame parity (post.cu). */
 #define Q_CUDA_SYNC_WORDS 33u
-Q_PLUGIN_EXPORT int Q_cuda_combine_shards_sync(const float* const* shards, uint32_t* const* flags,
-                                               uint32_t n_shards, uint32_t rank, uint32_t epoch,
-                                               uint64_t n_pixels, float scale, float* out, void* bgra,
-                                               void* stream);
+Q_PLUGIN_EXPORT int Q_cuda_reduce_slices_sync(const float* staging, uint32_t float4_per_slice,
+                                              uint32_t* const* flags, uint32_t n_shards, uint32_t rank,
+                                              uint32_t epoch, uint64_t n_float4, float scale, float* out,
+                                              void* stream);
+
+/* Pins `bytes` of host memory the caller owns (e.g. a shared-memory segment every rank has mapped) and
+ * returns the address kernels and copies of this process use for it. */
+Q_PLUGIN_EXPORT int Q_cuda_host_register(void* host_ptr, uint64_t bytes, void** out_device_ptr);
+Q_PLUGIN_EXPORT int Q_cuda_host_unregister(void* host_ptr);
 
 #ifdef __cplusplus
 } /* extern "C" */

@@ -98,6 +98,14 @@ class Q_cuda_ipc_handle(C.Structure):
     _fields_ = [("bytes", C.c_ubyte * 64)]
 
 
+Q_CUDA_MAX_EXPORT_SLICES = 16
+
+
+class Q_cuda_export_table(C.Structure):  # quasi_cuda_backend.h
+    _fields_ = [("struct_size", C.c_uint32), ("slices", C.c_uint32), ("float4_per_slice", C.c_uint32),
+                ("reserved", C.c_uint32), ("base", C.c_void_p * Q_CUDA_MAX_EXPORT_SLICES)]
+
+
 # Sizes on x86-64 Linux (probed from the reference headers).
 assert C.sizeof(Q_plugin_context) == 40
 assert C.sizeof(Q_render_frame) == 72
@@ -117,6 +125,7 @@ OPTIONAL_SYMBOLS = (  # loader.hpp:115-128
 CUDA_EXTENSION_SYMBOLS = (  # quasi_cuda_backend.h
     "Q_cuda_plugin_stats", "Q_cuda_plugin_layers", "Q_cuda_accumulate", "Q_cuda_tonemap_bgra8",
     "Q_cuda_combine_shards", "Q_cuda_alloc", "Q_cuda_free", "Q_cuda_ipc_export", "Q_cuda_ipc_open",
-    "Q_cuda_ipc_close", "Q_cuda_probe_sincos", "Q_cuda_plugin_mesh_view", "Q_cuda_combine_shards_sync",
-    "Q_cuda_memset_async",
+    "Q_cuda_ipc_close", "Q_cuda_probe_sincos", "Q_cuda_plugin_mesh_view", "Q_cuda_memset_async",
+    "Q_cuda_plugin_set_export", "Q_cuda_plugin_flush", "Q_cuda_push_slices", "Q_cuda_reduce_slices_sync",
+    "Q_cuda_host_register", "Q_cuda_host_unregister",
 )

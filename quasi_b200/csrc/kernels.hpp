@@ -6,9 +6,6 @@
 #include "scene_params.hpp"
 
 #include <cuda_runtime_api.h>
-#if defined(QUASI_PDL) && QUASI_PDL
-#include <cuda_runtime.h>
-#endif
 
 #include <cstdint>
 
@@ -32,47 +29,20 @@ struct alignas(16) mesh_params {
     float materials[k_mesh_materials * 8];  ///< per material: albedo.xyz, 0, emission.xyz, 0
 };
 
-/// Build-time option QUASI_PDL: launches `kernel` on `stream` as a programmatic dependent of
-/// the kernel before it on that stream (device_common.cuh:pdl_wait).
-#if defined(QUASI_PDL) && QUASI_PDL
-template <class... Params, class... Args>
-cudaError_t launch_persistent(void (*kernel)(Params...), uint32_t blocks, uint32_t threads, size_t dynamic_smem,
-                              cudaStream_t stream, Args&&... args) {
-    cudaLaunchConfig_t config{};
-    config.gridDim = dim3(blocks);
-    config.blockDim = dim3(threads);
-    config.dynamicSmemBytes = dynamic_smem;
-    config.stream = stream;
-    cudaLaunchAttribute attribute{};
-    attribute.id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attribute.val.programmaticStreamSerializationAllowed = 1;
-    config.attrs = &attribute;
-    config.numAttrs = 1;
-    return cudaLaunchKernelEx(&config, kernel, Params(args)...);
-}
-#endif
-
-/// @brief One new sample per pixel, folded into the four accumulated layers in place.
+/// @brief frame.batch_samples new samples per pixel (one by default), folded into the four accumulated
+/// layers in place (pathtrace.cu:pathtrace_accumulate_kernel).
+/// @param launch For frame.batch_samples > 1: the zeroed per-tile epochs (required) and where finished
+///        tiles are exported to (optional); ignored for a launch of one sample.
 /// @param layers Device pointers to beauty, albedo, normal, depth (RGBA32F, row 0 = top).
 /// @param ray_counter Device counter incremented by the number of closest-hit queries.
-/// @param tile_counters Two zero-initialised device uints: the tile work queue (device_common.cuh:tile_feed).
+/// @param tile_counters Two zero-initialised device uints: the device-wide work queue (next entry, warps finished).
 /// @param sm_count Multiprocessors of the device; the grid is 4 resident CTAs per SM.
 /// @param generic_scan Use the any-scene kernel (one loop per quad shape) even where a kernel
 ///        unrolled for the scene's layout exists.
-cudaError_t launch_pathtrace_accumulate(const scene_params& scene, const frame_params& frame,
+cudaError_t launch_pathtrace_accumulate(const scene_params& scene, const frame_params& frame, const batch_params& launch,
                                         float* const layers[4], unsigned long long* ray_counter,
                                         unsigned int* tile_counters, int sm_count, cudaStream_t stream,
-                                        bool generic_scan = false, bool sample_major = false);
-
-/// @brief For sample-major batched launches (`sample_major`, frame.batch_samples > 1): one zeroed
-/// word per 8x4 tile, ordered on `stream` before the launches that follow; the host zeroes the
-/// words before every such launch. Needs scene.max_bounces <= 7 (eight completion counters per warp).
-cudaError_t set_pathtrace_tile_epochs(unsigned int* epochs, cudaStream_t stream);
-
-/// @brief Where the batched demo-scene kernels also store every pixel's value after the last sample
-/// of a launch (pathtrace.cu:g_mirror): four pinned host buffers, or null for nowhere. Ordered on
-/// `stream` before the launches that follow on it. One table per device: for one plugin instance.
-cudaError_t set_pathtrace_mirror(float* const mirror[4], cudaStream_t stream);
+                                        bool generic_scan = false);
 
 /// @brief The mesh-scene form of launch_pathtrace_accumulate (BASELINE config 3).
 /// @param counters Device array of 3: rays, BVH nodes visited (box tests), triangles tested.
@@ -121,15 +91,20 @@ cudaError_t launch_combine_shards(const float* const* shards, uint32_t n_shards,
                                   uint64_t n_pixels, float scale, float* out, void* bgra,
                                   cudaStream_t stream);
 
-/// Words in a rank's flag block for launch_combine_shards_sync: arrive[16], done[16], CTA counter.
+/// Words in a rank's flag block for launch_reduce_slices_sync: arrive[16] (the rest is spare).
 inline constexpr uint32_t k_sync_words = 2 * k_max_shards + 1;
 
-/// @brief launch_combine_shards with the cross-GPU synchronisation inside the kernel.
-/// `shards[g]` / `flags[g]` are rank g's slice of its layer block and its zero-initialised
-/// flag block (k_sync_words uint32), both addressable from this GPU; `epoch` counts frames
-/// from 1 and is the same on every rank. See combine_shards_sync_kernel.
-cudaError_t launch_combine_shards_sync(const float* const* shards, uint32_t* const* flags, uint32_t n_shards,
-                                       uint32_t rank, uint32_t epoch, uint64_t n_pixels, float scale, float* out,
-                                       void* bgra, cudaStream_t stream);
+/// @brief The layer block slice by slice to base[i / float4_per_slice] + i % float4_per_slice (the addressing
+/// of batch_params' export), for a frame whose last launch exported nothing.
+cudaError_t launch_push_slices(const float* block, uint64_t n_float4, void* const* base, uint32_t slices,
+                               uint32_t float4_per_slice, cudaStream_t stream);
+
+/// @brief The owner's half of the multi-GPU exchange (post.cu:reduce_slices_sync_kernel): waits on device-side
+/// flags until all `n_shards` ranks have completed the frame `epoch`, then out[i] = (sum over g in rank order
+/// of staging[g * float4_per_slice + i]) * scale for i < n_float4 (scale 0 = 1/n_shards).
+/// `flags[g]`: rank g's zero-initialised flag block (k_sync_words uint32), addressable from this GPU.
+cudaError_t launch_reduce_slices_sync(const float* staging, uint32_t float4_per_slice, uint32_t* const* flags,
+                                      uint32_t n_shards, uint32_t rank, uint32_t epoch, uint64_t n_float4, float scale,
+                                      float* out, cudaStream_t stream);
 
 }  // namespace Q::cuda

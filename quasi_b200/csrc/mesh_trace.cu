@@ -198,15 +198,12 @@ __device__ __forceinline__ void wide_step(const float4* __restrict__ nodes, lane
     cur = slab::wide_visit(lx, ly, lz, hx, hy, hz, refs, inv, oi, closest, stack);
 }
 
-/// `Batch`: frame.batch_samples consecutive samples per pixel in one launch, a lane going on with
-/// the next sample of its own pixel when a path ends (pathtrace.cu, QUASI_CUDA_BATCH).
-template <bool Wide, bool Batch = false>
+template <bool Wide>
 __global__ void __launch_bounds__(k_block_threads, k_blocks_per_sm)
 mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_constant__ frame_params frame,
                       float4* __restrict__ beauty, float4* __restrict__ albedo, float4* __restrict__ normal,
                       float4* __restrict__ depth, unsigned long long* __restrict__ counters,
                       unsigned int* __restrict__ tile_counters) {
-    pdl_launch_dependents();
 #if defined(QUASI_HOST_EMULATION)  // tests/cuda_emulation: the dynamic shared memory of this CTA
     uint32_t* s_refs = static_cast<uint32_t*>(emu::dynamic_shared());
 #else
@@ -217,7 +214,6 @@ mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_co
         s_material[i] = scene.materials[i];
     }
     __syncthreads();
-    pdl_wait();  // layers, tile queue and counters belong to the previous launch until here
     lane_stack stack;
     stack.refs = s_refs + threadIdx.x;
     stack.dist = reinterpret_cast<uint16_t*>(s_refs + k_mesh_stack_entries * k_block_threads) + threadIdx.x;
@@ -245,11 +241,6 @@ mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_co
     uint32_t rays = 0, nodes_visited = 0, tris_tested = 0;
     uint32_t next_item = 0;  // warp-uniform cursor into this warp's pixel sequence
     tile_feed feed{tile_counters, n_tiles};
-    // Batch only: which sample of the launch this lane's path is, its pixel, that sample's constants
-    [[maybe_unused]] uint32_t sample_of_item = 0, pixel_xy = 0xffffffffu;
-    [[maybe_unused]] bool lane_first = first_sample;
-    [[maybe_unused]] float lane_weight = weight;
-    [[maybe_unused]] const uint32_t batch = frame.batch_samples > 1u ? frame.batch_samples : 1u;
 
     while (true) {
         // ---------------------------------------------------------- service ----
@@ -287,12 +278,12 @@ mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_co
                     first_t = best.t;
                 }
                 const float nd = fminf(fmaxf((first_t - 1.0f) / 4.0f, 0.0f), 1.0f);
-                accumulate_pixel(albedo, pixel, make_float4(a.x, a.y, a.z, 1.0f), Batch ? lane_first : first_sample,
-                                 Batch ? lane_weight : weight);
-                accumulate_pixel(normal, pixel, make_float4(nn.x, nn.y, nn.z, 1.0f), Batch ? lane_first : first_sample,
-                                 Batch ? lane_weight : weight);
-                accumulate_pixel(depth, pixel, make_float4(nd, nd, nd, 1.0f), Batch ? lane_first : first_sample,
-                                 Batch ? lane_weight : weight);
+                accumulate_pixel(albedo, pixel, make_float4(a.x, a.y, a.z, 1.0f), first_sample,
+                                 weight);
+                accumulate_pixel(normal, pixel, make_float4(nn.x, nn.y, nn.z, 1.0f), first_sample,
+                                 weight);
+                accumulate_pixel(depth, pixel, make_float4(nd, nd, nd, 1.0f), first_sample,
+                                 weight);
             }
 
             bool done = !is_hit;
@@ -320,72 +311,13 @@ mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_co
                 new_ray = true;  // the direction is drawn below, together with the new paths' camera rays
             } else {
                 accumulate_pixel(beauty, pixel, make_float4(color.x, color.y, color.z, 1.0f),
-                                 Batch ? lane_first : first_sample, Batch ? lane_weight : weight);
+                                 first_sample, weight);
                 active = false;
             }
         }
         __syncwarp();
 
         // Regeneration: lanes without a path take the warp's next pixels (see pathtrace.cu).
-        if constexpr (Batch) {
-            bool start = false;
-            uint32_t px = 0, py = 0;
-            if (!active && pixel_xy != 0xffffffffu) {
-                if (sample_of_item + 1u < batch) {
-                    sample_of_item++;
-                    px = pixel_xy & 0xffffu;
-                    py = pixel_xy >> 16;
-                    start = true;
-                } else {
-                    pixel_xy = 0xffffffffu;
-                }
-            }
-            const uint32_t idle = __ballot_sync(0xffffffffu, !active && !start);
-            if (idle != 0u) {
-                feed.open(next_item, next_item + __popc(idle) - 1u);
-                if (!active && !start) {
-                    const uint32_t item = next_item + __popc(idle & lanes_below);
-                    const uint32_t tile = feed.tile_of(item);
-                    if (tile < n_tiles) {
-                        uint32_t tile_y = __umulhi(tile, frame.tiles_x_magic);
-                        uint32_t tile_x = tile - tile_y * tiles_x;
-                        if (tile_x >= tiles_x) {
-                            tile_x -= tiles_x;
-                            tile_y++;
-                        }
-                        px = tile_x * 8u + (item & 7u);
-                        py = tile_y * 4u + ((item >> 3) & 3u);
-                        if (px < frame.width && py < frame.height) {
-                            pixel_xy = px | (py << 16);
-                            sample_of_item = 0;
-                            start = true;
-                            pixel = py * frame.width + px;
-                            if (!first_sample) {
-                                prefetch_l2(beauty + pixel);
-                                prefetch_l2(albedo + pixel);
-                                prefetch_l2(normal + pixel);
-                                prefetch_l2(depth + pixel);
-                            }
-                        }
-                    }
-                }
-                next_item += __popc(idle);
-            }
-            if (start) {
-                const uint32_t sample_index = frame.sample_index + sample_of_item;
-                uv_x = (static_cast<float>(px) + 0.5f) / static_cast<float>(frame.width);
-                uv_y = 1.0f - (static_cast<float>(py) + 0.5f) / static_cast<float>(frame.height);
-                rng = pcg_hash(px + py * 1920u + (frame.frame_index + sample_of_item * frame.frame_stride) * 1920u * 1080u);
-                fresh = true;
-                throughput = make_v3(1.0f, 1.0f, 1.0f);
-                color = make_v3(0.0f, 0.0f, 0.0f);
-                bounce = 0;
-                active = true;
-                new_ray = true;
-                lane_first = sample_index == 0u;
-                lane_weight = 1.0f / static_cast<float>(sample_index + 1u);
-            }
-        } else {
         const uint32_t idle = __ballot_sync(0xffffffffu, !active);
         if (idle != 0u) {
             feed.open(next_item, next_item + __popc(idle) - 1u);
@@ -423,7 +355,6 @@ mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_co
             }
             next_item += __popc(idle);
         }
-        }  // !Batch
 
         // Every lane with a new ray: its direction (get_camera_ray, plugin.mm:129-153, for a new
         // path; cosine_sample_hemisphere, plugin.mm:111-125, with the per-triangle frame for a
@@ -538,27 +469,15 @@ cudaError_t launch_mesh_pathtrace(const mesh_params& scene, const frame_params& 
     const uint32_t needed = (n_tiles + k_warps_per_block - 1u) / k_warps_per_block;
     if (needed < blocks) blocks = needed;
     if (blocks == 0) return cudaSuccess;
-    const bool batched = frame.batch_samples > 1u;
-    auto* kernel = scene.wide != 0u ? (batched ? mesh_pathtrace_kernel<true, true> : mesh_pathtrace_kernel<true>)
-                                    : (batched ? mesh_pathtrace_kernel<false, true> : mesh_pathtrace_kernel<false>);
-    static const cudaError_t attr[4] = {
+    auto* kernel = scene.wide != 0u ? mesh_pathtrace_kernel<true> : mesh_pathtrace_kernel<false>;
+    static const cudaError_t attr[2] = {
         cudaFuncSetAttribute(mesh_pathtrace_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              static_cast<int>(k_stack_bytes)),
         cudaFuncSetAttribute(mesh_pathtrace_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             static_cast<int>(k_stack_bytes)),
-        cudaFuncSetAttribute(mesh_pathtrace_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             static_cast<int>(k_stack_bytes)),
-        cudaFuncSetAttribute(mesh_pathtrace_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              static_cast<int>(k_stack_bytes))};
     for (cudaError_t e : attr) {
         if (e != cudaSuccess) return e;
     }
-#if defined(QUASI_PDL) && QUASI_PDL
-    return launch_persistent(kernel, blocks, k_block_threads, k_stack_bytes, stream, scene, frame,
-                             reinterpret_cast<float4*>(layers[0]), reinterpret_cast<float4*>(layers[1]),
-                             reinterpret_cast<float4*>(layers[2]), reinterpret_cast<float4*>(layers[3]), counters,
-                             tile_counters);
-#endif
     kernel<<<blocks, k_block_threads, k_stack_bytes, stream>>>(
         scene, frame, reinterpret_cast<float4*>(layers[0]), reinterpret_cast<float4*>(layers[1]),
         reinterpret_cast<float4*>(layers[2]), reinterpret_cast<float4*>(layers[3]), counters, tile_counters);

@@ -9,13 +9,13 @@
 /// 128 B/px of HBM traffic per call instead of 276.
 ///
 /// Execution model (DESIGN.md "Kernels"):
-///  - Persistent warps with path regeneration. The grid is resident CTAs only
-///    (4 per SM); warps take 8x4 pixel tiles from a device-wide work queue (one
-///    atomic per tile, device_common.cuh:tile_feed). A lane whose
-///    path ended writes its pixel and immediately starts the warp's next pixel
-///    (ballot + popc compaction of the idle lanes), so every lane of the warp is
-///    always inside the same bounce step. In the thread-per-pixel form the warp
-///    ran at 18 of 32 lanes (ncu, profiles/r1_v1_*).
+///  - Persistent warps, wavefront inside the warp. The grid is resident CTAs only (4 per SM);
+///    a warp takes 8x4 pixel tiles from a device-wide work queue (one atomic per tile) into a
+///    queue of primary items in shared memory, paths that go on after a hit go to a queue of
+///    bounce items, and every warp iteration pops 32 items of ONE queue: all lanes of an
+///    iteration do the same kind of work (pathtrace_accumulate_kernel below). In the
+///    thread-per-pixel form the warp ran at 18 of 32 lanes (ncu, profiles/r1_v1_*), in the
+///    lane-owns-a-path form of round 1 at 23.8, here at 28.4.
 ///  - The 16-quad scan is fully unrolled; plane, edge and margin constants are
 ///    immediate constant-bank operands. The scan DECIDES with cheap forms
 ///    (MUFU.RCP instead of IEEE division, one dot product per barycentric
@@ -207,371 +207,211 @@ constexpr int k_block_threads = QUASI_QUAD_BLOCK_THREADS;
 constexpr int k_blocks_per_sm = QUASI_QUAD_BLOCKS_PER_SM;
 constexpr int k_warps_per_block = k_block_threads / 32;
 
-/// Batched launches only (QUASI_CUDA_MIRROR, plugin.cu): pinned host buffers, one per layer, that
-/// receive every pixel's value after the LAST sample of the launch, written by the lane that
-/// computed it, so that the device-to-host transfer of a frame is spread over the launch that
-/// renders it instead of following it. Null entries: nothing is mirrored.
-__device__ float4* g_mirror[4];
+// ------------------------------------------------------------------------------------------------
+// Path state lives in per-warp queues in shared memory; every warp iteration is ONE kind of work
+// for 32 paths.
+//
+// Round 1's kernel let a lane own a path from its camera ray to its end, and each iteration of the
+// warp served two populations at once: about 14 lanes that had just taken a new pixel (tile
+// decode, uv, seed, camera ray, and after the scan the three first-hit AOV read-modify-writes) and
+// about 18 that continued a path (binary64 sin/cos, the scatter frame). SIMT executes the two one
+// after the other, so ~380 of the ~1210 instructions of an iteration ran at half the lanes (ncu,
+// profiles/r2_quad_lane_owned_regions.txt: 23.8 of 32 lanes overall, 40.0 warp instructions per ray).
+// Here a warp keeps two queues in shared memory:
+//   P  primary items  (pixel, sample of the launch): a pixel that needs a camera ray
+//   B  bounce items   (origin, RNG state, the quad scattered from, throughput, colour, pixel)
+// and every iteration pops up to 32 items of ONE queue, traces one ray for each and pushes the
+// paths that go on to B. The queue is the compaction: all 32 lanes of an iteration run the same
+// code, new-pixel work is issued only in primary iterations and scatter work only in bounce
+// iterations, and only the origin, the direction and the RNG state are live across the scan
+// (throughput, colour and pixel stay in the queue slot until the hit is shaded).
+// Measured (B200, 1080p, 64 spp, one launch per sample): 26.5 against 22.9 Grays/s, 34.4 against
+// 40.0 warp instructions per ray at 28.4 against 23.8 lanes (profiles/r2_wavefront_*).
+// Policy (warp-uniform): B holds 32 -> bounce iteration; else P holds 32 -> primary iteration; else
+// take a tile from the device-wide queue into P; when that has run dry, drain P, then B.
+// An item yields at most one item and a tile is taken only when both queues are below 32, so B never
+// exceeds 63 items and P never 95: 64 and 128 slots.
+//
+// `Batch` (frame.batch_samples = k > 1, plugin.cu:QUASI_CUDA_BATCH): one launch gives every pixel k
+// samples. The samples of a pixel must be folded in in order (the running mean of plugin.mm:326), so
+// a tile stays with the warp that took it: when a path ends before the pixel's last sample of the
+// launch, the pixel goes back into P with the next sample. Every read-modify-write of a pixel is then
+// separated from the previous one by a __syncwarp of the one warp that touches that pixel in the launch.
+// A slot table in shared memory counts, per tile the warp holds, the pixels that have not had their last
+// sample; when the count reaches zero the warp EXPORTS the tile (batch_params): the 32 pixels of all four
+// layers, rows of 8 pixels (128 bytes) at a time, to pinned host memory (the plugin's readback mirror: the
+// frame is on the host when the launch ends, its 64 B/px transfer spread over the launch that renders it)
+// or to the GPUs that own the slices (multi-GPU: the reduce-scatter is part of the render). Tiles finish
+// all through the launch, so the export overlaps the rendering of the rest of the image.
+// Tried and dropped (round 2, profiles/r2_call3.log): k passes over the image inside the launch, entry
+// q = tile q % n_tiles at sample q / n_tiles, ordered by a per-tile epoch in global memory. It removes the
+// tail of this form (the last pixels of a warp walk through their k samples one after the other, 4.8 % of
+// the SM cycles at k = 64) but every tile then finishes in the last pass, so the whole export lands at the
+// end (14.5 ms per frame instead of 12.0 with the export off), and its fences and L2 history reads cost
+// 4 % more instructions at 67 % issue utilisation instead of 82 %.
+constexpr uint32_t k_bq = 64, k_pq = 128;  // queue slots (powers of two)
+constexpr uint32_t k_bq_fields = 13;       // ro.xyz, rng, meta, throughput.xyz, colour.xyz, pixel_xy, tag
+constexpr uint32_t k_tile_slots = 16;      // Batch: tiles a warp may hold at once
+constexpr uint32_t k_queue_words = k_bq_fields * k_bq + 2 * k_pq + 2 * k_tile_slots;  // per warp
+constexpr size_t k_wavefront_smem = static_cast<size_t>(k_warps_per_block) * k_queue_words * sizeof(uint32_t);
 
-__device__ __forceinline__ void mirror_pixel(int layer, size_t pixel, float4 value) {
-    float4* to = g_mirror[layer];
-    if (to != nullptr) to[pixel] = value;
-}
-
-/// Sample-major batched launches only: one word per tile, the number of samples of THIS launch
-/// that every pixel of the tile has received (zeroed by the host before the launch).
-__device__ unsigned int* g_tile_epochs;
-
-__device__ __forceinline__ unsigned int load_acquire_gpu(const unsigned int* p) {
-#if defined(QUASI_HOST_EMULATION)
-    return std::atomic_ref<const unsigned int>(*p).load(std::memory_order_acquire);
-#else
-    unsigned int v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-#endif
-}
-__device__ __forceinline__ void store_release_gpu(unsigned int* p, unsigned int v) {
-#if defined(QUASI_HOST_EMULATION)
-    std::atomic_ref<unsigned int>(*p).store(v, std::memory_order_release);
-#else
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-#endif
-}
-
-/// The work queue of a sample-major launch: entry q of n_tiles * k is tile q % n_tiles at sample
-/// q / n_tiles, so all tiles get sample 0, then all get sample 1, ...; otherwise tile_feed
-/// (device_common.cuh). An entry with sample s > 0 is READY once the tile's epoch says sample
-/// s - 1 is complete. Entries are handed out in order, so that sample was handed out n_tiles
-/// entries ago and is all but always complete; when it is not, the warp hands out no pixel of the
-/// entry and looks again on its next iteration, never spinning while it holds paths itself (on a
-/// small image the unfinished sample may be in this very warp). It is what lets ONE launch hold k
-/// samples per pixel without a lane being tied to a pixel: the launch ends when the last paths of
-/// the last sample end, the same few iterations that end a one-sample launch, once instead of k times.
-struct sample_major_feed {
-    static constexpr uint32_t k_unfetched = 0xffffffffu;
-    unsigned int* counters;
-    uint32_t n_tiles, n_entries;
-    uint32_t slot0 = 0;
-    uint32_t entry0 = k_unfetched, entry1 = k_unfetched;  ///< queue entries of positions slot0, slot0 + 1
-    uint32_t tile0 = 0, tile1 = 0, sample0 = 0, sample1 = 0;
-    bool ready0 = false, ready1 = false;
-    bool dry = false;
-
-    /// Warp-uniform (every lane looks, the warp takes the answer all lanes agree on: the feed's
-    /// state must be the same in every lane).
-    __device__ __forceinline__ bool is_ready(uint32_t tile, uint32_t sample) const {
-        if (sample == 0u) return true;
-        return __ballot_sync(0xffffffffu, load_acquire_gpu(g_tile_epochs + tile) >= sample) == 0xffffffffu;
-    }
-    __device__ __forceinline__ void fetch(uint32_t& entry, uint32_t& tile, uint32_t& sample, bool& ready) {
-        uint32_t q = 0;
-        if ((threadIdx.x & 31u) == 0u) q = atomicAdd(counters, 1u);
-        q = __shfl_sync(0xffffffffu, q, 0);
-        dry = q >= n_entries;
-        entry = q;
-        ready = false;
-        if (dry) return;
-        sample = q / n_tiles;
-        tile = q - sample * n_tiles;
-        ready = is_ready(tile, sample);
-    }
-    /// Warp-uniform: makes the entries of items [first, last] available and looks again at the
-    /// epochs of those that were not ready.
-    __device__ __forceinline__ void open(uint32_t first, uint32_t last) {
-        if (slot0 < (first >> 5)) {
-            slot0 = first >> 5;
-            entry0 = entry1, tile0 = tile1, sample0 = sample1, ready0 = ready1;
-            entry1 = k_unfetched;
-            ready1 = false;
-        }
-        if (entry0 == k_unfetched && !dry) fetch(entry0, tile0, sample0, ready0);
-        if (entry0 < n_entries && !ready0) ready0 = is_ready(tile0, sample0);
-        if (!dry && (last >> 5) > slot0 && entry1 == k_unfetched) fetch(entry1, tile1, sample1, ready1);
-        if (entry1 < n_entries && !ready1) ready1 = is_ready(tile1, sample1);
-    }
-    __device__ __forceinline__ bool has(uint32_t item) const { return ((item >> 5) == slot0 ? entry0 : entry1) < n_entries; }
-    __device__ __forceinline__ uint32_t tile_of(uint32_t item) const { return (item >> 5) == slot0 ? tile0 : tile1; }
-    __device__ __forceinline__ uint32_t sample_of(uint32_t item) const { return (item >> 5) == slot0 ? sample0 : sample1; }
-    /// How many of the `wanted` items starting at `first` may be handed out now: up to the first
-    /// one that belongs to an entry that is not ready (an entry past the end of the queue counts as
-    /// ready: its items are skipped).
-    __device__ __forceinline__ uint32_t grantable(uint32_t first, uint32_t wanted) const {
-        const bool ok0 = ready0 || entry0 >= n_entries;
-        const bool ok1 = ready1 || entry1 >= n_entries;
-        if (!ok0) return 0u;
-        const uint32_t in_entry0 = 32u - (first & 31u);
-        return (wanted <= in_entry0 || ok1) ? wanted : in_entry0;
-    }
-    /// Warp-uniform: the queue has run out at item `next` (false while an entry is only not ready).
-    __device__ __forceinline__ bool exhausted(uint32_t next) {
-        open(next, next);
-        return dry && entry0 >= n_entries;  // (an entry never fetched because the queue had run out counts as past its end)
-    }
-    __device__ __forceinline__ void finish(uint32_t n_warps) {
-        if ((threadIdx.x & 31u) == 0u) {
-            if (atomicAdd(counters + 1, 1u) == n_warps - 1u) {
-                counters[0] = 0u;
-                counters[1] = 0u;
-            }
-        }
-    }
-};
-
-/// `Batch` (QUASI_CUDA_BATCH, plugin.cu): one launch gives every pixel frame.batch_samples
-/// consecutive samples instead of one. A lane that ends a path starts the next sample of the
-/// SAME pixel, so the samples of a pixel are accumulated in order by one thread (the running
-/// mean of plugin.mm:326 depends on the order) and its 64 bytes of history stay in L1/L2
-/// between them; what lies between two launches is paid once per batch instead of once per
-/// sample (the drain inside a launch scales with the item, which is k samples long now).
-/// `SampleMajor` (with Batch): the k samples are k passes over the image inside the one launch
-/// (sample_major_feed) instead of k consecutive samples per lane and pixel.
-template <int NQ, class Layout, bool Batch = false, bool SampleMajor = false>
+template <int NQ, class Layout, bool Batch = false>
 __global__ void __launch_bounds__(k_block_threads, k_blocks_per_sm)
-pathtrace_accumulate_kernel(const __grid_constant__ scene_params scene,
-                            const __grid_constant__ frame_params frame, float4* __restrict__ beauty,
-                            float4* __restrict__ albedo, float4* __restrict__ normal,
-                            float4* __restrict__ depth, unsigned long long* __restrict__ ray_counter,
-                            unsigned int* __restrict__ tile_counters) {
-    pdl_launch_dependents();
+pathtrace_accumulate_kernel(const __grid_constant__ scene_params scene, const __grid_constant__ frame_params frame,
+                           const __grid_constant__ batch_params launch, float4* __restrict__ beauty,
+                           float4* __restrict__ albedo, float4* __restrict__ normal, float4* __restrict__ depth,
+                           unsigned long long* __restrict__ ray_counter, unsigned int* __restrict__ tile_counters) {
     __shared__ float s_shade[NQ * k_shade_stride];
     for (int idx = threadIdx.x; idx < NQ * static_cast<int>(k_shade_floats); idx += k_block_threads) {
         const int qi = idx / static_cast<int>(k_shade_floats);
         const int k = idx - qi * static_cast<int>(k_shade_floats);
-        s_shade[qi * k_shade_stride + k] =
-            reinterpret_cast<const float*>(&scene.quads[qi])[k_shade_offset + k];
+        s_shade[qi * k_shade_stride + k] = reinterpret_cast<const float*>(&scene.quads[qi])[k_shade_offset + k];
     }
+#if defined(QUASI_HOST_EMULATION)
+    uint32_t* s_queues = static_cast<uint32_t*>(emu::dynamic_shared());
+#else
+    extern __shared__ uint32_t s_queues[];
+#endif
+    uint32_t* const q = s_queues + (threadIdx.x >> 5) * k_queue_words;
+    float* const b_ro = reinterpret_cast<float*>(q);              // [3][k_bq]
+    uint32_t* const b_rng = q + 3 * k_bq;
+    uint32_t* const b_meta = q + 4 * k_bq;                        // bounce | quad << 8 | hit from behind << 16
+    float* const b_thr = reinterpret_cast<float*>(q + 5 * k_bq);  // [3][k_bq]
+    float* const b_col = reinterpret_cast<float*>(q + 8 * k_bq);  // [3][k_bq]
+    uint32_t* const b_pxy = q + 11 * k_bq;
+    uint32_t* const b_tag = q + 12 * k_bq;                        // Batch: tile slot | sample << 4
+    uint32_t* const p_xy = q + k_bq_fields * k_bq;
+    uint32_t* const p_tag = p_xy + k_pq;
+    uint32_t* const t_tile = p_tag + k_pq;                        // Batch: tile of a slot
+    uint32_t* const t_left = t_tile + k_tile_slots;               // Batch: its paths that have not ended yet
     __syncthreads();
-    pdl_wait();  // layers, tile queue and counters belong to the previous launch until here
 
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lanes_below = (1u << lane) - 1u;
     const uint32_t tiles_x = (frame.width + 7u) >> 3;
     const uint32_t n_tiles = tiles_x * ((frame.height + 3u) >> 2);
-    const bool first_sample = frame.sample_index == 0;
-    const float weight = frame.weight;
+    const uint32_t n_px = frame.width * frame.height;
     const uint32_t max_bounces = scene.max_bounces;
     const v3 cam_origin = load_v3(frame.position);
-
-    // Path state of this lane.
-    bool active = false;
-    v3 ro = cam_origin, rd = make_v3(0.0f, 0.0f, -1.0f);
-    v3 throughput = make_v3(1.0f, 1.0f, 1.0f), color = make_v3(0.0f, 0.0f, 0.0f);
-    uint32_t rng = 0, bounce = 0;
-    size_t pixel = 0;
-    uint32_t rays = 0;
-    uint32_t next_item = 0;  // warp-uniform cursor into this warp's pixel sequence
-    tile_feed feed{tile_counters, n_tiles};
-    // Where a continuing path scatters from: the quad it hit, complemented when it was hit
-    // from behind. Set by the shading step, consumed at the top of the next iteration.
-    int scatter = 0;
-    // Batch only: which sample of the launch this lane's path is, its pixel, and that sample's
-    // accumulation constants (first_sample / weight are per launch otherwise).
-    [[maybe_unused]] uint32_t sample_of_item = 0, pixel_xy = 0xffffffffu;
-    [[maybe_unused]] bool lane_first = first_sample;
-    [[maybe_unused]] float lane_weight = weight;
+    const launch_divisor by_width(static_cast<float>(frame.width)), by_height(static_cast<float>(frame.height));
     [[maybe_unused]] const uint32_t batch = frame.batch_samples > 1u ? frame.batch_samples : 1u;
-    // SampleMajor only: the queue, this warp's eight completion counters (dynamic shared memory,
-    // zeroed here), and per lane tile << 9 | pixels of the tile inside the image << 3 | counter
-    [[maybe_unused]] sample_major_feed sfeed{tile_counters, n_tiles, n_tiles * batch};
-    [[maybe_unused]] unsigned int* tile_done = nullptr;
-    [[maybe_unused]] uint32_t item_tag = 0;
-    if constexpr (SampleMajor) {
-#if defined(QUASI_HOST_EMULATION)
-        unsigned int* s_done = static_cast<unsigned int*>(emu::dynamic_shared());
-#else
-        extern __shared__ unsigned int s_done[];
-#endif
-        tile_done = s_done + (threadIdx.x >> 5) * 8u;
-        if (lane < 8u) tile_done[lane] = 0u;
-        __syncthreads();
-    }
+
+    uint32_t b_head = 0, b_count = 0, p_head = 0, p_count = 0;  // warp-uniform
+    [[maybe_unused]] uint32_t free_slots = (1u << k_tile_slots) - 1u;  // Batch, warp-uniform
+    bool dry = false;
+    uint32_t rays = 0;
 
     while (true) {
-        // Regeneration: idle lanes take the warp's next pixels, compacted.
-        bool fresh = false;
-        float uv_x = 0.0f, uv_y = 0.0f;
-        if constexpr (Batch && SampleMajor) {
-            bool start = false;
-            uint32_t px = 0, py = 0;
-            const uint32_t idle = __ballot_sync(0xffffffffu, !active);
-            if (idle != 0u) {
-                sfeed.open(next_item, next_item + __popc(idle) - 1u);
-                const uint32_t granted = sfeed.grantable(next_item, __popc(idle));
-                if (!active) {
-                    const uint32_t item = next_item + __popc(idle & lanes_below);
-                    if (item < next_item + granted && sfeed.has(item)) {
-                        const uint32_t tile = sfeed.tile_of(item);
-                        uint32_t tile_y = __umulhi(tile, frame.tiles_x_magic);
-                        uint32_t tile_x = tile - tile_y * tiles_x;
-                        if (tile_x >= tiles_x) {
-                            tile_x -= tiles_x;
-                            tile_y++;
-                        }
-                        px = tile_x * 8u + (item & 7u);
-                        py = tile_y * 4u + ((item >> 3) & 3u);
-                        if (px < frame.width && py < frame.height) {
-                            const uint32_t in_x = frame.width - tile_x * 8u, in_y = frame.height - tile_y * 4u;
-                            const uint32_t valid = (in_x < 8u ? in_x : 8u) * (in_y < 4u ? in_y : 4u);
-                            sample_of_item = sfeed.sample_of(item);
-                            item_tag = (tile << 9) | (valid << 3) | ((item >> 5) & 7u);
-                            start = true;
-                            pixel = static_cast<size_t>(py) * frame.width + px;
-                            if (!(first_sample && sample_of_item == 0u)) {
-                                prefetch_l2(beauty + pixel);
-                                prefetch_l2(albedo + pixel);
-                                prefetch_l2(normal + pixel);
-                                prefetch_l2(depth + pixel);
-                            }
-                        }
-                    }
-                }
-                next_item += granted;
+        bool primary;
+        uint32_t n;
+        if (b_count >= 32u) {
+            primary = false, n = 32u;
+        } else if (p_count >= 32u) {
+            primary = true, n = 32u;
+        } else if (!dry && (!Batch || free_slots != 0u)) {
+            // Take the next tile of the device-wide queue.
+            uint32_t tile = 0;
+            if (lane == 0u) tile = atomicAdd(tile_counters, 1u);
+            tile = __shfl_sync(0xffffffffu, tile, 0);
+            if (tile >= n_tiles) {
+                dry = true;
+                continue;
             }
-            if (start) {
-                const uint32_t sample_index = frame.sample_index + sample_of_item;
-                uv_x = (static_cast<float>(px) + 0.5f) / static_cast<float>(frame.width);
-                uv_y = 1.0f - (static_cast<float>(py) + 0.5f) / static_cast<float>(frame.height);
-                rng = pcg_hash(px + py * 1920u + (frame.frame_index + sample_of_item * frame.frame_stride) * 1920u * 1080u);
-                fresh = true;
-                throughput = make_v3(1.0f, 1.0f, 1.0f);
-                color = make_v3(0.0f, 0.0f, 0.0f);
-                bounce = 0;
-                active = true;
-                lane_first = sample_index == 0u;
-                lane_weight = 1.0f / static_cast<float>(sample_index + 1u);
+            // tile / tiles_x by multiply-high with floor(2^32 / tiles_x): at most one too small
+            // for any 32-bit tile, fixed up by one compare.
+            uint32_t tile_y = __umulhi(tile, frame.tiles_x_magic);
+            uint32_t tile_x = tile - tile_y * tiles_x;
+            if (tile_x >= tiles_x) {
+                tile_x -= tiles_x;
+                tile_y++;
             }
-        } else if constexpr (Batch) {
-            // A lane whose path has ended goes on with the next sample of its pixel; only a lane
-            // that has given its pixel all its samples takes a new pixel from the queue.
-            bool start = false;
-            uint32_t px = 0, py = 0;
-            if (!active && pixel_xy != 0xffffffffu) {
-                if (sample_of_item + 1u < batch) {
-                    sample_of_item++;
-                    px = pixel_xy & 0xffffu;
-                    py = pixel_xy >> 16;
-                    start = true;
-                } else {
-                    pixel_xy = 0xffffffffu;
+            const uint32_t px = tile_x * 8u + (lane & 7u), py = tile_y * 4u + (lane >> 3);
+            const bool inside = px < frame.width && py < frame.height;
+            const uint32_t m_inside = __ballot_sync(0xffffffffu, inside);
+            uint32_t tag = 0;
+            if constexpr (Batch) {
+                const uint32_t slot = static_cast<uint32_t>(__ffs(static_cast<int>(free_slots))) - 1u;
+                free_slots &= ~(1u << slot);
+                tag = slot;  // | sample << 4, sample 0
+                if (lane == 0u) {
+                    t_tile[slot] = tile;
+                    t_left[slot] = static_cast<uint32_t>(__popc(m_inside));
                 }
             }
-            const uint32_t idle = __ballot_sync(0xffffffffu, !active && !start);
-            if (idle != 0u) {
-                feed.open(next_item, next_item + __popc(idle) - 1u);
-                if (!active && !start) {
-                    const uint32_t item = next_item + __popc(idle & lanes_below);
-                    const uint32_t tile = feed.tile_of(item);
-                    if (tile < n_tiles) {
-                        uint32_t tile_y = __umulhi(tile, frame.tiles_x_magic);
-                        uint32_t tile_x = tile - tile_y * tiles_x;
-                        if (tile_x >= tiles_x) {
-                            tile_x -= tiles_x;
-                            tile_y++;
-                        }
-                        px = tile_x * 8u + (item & 7u);
-                        py = tile_y * 4u + ((item >> 3) & 3u);
-                        if (px < frame.width && py < frame.height) {
-                            pixel_xy = px | (py << 16);  // the ABI's sizes are far below 65536
-                            sample_of_item = 0;
-                            start = true;
-                            pixel = static_cast<size_t>(py) * frame.width + px;
-                            if (!first_sample) {
-                                prefetch_l2(beauty + pixel);
-                                prefetch_l2(albedo + pixel);
-                                prefetch_l2(normal + pixel);
-                                prefetch_l2(depth + pixel);
-                            }
-                        }
-                    }
-                }
-                next_item += __popc(idle);
+            if (inside) {
+                const uint32_t at = (p_head + p_count + __popc(m_inside & lanes_below)) & (k_pq - 1u);
+                p_xy[at] = px | (py << 16);  // the ABI's sizes are far below 65536 (plugin.cu checks)
+                if constexpr (Batch) p_tag[at] = tag;
             }
-            if (start) {
-                const uint32_t sample_index = frame.sample_index + sample_of_item;
-                uv_x = (static_cast<float>(px) + 0.5f) / static_cast<float>(frame.width);
-                uv_y = 1.0f - (static_cast<float>(py) + 0.5f) / static_cast<float>(frame.height);
-                rng = pcg_hash(px + py * 1920u + (frame.frame_index + sample_of_item * frame.frame_stride) * 1920u * 1080u);
-                fresh = true;
-                throughput = make_v3(1.0f, 1.0f, 1.0f);
-                color = make_v3(0.0f, 0.0f, 0.0f);
-                bounce = 0;
-                active = true;
-                lane_first = sample_index == 0u;
-                lane_weight = 1.0f / static_cast<float>(sample_index + 1u);  // scene_params.hpp:prepare_frame
-            }
+            p_count += __popc(m_inside);
+            __syncwarp();
+            continue;
+        } else if (p_count > 0u) {  // the device-wide queue has run dry (or every tile slot is taken): drain
+            primary = true, n = p_count;
+        } else if (b_count > 0u) {
+            primary = false, n = b_count;
         } else {
-        const uint32_t idle = __ballot_sync(0xffffffffu, !active);
-        if (idle != 0u) {
-            feed.open(next_item, next_item + __popc(idle) - 1u);
-            if (!active) {
-                const uint32_t item = next_item + __popc(idle & lanes_below);
-                const uint32_t tile = feed.tile_of(item);
-                if (tile < n_tiles) {
-                    // tile / tiles_x by multiply-high with floor(2^32 / tiles_x): at most
-                    // one too small for any 32-bit tile, fixed up by one compare.
-                    uint32_t tile_y = __umulhi(tile, frame.tiles_x_magic);
-                    uint32_t tile_x = tile - tile_y * tiles_x;
-                    if (tile_x >= tiles_x) {
-                        tile_x -= tiles_x;
-                        tile_y++;
-                    }
-                    const uint32_t px = tile_x * 8u + (item & 7u);
-                    const uint32_t py = tile_y * 4u + ((item >> 3) & 3u);
-                    if (px < frame.width && py < frame.height) {
-                        // pathtrace_frag, plugin.mm:287-309; uv is the closed form of
-                        // the rasteriser's interpolation, py = 0 on top.
-                        uv_x = (static_cast<float>(px) + 0.5f) / static_cast<float>(frame.width);
-                        uv_y = 1.0f - (static_cast<float>(py) + 0.5f) / static_cast<float>(frame.height);
-                        rng = pcg_hash(px + py * 1920u + frame.frame_index * 1920u * 1080u);
-                        fresh = true;
-                        throughput = make_v3(1.0f, 1.0f, 1.0f);
-                        color = make_v3(0.0f, 0.0f, 0.0f);
-                        bounce = 0;
-                        pixel = static_cast<size_t>(py) * frame.width + px;
-                        active = true;
-                        // The history of this pixel is needed ~1000 cycles from now
-                        // (after the first trace); start pulling it out of HBM.
-                        if (!first_sample) {
-                            prefetch_l2(beauty + pixel);
-                            prefetch_l2(albedo + pixel);
-                            prefetch_l2(normal + pixel);
-                            prefetch_l2(depth + pixel);
-                        }
-                    }
-                }
-            }
-            next_item += __popc(idle);
-        }
-        }  // !Batch
-        if (!__any_sync(0xffffffffu, active)) {
-            if constexpr (SampleMajor) {
-                if (sfeed.exhausted(next_item)) break;
-            } else {
-                if (feed.exhausted(next_item)) break;
-            }
-            continue;  // only off-image pixels of an edge tile were handed out
+            break;
         }
 
-        if (active) {
-            // Every path needs a direction now: a new one its camera ray (get_camera_ray,
-            // plugin.mm:129-153, jitter x drawn before y), a continuing one its scattered ray
-            // (cosine_sample_hemisphere, plugin.mm:111-125, r1 before r2, with the per-quad
-            // frame). Both take two draws and end in a normalisation; those are issued once
-            // for the whole warp instead of once per kind of lane.
+        const bool live = lane < n;
+        uint32_t slot, rng = 0, pxy = 0, tag = 0, meta = 0;
+        v3 ro = cam_origin, d = make_v3(0.0f, 0.0f, -1.0f);
+        float uv_x = 0.0f, uv_y = 0.0f;
+        if (primary) {
+            slot = (p_head + lane) & (k_pq - 1u);
+            p_head = (p_head + n) & (k_pq - 1u);
+            p_count -= n;
+            if (live) {
+                pxy = p_xy[slot];
+                if constexpr (Batch) tag = p_tag[slot];
+                const uint32_t px = pxy & 0xffffu, py = pxy >> 16, smp = tag >> 4;
+                // pathtrace_frag, plugin.mm:287-309; uv is the closed form of the rasteriser's
+                // interpolation, py = 0 on top.
+                uv_x = by_width.quotient(static_cast<float>(px) + 0.5f);
+                uv_y = 1.0f - by_height.quotient(static_cast<float>(py) + 0.5f);
+                rng = pcg_hash(px + py * 1920u + (frame.frame_index + smp * frame.frame_stride) * 1920u * 1080u);
+                if (frame.sample_index + smp != 0u) {  // the history is needed after the scan: start pulling it out of HBM
+                    const size_t pixel = static_cast<size_t>(py) * frame.width + px;
+                    prefetch_l2(beauty + pixel);
+                    prefetch_l2(albedo + pixel);
+                    prefetch_l2(normal + pixel);
+                    prefetch_l2(depth + pixel);
+                }
+            }
+        } else {
+            slot = (b_head + lane) & (k_bq - 1u);
+            b_head = (b_head + n) & (k_bq - 1u);
+            b_count -= n;
+            if (live) {
+                ro = make_v3(b_ro[slot], b_ro[k_bq + slot], b_ro[2 * k_bq + slot]);
+                rng = b_rng[slot];
+                meta = b_meta[slot];
+            }
+        }
+
+        hit_record hit;
+        hit.index = -1;
+        hit.front = true;
+        hit.t = 0.0f;
+        hit.point = make_v3(0.0f, 0.0f, 0.0f);
+        v3 rd = d;
+        if (live) {
+            // Two draws and a normalisation either way: get_camera_ray (plugin.mm:129-153, jitter x
+            // before y) in a primary iteration, cosine_sample_hemisphere (plugin.mm:111-125, r1 before
+            // r2, with the per-quad frame) in a bounce iteration. The branch is warp-uniform.
             const float draw_a = random_float(rng);
             const float draw_b = random_float(rng);
-            v3 d;
-            if (fresh) {
+            if (primary) {
                 uv_x += (draw_a - 0.5f) * 0.001f;
                 uv_y += (draw_b - 0.5f) * 0.001f;
                 const v3 target = load_v3(frame.lower_left) + load_v3(frame.horizontal) * uv_x +
                                   load_v3(frame.vertical) * uv_y;
-                ro = cam_origin;
                 d = target - cam_origin;
             } else {
-                const float* from = s_shade + (scatter < 0 ? ~scatter : scatter) * k_shade_stride;
-                const float side = scatter < 0 ? -1.0f : 1.0f;
+                const bool behind = (meta & 0x10000u) != 0u;
+                const float* from = s_shade + ((meta >> 8) & 0xffu) * k_shade_stride;
+                const float side = behind ? -1.0f : 1.0f;
                 const float phi = 6.28318548202514648f * draw_a;  // 2.0f * M_PI_F, exact product
                 const float cos_theta = sqrtf(1.0f - draw_b);
                 const float sin_theta = sqrtf(draw_b);
@@ -583,45 +423,44 @@ pathtrace_accumulate_kernel(const __grid_constant__ scene_params scene,
                 d = (fu * cos_phi) * sin_theta + (fv * sin_phi) * sin_theta + fw * cos_theta;
             }
             rd = normalize(d);
-
-            // One bounce of path_trace, plugin.mm:232-273.
-            hit_record hit;
-            trace_scene<Layout>(scene, s_shade, ro, rd, hit);
+            trace_scene<Layout>(scene, s_shade, ro, rd, hit);  // one bounce of path_trace, plugin.mm:232-273
             rays++;
+        }
+
+        bool goes_on = false, ended = false;
+        v3 throughput = make_v3(1.0f, 1.0f, 1.0f), color = make_v3(0.0f, 0.0f, 0.0f);
+        if (live) {
             const bool is_hit = hit.index >= 0;
             const float* sh = s_shade + (is_hit ? hit.index : 0) * k_shade_stride;
             const float side = (is_hit && !hit.front) ? -1.0f : 1.0f;
-            const v3 n = load_v3(sh + k_sh_normal) * side;  // exact sign flip
+            const v3 nrm = load_v3(sh + k_sh_normal) * side;  // exact sign flip
             const v3 q_emission = load_v3(sh + k_sh_emission);
             const v3 q_albedo = load_v3(sh + k_sh_albedo);
             const bool is_light = sh[k_sh_is_light] != 0.0f;
-
-            if (bounce == 0) {
-                // First-hit AOVs (plugin.mm:241-249, 300-307) go out now, so the
-                // lane does not carry them to the end of the path.
+            uint32_t bounce = 0;
+            if (primary) {
+                // First-hit AOVs (plugin.mm:241-249, 300-307).
                 v3 a = make_v3(0.0f, 0.0f, 0.0f), nn = a;
                 float first_t = 0.0f;
                 if (is_hit) {
                     a = is_light ? q_emission : q_albedo;
-                    nn = make_v3(n.x * 0.5f + 0.5f, n.y * 0.5f + 0.5f, n.z * 0.5f + 0.5f);
+                    nn = make_v3(nrm.x * 0.5f + 0.5f, nrm.y * 0.5f + 0.5f, nrm.z * 0.5f + 0.5f);
                     first_t = hit.t;
                 }
                 const float nd = fminf(fmaxf((first_t - 1.0f) / 4.0f, 0.0f), 1.0f);
-                if constexpr (Batch) {
-                    constexpr auto accumulate = SampleMajor ? accumulate_pixel_value_cg : accumulate_pixel_value;
-                    const float4 va = accumulate(albedo, pixel, make_float4(a.x, a.y, a.z, 1.0f), lane_first, lane_weight);
-                    const float4 vn = accumulate(normal, pixel, make_float4(nn.x, nn.y, nn.z, 1.0f), lane_first, lane_weight);
-                    const float4 vd = accumulate(depth, pixel, make_float4(nd, nd, nd, 1.0f), lane_first, lane_weight);
-                    if (sample_of_item + 1u == batch) {  // the pixel's last sample of this launch
-                        mirror_pixel(1, pixel, va);
-                        mirror_pixel(2, pixel, vn);
-                        mirror_pixel(3, pixel, vd);
-                    }
-                } else {
-                accumulate_pixel(albedo, pixel, make_float4(a.x, a.y, a.z, 1.0f), first_sample, weight);
-                accumulate_pixel(normal, pixel, make_float4(nn.x, nn.y, nn.z, 1.0f), first_sample, weight);
-                accumulate_pixel(depth, pixel, make_float4(nd, nd, nd, 1.0f), first_sample, weight);
-                }
+                const uint32_t sample_index = frame.sample_index + (tag >> 4);
+                const bool first = sample_index == 0u;
+                const float weight = Batch ? 1.0f / static_cast<float>(sample_index + 1u) : frame.weight;
+                const size_t pixel = static_cast<size_t>(pxy >> 16) * frame.width + (pxy & 0xffffu);
+                accumulate_rgb1<false>(albedo, pixel, a, first, weight);
+                accumulate_rgb1<false>(normal, pixel, nn, first, weight);
+                accumulate_grey1<false>(depth, pixel, nd, first, weight);
+            } else {
+                throughput = make_v3(b_thr[slot], b_thr[k_bq + slot], b_thr[2 * k_bq + slot]);
+                color = make_v3(b_col[slot], b_col[k_bq + slot], b_col[2 * k_bq + slot]);
+                pxy = b_pxy[slot];
+                if constexpr (Batch) tag = b_tag[slot];
+                bounce = meta & 0xffu;
             }
 
             bool done = !is_hit;
@@ -642,40 +481,91 @@ pathtrace_accumulate_kernel(const __grid_constant__ scene_params scene,
             }
             bounce++;
             done = done || bounce >= max_bounces;  // the shader's last scatter is never observed
-
-            if (!done) {
-                ro = hit.point + n * 0.001f;
-                scatter = hit.front ? hit.index : ~hit.index;  // the direction is drawn at the top
-            } else {
-                if constexpr (Batch) {
-                    constexpr auto accumulate = SampleMajor ? accumulate_pixel_value_cg : accumulate_pixel_value;
-                    const float4 vb = accumulate(beauty, pixel, make_float4(color.x, color.y, color.z, 1.0f), lane_first, lane_weight);
-                    if (sample_of_item + 1u == batch) mirror_pixel(0, pixel, vb);
-                    if constexpr (SampleMajor) {
-                        // this pixel has its sample; the lane that completes the tile publishes the tile's epoch
-                        __threadfence_block();
-                        const uint32_t counter = item_tag & 7u, valid = (item_tag >> 3) & 63u;
-                        if (atomicAdd(tile_done + counter, 1u) + 1u == valid) {
-                            tile_done[counter] = 0u;
-                            __threadfence();
-                            store_release_gpu(g_tile_epochs + (item_tag >> 9), sample_of_item + 1u);
-                        }
-                    }
-                } else {
-                accumulate_pixel(beauty, pixel, make_float4(color.x, color.y, color.z, 1.0f),
-                                 first_sample, weight);
-                }
-                active = false;
+            goes_on = !done;
+            ended = done;
+            if (goes_on) {
+                ro = hit.point + nrm * 0.001f;
+                meta = bounce | (static_cast<uint32_t>(hit.index) << 8) | (hit.front ? 0u : 0x10000u);
             }
         }
+        __syncwarp();  // every lane has read what it needs from the slot it popped
+
+        const uint32_t m_goes_on = __ballot_sync(0xffffffffu, goes_on);
+        if (goes_on) {
+            const uint32_t at = (b_head + b_count + __popc(m_goes_on & lanes_below)) & (k_bq - 1u);
+            b_ro[at] = ro.x, b_ro[k_bq + at] = ro.y, b_ro[2 * k_bq + at] = ro.z;
+            b_rng[at] = rng;
+            b_meta[at] = meta;
+            b_thr[at] = throughput.x, b_thr[k_bq + at] = throughput.y, b_thr[2 * k_bq + at] = throughput.z;
+            b_col[at] = color.x, b_col[k_bq + at] = color.y, b_col[2 * k_bq + at] = color.z;
+            b_pxy[at] = pxy;
+            if constexpr (Batch) b_tag[at] = tag;
+        }
+        b_count += __popc(m_goes_on);
+
+        [[maybe_unused]] bool again = false, completes = false;  // Batch
+        if (ended) {
+            const uint32_t sample_index = frame.sample_index + (tag >> 4);
+            const float weight = Batch ? 1.0f / static_cast<float>(sample_index + 1u) : frame.weight;
+            const size_t pixel = static_cast<size_t>(pxy >> 16) * frame.width + (pxy & 0xffffu);
+            accumulate_rgb1<false>(beauty, pixel, color, sample_index == 0u, weight);
+            if constexpr (Batch) {
+                again = (tag >> 4) + 1u < batch;  // the pixel's next sample may start now
+                if (!again) completes = atomicSub(t_left + (tag & 15u), 1u) == 1u;  // the tile's last pixel has its last sample
+            }
+        }
+        if constexpr (Batch) {
+            const uint32_t m_again = __ballot_sync(0xffffffffu, again);
+            if (again) {
+                const uint32_t at = (p_head + p_count + __popc(m_again & lanes_below)) & (k_pq - 1u);
+                p_xy[at] = pxy;
+                p_tag[at] = tag + 16u;
+            }
+            p_count += __popc(m_again);
+            uint32_t m_completes = __ballot_sync(0xffffffffu, completes);
+            if (m_completes != 0u) __syncwarp();  // the tile's pixels were written by lanes of this warp, now and earlier
+            while (m_completes != 0u) {
+                const int from_lane = __ffs(static_cast<int>(m_completes)) - 1;
+                m_completes &= m_completes - 1u;
+                const uint32_t done_slot = __shfl_sync(0xffffffffu, tag, from_lane) & 15u;
+                if (launch.export_slices != 0u) {  // the tile has its last sample of the launch: out it goes
+                    const uint32_t done_tile = t_tile[done_slot];
+                    uint32_t tile_y = __umulhi(done_tile, frame.tiles_x_magic);
+                    uint32_t tile_x = done_tile - tile_y * tiles_x;
+                    if (tile_x >= tiles_x) {
+                        tile_x -= tiles_x;
+                        tile_y++;
+                    }
+                    const uint32_t px = tile_x * 8u + (lane & 7u), py = tile_y * 4u + (lane >> 3);
+                    if (px < frame.width && py < frame.height) {
+                        const uint32_t pixel = py * frame.width + px;
+                        const float4* const layers[4] = {beauty, albedo, normal, depth};
+#pragma unroll
+                        for (uint32_t l = 0; l < 4u; l++) {
+                            const uint32_t i = l * n_px + pixel;
+                            uint32_t slice = __umulhi(i, launch.export_per_magic);
+                            uint32_t within = i - slice * launch.export_per;
+                            if (within >= launch.export_per) {
+                                within -= launch.export_per;
+                                slice++;
+                            }
+                            static_cast<float4*>(launch.export_base[slice])[within] = layers[l][pixel];
+                        }
+                    }
+                }
+                free_slots |= 1u << done_slot;
+            }
+        }
+        __syncwarp();  // pushes and pixel writes are ordered before the next iteration's pops and reads
     }
 
-    if constexpr (SampleMajor) {
-        sfeed.finish(gridDim.x * k_warps_per_block);
-    } else {
-        feed.finish(gridDim.x * k_warps_per_block);
+    // The last warp to finish resets the device-wide queue for the next launch (stream-ordered).
+    if (lane == 0u) {
+        if (atomicAdd(tile_counters + 1, 1u) == gridDim.x * k_warps_per_block - 1u) {
+            tile_counters[0] = 0u;
+            tile_counters[1] = 0u;
+        }
     }
-    // One atomic per warp for the ray statistic (SURVEY.md 8d "Ray counting").
     rays = __reduce_add_sync(0xffffffffu, rays);
     if (lane == 0 && rays != 0) atomicAdd(ray_counter, static_cast<unsigned long long>(rays));
 }
@@ -696,22 +586,11 @@ cudaError_t launch_sincos_probe(const float* phi, float* sin_out, float* cos_out
     return cudaGetLastError();
 }
 
-cudaError_t set_pathtrace_mirror(float* const mirror[4], cudaStream_t stream) {
-    float4* table[4];
-    for (int i = 0; i < 4; i++) table[i] = mirror ? reinterpret_cast<float4*>(mirror[i]) : nullptr;
-    return cudaMemcpyToSymbolAsync(g_mirror, table, sizeof table, 0, cudaMemcpyHostToDevice, stream);
-}
-
-cudaError_t set_pathtrace_tile_epochs(unsigned int* epochs, cudaStream_t stream) {
-    return cudaMemcpyToSymbolAsync(g_tile_epochs, &epochs, sizeof epochs, 0, cudaMemcpyHostToDevice, stream);
-}
-
-cudaError_t launch_pathtrace_accumulate(const scene_params& scene, const frame_params& frame,
-                                        float* const layers[4], unsigned long long* ray_counter,
-                                        unsigned int* tile_counters, int sm_count, cudaStream_t stream,
-                                        bool generic_scan, bool sample_major) {
+cudaError_t launch_pathtrace_accumulate(const scene_params& scene, const frame_params& frame, const batch_params& launch,
+                                       float* const layers[4], unsigned long long* ray_counter,
+                                       unsigned int* tile_counters, int sm_count, cudaStream_t stream, bool generic_scan) {
     const uint32_t n_tiles = ((frame.width + 7u) / 8u) * ((frame.height + 3u) / 4u);
-    uint32_t blocks = static_cast<uint32_t>(sm_count) * k_blocks_per_sm;
+    uint32_t blocks = static_cast<uint32_t>(sm_count) * k_blocks_per_sm;  // resident CTAs only: a warp may wait for another
     const uint32_t needed = (n_tiles + k_warps_per_block - 1u) / k_warps_per_block;
     if (needed < blocks) blocks = needed;
     if (blocks == 0) return cudaSuccess;
@@ -719,56 +598,22 @@ cudaError_t launch_pathtrace_accumulate(const scene_params& scene, const frame_p
     auto* a = reinterpret_cast<float4*>(layers[1]);
     auto* n = reinterpret_cast<float4*>(layers[2]);
     auto* d = reinterpret_cast<float4*>(layers[3]);
-#if defined(QUASI_PDL) && QUASI_PDL
+    const bool batched = frame.batch_samples > 1u;
+    auto run = [&](auto kernel) {
+        kernel<<<blocks, k_block_threads, k_wavefront_smem, stream>>>(scene, frame, launch, b, a, n, d, ray_counter,
+                                                                     tile_counters);
+        return cudaGetLastError();
+    };
     if (!generic_scan && cornell_layout::matches(scene)) {
-        return launch_persistent(pathtrace_accumulate_kernel<16, cornell_layout>, blocks, k_block_threads, 0, stream, scene,
-                                 frame, b, a, n, d, ray_counter, tile_counters);
+        return batched ? run(pathtrace_accumulate_kernel<16, cornell_layout, true>)
+                       : run(pathtrace_accumulate_kernel<16, cornell_layout, false>);
     }
     if (!generic_scan && cornell_quads_layout::matches(scene)) {
-        return launch_persistent(pathtrace_accumulate_kernel<16, cornell_quads_layout>, blocks, k_block_threads, 0, stream,
-                                 scene, frame, b, a, n, d, ray_counter, tile_counters);
+        return batched ? run(pathtrace_accumulate_kernel<16, cornell_quads_layout, true>)
+                       : run(pathtrace_accumulate_kernel<16, cornell_quads_layout, false>);
     }
-    return launch_persistent(pathtrace_accumulate_kernel<32, dynamic_layout>, blocks, k_block_threads, 0, stream, scene, frame,
-                             b, a, n, d, ray_counter, tile_counters);
-#endif
-    if (frame.batch_samples > 1u && sample_major) {  // QUASI_CUDA_BATCH_ORDER=sample: k passes over the image in one launch
-        constexpr size_t smem = k_warps_per_block * 8 * sizeof(unsigned int);  // completion counters, eight per warp
-        if (!generic_scan && cornell_layout::matches(scene)) {
-            pathtrace_accumulate_kernel<16, cornell_layout, true, true>
-                <<<blocks, k_block_threads, smem, stream>>>(scene, frame, b, a, n, d, ray_counter, tile_counters);
-        } else if (!generic_scan && cornell_quads_layout::matches(scene)) {
-            pathtrace_accumulate_kernel<16, cornell_quads_layout, true, true>
-                <<<blocks, k_block_threads, smem, stream>>>(scene, frame, b, a, n, d, ray_counter, tile_counters);
-        } else {
-            pathtrace_accumulate_kernel<32, dynamic_layout, true, true>
-                <<<blocks, k_block_threads, smem, stream>>>(scene, frame, b, a, n, d, ray_counter, tile_counters);
-        }
-        return cudaGetLastError();
-    }
-    if (frame.batch_samples > 1u) {  // QUASI_CUDA_BATCH: several samples per pixel in one launch
-        if (!generic_scan && cornell_layout::matches(scene)) {
-            pathtrace_accumulate_kernel<16, cornell_layout, true>
-                <<<blocks, k_block_threads, 0, stream>>>(scene, frame, b, a, n, d, ray_counter, tile_counters);
-        } else if (!generic_scan && cornell_quads_layout::matches(scene)) {
-            pathtrace_accumulate_kernel<16, cornell_quads_layout, true>
-                <<<blocks, k_block_threads, 0, stream>>>(scene, frame, b, a, n, d, ray_counter, tile_counters);
-        } else {
-            pathtrace_accumulate_kernel<32, dynamic_layout, true>
-                <<<blocks, k_block_threads, 0, stream>>>(scene, frame, b, a, n, d, ray_counter, tile_counters);
-        }
-        return cudaGetLastError();
-    }
-    if (!generic_scan && cornell_layout::matches(scene)) {
-        pathtrace_accumulate_kernel<16, cornell_layout>
-            <<<blocks, k_block_threads, 0, stream>>>(scene, frame, b, a, n, d, ray_counter, tile_counters);
-    } else if (!generic_scan && cornell_quads_layout::matches(scene)) {
-        pathtrace_accumulate_kernel<16, cornell_quads_layout>
-            <<<blocks, k_block_threads, 0, stream>>>(scene, frame, b, a, n, d, ray_counter, tile_counters);
-    } else {
-        pathtrace_accumulate_kernel<32, dynamic_layout>
-            <<<blocks, k_block_threads, 0, stream>>>(scene, frame, b, a, n, d, ray_counter, tile_counters);
-    }
-    return cudaGetLastError();
+    return batched ? run(pathtrace_accumulate_kernel<32, dynamic_layout, true>)
+                   : run(pathtrace_accumulate_kernel<32, dynamic_layout, false>);
 }
 
 }  // namespace Q::cuda

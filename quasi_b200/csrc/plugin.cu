@@ -114,10 +114,6 @@ struct plugin_state {
     unsigned long long* ray_counter = nullptr;
     cudaEvent_t last_render = nullptr;
     bool render_pending = false;
-#if defined(QUASI_PDL) && QUASI_PDL
-    cudaStream_t last_stream = nullptr;  ///< where the most recent render was enqueued
-    bool event_recorded = false;         ///< last_render has been recorded behind it
-#endif
 
     uint32_t frame_count = 0;
     uint32_t last_width = 0;
@@ -128,23 +124,22 @@ struct plugin_state {
 
     bool generic_scan = false;  ///< QUASI_CUDA_SCAN=generic: the any-scene kernel
 
-    // QUASI_CUDA_BATCH=k (k > 1, headless): render calls are collected and every k of
-    // them become ONE launch that gives each pixel k consecutive samples (pathtrace.cu, Batch).
-    // Anything that looks at the layers, and any call with another camera or size, launches
-    // what has been collected first, so the only observable difference is time.
+    // QUASI_CUDA_BATCH=k (default 64; demo scene, headless calls): render calls are collected and every
+    // k of them become ONE launch that gives each pixel k samples, a pixel's samples one after the other in
+    // the warp that took its tile (pathtrace.cu, Batch). Anything that looks at the layers, and any call with another
+    // camera or size, launches what has been collected first, so the only observable difference is time.
     uint32_t batch = 1;
-    // QUASI_CUDA_MIRROR=1 (with a batch, demo scene): the batched launch also writes every pixel's
-    // final value of the launch into pinned host buffers, so a readback that follows finds the
-    // frame already on the host: the transfer is spread over the launch instead of following it.
-    // QUASI_CUDA_BATCH_ORDER=sample (demo scene, at most 7 bounces): the batched launch makes k passes
-    // over the image (pathtrace.cu:sample_major_feed) instead of giving each lane k samples of a pixel;
-    // one word per tile orders a pass after the previous one.
-    bool sample_major = false;
-    unsigned int* tile_epochs = nullptr;
-    size_t tile_epoch_words = 0;
+    // QUASI_CUDA_MIRROR (default on, with a batch): a batched launch exports every tile that has received its
+    // last sample into pinned host buffers (batch_params), so a readback that follows finds the frame already
+    // on the host: the 64 B/px device-to-host transfer is spread over the launch instead of following it.
     bool mirror_enabled = false;
     bool mirror_valid = false;         ///< the buffers hold what the layers hold
     float* mirror[Q_AOV_COUNT] = {nullptr, nullptr, nullptr, nullptr};
+    // Q_cuda_plugin_set_export: a multi-GPU host has the batched launches push every slice of the layer
+    // block to the GPU that owns it (peer memory) instead; takes the place of the mirror while set.
+    bool external_export = false;
+    Q_cuda_export_table export_table{};
+    bool last_launch_exported = false;  ///< the most recent launch sent every tile of the layers to the export target
     uint32_t pending = 0;              ///< render calls collected and not yet launched
     uint32_t pending_first_sample = 0; ///< frame_count of the first of them
     Q_render_frame pending_frame{};    ///< that call's frame (camera, size, stream)
@@ -172,22 +167,6 @@ void free_layers(plugin_state* state) {
     for (auto& l : state->layers) l = nullptr;
 }
 
-#if defined(QUASI_PDL) && QUASI_PDL
-/// Build-time option QUASI_PDL (programmatic dependent launch, kernels.hpp): consecutive render
-/// kernels on one stream are launched so that the next one's CTAs may start their prologue
-/// while the previous one drains, which only works if no other stream operation sits between
-/// them. So the event that marks the end of a render is recorded when somebody needs it.
-void ensure_render_event(plugin_state* state) {
-    if (state->render_pending && !state->event_recorded) {
-        cudaEventRecord(state->last_render, state->last_stream);
-        state->event_recorded = true;
-    }
-}
-#define QUASI_RENDER_EVENT(state) ensure_render_event(state)
-#else
-#define QUASI_RENDER_EVENT(state) ((void)0)
-#endif
-
 void drop_mirror(plugin_state* state);
 
 /// Counterpart of create_textures (plugin.mm:491-535): four RGBA32F layers,
@@ -195,7 +174,6 @@ void drop_mirror(plugin_state* state);
 /// of 16 B/px. The layers are contiguous (beauty, albedo, normal, depth) so a
 /// multi-GPU host can reduce all four with a single collective.
 bool create_layers(plugin_state* state, uint32_t width, uint32_t height) {
-    QUASI_RENDER_EVENT(state);
     if (state->render_pending) cudaEventSynchronize(state->last_render);
     free_layers(state);
     drop_mirror(state);
@@ -443,10 +421,6 @@ Q_aov_buffer download_layer(plugin_state* state, int layer) {
 
 /// Orders `stream` after the most recent render without blocking the host.
 void order_after_render(plugin_state* state, cudaStream_t stream) {
-#if defined(QUASI_PDL) && QUASI_PDL
-    if (state->render_pending && stream == state->last_stream) return;  // stream order does it
-    ensure_render_event(state);
-#endif
     if (state->render_pending) cudaStreamWaitEvent(stream, state->last_render, 0);
 }
 
@@ -472,6 +446,8 @@ void flush_pending(plugin_state* state, cudaStream_t stream = nullptr) {
     const Q_render_frame& f = state->pending_frame;
     if (stream == nullptr) stream = state->queue;
     const uint32_t collected = state->pending;
+    state->pending = 0;
+    state->mirror_valid = false;
     auto take_back = [state, collected, &f]() {
         state->frame_count -= collected < state->frame_count ? collected : state->frame_count;
         state->paths -= static_cast<uint64_t>(collected) * f.width * f.height;
@@ -481,67 +457,48 @@ void flush_pending(plugin_state* state, cudaStream_t stream = nullptr) {
     const uint32_t frame_index = state->shard_index + state->pending_first_sample * state->shard_count;
     Q::cuda::prepare_frame(f.camera.position, f.camera.target, f.camera.up, f.camera.fov, f.width, f.height, frame_index,
                            state->pending_first_sample, fp);
-    fp.batch_samples = state->pending;
+    fp.batch_samples = collected;
     fp.frame_stride = state->shard_count;
-    const bool mirror = state->mirror_enabled && !state->use_mesh && fp.batch_samples > 1u;
-    bool sample_major = state->sample_major && !state->use_mesh && fp.batch_samples > 1u && state->scene.max_bounces <= 7u;
-    if (sample_major) {
-        const size_t words = static_cast<size_t>((f.width + 7u) / 8u) * ((f.height + 3u) / 4u);
-        if (state->tile_epoch_words != words) {
-            if (state->tile_epochs) cudaFree(state->tile_epochs);
-            state->tile_epochs = nullptr;
-            state->tile_epoch_words = 0;
-            if (cudaMalloc(reinterpret_cast<void**>(&state->tile_epochs), words * sizeof(unsigned int)) == cudaSuccess) {
-                state->tile_epoch_words = words;
-            } else {
-                (void)cudaGetLastError();
-                sample_major = false;  // the other order needs nothing
+    Q::cuda::batch_params launch{};
+    bool mirrored = false;
+    if (collected > 1u) {
+        const uint64_t n_px = static_cast<uint64_t>(f.width) * f.height;
+        if (state->external_export) {
+            const Q_cuda_export_table& t = state->export_table;
+            launch.export_slices = t.slices;
+            launch.export_per = t.float4_per_slice;
+            launch.export_per_magic = static_cast<uint32_t>((uint64_t{1} << 32) / t.float4_per_slice);
+            for (uint32_t i = 0; i < t.slices; i++) launch.export_base[i] = t.base[i];
+        } else if (state->mirror_enabled && n_px < (uint64_t{1} << 30)) {
+            const size_t bytes = static_cast<size_t>(n_px) * 4 * sizeof(float);
+            bool have = true;
+            for (int i = 0; i < Q_AOV_COUNT && have; i++) {
+                // buffers handed to a caller are never written again: a readback takes them away, fresh ones come here
+                if (!state->mirror[i]) state->mirror[i] = g_pool.acquire(bytes);
+                have = state->mirror[i] != nullptr;
+            }
+            if (have) {  // one slice per layer
+                launch.export_slices = Q_AOV_COUNT;
+                launch.export_per = static_cast<uint32_t>(n_px);
+                launch.export_per_magic = static_cast<uint32_t>((uint64_t{1} << 32) / n_px);
+                for (int i = 0; i < Q_AOV_COUNT; i++) launch.export_base[i] = state->mirror[i];
+                mirrored = true;
             }
         }
     }
-    state->pending = 0;
     Q::cuda::set_decision_margins(state->scene, f.camera.position);
     order_after_render(state, stream);
-    state->mirror_valid = false;
-    if (state->mirror_enabled && !state->use_mesh) {
-        const size_t bytes = static_cast<size_t>(f.width) * f.height * 4 * sizeof(float);
-        bool have = mirror;
-        for (int i = 0; i < Q_AOV_COUNT && have; i++) {
-            if (!state->mirror[i]) state->mirror[i] = g_pool.acquire(bytes);
-            have = state->mirror[i] != nullptr;
-        }
-        // the table is set before every batched launch: buffers handed to a caller must never be written again
-        if (!check(state, Q::cuda::set_pathtrace_mirror(have ? state->mirror : nullptr, stream), "set_pathtrace_mirror")) {
-            take_back();
-            return;
-        }
-        state->mirror_valid = have;
-    }
-    if (sample_major &&
-        (!check(state, cudaMemsetAsync(state->tile_epochs, 0, state->tile_epoch_words * sizeof(unsigned int), stream),
-                "memset(tile epochs)") ||
-         !check(state, Q::cuda::set_pathtrace_tile_epochs(state->tile_epochs, stream), "set_pathtrace_tile_epochs"))) {
-        take_back();
-        return;
-    }
     auto* tile_counters = reinterpret_cast<unsigned int*>(state->ray_counter + 3);
-    const cudaError_t launched =
-        state->use_mesh ? Q::cuda::launch_mesh_pathtrace(state->mesh_device, fp, state->layers, state->ray_counter,
-                                                         tile_counters, state->sm_count, stream)
-                        : Q::cuda::launch_pathtrace_accumulate(state->scene, fp, state->layers, state->ray_counter,
-                                                               tile_counters, state->sm_count, stream, state->generic_scan,
-                                                               sample_major);
+    const cudaError_t launched = Q::cuda::launch_pathtrace_accumulate(state->scene, fp, launch, state->layers, state->ray_counter,
+                                                                      tile_counters, state->sm_count, stream, state->generic_scan);
     if (!check(state, launched, "pathtrace_accumulate (batch)")) {
         take_back();
         return;
     }
     state->kernel_launches++;
-#if defined(QUASI_PDL) && QUASI_PDL
-    state->last_stream = stream;
-    state->event_recorded = false;
-#else
+    state->mirror_valid = mirrored;
+    state->last_launch_exported = launch.export_slices != 0u;
     cudaEventRecord(state->last_render, stream);
-#endif
     state->render_pending = true;
 }
 
@@ -635,13 +592,12 @@ Q_PLUGIN_EXPORT Q_plugin_handle* Q_plugin_create(Q_plugin_context* ctx) {
         state->generic_scan = scan && std::strncmp(scan, "generic", 7) == 0;
         const bool group_boxes = scan && std::strstr(scan, "boxes") != nullptr;
         Q::cuda::prepare_scene(state->scene_desc, bounces, state->scene, group_boxes);
-        state->batch = env_u32("QUASI_CUDA_BATCH", 1, 1, 1024);
-        state->mirror_enabled = state->batch > 1 && env_u32("QUASI_CUDA_MIRROR", 0, 0, 1) != 0;
-        const char* order = std::getenv("QUASI_CUDA_BATCH_ORDER");
-        state->sample_major = state->batch > 1 && order && std::strcmp(order, "sample") == 0;
+        state->batch = env_u32("QUASI_CUDA_BATCH", 64, 1, 1024);
+        state->mirror_enabled = env_u32("QUASI_CUDA_MIRROR", 1, 0, 1) != 0;
         const char* scene_name = std::getenv("QUASI_CUDA_SCENE");
         if (scene_name && std::strcmp(scene_name, "mesh") == 0) {
             state->use_mesh = true;
+            state->batch = 1;  // the mesh kernel takes one sample per launch (a batched form was 0.7 % slower)
             ok = create_mesh(state, env_u32("QUASI_CUDA_MESH_GRID", 707, 1, 4000),
                              env_u32("QUASI_CUDA_MESH_SEED", 1, 0, 65535), bounces);
         }
@@ -680,13 +636,11 @@ Q_PLUGIN_EXPORT void Q_plugin_destroy(Q_plugin_handle* handle) {
 
     cudaSetDevice(state->device);
     flush_pending(state);
-    QUASI_RENDER_EVENT(state);
     if (state->render_pending) cudaEventSynchronize(state->last_render);
     cudaStreamSynchronize(state->queue);
     free_mesh(state);
     if (!leave_layers_with_host(state)) free_layers(state);
     drop_mirror(state);
-    if (state->tile_epochs) cudaFree(state->tile_epochs);
     if (state->ray_counter) cudaFree(state->ray_counter);
     if (state->last_render) cudaEventDestroy(state->last_render);
     delete state;
@@ -755,11 +709,12 @@ Q_PLUGIN_EXPORT void Q_plugin_render(Q_plugin_handle* handle, Q_render_frame* fr
     const cudaError_t launched =
         state->use_mesh ? Q::cuda::launch_mesh_pathtrace(state->mesh_device, fp, state->layers,
                                                          state->ray_counter, tile_counters, state->sm_count, stream)
-                        : Q::cuda::launch_pathtrace_accumulate(state->scene, fp, state->layers,
+                        : Q::cuda::launch_pathtrace_accumulate(state->scene, fp, Q::cuda::batch_params{}, state->layers,
                                                                state->ray_counter, tile_counters, state->sm_count,
                                                                stream, state->generic_scan);
     if (!check(state, launched, "pathtrace_accumulate")) return;
     state->kernel_launches++;
+    state->last_launch_exported = false;
 
     // plugin.mm:776-788
     if (drawable && drawable->pixels) {
@@ -771,12 +726,7 @@ Q_PLUGIN_EXPORT void Q_plugin_render(Q_plugin_handle* handle, Q_render_frame* fr
         }
     }
 
-#if defined(QUASI_PDL) && QUASI_PDL
-    state->last_stream = stream;
-    state->event_recorded = false;
-#else
     cudaEventRecord(state->last_render, stream);
-#endif
     state->render_pending = true;
 
     state->paths += static_cast<uint64_t>(width) * height;
@@ -791,6 +741,18 @@ Q_PLUGIN_EXPORT Q_readback_result Q_plugin_readback(Q_plugin_handle* handle) {
     if (cudaSetDevice(state->device) != cudaSuccess) return result;
     flush_pending(state);
 
+    if (state->mirror_valid && state->render_pending &&
+        check(state, cudaEventSynchronize(state->last_render), "readback sync (mirror)")) {
+        // the batched launch has put the frame into pinned host buffers itself: hand the beauty layer over
+        result.data = state->mirror[Q_AOV_BEAUTY];
+        result.width = state->last_width;
+        result.height = state->last_height;
+        result.channels = 4;
+        state->mirror[Q_AOV_BEAUTY] = nullptr;  // the caller's now; the next batch gets a fresh one
+        state->mirror_valid = false;
+        log_msg(state, "HDR readback complete (mirrored during the render)");
+        return result;
+    }
     order_after_render(state, state->queue);
     Q_aov_buffer buf = download_layer(state, Q_AOV_BEAUTY);
     if (buf.data && !check(state, cudaStreamSynchronize(state->queue), "readback sync")) {
@@ -824,8 +786,7 @@ Q_PLUGIN_EXPORT Q_readback_aov_result Q_plugin_readback_aov(Q_plugin_handle* han
 
     if (state->mirror_valid) {
         // the batched launch has put the frame into pinned host buffers itself: wait for it, hand them over
-        QUASI_RENDER_EVENT(state);
-        if (state->render_pending && check(state, cudaEventSynchronize(state->last_render), "readback sync (mirror)")) {
+            if (state->render_pending && check(state, cudaEventSynchronize(state->last_render), "readback sync (mirror)")) {
             for (int i = 0; i < Q_AOV_COUNT; i++) {
                 result.buffers[i] = Q_aov_buffer{state->mirror[i], state->last_width, state->last_height, 4};
                 state->mirror[i] = nullptr;  // the caller's now; the next batch gets fresh ones
@@ -868,7 +829,6 @@ Q_PLUGIN_EXPORT int Q_cuda_plugin_stats(Q_plugin_handle* handle, Q_cuda_stats* o
     auto* state = reinterpret_cast<plugin_state*>(handle);
     if (cudaSetDevice(state->device) != cudaSuccess) return -1;
     flush_pending(state);
-    QUASI_RENDER_EVENT(state);
     if (state->render_pending) cudaEventSynchronize(state->last_render);
     unsigned long long counters[3] = {0, 0, 0};
     order_after_render(state, state->queue);
@@ -902,6 +862,34 @@ Q_PLUGIN_EXPORT int Q_cuda_plugin_layers(Q_plugin_handle* handle, void* stream,
     out->height = state->last_height;
     out->frame_count = state->frame_count;
     return 0;
+}
+
+Q_PLUGIN_EXPORT int Q_cuda_plugin_set_export(Q_plugin_handle* handle, const Q_cuda_export_table* table) {
+    if (!handle) return -1;
+    auto* state = reinterpret_cast<plugin_state*>(handle);
+    if (cudaSetDevice(state->device) != cudaSuccess) return -1;
+    if (table != nullptr) {
+        if (table->struct_size < sizeof(Q_cuda_export_table) || table->slices == 0 ||
+            table->slices > Q_CUDA_MAX_EXPORT_SLICES || table->float4_per_slice == 0) {
+            return -1;
+        }
+        for (uint32_t i = 0; i < table->slices; i++) {
+            if (table->base[i] == nullptr) return -1;
+        }
+    }
+    flush_pending(state);  // what has been collected goes where it was meant to go
+    state->external_export = table != nullptr;
+    if (table != nullptr) state->export_table = *table;
+    state->mirror_valid = false;
+    return 0;
+}
+
+Q_PLUGIN_EXPORT int Q_cuda_plugin_flush(Q_plugin_handle* handle, void* stream) {
+    if (!handle) return -1;
+    auto* state = reinterpret_cast<plugin_state*>(handle);
+    if (cudaSetDevice(state->device) != cudaSuccess) return -1;
+    flush_pending(state, static_cast<cudaStream_t>(stream));
+    return state->last_launch_exported ? 1 : 0;
 }
 
 Q_PLUGIN_EXPORT int Q_cuda_plugin_mesh_view(Q_plugin_handle* handle, Q_cuda_mesh_view* out) {
@@ -942,13 +930,43 @@ Q_PLUGIN_EXPORT int Q_cuda_combine_shards(const float* const* shards, uint32_t n
                                           static_cast<cudaStream_t>(stream)) == cudaSuccess ? 0 : -1;
 }
 
-Q_PLUGIN_EXPORT int Q_cuda_combine_shards_sync(const float* const* shards, uint32_t* const* flags,
-                                               uint32_t n_shards, uint32_t rank, uint32_t epoch,
-                                               uint64_t n_pixels, float scale, float* out, void* bgra,
-                                               void* stream) {
-    if (!shards || !flags || !out || epoch == 0) return -1;
-    return Q::cuda::launch_combine_shards_sync(shards, flags, n_shards, rank, epoch, n_pixels, scale, out,
-                                               bgra, static_cast<cudaStream_t>(stream)) == cudaSuccess ? 0 : -1;
+Q_PLUGIN_EXPORT int Q_cuda_push_slices(const float* block, uint64_t n_float4, const Q_cuda_export_table* table,
+                                       void* stream) {
+    if (!block || !table || table->struct_size < sizeof(Q_cuda_export_table)) return -1;
+    return Q::cuda::launch_push_slices(block, n_float4, table->base, table->slices, table->float4_per_slice,
+                                       static_cast<cudaStream_t>(stream)) == cudaSuccess ? 0 : -1;
+}
+
+Q_PLUGIN_EXPORT int Q_cuda_reduce_slices_sync(const float* staging, uint32_t float4_per_slice, uint32_t* const* flags,
+                                              uint32_t n_shards, uint32_t rank, uint32_t epoch, uint64_t n_float4,
+                                              float scale, float* out, void* stream) {
+    if (!staging || !flags || !out || epoch == 0) return -1;
+    return Q::cuda::launch_reduce_slices_sync(staging, float4_per_slice, flags, n_shards, rank, epoch, n_float4, scale, out,
+                                              static_cast<cudaStream_t>(stream)) == cudaSuccess ? 0 : -1;
+}
+
+Q_PLUGIN_EXPORT int Q_cuda_host_register(void* host_ptr, uint64_t bytes, void** out_device_ptr) {
+    if (!host_ptr || !out_device_ptr || bytes == 0) return -1;
+    *out_device_ptr = nullptr;
+    if (cudaHostRegister(host_ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return -1;
+    }
+    if (cudaHostGetDevicePointer(out_device_ptr, host_ptr, 0) != cudaSuccess) {
+        (void)cudaGetLastError();
+        cudaHostUnregister(host_ptr);
+        return -1;
+    }
+    return 0;
+}
+
+Q_PLUGIN_EXPORT int Q_cuda_host_unregister(void* host_ptr) {
+    if (!host_ptr) return 0;
+    if (cudaHostUnregister(host_ptr) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return -1;
+    }
+    return 0;
 }
 
 Q_PLUGIN_EXPORT int Q_cuda_memset_async(void* device_ptr, int value, uint64_t bytes, void* stream) {

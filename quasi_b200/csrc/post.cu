@@ -29,27 +29,66 @@ inline unsigned grid_for(uint64_t items) {
 
 __device__ __forceinline__ float4 ld_stream(const float4* p) { return __ldcs(p); }
 
-/// plugin.mm:313-330: mix(accumulated, new_sample, weight).
+/// plugin.mm:313-330: mix(accumulated, new_sample, weight). Two float4 per thread and iteration,
+/// all four loads issued before the first use (the pass is pure HBM streaming: what limits it is
+/// bytes in flight per SM).
 __global__ void __launch_bounds__(k_threads)
 accumulate_kernel(const float4* __restrict__ current, const float4* __restrict__ history,
                   float4* __restrict__ output, uint64_t n, float weight) {
     const uint64_t stride = static_cast<uint64_t>(gridDim.x) * k_threads;
-    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * k_threads + threadIdx.x; i < n;
-         i += stride) {
-        float4 c = ld_stream(current + i);
-        float4 h = ld_stream(history + i);
-        float4 r = make_float4(h.x + (c.x - h.x) * weight, h.y + (c.y - h.y) * weight,
-                               h.z + (c.z - h.z) * weight, h.w + (c.w - h.w) * weight);
-        __stcs(output + i, r);
+    auto mix = [weight](float4 c, float4 h) {
+        return make_float4(h.x + (c.x - h.x) * weight, h.y + (c.y - h.y) * weight, h.z + (c.z - h.z) * weight,
+                           h.w + (c.w - h.w) * weight);
+    };
+    uint64_t i = static_cast<uint64_t>(blockIdx.x) * k_threads + threadIdx.x;
+    for (; i + stride < n; i += 2 * stride) {
+        const float4 c0 = ld_stream(current + i), h0 = ld_stream(history + i);
+        const float4 c1 = ld_stream(current + i + stride), h1 = ld_stream(history + i + stride);
+        __stcs(output + i, mix(c0, h0));
+        __stcs(output + i + stride, mix(c1, h1));
     }
+    if (i < n) __stcs(output + i, mix(ld_stream(current + i), ld_stream(history + i)));
 }
 
-/// plugin.mm:343-349 for one channel, then Metal's unorm8 conversion.
-__device__ __forceinline__ unsigned tonemap_channel(float c) {
+__device__ __forceinline__ float mufu_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float mufu_lg2(float x) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float mufu_ex2(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+/// plugin.mm:343-349 for one channel, then Metal's unorm8 conversion: the literal form.
+__device__ __noinline__ unsigned tonemap_channel_precise(float c) {
     c = c / (c + 1.0f);
     c = powf(c, 1.0f / 2.2f);
     c = fminf(fmaxf(c, 0.0f), 1.0f);
     return static_cast<unsigned>(__float2int_rn(c * 255.0f));
+}
+
+/// The same 8-bit value, cheaply: three MUFU operations give 255 * (c / (c + 1))^(1/2.2) to within
+/// 6e-4 (rcp 2^-23, lg2 2^-22 absolute on an exponent of at most 22 where the result is not yet
+/// zero, ex2 2^-22), which rounds to the same integer as the literal form unless it lies within
+/// 2e-3 of a rounding boundary; those channels (0.4 %), and anything not finite, take the literal
+/// form. Rounding and conversion are done by the adder (y + 2^23 is y rounded to nearest even, its
+/// low mantissa bits are the integer): F2I and FRND share the MUFU pipe, which is what bounds this
+/// pass once powf is gone (ncu, round 2: powf for every channel ran at 0.24 of HBM bandwidth, the
+/// MUFU form with floorf and F2I at 0.43 with the XU pipe 71 % busy).
+__device__ __forceinline__ unsigned tonemap_channel(float c) {
+    const float r = c * mufu_rcp(c + 1.0f);
+    const float y = mufu_ex2(mufu_lg2(r) * (1.0f / 2.2f)) * 255.0f;
+    const float rounded = y + 8388608.0f;
+    const float off = y - (rounded - 8388608.0f);  // in [-1/2, 1/2]
+    if (!(fabsf(off) <= 0.5f - 2e-3f)) return tonemap_channel_precise(c);  // near a boundary, or NaN
+    return __float_as_uint(rounded) & 0xffu;
 }
 
 __device__ __forceinline__ uchar4 tonemap_pixel(float4 c) {
@@ -59,19 +98,30 @@ __device__ __forceinline__ uchar4 tonemap_pixel(float4 c) {
 }
 
 /// plugin.mm:334-350. Output texel (x, y) reads accumulated texel (x, y): the
-/// shader's Y flip undoes the rasteriser's.
+/// shader's Y flip undoes the rasteriser's. `Packed`: rows follow each other without padding,
+/// so the texel index is the pixel index (no division per pixel).
+template <bool Packed>
 __global__ void __launch_bounds__(k_threads)
 tonemap_kernel(const float4* __restrict__ accumulated, uint32_t width, uint32_t height,
                unsigned char* __restrict__ bgra, uint32_t pitch_bytes) {
     const uint64_t n = static_cast<uint64_t>(width) * height;
     const uint64_t stride = static_cast<uint64_t>(gridDim.x) * k_threads;
-    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * k_threads + threadIdx.x; i < n;
-         i += stride) {
-        uint32_t y = static_cast<uint32_t>(i / width);
-        uint32_t x = static_cast<uint32_t>(i - static_cast<uint64_t>(y) * width);
-        uchar4 o = tonemap_pixel(__ldg(accumulated + i));
-        *reinterpret_cast<uchar4*>(bgra + static_cast<size_t>(y) * pitch_bytes + 4u * x) = o;
+    auto store = [&](uint64_t i, uchar4 o) {
+        if constexpr (Packed) {
+            __stcs(reinterpret_cast<uchar4*>(bgra) + i, o);
+        } else {
+            const uint32_t y = static_cast<uint32_t>(i / width);
+            const uint32_t x = static_cast<uint32_t>(i - static_cast<uint64_t>(y) * width);
+            *reinterpret_cast<uchar4*>(bgra + static_cast<size_t>(y) * pitch_bytes + 4u * x) = o;
+        }
+    };
+    uint64_t i = static_cast<uint64_t>(blockIdx.x) * k_threads + threadIdx.x;
+    for (; i + stride < n; i += 2 * stride) {
+        const float4 a = ld_stream(accumulated + i), b = ld_stream(accumulated + i + stride);
+        store(i, tonemap_pixel(a));
+        store(i + stride, tonemap_pixel(b));
     }
+    if (i < n) store(i, tonemap_pixel(ld_stream(accumulated + i)));
 }
 
 struct shard_list {
@@ -106,10 +156,6 @@ struct sync_list {
     uint32_t* flags[k_max_shards];  ///< rank g's flag block (k_sync_words uint32), peer-mapped
 };
 
-constexpr uint32_t k_sync_arrive = 0;               ///< [from rank]: that rank's layers are final for this epoch
-constexpr uint32_t k_sync_done = k_max_shards;      ///< [from rank]: that rank has read and written all it will
-constexpr uint32_t k_sync_blocks = 2 * k_max_shards;  ///< local: CTAs of this launch that have finished
-
 __device__ __forceinline__ void store_release_system(uint32_t* p, uint32_t v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -123,60 +169,67 @@ __device__ __forceinline__ void wait_epoch(const uint32_t* p, uint32_t epoch) {
     while (static_cast<int32_t>(load_acquire_system(p) - epoch) < 0) __nanosleep(64);
 }
 
-/// The whole multi-GPU exchange of one frame as ONE kernel per GPU, with no host
-/// synchronisation: every rank runs this on its 1/G slice of the contiguous layer block.
-///   arrive   the kernel starts after this rank's render (stream order): it stores
-///            `epoch` into every peer's arrive[rank], then waits until every peer has
-///            arrived in its own flag block. From here on all layers are final.
-///   combine  rank-ordered sum of the G per-rank means over NVLink (16-byte peer
-///            loads), 1/G scale, slice stored straight into the root GPU's result
-///            buffer (a peer store for every rank but the root): reduce-scatter and
-///            gather, no staging.
-///   done     the last CTA of this launch stores `epoch` into every peer's done[rank] and
-///            waits for every peer's done: when the kernel ends on the root all slices have
-///            landed there, and when it ends anywhere nobody still reads this rank's
-///            layers, so the next render may overwrite them.
-/// Nothing here waits for another CTA of the same launch, and a peer's flags are written by
-/// a kernel that itself waits only for `arrive`, so there is no cycle as long as every rank
-/// launches the kernel for the same epoch.
+struct export_list {
+    float4* base[k_max_export_slices];
+};
+
+/// The layer block of this GPU, slice by slice, to where batch_params' export would have sent it
+/// (scene_params.hpp): for frames whose last launch was not a batched one (a launch of one sample
+/// exports nothing). Reads HBM once, writes over NVLink (or PCIe) with 16-byte stores.
 __global__ void __launch_bounds__(k_threads)
-combine_shards_sync_kernel(const __grid_constant__ shard_list shards, const __grid_constant__ sync_list sync,
-                           uint32_t n_shards, uint32_t rank, uint32_t epoch, uint64_t n, float scale,
-                           float4* __restrict__ out, uchar4* __restrict__ bgra) {
+push_slices_kernel(const float4* __restrict__ block, const __grid_constant__ export_list to, uint32_t per,
+                   uint32_t per_magic, uint64_t n) {
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * k_threads;
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * k_threads + threadIdx.x; i < n; i += stride) {
+        const uint32_t index = static_cast<uint32_t>(i);
+        uint32_t slice = __umulhi(index, per_magic);
+        uint32_t within = index - slice * per;
+        if (within >= per) {
+            within -= per;
+            slice++;
+        }
+        to.base[slice][within] = ld_stream(block + i);
+    }
+}
+
+/// The multi-GPU exchange of one frame, on the GPU that owns a slice: every rank has PUSHED its part of this
+/// slice into this GPU's staging memory while it rendered (the export of the batched launches, or
+/// push_slices_kernel), so what is left is a local pass: wait until every rank has said that its frame is
+/// complete, sum the G staged copies in rank order, scale by 1/G, store the slice where the frame is wanted
+/// (pinned host memory: each GPU sends its own slice over its own PCIe link; or device memory).
+///   arrive   this kernel follows this rank's render in stream order: block 0 stores `epoch` into every
+///            rank's arrive[rank] (release, system scope), then every block waits until all G ranks have
+///            arrived in this GPU's own flag block. From here on all G staged copies are complete.
+/// Nothing waits for another block of this launch or for a later kernel of a peer, so there is no cycle as
+/// long as every rank launches the kernel for the same epoch. The staging memory is double-buffered by the
+/// caller (epoch parity): a rank can push frame e + 2 only after its reduce of frame e + 1 has seen every
+/// rank arrive, i.e. after every rank's reduce of frame e (which precedes its render of e + 1 in stream
+/// order) has finished reading the buffer of frame e.
+/// Pull (the first form: every rank loads its slice of all G layer blocks over NVLink, round trips) took
+/// 0.75 ms for a 1080p frame on 8 GPUs against 0.65 ms for ncclReduce + scale.
+__global__ void __launch_bounds__(k_threads)
+reduce_slices_sync_kernel(const float4* __restrict__ staging, uint32_t per, const __grid_constant__ sync_list sync,
+                          uint32_t n_shards, uint32_t rank, uint32_t epoch, uint64_t n, float scale,
+                          float4* __restrict__ out) {
     uint32_t* mine = sync.flags[rank];
     if (blockIdx.x == 0 && threadIdx.x < n_shards) {
-        store_release_system(sync.flags[threadIdx.x] + k_sync_arrive + rank, epoch);
+        __threadfence_system();
+        store_release_system(sync.flags[threadIdx.x] + rank, epoch);
     }
-    if (threadIdx.x < n_shards) wait_epoch(mine + k_sync_arrive + threadIdx.x, epoch);
+    if (threadIdx.x < n_shards) wait_epoch(mine + threadIdx.x, epoch);
     __syncthreads();
 
     const uint64_t stride = static_cast<uint64_t>(gridDim.x) * k_threads;
     for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * k_threads + threadIdx.x; i < n; i += stride) {
-        float4 s = ld_stream(shards.ptr[0] + i);
+        float4 s = ld_stream(staging + i);
         for (uint32_t g = 1; g < n_shards; g++) {
-            float4 v = ld_stream(shards.ptr[g] + i);
+            const float4 v = ld_stream(staging + static_cast<uint64_t>(g) * per + i);
             s.x = s.x + v.x;
             s.y = s.y + v.y;
             s.z = s.z + v.z;
             s.w = s.w + v.w;
         }
-        s = make_float4(s.x * scale, s.y * scale, s.z * scale, s.w * scale);
-        out[i] = s;
-        if (bgra != nullptr) bgra[i] = tonemap_pixel(s);
-    }
-
-    __threadfence_system();  // this thread's slice stores are visible before the done flag is
-    __syncthreads();
-    __shared__ bool s_last;
-    if (threadIdx.x == 0) {
-        s_last = atomicAdd(mine + k_sync_blocks, 1u) == gridDim.x - 1u;
-        if (s_last) mine[k_sync_blocks] = 0u;  // for the next launch (ordered by the stream)
-    }
-    __syncthreads();
-    if (s_last && threadIdx.x < n_shards) {
-        __threadfence_system();
-        store_release_system(sync.flags[threadIdx.x] + k_sync_done + rank, epoch);
-        wait_epoch(mine + k_sync_done + threadIdx.x, epoch);
+        __stcs(out + i, make_float4(s.x * scale, s.y * scale, s.z * scale, s.w * scale));
     }
 }
 
@@ -196,9 +249,13 @@ cudaError_t launch_tonemap_bgra8(const float* accumulated, uint32_t width, uint3
                                  void* bgra, uint32_t pitch_bytes, cudaStream_t stream) {
     uint64_t n = static_cast<uint64_t>(width) * height;
     if (n == 0) return cudaSuccess;
-    tonemap_kernel<<<grid_for(n), k_threads, 0, stream>>>(
-        reinterpret_cast<const float4*>(accumulated), width, height,
-        static_cast<unsigned char*>(bgra), pitch_bytes);
+    if (pitch_bytes == 4u * width) {
+        tonemap_kernel<true><<<grid_for(n), k_threads, 0, stream>>>(
+            reinterpret_cast<const float4*>(accumulated), width, height, static_cast<unsigned char*>(bgra), pitch_bytes);
+    } else {
+        tonemap_kernel<false><<<grid_for(n), k_threads, 0, stream>>>(
+            reinterpret_cast<const float4*>(accumulated), width, height, static_cast<unsigned char*>(bgra), pitch_bytes);
+    }
     return cudaGetLastError();
 }
 
@@ -220,21 +277,40 @@ cudaError_t launch_combine_shards(const float* const* shards, uint32_t n_shards,
 
 namespace Q::cuda {
 
-cudaError_t launch_combine_shards_sync(const float* const* shards, uint32_t* const* flags, uint32_t n_shards,
-                                       uint32_t rank, uint32_t epoch, uint64_t n_pixels, float scale, float* out,
-                                       void* bgra, cudaStream_t stream) {
-    if (n_shards == 0 || n_shards > k_max_shards || rank >= n_shards) return cudaErrorInvalidValue;
-    shard_list list{};
+cudaError_t launch_push_slices(const float* block, uint64_t n_float4, void* const* base, uint32_t slices,
+                               uint32_t float4_per_slice, cudaStream_t stream) {
+    if (slices == 0 || slices > k_max_export_slices || float4_per_slice == 0 || n_float4 >= (uint64_t{1} << 32) ||
+        n_float4 > static_cast<uint64_t>(slices) * float4_per_slice) {
+        return cudaErrorInvalidValue;
+    }
+    if (n_float4 == 0) return cudaSuccess;
+    export_list to{};
+    for (uint32_t g = 0; g < slices; g++) {
+        if (base[g] == nullptr) return cudaErrorInvalidValue;
+        to.base[g] = static_cast<float4*>(base[g]);
+    }
+    push_slices_kernel<<<grid_for(n_float4), k_threads, 0, stream>>>(
+        reinterpret_cast<const float4*>(block), to, float4_per_slice,
+        static_cast<uint32_t>((uint64_t{1} << 32) / float4_per_slice), n_float4);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_reduce_slices_sync(const float* staging, uint32_t float4_per_slice, uint32_t* const* flags,
+                                      uint32_t n_shards, uint32_t rank, uint32_t epoch, uint64_t n_float4, float scale,
+                                      float* out, cudaStream_t stream) {
+    if (n_shards == 0 || n_shards > k_max_shards || rank >= n_shards || n_float4 > float4_per_slice) {
+        return cudaErrorInvalidValue;
+    }
     sync_list sync{};
     for (uint32_t g = 0; g < n_shards; g++) {
-        list.ptr[g] = reinterpret_cast<const float4*>(shards[g]);
-        sync.flags[g] = flags[g];
         if (flags[g] == nullptr) return cudaErrorInvalidValue;
+        sync.flags[g] = flags[g];
     }
     if (scale == 0.0f) scale = 1.0f / static_cast<float>(n_shards);
-    combine_shards_sync_kernel<<<grid_for(n_pixels), k_threads, 0, stream>>>(
-        list, sync, n_shards, rank, epoch, n_pixels, scale, reinterpret_cast<float4*>(out),
-        static_cast<uchar4*>(bgra));
+    // at least one block even for an empty slice: the arrive flags are part of every rank's protocol
+    reduce_slices_sync_kernel<<<grid_for(n_float4 ? n_float4 : 1), k_threads, 0, stream>>>(
+        reinterpret_cast<const float4*>(staging), float4_per_slice, sync, n_shards, rank, epoch, n_float4, scale,
+        reinterpret_cast<float4*>(out));
     return cudaGetLastError();
 }
 

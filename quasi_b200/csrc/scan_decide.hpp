@@ -85,18 +85,6 @@ struct scan_state {
 /// With denom == 0 the reciprocal is infinite and t' is +-inf or NaN: the point, alpha', beta'
 /// and m are then infinite or NaN, never finite, so neither `maybe` nor `sure` holds
 /// (comparisons with NaN are false; fmax(|a|, |b|) is NaN only if both are).
-QUASI_SCAN_FN void consider(scan_state& s, const quad_params& q, int i, float t_fast,
-                                         float m, bool ahead) {
-    const bool maybe = ahead && m <= q.half_plus;
-    const bool sure = ahead && m < q.half_minus;  // t_min_hi and |denom|: once per ray, accept_winner()
-    const bool better = sure && t_fast < s.best_t;
-    // Whoever does not become the winner challenges it.
-    const float loser = better ? s.best_t : (maybe ? t_fast : k_inf);
-    s.challenger_t = std::fmin(s.challenger_t, loser);
-    s.best_t = better ? t_fast : s.best_t;
-    s.best_i = better ? i : s.best_i;
-}
-/// consider() with the two margins given as values (the packed-record forms below).
 QUASI_SCAN_FN void consider(scan_state& s, float half_plus, float half_minus, int i, float t_fast, float m, bool ahead) {
     const bool maybe = ahead && m <= half_plus;
     const bool sure = ahead && m < half_minus;
@@ -112,23 +100,9 @@ QUASI_SCAN_FN float axis(v3 a, int k) { return k == 0 ? a.x : (k == 1 ? a.y : a.
 /// Quad whose normal is along axis K (two normal components are exactly zero, so
 /// the shader's three-term dot products collapse to one product, bit for bit)
 /// and whose barycentrics do not depend on coordinate K.
-template <int K>
-QUASI_SCAN_FN void scan_flat(scan_state& s, const quad_params& q, int i, v3 ro, v3 rd) {
-    constexpr int I = (K + 1) % 3, J = (K + 2) % 3;
-    const float denom = q.normal[K] * axis(rd, K);
-    const float num = q.plane_d - q.normal[K] * axis(ro, K);
-    const float t_fast = num * rcp(denom);
-    const bool ahead = t_fast > k_t_min_lo;
-    // p', alpha', beta' only feed margin decisions: contracted (FFMA), unlike num and denom
-    const float pi = fma_rn(axis(rd, I), t_fast, axis(ro, I)) - q.center[I];
-    const float pj = fma_rn(axis(rd, J), t_fast, axis(ro, J)) - q.center[J];
-    const float alpha = fma_rn(pi, q.fast_a[I], pj * q.fast_a[J]);
-    const float beta = fma_rn(pi, q.fast_b[I], pj * q.fast_b[J]);
-    consider(s, q, i, t_fast, std::fmax(std::fabs(alpha), std::fabs(beta)), ahead);
-}
-
-/// scan_flat<K> reading the packed record of the quad (scene_params.hpp:scan_record): the
-/// same operations on the same values.
+/// The constants come from the quad's packed record (scene_params.hpp:scan_record), in the order
+/// the scan uses them: sm_100 has no constant-bank operands for FP32 instructions, every scene
+/// constant costs an LDCU issue slot, and three 16-byte loads per quad replace eight small ones.
 template <int K>
 QUASI_SCAN_FN void scan_flat(scan_state& s, const scan_record& q, int i, v3 ro, v3 rd) {
     constexpr int I = (K + 1) % 3, J = (K + 2) % 3;
@@ -145,20 +119,6 @@ QUASI_SCAN_FN void scan_flat(scan_state& s, const scan_record& q, int i, v3 ro, 
 
 /// Quad with a horizontal normal and one vertical edge (the side of a box
 /// standing on the floor): alpha lives in (x, z), beta along y.
-QUASI_SCAN_FN void scan_upright(scan_state& s, const quad_params& q, int i, v3 ro, v3 rd) {
-    const float denom = q.normal[0] * rd.x + q.normal[2] * rd.z;
-    const float num = q.plane_d - (q.normal[0] * ro.x + q.normal[2] * ro.z);
-    const float t_fast = num * rcp(denom);
-    const bool ahead = t_fast > k_t_min_lo;
-    const float px = fma_rn(rd.x, t_fast, ro.x) - q.center[0];
-    const float py = fma_rn(rd.y, t_fast, ro.y) - q.center[1];
-    const float pz = fma_rn(rd.z, t_fast, ro.z) - q.center[2];
-    const float alpha = fma_rn(px, q.fast_a[0], pz * q.fast_a[2]);
-    const float beta = py * q.fast_b[1];
-    consider(s, q, i, t_fast, std::fmax(std::fabs(alpha), std::fabs(beta)), ahead);
-}
-
-/// scan_upright reading the packed record of the quad.
 QUASI_SCAN_FN void scan_upright(scan_state& s, const scan_record& q, int i, v3 ro, v3 rd) {
     const float denom = q.r[0] * rd.x + q.r[1] * rd.z;
     const float num = q.r[2] - (q.r[0] * ro.x + q.r[1] * ro.z);
@@ -183,7 +143,7 @@ QUASI_SCAN_FN void scan_general(scan_state& s, const quad_params& q, int i, v3 r
                         fma_rn(rd.z, t_fast, ro.z) - q.center[2]};
         const float alpha = fma_rn(planar.x, q.fast_a[0], fma_rn(planar.y, q.fast_a[1], planar.z * q.fast_a[2]));
         const float beta = fma_rn(planar.x, q.fast_b[0], fma_rn(planar.y, q.fast_b[1], planar.z * q.fast_b[2]));
-        consider(s, q, i, t_fast, std::fmax(std::fabs(alpha), std::fabs(beta)), ahead);
+        consider(s, q.half_plus, q.half_minus, i, t_fast, std::fmax(std::fabs(alpha), std::fabs(beta)), ahead);
     }
 }
 
@@ -269,13 +229,8 @@ QUASI_SCAN_FN void scan_box(scan_state& s, const box_params& b, v3 ro, v3 rd) {
     s.best_i = better ? face : s.best_i;
 }
 
-/// What scan_flat and scan_upright read a quad from: its packed record with
-/// -DQUASI_SCAN_RECORDS=1, the quad_params fields otherwise. Same values either way.
-#if defined(QUASI_SCAN_RECORDS) && QUASI_SCAN_RECORDS
+/// What scan_flat and scan_upright read a quad from: its packed record.
 #define QUASI_SCAN_SOURCE(scene, i) (scene).records[i]
-#else
-#define QUASI_SCAN_SOURCE(scene, i) (scene).quads[i]
-#endif
 
 /// The whole fast scan for any scene (one loop per shape with launch-uniform bounds, then
 /// the boxes). The kernel unrolls the same calls for the demo scene's layout.

@@ -145,9 +145,7 @@ struct alignas(16) scene_params {
     float corner_radius;    ///< farthest quad corner from the world origin
     uint32_t box_count;
     box_params boxes[k_max_boxes];
-#if defined(QUASI_SCAN_RECORDS) && QUASI_SCAN_RECORDS
-    scan_record records[k_max_quads];        ///< per position in `quads` (fill_scan_records); build-time option
-#endif
+    scan_record records[k_max_quads];        ///< per position in `quads` (fill_scan_records): what the scan reads
 };
 
 /// Per-call camera and sample bookkeeping.
@@ -164,6 +162,23 @@ struct alignas(16) frame_params {
     uint32_t tiles_x_magic; ///< floor(2^32 / ceil(width / 8)), for the kernel's tile -> (x, y)
     uint32_t batch_samples; ///< samples per pixel in this launch (0 or 1: one; QUASI_CUDA_BATCH)
     uint32_t frame_stride;  ///< RNG frame index of sample s of the launch: frame_index + s * frame_stride
+};
+
+/// Where a launch of several samples per pixel (frame.batch_samples > 1) sends finished tiles.
+/// When a tile has received the LAST sample of the launch, the warp that rendered it copies the
+/// tile's pixels of all four layers out of the accumulation block, rows of 8 pixels (128 bytes) at a
+/// time: into pinned host memory (the frame is on the host when the launch ends: plugin.cu, readback) or
+/// into other GPUs' memory over NVLink (multi-GPU: each rank pushes every slice of its layers to the
+/// slice's owner while it renders). The block of 4 * width * height float4 is cut into `export_slices`
+/// slices of `export_per` float4 (the last one shorter); float4 i goes to
+/// export_base[i / export_per] + (i % export_per). 0 slices: nothing is exported.
+inline constexpr uint32_t k_max_export_slices = 16;
+struct alignas(16) batch_params {
+    void* export_base[k_max_export_slices];
+    uint32_t export_slices;
+    uint32_t export_per;
+    uint32_t export_per_magic;  ///< floor(2^32 / export_per)
+    uint32_t reserved;
 };
 
 /// The scene as the host describes it: the same 12+8 floats per quad the Metal
@@ -484,8 +499,7 @@ inline void prepare_scene(const scene_desc& desc, uint32_t max_bounces, scene_pa
 }
 
 /// @brief Copies what the scan reads of every flat and upright quad into scene.records.
-inline void fill_scan_records([[maybe_unused]] scene_params& scene) {
-#if defined(QUASI_SCAN_RECORDS) && QUASI_SCAN_RECORDS
+inline void fill_scan_records(scene_params& scene) {
     for (uint32_t i = 0; i < scene.quad_count; i++) {
         const quad_params& g = scene.quads[i];
         float* r = scene.records[i].r;
@@ -505,7 +519,6 @@ inline void fill_scan_records([[maybe_unused]] scene_params& scene) {
             for (int k = 0; k < 11; k++) r[k] = packed[k];
         }
     }
-#endif
 }
 
 /// @brief Sets the per-quad decision margin of the fast scan for a camera position.

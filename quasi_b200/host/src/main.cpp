@@ -85,6 +85,8 @@ struct options {
     bool present = false;
     bool json = false;
     bool keep_accumulation = false;  ///< --keep-accumulation: a reloaded backend continues the image
+    int repeat = 1;                  ///< --repeat R: render the N-frame set R times (accumulation restarted each time)
+    bool readback_each = false;      ///< --readback-each: every set ends with the blocking AOV readback (end to end)
 };
 
 struct gpu_worker {
@@ -96,15 +98,35 @@ struct gpu_worker {
     bool finished = false;
     std::vector<float> frame_gap_ms;  ///< wall time between consecutive frame submissions
     clock_type::time_point last_submit{};
+    std::vector<float> set_ms;        ///< --repeat: wall time of every N-frame set, first submission to idle (+ readback)
 };
 
 /// The main loop of main.cpp:243-323 for one GPU, as a coroutine: it never blocks,
 /// so one scheduler thread keeps every GPU and the reload watcher going.
 Q::async::task<void> frame_loop(gpu_worker& w, const options& opt, clock_type::time_point deadline) {
     auto last_time = clock_type::now();
+    auto set_start = last_time;
+    uint64_t frames_in_set = 0;
+    int sets_done = 0;
     for (;;) {
         if (g_shutdown_requested) break;
-        if (opt.render_frames > 0 && w.frames >= static_cast<uint64_t>(opt.render_frames)) break;
+        if (opt.render_frames > 0 && frames_in_set >= static_cast<uint64_t>(opt.render_frames)) {
+            // One frame set is complete: wait for the GPU (and, with --readback-each, bring the four layers to the
+            // host exactly as the save path does), note the wall time, start the next set from sample 0.
+            co_await w.context.wait_idle();
+            if (opt.readback_each) {
+                if (auto* plugin = w.manager->plugin(); plugin && plugin->supports_readback_aov()) {
+                    auto rb = plugin->readback_aov();
+                    plugin->readback_aov_free(&rb);
+                }
+            }
+            w.set_ms.push_back(std::chrono::duration<float, std::milli>(clock_type::now() - set_start).count());
+            if (++sets_done >= opt.repeat) break;
+            frames_in_set = 0;
+            w.camera.dirty = true;
+            set_start = clock_type::now();
+            continue;
+        }
         if (opt.progressive_s > 0.0 && clock_type::now() >= deadline) break;
 
         if (!w.manager->is_loaded() || w.manager->is_reloading()) {
@@ -128,6 +150,7 @@ Q::async::task<void> frame_loop(gpu_worker& w, const options& opt, clock_type::t
             w.manager->render(&*frame);
             w.context.end_frame(*frame);
             ++w.frames;
+            ++frames_in_set;
             if (w.last_submit != clock_type::time_point{}) {
                 w.frame_gap_ms.push_back(std::chrono::duration<float, std::milli>(now - w.last_submit).count());
             }
@@ -149,7 +172,8 @@ float percentile(std::vector<float> v, double p) {
 void usage(const char* argv0) {
     std::fprintf(stderr,
                  "Usage: %s [--render N] [--progressive SECONDS] [--width W] [--height H] [--out FILE.exr]\n"
-                 "          [--gpus G] [--device D] [--watch] [--keep-accumulation] [--present] [--json] <plugin.so>\n",
+                 "          [--gpus G] [--device D] [--watch] [--keep-accumulation] [--present] [--json]\n"
+                 "          [--repeat R] [--readback-each] <plugin.so>\n",
                  argv0);
 }
 
@@ -199,6 +223,12 @@ bool parse(int argc, char* argv[], options& opt) {
             opt.json = true;
         } else if (arg == "--keep-accumulation") {
             opt.keep_accumulation = true;
+        } else if (arg == "--repeat") {
+            const char* v = value("--repeat");
+            if (!v) return false;
+            opt.repeat = std::max(1, std::atoi(v));
+        } else if (arg == "--readback-each") {
+            opt.readback_each = true;
         } else if (!arg.empty() && arg[0] != '-') {
             opt.plugin_path = arg;
         } else {
@@ -431,17 +461,23 @@ int main(int argc, char* argv[]) {
     if (opt.json || opt.progressive_s > 0.0) {
         const auto& gaps = workers[0]->frame_gap_ms;
         const auto& st = workers[0]->manager->stats();
+        std::string set_ms_list;  // wall time of every frame set of GPU 0 (--repeat)
+        for (float ms : workers[0]->set_ms) {
+            char item[32];
+            std::snprintf(item, sizeof item, "%s%.4f", set_ms_list.empty() ? "" : ", ", ms);
+            set_ms_list += item;
+        }
         std::printf(
             "{\"frames\": %llu, \"seconds\": %.4f, \"rays\": %llu, \"mrays_per_s\": %.2f, \"kernel_launches\": %llu, "
             "\"frame_ms_p50\": %.4f, \"frame_ms_p95\": %.4f, \"frame_ms_p99\": %.4f, \"frame_ms_max\": %.3f, "
             "\"reloads\": %llu, \"reload_failures\": %llu, \"last_reload_ms\": %.2f, \"gpus\": %d, "
-            "\"width\": %u, \"height\": %u}\n",
+            "\"width\": %u, \"height\": %u, \"set_ms\": [%s]}\n",
             static_cast<unsigned long long>(frames), elapsed_s, static_cast<unsigned long long>(rays),
             static_cast<double>(rays) / elapsed_s / 1e6, static_cast<unsigned long long>(launches),
             percentile(gaps, 0.50), percentile(gaps, 0.95), percentile(gaps, 0.99),
             gaps.empty() ? 0.0f : *std::max_element(gaps.begin(), gaps.end()),
             static_cast<unsigned long long>(st.success_count), static_cast<unsigned long long>(st.failure_count),
-            st.last_reload_time * 1000.0f, opt.gpus, opt.width, opt.height);
+            st.last_reload_time * 1000.0f, opt.gpus, opt.width, opt.height, set_ms_list.c_str());
     }
 
     std::printf("Shutting down...\n");

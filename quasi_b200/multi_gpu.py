@@ -7,18 +7,23 @@ layers (the plugin does this itself from Q_cuda_device_desc.shard_index/count).
 The only exchange is the combine: result = (sum over ranks of the per-rank
 means) * (1/N). Two implementations of that exchange:
 
-  nccl  torch.distributed.reduce(SUM) of the contiguous 4-layer block to rank 0
-        on the frame stream, then the 1/N scale kernel on rank 0. The baseline.
-  p2p   the layer blocks of all ranks are mapped into every process with CUDA
-        IPC. Each rank runs ONE kernel (Q_cuda_combine_shards_sync on peer
-        pointers) that waits on device-side flags until every rank's render has
-        finished, loads its 1/N slice of every rank's layers over NVLink in rank
-        order, scales, stores the slice straight into rank 0's result buffer and
-        signals completion: reduce-scatter + gather fused, no staging copy, no
-        host barrier, and unlike NCCL's ring/tree the summation order is fixed,
-        so the result is bit-identical to the oracle's rank-ordered combine.
-  p2p_host  the same data path with Q_cuda_combine_shards and two host barriers
-        per frame instead of the flags (the first form; kept for comparison).
+  push  (default) reduce-scatter by peer stores, fused into the render. The contiguous
+        4-layer block is cut into N slices; rank s owns slice s and a staging area of N
+        slots (CUDA IPC, mapped by every rank). A rank's batched render kernel sends every
+        8x4 tile that has received its last sample to the owners of its four layers' slices
+        over NVLink, 128 bytes at a time, while the rest of the image is still being
+        rendered (Q_cuda_plugin_set_export; Q_cuda_push_slices does the same after the
+        fact for a frame whose last launch was a single sample). What follows the render
+        is ONE local kernel per rank (Q_cuda_reduce_slices_sync): it waits on device-side
+        flags until every rank's frame is complete, sums the N staged copies of its slice
+        in rank order, scales, and stores the slice straight into pinned host memory that
+        all ranks share, so the finished frame reaches the host over N PCIe links at once
+        instead of through rank 0's. No host barrier, no staging copy, no NCCL, and unlike
+        NCCL's ring/tree the summation order is fixed: the result is bit-identical to the
+        oracle's rank-ordered combine.
+  nccl  torch.distributed.reduce(SUM) of a copy of the block to rank 0 on the frame
+        stream, the 1/N scale kernel on rank 0, then rank 0 copies the frame to the
+        host. The baseline.
 
 The reference has no multi-GPU path; the oracle for the combine
 is oracle/quasi_oracle.c:qo_combine_shards.
@@ -26,6 +31,7 @@ is oracle/quasi_oracle.c:qo_combine_shards.
 from __future__ import annotations
 
 import ctypes as C
+import time
 
 from . import abi
 
@@ -67,80 +73,113 @@ def device_tensor(ptr: int, n_floats: int, device):
     return torch.as_tensor(_holder(), device=device)
 
 
-class shard_reducer:
-    """Combines the per-rank accumulation layers into rank 0's result buffer."""
+class host_frame:
+    """The finished frame in host memory every rank has mapped: a POSIX shared-memory segment created
+    by rank 0 (4 layers of H x W x 4 float32, then one uint32 per rank and one for rank 0's reader:
+    'my slice of frame e has landed' / 'frame e has been looked at')."""
 
-    def __init__(self, host, dist, mode: str = "p2p"):
+    def __init__(self, dist, n_floats: int):
+        from multiprocessing import shared_memory
+
+        import numpy as np
+
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.data_bytes = n_floats * 4
+        size = self.data_bytes + 4096
+        name = [None]
+        if self.rank == 0:
+            self.shm = shared_memory.SharedMemory(create=True, size=size)
+            name[0] = self.shm.name
+        dist.broadcast_object_list(name, src=0)
+        if self.rank != 0:
+            self.shm = shared_memory.SharedMemory(name=name[0])
+        self.floats = np.frombuffer(self.shm.buf, dtype=np.float32, count=n_floats)
+        self.flags = np.frombuffer(self.shm.buf, dtype=np.uint32, count=64, offset=self.data_bytes)
+        if self.rank == 0:
+            self.flags[:] = 0
+        dist.barrier()
+        self._anchor = C.c_char.from_buffer(self.shm.buf)
+        self.address = C.addressof(self._anchor)
+
+    def landed(self, epoch: int):
+        """This rank's slice of frame `epoch` is in the segment."""
+        self.flags[self.rank] = epoch
+
+    def wait_all_landed(self, epoch: int, timeout_s: float = 60.0):
+        """Rank 0: spins until every rank's slice of frame `epoch` is in the segment."""
+        t0 = time.perf_counter()
+        while int(self.flags[:self.world].min()) < epoch:
+            if time.perf_counter() - t0 > timeout_s:
+                raise TimeoutError(f"frame {epoch}: slices landed {self.flags[:self.world].tolist()}")
+
+    def consumed(self, epoch: int):
+        """Rank 0: whoever reads the segment is done with frame `epoch`; its memory may be overwritten."""
+        self.flags[32] = epoch
+
+    def wait_consumed(self, epoch: int, timeout_s: float = 60.0):
+        t0 = time.perf_counter()
+        while int(self.flags[32]) < epoch:
+            if time.perf_counter() - t0 > timeout_s:
+                raise TimeoutError(f"frame {epoch} was never released by rank 0")
+
+    def close(self):
+        self.floats = self.flags = self._anchor = None
+        try:
+            self.shm.close()
+            if self.rank == 0:
+                self.shm.unlink()
+        except Exception:
+            pass
+
+
+class shard_exchange:
+    """Combines the per-rank accumulation layers of one frame: begin_frame() before the frame's render
+    calls, combine() after them (enqueue only), finish_frame() when the frame is wanted on the host."""
+
+    def __init__(self, host, dist, mode: str = "push"):
         import torch
 
+        if mode not in ("push", "nccl"):
+            raise ValueError(mode)
         self.torch, self.host, self.dist, self.mode = torch, host, dist, mode
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.device = host.context.device
         self.stream = host.context.frame_stream()
         self.fn = host.plugin.fn
+        self.handle = host.plugin._handle
         self.n_px = host.context.width * host.context.height
         self.total_float4 = self.n_px * 4  # four layers, contiguous
-        self.result_ptr = None            # rank 0: the combined layers (own memory)
-        self._opened = []
+        self.per = (self.total_float4 + self.world - 1) // self.world
+        self.lo, self.hi = slice_bounds(self.total_float4, self.world, self.rank)
         self.launches = 0
         self.epoch = 0
-        self.flag_ptrs = None
-        self._own_flags = None
-        if mode in ("p2p", "p2p_host"):
-            self._setup_p2p()
-        elif mode == "nccl":
-            self._setup_nccl()
+        self._handed_out = 0  # the frame finish_frame() last returned and release_frame() has not yet been called for
+        self._opened = []
+        self._own = []
+        self.frame = None
+        if mode == "push":
+            self._setup_push()
         else:
-            raise ValueError(mode)
+            self._setup_nccl()
 
     # ---- setup ----
     def _layer_block(self):
+        """Device pointer of this rank's contiguous 4-layer block; launches what the plugin has collected."""
         layers = self.host.plugin.cuda_layers(self.stream.cuda_stream)
         return layers.device_ptr[0]
 
-    def _setup_nccl(self):
-        self.result = self.torch.empty(self.total_float4 * 4, dtype=self.torch.float32, device=self.device)
-        self.result_ptr = self.result.data_ptr()
-
-    def _setup_p2p(self):
-        # The plugin allocates its layers at create; render once so the block exists
-        # even if a host resized, then export it.
-        block = self._layer_block()
-        mine = abi.Q_cuda_ipc_handle()
-        if self.fn("Q_cuda_ipc_export")(block, C.byref(mine)) != 0:
-            raise RuntimeError("Q_cuda_ipc_export(layers) failed")
-        result_handle = None
-        if self.rank == 0:
-            p = C.c_void_p()
-            if self.fn("Q_cuda_alloc")(self.total_float4 * 16, C.byref(p)) != 0:
-                raise RuntimeError("Q_cuda_alloc(result) failed")
-            self.result_ptr = p.value
-            rh = abi.Q_cuda_ipc_handle()
-            if self.fn("Q_cuda_ipc_export")(self.result_ptr, C.byref(rh)) != 0:
-                raise RuntimeError("Q_cuda_ipc_export(result) failed")
-            result_handle = bytes(rh.bytes)
-        # this rank's flag block for the in-kernel synchronisation, zeroed before anyone can see it
+    def _alloc(self, n_bytes: int) -> int:
         p = C.c_void_p()
-        if self.fn("Q_cuda_alloc")(256, C.byref(p)) != 0:
-            raise RuntimeError("Q_cuda_alloc(flags) failed")
-        self._own_flags = p.value
-        if self.fn("Q_cuda_memset_async")(self._own_flags, 0, 256, self.stream.cuda_stream) != 0:
-            raise RuntimeError("Q_cuda_memset_async(flags) failed")
-        self.stream.synchronize()
-        fh = abi.Q_cuda_ipc_handle()
-        if self.fn("Q_cuda_ipc_export")(self._own_flags, C.byref(fh)) != 0:
-            raise RuntimeError("Q_cuda_ipc_export(flags) failed")
-        gathered = [None] * self.world
-        self.dist.all_gather_object(gathered, (bytes(mine.bytes), result_handle, bytes(fh.bytes)))
-        self.block_ptrs, self.flag_ptrs = [], []
-        for g, (layer_handle, _, flag_handle) in enumerate(gathered):
-            if g == self.rank:
-                self.block_ptrs.append(block)
-                self.flag_ptrs.append(self._own_flags)
-            else:
-                self.block_ptrs.append(self._open(layer_handle))
-                self.flag_ptrs.append(self._open(flag_handle))
-        self.out_ptr = self.result_ptr if self.rank == 0 else self._open(gathered[0][1])
+        if self.fn("Q_cuda_alloc")(n_bytes, C.byref(p)) != 0:
+            raise RuntimeError(f"Q_cuda_alloc({n_bytes}) failed")
+        self._own.append(p.value)
+        return p.value
+
+    def _export(self, ptr: int) -> bytes:
+        h = abi.Q_cuda_ipc_handle()
+        if self.fn("Q_cuda_ipc_export")(ptr, C.byref(h)) != 0:
+            raise RuntimeError("Q_cuda_ipc_export failed")
+        return bytes(h.bytes)
 
     def _open(self, raw: bytes) -> int:
         h = abi.Q_cuda_ipc_handle()
@@ -151,73 +190,135 @@ class shard_reducer:
         self._opened.append(p.value)
         return p.value
 
+    def _setup_nccl(self):
+        self.result = self.torch.empty(self.total_float4 * 4, dtype=self.torch.float32, device=self.device)
+        self.pinned = self.torch.empty(self.total_float4 * 4, dtype=self.torch.float32).pin_memory() \
+            if self.rank == 0 else None
+
+    def _setup_push(self):
+        # staging: two frames (parity) x `world` slots x `per` float4; flags: one block, zeroed before anyone sees it
+        slot_bytes = self.per * 16
+        self.staging = self._alloc(2 * self.world * slot_bytes)
+        self.flags = self._alloc(256)
+        if self.fn("Q_cuda_memset_async")(self.flags, 0, 256, self.stream.cuda_stream) != 0:
+            raise RuntimeError("Q_cuda_memset_async(flags) failed")
+        self.stream.synchronize()
+        gathered = [None] * self.world
+        self.dist.all_gather_object(gathered, (self._export(self.staging), self._export(self.flags)))
+        self.staging_ptrs, self.flag_ptrs = [], []
+        for g, (staging_handle, flag_handle) in enumerate(gathered):
+            mine = g == self.rank
+            self.staging_ptrs.append(self.staging if mine else self._open(staging_handle))
+            self.flag_ptrs.append(self.flags if mine else self._open(flag_handle))
+        # where rank g's staging expects THIS rank's copy of slice g, per parity
+        self.tables = []
+        for parity in range(2):
+            t = abi.Q_cuda_export_table()
+            t.struct_size = C.sizeof(abi.Q_cuda_export_table)
+            t.slices, t.float4_per_slice = self.world, self.per
+            for g in range(self.world):
+                t.base[g] = self.staging_ptrs[g] + (parity * self.world + self.rank) * slot_bytes
+            self.tables.append(t)
+        # the finished frame: host memory shared by all ranks, pinned by each
+        self.frame = host_frame(self.dist, self.total_float4 * 4)
+        dev = C.c_void_p()
+        if self.fn("Q_cuda_host_register")(self.frame.address, self.frame.data_bytes, C.byref(dev)) != 0:
+            raise RuntimeError("Q_cuda_host_register(frame) failed")
+        self.frame_device_ptr = dev.value
+
     # ---- per frame ----
+    def begin_frame(self):
+        """Before the frame's first render call: from here on the batched launches push their tiles."""
+        self.epoch += 1
+        if self.mode == "push":
+            rc = self.fn("Q_cuda_plugin_set_export")(self.handle, C.byref(self.tables[self.epoch & 1]))
+            assert rc == 0
+
     def combine(self):
+        """After the frame's last render call; enqueue only."""
         if self.mode == "nccl":
-            self._combine_nccl()
-        elif self.mode == "p2p":
-            self._combine_p2p()
-        else:
-            self._combine_p2p_host()
+            return self._combine_nccl()
+        slot_bytes = self.per * 16
+        exported = self.fn("Q_cuda_plugin_flush")(self.handle, self.stream.cuda_stream)
+        assert exported >= 0
+        if exported == 0:  # the frame's last launch was a single sample: send the layers now
+            block = self._layer_block()
+            rc = self.fn("Q_cuda_push_slices")(block, self.total_float4, C.byref(self.tables[self.epoch & 1]),
+                                               self.stream.cuda_stream)
+            assert rc == 0
+            self.launches += 1
+        if self._handed_out:
+            self.frame.wait_consumed(self._handed_out)  # the segment still holds a frame rank 0 is looking at
+            self._handed_out = 0
+        flags = (C.c_void_p * self.world)(*self.flag_ptrs)
+        mine = self.staging + (self.epoch & 1) * self.world * slot_bytes
+        rc = self.fn("Q_cuda_reduce_slices_sync")(mine, self.per, flags, self.world, self.rank, self.epoch,
+                                                  self.hi - self.lo, 0.0, self.frame_device_ptr + self.lo * 16,
+                                                  self.stream.cuda_stream)
+        assert rc == 0
+        self.launches += 1
 
     def _combine_nccl(self):
         torch, dist = self.torch, self.dist
         block = device_tensor(self._layer_block(), self.total_float4 * 4, self.device)
         with torch.cuda.stream(self.stream):
-            dist.reduce(block, dst=0, op=dist.ReduceOp.SUM)
+            self.result.copy_(block)  # the plugin's layers stay what they are: the next call may accumulate onto them
+            dist.reduce(self.result, dst=0, op=dist.ReduceOp.SUM)
         if self.rank == 0:
-            ptrs = (C.c_void_p * 1)(block.data_ptr())
+            ptrs = (C.c_void_p * 1)(self.result.data_ptr())
             rc = self.fn("Q_cuda_combine_shards")(ptrs, 1, self.total_float4, 1.0 / self.world,
-                                                  self.result_ptr, None, self.stream.cuda_stream)
+                                                  self.result.data_ptr(), None, self.stream.cuda_stream)
             assert rc == 0
             self.launches += 1
 
-    def _combine_p2p(self):
-        """One launch per rank, enqueue only: the kernel itself waits for the peers' renders
-        and for their slices (combine_shards_sync_kernel)."""
-        self.epoch += 1
-        lo, hi = slice_bounds(self.total_float4, self.world, self.rank)
-        off = lo * 16
-        ptrs = (C.c_void_p * self.world)(*[p + off for p in self.block_ptrs])
-        flags = (C.c_void_p * self.world)(*self.flag_ptrs)
-        rc = self.fn("Q_cuda_combine_shards_sync")(ptrs, flags, self.world, self.rank, self.epoch, hi - lo, 0.0,
-                                                   self.out_ptr + off, None, self.stream.cuda_stream)
-        assert rc == 0
-        self.launches += 1
-
-    def _combine_p2p_host(self):
-        # All ranks must have finished rendering before anyone reads their layers,
-        # and all slices must have landed before rank 0 uses the result (or anyone
-        # restarts accumulation). Host-side barriers; the kernels are one per rank.
+    def finish_frame(self):
+        """Blocks until this rank's part of the frame is on the host; on rank 0, until the whole frame is.
+        Returns, on rank 0, the four layers as one float32 array (a view: valid until the next combine)."""
+        if self.mode == "nccl":
+            if self.rank != 0:
+                self.stream.synchronize()
+                return None
+            with self.torch.cuda.stream(self.stream):
+                self.pinned.copy_(self.result, non_blocking=True)
+            self.stream.synchronize()
+            return self.pinned.numpy()
         self.stream.synchronize()
-        self.dist.barrier()
-        lo, hi = slice_bounds(self.total_float4, self.world, self.rank)
-        if hi > lo:
-            off = lo * 16
-            ptrs = (C.c_void_p * self.world)(*[p + off for p in self.block_ptrs])
-            rc = self.fn("Q_cuda_combine_shards")(ptrs, self.world, hi - lo, 0.0, self.out_ptr + off,
-                                                  None, self.stream.cuda_stream)
-            assert rc == 0
-            self.launches += 1
-        self.stream.synchronize()
-        self.dist.barrier()
-
-    def result_numpy(self):
-        """Rank 0: the four combined layers as (H, W, 4) float32 arrays."""
+        self.frame.landed(self.epoch)
+        self._handed_out = self.epoch
         if self.rank != 0:
             return None
-        self.stream.synchronize()
-        t = device_tensor(self.result_ptr, self.total_float4 * 4, self.device).cpu().numpy()
-        h, w = self.host.context.height, self.host.context.width
-        return [t[i * self.n_px * 4:(i + 1) * self.n_px * 4].reshape(h, w, 4).copy() for i in range(4)]
+        self.frame.wait_all_landed(self.epoch)
+        return self.frame.floats
+
+    def release_frame(self):
+        """Rank 0 is done with what finish_frame returned."""
+        if self.mode == "push" and self.rank == 0:
+            self.frame.consumed(self.epoch)
+
+    def result_numpy(self):
+        """Rank 0: the four combined layers as (H, W, 4) float32 arrays (copies). Collective: every rank calls it."""
+        flat = self.finish_frame()
+        out = None
+        if self.rank == 0:
+            h, w = self.host.context.height, self.host.context.width
+            out = [flat[i * self.n_px * 4:(i + 1) * self.n_px * 4].reshape(h, w, 4).copy() for i in range(4)]
+        self.release_frame()
+        return out
 
     def close(self):
+        if self.mode == "push":
+            self.fn("Q_cuda_plugin_set_export")(self.handle, None)
+            self.stream.synchronize()
+            self.fn("Q_cuda_host_unregister")(self.frame.address)
+            self.dist.barrier()  # nobody still pushes into, or waits on, memory that is about to go
         for p in self._opened:
             self.fn("Q_cuda_ipc_close")(p)
         self._opened = []
-        if self.mode != "nccl" and self.rank == 0 and self.result_ptr:
-            self.fn("Q_cuda_free")(self.result_ptr)
-            self.result_ptr = None
-        if self._own_flags:
-            self.fn("Q_cuda_free")(self._own_flags)
-            self._own_flags = None
+        if self.mode == "push":
+            self.dist.barrier()
+        for p in self._own:
+            self.fn("Q_cuda_free")(p)
+        self._own = []
+        if self.frame is not None:
+            self.frame.close()
+            self.frame = None

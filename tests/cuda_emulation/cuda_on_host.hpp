@@ -158,6 +158,8 @@ inline T __ldcg(const T* p) { return *p; }
 inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 inline void __threadfence_block() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 inline unsigned atomicAdd(unsigned* p, unsigned v) { return std::atomic_ref<unsigned>(*p).fetch_add(v); }
+inline unsigned atomicSub(unsigned* p, unsigned v) { return std::atomic_ref<unsigned>(*p).fetch_sub(v); }
+inline int __ffs(int x) { return __builtin_ffs(x); }
 inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) {
     return std::atomic_ref<unsigned long long>(*p).fetch_add(v);
 }

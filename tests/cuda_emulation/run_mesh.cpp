@@ -20,7 +20,6 @@ int main(int argc, char** argv) {
     const uint32_t width = static_cast<uint32_t>(std::atoi(argv[2])), height = static_cast<uint32_t>(std::atoi(argv[3]));
     const uint32_t frames = static_cast<uint32_t>(std::atoi(argv[4]));
     const bool wide = std::atoi(argv[5]) != 0;
-    const uint32_t batch = argc > 7 ? static_cast<uint32_t>(std::atoi(argv[7])) : 1u;
 
     mesh::scene s;
     mesh::generate_triangles(grid_cells, 1, s);
@@ -57,20 +56,14 @@ int main(int argc, char** argv) {
     const uint32_t n_tiles = ((width + 7u) / 8u) * ((height + 3u) / 4u);
     const uint32_t needed = (n_tiles + k_warps_per_block - 1u) / k_warps_per_block;
     const uint32_t grid = needed < 2u ? needed : 2u;
-    for (uint32_t f = 0; f < frames; f += batch) {
+    for (uint32_t f = 0; f < frames; f++) {  // one launch per sample: the mesh kernel has no batched form
         frame_params frame;
         prepare_frame(position, target, up, 40.0f, width, height, f, f, frame);
-        frame.batch_samples = std::min(batch, frames - f);
-        frame.frame_stride = 1;
         auto run = [&](auto kernel) {
             emu::launch_with_shared(kernel, grid, k_block_threads, 1u, k_stack_bytes, scene, frame, layers[0].data(),
                                     layers[1].data(), layers[2].data(), layers[3].data(), counters, tile_counters);
         };
-        if (frame.batch_samples > 1u) {
-            wide ? run(mesh_pathtrace_kernel<true, true>) : run(mesh_pathtrace_kernel<false, true>);
-        } else {
-            wide ? run(mesh_pathtrace_kernel<true, false>) : run(mesh_pathtrace_kernel<false, false>);
-        }
+        wide ? run(mesh_pathtrace_kernel<true>) : run(mesh_pathtrace_kernel<false>);
     }
     FILE* out = std::fopen(argv[6], "wb");
     if (!out) return 5;

@@ -1,8 +1,8 @@
 // Runs the SOURCE of the quad path-tracing kernel (quasi_b200/csrc/pathtrace.cu) on the host under
 // tests/cuda_emulation/cuda_on_host.hpp and writes the four accumulated layers as raw binary32.
 //   usage: run_pathtrace WIDTH HEIGHT FRAMES BATCH SCAN OUT.bin
-//     BATCH  samples per launch (1 = one launch per frame, the default of the backend); with an "s"
-//            appended, the sample-major form (k passes over the image inside the launch)
+//     BATCH  samples per launch (1 = one launch per render call; k > 1 = the batched form: every pixel gets k
+//            samples in one launch, every tile is exported when its last pixel has had its last sample)
 //     SCAN   "quads" (kernel unrolled for the demo scene), "boxes" (blocks as slab tests), "generic"
 //   prints "rays N launches M"
 #define QUASI_HOST_EMULATION 1
@@ -21,7 +21,6 @@ int main(int argc, char** argv) {
     const uint32_t width = static_cast<uint32_t>(std::atoi(argv[1])), height = static_cast<uint32_t>(std::atoi(argv[2]));
     const uint32_t frames = static_cast<uint32_t>(std::atoi(argv[3])), batch = static_cast<uint32_t>(std::atoi(argv[4]));
     const std::string scan = argv[5];
-    const bool sample_major = std::string(argv[4]).find('s') != std::string::npos;
 
     scene_desc desc = make_cornell_box();
     static scene_params scene;
@@ -35,43 +34,32 @@ int main(int argc, char** argv) {
     for (auto& l : layers) l.assign(n, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
     unsigned long long rays = 0;
     unsigned int tile_counters[2] = {0, 0};
-    // batched launches also mirror every pixel's last value of the launch (QUASI_CUDA_MIRROR)
+    // batched launches export every finished tile: here into one buffer per layer (what the plugin's readback mirror is)
     std::vector<float4> mirror[4];
-    for (int i = 0; i < 4; i++) {
-        mirror[i].assign(n, make_float4(-1.0f, -1.0f, -1.0f, -1.0f));
-        g_mirror[i] = batch > 1u ? mirror[i].data() : nullptr;
-    }
+    for (auto& m : mirror) m.assign(n, make_float4(-1.0f, -1.0f, -1.0f, -1.0f));
 
     const uint32_t n_tiles = ((width + 7u) / 8u) * ((height + 3u) / 4u);
     const uint32_t needed = (n_tiles + k_warps_per_block - 1u) / k_warps_per_block;
     const uint32_t grid = needed < 3u ? needed : 3u;  // a persistent grid smaller than the work, as on the device
     uint32_t launches = 0;
-    std::vector<unsigned int> epochs(n_tiles, 0u);
-    g_tile_epochs = epochs.data();
     for (uint32_t first = 0; first < frames; first += batch) {
-        std::fill(epochs.begin(), epochs.end(), 0u);
         frame_params frame;
         prepare_frame(position, target, up, 40.0f, width, height, /*frame_index*/ first, /*sample_index*/ first, frame);
         frame.batch_samples = std::min(batch, frames - first);
         frame.frame_stride = 1;
-        auto run = [&](auto kernel) {
-            // sample-major: a CTA may wait for a tile another CTA is finishing, so all of them run at once, as on the device
-            emu::launch_with_shared(kernel, grid, k_block_threads, /*concurrent CTAs*/ sample_major ? grid : 1u,
-                                    k_warps_per_block * 8 * sizeof(unsigned int), scene, frame, layers[0].data(), layers[1].data(),
-                                    layers[2].data(), layers[3].data(), &rays, tile_counters);
-        };
         const bool batched = frame.batch_samples > 1u;
-        if (batched && sample_major) {
-            if (scan == "generic") {
-                run(pathtrace_accumulate_kernel<32, dynamic_layout, true, true>);
-            } else if (scan == "boxes" && cornell_layout::matches(scene)) {
-                run(pathtrace_accumulate_kernel<16, cornell_layout, true, true>);
-            } else if (scan == "quads" && cornell_quads_layout::matches(scene)) {
-                run(pathtrace_accumulate_kernel<16, cornell_quads_layout, true, true>);
-            } else {
-                return 3;
-            }
-        } else if (scan == "generic") {
+        batch_params launch{};
+        if (batched) {
+            launch.export_slices = 4;
+            launch.export_per = static_cast<uint32_t>(n);
+            launch.export_per_magic = static_cast<uint32_t>((uint64_t{1} << 32) / n);
+            for (int i = 0; i < 4; i++) launch.export_base[i] = mirror[i].data();
+        }
+        auto run = [&](auto kernel) {
+            emu::launch_with_shared(kernel, grid, k_block_threads, 1u, k_wavefront_smem, scene, frame, launch,
+                                    layers[0].data(), layers[1].data(), layers[2].data(), layers[3].data(), &rays, tile_counters);
+        };
+        if (scan == "generic") {
             batched ? run(pathtrace_accumulate_kernel<32, dynamic_layout, true>) : run(pathtrace_accumulate_kernel<32, dynamic_layout, false>);
         } else if (scan == "boxes" && cornell_layout::matches(scene)) {
             batched ? run(pathtrace_accumulate_kernel<16, cornell_layout, true>) : run(pathtrace_accumulate_kernel<16, cornell_layout, false>);
@@ -84,14 +72,14 @@ int main(int argc, char** argv) {
         }
         launches++;
         if (tile_counters[0] != 0u || tile_counters[1] != 0u) {
-            std::fprintf(stderr, "tile queue not reset after launch %u\n", launches);
+            std::fprintf(stderr, "work queue not reset after launch %u\n", launches);
             return 4;
         }
     }
-    if (batch > 1u && frames % batch != 1u) {  // (a last launch of one sample takes the plain kernel: nothing mirrored)
+    if (batch > 1u && frames % batch != 1u) {  // (a last launch of one sample exports nothing)
         for (int i = 0; i < 4; i++) {
             if (std::memcmp(mirror[i].data(), layers[i].data(), n * sizeof(float4)) != 0) {
-                std::fprintf(stderr, "mirror of layer %d differs from the layer\n", i);
+                std::fprintf(stderr, "export of layer %d differs from the layer\n", i);
                 return 6;
             }
         }

@@ -4,10 +4,14 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
         --master-port 29533 tests/multi_gpu_check.py
 
-Each rank renders its sample shard through the plugin C ABI; the shards are
-combined with the fused peer-memory kernel (p2p) and with NCCL. Rank 0 checks:
-every shard bit-exact against the oracle, the p2p result bit-exact against the
-oracle's rank-ordered combine, the NCCL result within float tolerance.
+Each rank renders its sample shard through the plugin C ABI; the shards are combined by the
+push exchange (quasi_b200/multi_gpu.py: tiles pushed to the slice owners by the batched render
+kernel, one local reduce kernel per rank, the frame landing in host memory shared by all ranks)
+and by NCCL. Rank 0 checks: every shard bit-exact against the oracle; the push result bit-exact
+against the oracle's rank-ordered combine, with batched launches (export fused into the render),
+with one launch per sample (Q_cuda_push_slices after the fact), and over back-to-back frames of
+different length with no host synchronisation in between; the NCCL result within float tolerance,
+and the plugin's own layers untouched by it.
 (test_cuda_multi_gpu.py runs this under pytest when >= 2 GPUs are visible.)
 """
 import os
@@ -26,68 +30,90 @@ def main():
     import torch.distributed as dist
     from oracle_lib import Oracle, bits
     from quasi_b200.headless import headless_host
-    from quasi_b200.multi_gpu import shard_reducer
+    from quasi_b200.multi_gpu import shard_exchange
 
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    w, h, per_rank = 320, 180, 5
-    host = headless_host(w, h, device_ordinal=local, shard_index=rank, shard_count=world, single_stream=True)
-    results = {}
-    for mode in ("p2p", "p2p_host", "nccl"):
-        reducer = shard_reducer(host, dist, mode=mode)
+    w, h = 320, 180
+    failures = []
+
+    def render(host, samples):
         host.render_frame(camera_dirty=True)
-        for _ in range(per_rank - 1):
+        for _ in range(samples - 1):
             host.render_frame(camera_dirty=False)
-        mine = host.readback_aov()           # this rank's shard mean (before the in-place NCCL sum)
-        reducer.combine()
-        results[mode] = reducer.result_numpy()
-        if mode == "p2p":
-            # back-to-back frames with no host synchronisation in between: the in-kernel
-            # flags alone must order render -> combine -> next render across the GPUs
-            for _ in range(3):
-                host.render_frame(camera_dirty=True)
-                for _ in range(per_rank - 1):
-                    host.render_frame(camera_dirty=False)
-                reducer.combine()
-            again = reducer.result_numpy()
-            if rank == 0 and not all(np.array_equal(bits(a), bits(b)) for a, b in zip(again, results[mode])):
-                print("FAIL p2p: repeated frames without host barriers differ")
-                results["p2p_repeat_failed"] = True
-        dist.barrier()
+
+    oracle = Oracle() if rank == 0 else None
+    expected = {}
+
+    def want(samples):  # rank 0: the oracle's shards and their rank-ordered combine for `samples` calls per rank
+        if samples not in expected:
+            u = oracle.scene(w, h)
+            shards = [oracle.render_frames(u, w, h, samples, frame_first=g, frame_stride=world)[0] for g in range(world)]
+            expected[samples] = (shards, [oracle.combine_shards([s[l] for s in shards]) for l in range(4)])
+        return expected[samples]
+
+    def check(name, got, samples, exact=True):
         if rank != 0:
-            reducer.close()
-        dist.barrier()
-        if rank == 0:
-            reducer.close()
-    gathered = [None] * world
-    dist.all_gather_object(gathered, [m.copy() for m in mine])
-    ok = True
-    if rank == 0:
-        oracle = Oracle()
-        u = oracle.scene(w, h)
+            return
+        _, combined = want(samples)
         for l in range(4):
-            shards = []
+            if exact and not np.array_equal(bits(got[l]), bits(combined[l])):
+                failures.append(f"{name}: layer {l}: {(bits(got[l]) != bits(combined[l])).sum()} floats differ from the oracle")
+            if not exact and not np.allclose(got[l], combined[l], rtol=2e-6, atol=2e-6):
+                failures.append(f"{name}: layer {l} outside the float tolerance")
+
+    for label, env in (("batched", {}), ("one launch per sample", {"QUASI_CUDA_BATCH": 1})):
+        host = headless_host(w, h, device_ordinal=local, shard_index=rank, shard_count=world, single_stream=True, env=env)
+        # every shard on its own, before any exchange
+        render(host, 5)
+        mine = host.readback_aov()
+        gathered = [None] * world
+        dist.all_gather_object(gathered, [m.copy() for m in mine])
+        if rank == 0:
+            shards, _ = want(5)
             for g in range(world):
-                want, _ = oracle.render_frames(u, w, h, per_rank, frame_first=g, frame_stride=world)
-                if not np.array_equal(bits(gathered[g][l]), bits(want[l])):
-                    print(f"FAIL shard {g} layer {l} differs from the oracle")
-                    ok = False
-                shards.append(want[l])
-            combined = oracle.combine_shards(shards)
-            if not np.array_equal(bits(results["p2p"][l]), bits(combined)):
-                print(f"FAIL p2p combine layer {l}: {(bits(results['p2p'][l]) != bits(combined)).sum()} floats differ")
-                ok = False
-            if not np.array_equal(bits(results["p2p_host"][l]), bits(combined)):
-                print(f"FAIL p2p_host combine layer {l}")
-                ok = False
-            if not np.allclose(results["nccl"][l], combined, rtol=2e-6, atol=2e-6):
-                print(f"FAIL nccl combine layer {l}")
-                ok = False
-        ok = ok and not results.get("p2p_repeat_failed", False)
-        print("MULTI_GPU_CHECK", "OK" if ok else "FAILED", f"world={world} {w}x{h} {per_rank} spp/rank")
-    host.close()
+                for l in range(4):
+                    if not np.array_equal(bits(gathered[g][l]), bits(shards[g][l])):
+                        failures.append(f"{label}: shard {g} layer {l} differs from the oracle")
+
+        exchange = shard_exchange(host, dist, mode="push")
+        exchange.begin_frame()
+        render(host, 5)
+        exchange.combine()
+        check(f"push, {label}", exchange.result_numpy(), 5)
+        # back-to-back frames of different length, nothing between them on the host but the enqueue calls: the
+        # device-side flags and the two staging buffers alone order push -> reduce -> next push across the GPUs
+        for samples in (3, 7, 2, 5):
+            exchange.begin_frame()
+            render(host, samples)
+            exchange.combine()
+        check(f"push, {label}, after four unsynchronised frames", exchange.result_numpy(), 5)
+        exchange.begin_frame()
+        render(host, 1)  # a frame of ONE sample: nothing is exported by a single-sample launch
+        exchange.combine()
+        check(f"push, {label}, one-sample frame", exchange.result_numpy(), 1)
+        exchange.close()
+
+        exchange = shard_exchange(host, dist, mode="nccl")
+        exchange.begin_frame()
+        render(host, 5)
+        exchange.combine()
+        check(f"nccl, {label}", exchange.result_numpy(), 5, exact=False)
+        after = host.readback_aov()  # the reduce worked on a copy: the plugin's layers are still this rank's mean
+        if not all(np.array_equal(bits(a), bits(b)) for a, b in zip(after, mine)):
+            failures.append(f"nccl, {label}: rank {rank}'s own layers changed under the combine")
+        exchange.close()
+        host.close()
+
+    all_failures = [None] * world
+    dist.all_gather_object(all_failures, failures)
+    ok = not any(all_failures)
+    if rank == 0:
+        for f in sum(all_failures, []):
+            print("FAIL", f)
+        print("MULTI_GPU_CHECK", "OK" if ok else "FAILED", f"world={world} {w}x{h}")
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

@@ -45,22 +45,6 @@ int literal_winner(const scene_params& scene, v3 ro, v3 rd) {
     return index;
 }
 
-#if defined(QUASI_SCAN_RECORDS) && QUASI_SCAN_RECORDS
-/// scan_decide.hpp:scan_scene with every quad read from quad_params (the default build's form).
-void scan_from_quad_params(scan::scan_state& s, const scene_params& scene, v3 ro, v3 rd) {
-    using namespace scan;
-    auto range = [&](uint32_t shape, auto&& fn) {
-        for (uint32_t i = scene.shape_begin[shape]; i < scene.shape_begin[shape + 1]; i++) fn(scene.quads[i], static_cast<int>(i));
-    };
-    range(k_shape_flat_y, [&](const quad_params& q, int i) { scan_flat<1>(s, q, i, ro, rd); });
-    range(k_shape_upright, [&](const quad_params& q, int i) { scan_upright(s, q, i, ro, rd); });
-    range(k_shape_flat_x, [&](const quad_params& q, int i) { scan_flat<0>(s, q, i, ro, rd); });
-    range(k_shape_flat_z, [&](const quad_params& q, int i) { scan_flat<2>(s, q, i, ro, rd); });
-    range(k_shape_general, [&](const quad_params& q, int i) { scan_general(s, q, i, ro, rd); });
-    for (uint32_t n = 0; n < scene.box_count; n++) scan_box(s, scene.boxes[n], ro, rd);
-}
-#endif
-
 bool inside_a_box_or_outside_the_room(const scene_params& scene, v3 p) {  // `scene`: the grouped form
     if (std::fabs(p.x) > 1.0f || p.y < 0.0f || p.y > 2.0f || p.z < -1.0f) return true;
     for (uint32_t n = 0; n < scene.box_count; n++) {
@@ -214,17 +198,6 @@ int main(int argc, char** argv) {
         scan::scan_state state;
         scan::scan_scene(state, scene, ro, rd);
         tested++;
-#if defined(QUASI_SCAN_RECORDS) && QUASI_SCAN_RECORDS
-        // scan_scene has read the packed records; the quad_params forms must file the same bits
-        {
-            scan::scan_state from_quads;
-            scan_from_quad_params(from_quads, scene, ro, rd);
-            if (std::memcmp(&from_quads, &state, sizeof state) != 0) {
-                if (mismatches < 10) std::printf("MISMATCH records vs quad_params at ray %ld\n", tested);
-                mismatches++;
-            }
-        }
-#endif
         bool to_literal = scan::needs_literal_scan(state);
         if (!to_literal && state.best_i >= 0) {  // the kernel's finalisation: the winner's own denominator
             to_literal = !scan::accept_winner(dot3(scene.quads[state.best_i].normal, rd));

@@ -1,5 +1,5 @@
-// Host check of quasi_b200/csrc/sincos_table.hpp (the code the CUDA kernel compiles with
-// -DQUASI_SINCOS_LOOKUP=1) against the oracle's definition of the shader's sin and cos
+// Host check of quasi_b200/csrc/sincos_table.hpp (the code the CUDA kernels compile:
+// device_common.cuh:sincos_round_once) against the oracle's definition of the shader's sin and cos
 // (oracle/quasi_oracle.c:qo_sin: the binary64 libm value rounded once to binary32), for every
 // phi = 2*pi*r1 the shader can draw: r1 = float(state) * 2^-32 over all 2^32 states takes
 // 2^24 + 8 * 2^23 distinct values (plugin.mm:104-107, 113).

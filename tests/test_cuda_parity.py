@@ -91,7 +91,7 @@ def test_golden_accumulated_frames(torch_cuda, golden):
     g = golden.npz("ref_64x36_acc4.npz")
     got, stats = render(64, 36, 4)
     assert_bit_exact(got, [g[n] for n in LAYERS])
-    assert stats.frame_count == 4 and stats.kernel_launches == 4
+    assert stats.frame_count == 4 and stats.kernel_launches == 1  # four collected calls, one batched launch
 
 
 def test_golden_sample_shard(torch_cuda, golden):
@@ -364,57 +364,66 @@ def test_every_scan_variant_is_bit_exact(torch_cuda, oracle, scan):
     assert stats.rays == rays
 
 
-@pytest.mark.skipif(__import__("os").environ.get("QUASI_TEST_BATCH") != "1",
-                    reason="QUASI_CUDA_BATCH has not run on a GPU yet (DESIGN.md section 9); QUASI_TEST_BATCH=1 runs it")
-@pytest.mark.parametrize("order", ["pixel", "sample"])
 @pytest.mark.parametrize("mirror", [0, 1], ids=["copy-after", "mirrored-during"])
-@pytest.mark.parametrize("batch,frames,scan", [(4, 10, ""), (64, 64, ""), (3, 7, "boxes"), (8, 8, "generic")])
-def test_batched_launches_render_the_same_bits(torch_cuda, oracle, batch, frames, scan, mirror, order):
-    """QUASI_CUDA_BATCH=k collects render calls and gives every pixel k consecutive samples in one
-    launch (pathtrace.cu, Batch): full batches, a partial one flushed by the readback, and a
-    camera_dirty restart in the middle of a batch must all give the bits of call-by-call launches.
-    With QUASI_CUDA_MIRROR=1 the batched launch writes the frame into the pinned buffers the
-    readback then returns."""
+@pytest.mark.parametrize("batch,frames,scan", [(1, 5, ""), (4, 10, ""), (64, 64, ""), (3, 7, "boxes"), (8, 8, "generic"), (64, 9, "")])
+def test_batched_launches_render_the_same_bits(torch_cuda, oracle, batch, frames, scan, mirror):
+    """QUASI_CUDA_BATCH=k (default 64) collects render calls and gives every pixel k samples in one launch,
+    as k passes over the image ordered by per-tile epochs (pathtrace.cu, Batch): launch by launch (k = 1),
+    full batches, a partial one flushed by the readback, a batch longer than the run, and a camera_dirty
+    restart in the middle of a batch must all give the oracle's bits. With QUASI_CUDA_MIRROR=1 (the
+    default) the batched launch exports every finished tile into the pinned buffers the readback then
+    returns; a second readback of the same frame, with the buffers gone, copies from the device."""
     from quasi_b200.headless import headless_host
 
     w, h = 211, 119
-    host = headless_host(w, h, env={"QUASI_CUDA_BATCH": batch, "QUASI_CUDA_SCAN": scan, "QUASI_CUDA_MIRROR": mirror,
-                                    "QUASI_CUDA_BATCH_ORDER": order})
+    host = headless_host(w, h, env={"QUASI_CUDA_BATCH": batch, "QUASI_CUDA_SCAN": scan, "QUASI_CUDA_MIRROR": mirror})
     host.render(frames)
     got, stats = host.readback_aov(), host.stats()
-    if mirror and frames % batch != 1:
-        assert any("mirrored during the render" in m for m in host.messages)
+    mirrored = any("mirrored during the render" in m for m in host.messages)
+    last_launch = frames % batch if frames % batch else min(batch, frames)  # samples in the launch before the readback
+    assert mirrored == bool(mirror and last_launch > 1)
     want, rays = oracle.render_frames(oracle.scene(w, h), w, h, frames)
     for name, g, wv in zip(LAYERS, got, want):
         assert np.array_equal(bits(g), bits(wv)), f"batch {batch}: {name}"
     assert stats.rays == rays
     assert stats.kernel_launches == -(-frames // batch)
+    again = host.readback_aov()  # the mirror has been handed over: this one is a device-to-host copy of the layers
+    for name, g, wv in zip(LAYERS, again, want):
+        assert np.array_equal(bits(g), bits(wv)), f"second readback: {name}"
+    beauty = host.plugin.readback_numpy()
+    assert np.array_equal(bits(beauty), bits(want[0]))
     # restart in the middle of a batch: two calls, then a dirty camera, then three more
     host.render_frame(camera_dirty=True)
     host.render_frame(camera_dirty=False)
     host.render_frame(camera_dirty=True)
     host.render(2)
+    beauty = host.plugin.readback_numpy()   # the beauty layer alone, from the mirror when there is one
     got = host.readback_aov()
     host.close()
     want3, _ = oracle.render_frames(oracle.scene(w, h), w, h, 3)
+    assert np.array_equal(bits(beauty), bits(want3[0]))
     for name, g, wv in zip(LAYERS, got, want3):
         assert np.array_equal(bits(g), bits(wv)), f"after restart: {name}"
 
 
-@pytest.mark.skipif(__import__("os").environ.get("QUASI_TEST_BATCH") != "1",
-                    reason="QUASI_CUDA_BATCH has not run on a GPU yet (DESIGN.md section 9); QUASI_TEST_BATCH=1 runs it")
-@pytest.mark.parametrize("wide", [0, 1])
-def test_batched_launches_of_the_mesh_scene_render_the_same_bits(torch_cuda, wide):
-    from oracle_lib import MeshOracle
+def test_two_instances_with_different_export_settings_do_not_meet(torch_cuda, oracle):
+    """The export target of a batched launch travels as a kernel parameter of that launch. (Round 1 kept it in
+    a device global: an instance without a mirror then wrote into the freed buffers of an earlier one.)"""
     from quasi_b200.headless import headless_host
 
-    grid, w, h, frames = 24, 160, 90, 7
-    host = headless_host(w, h, env={"QUASI_CUDA_SCENE": "mesh", "QUASI_CUDA_MESH_GRID": grid, "QUASI_CUDA_MESH_SEED": 1,
-                                    "QUASI_CUDA_MAX_BOUNCES": 4, "QUASI_CUDA_MESH_WIDE": wide, "QUASI_CUDA_BATCH": 3})
-    host.render(frames)
-    got, stats = host.readback_aov(), host.stats()
-    host.close()
-    want, st = MeshOracle(grid).render_frames(w, h, frames, max_bounces=4, use_bvh=True)
-    for name, g, wv in zip(LAYERS, got, want):
-        assert np.array_equal(bits(g), bits(wv)), f"mesh batch: {name}"
-    assert stats.rays == st["rays"] and stats.kernel_launches == 3
+    w, h, frames = 160, 90, 6
+    a = headless_host(w, h, env={"QUASI_CUDA_BATCH": 3, "QUASI_CUDA_MIRROR": 1})
+    b = headless_host(w, h, env={"QUASI_CUDA_BATCH": 2, "QUASI_CUDA_MIRROR": 0})
+    a.render(frames)
+    b.render(frames)
+    got_a = a.readback_aov()
+    a.close()
+    b.render(2)          # a's buffers are back in the pool or freed by now
+    got_b = b.readback_aov()
+    b.close()
+    want6, _ = oracle.render_frames(oracle.scene(w, h), w, h, frames)
+    want8, _ = oracle.render_frames(oracle.scene(w, h), w, h, frames + 2)
+    for name, g, wv in zip(LAYERS, got_a, want6):
+        assert np.array_equal(bits(g), bits(wv)), name
+    for name, g, wv in zip(LAYERS, got_b, want8):
+        assert np.array_equal(bits(g), bits(wv)), name

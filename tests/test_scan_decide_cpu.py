@@ -29,19 +29,6 @@ def test_fast_scan_names_the_literal_winner(tmp_path, form):
     assert int(counts["literal"]) > 0          # the margins do fire on these rays
 
 
-@pytest.mark.parametrize("form", ["quads", "boxes"])
-def test_packed_scan_records_file_the_same_bits(tmp_path, form):
-    """-DQUASI_SCAN_RECORDS=1 (a build-time option of the kernel): the scan reads every flat and
-    upright quad from its packed record (three 16-byte constant loads instead of eight small
-    ones). For every ray the scan state must be the bits the quad_params forms produce, and the
-    usual check against the literal loop holds."""
-    exe = build(tmp_path, ROOT / "quasi_b200" / "csrc", "-DQUASI_SCAN_RECORDS=1")
-    out = subprocess.run([str(exe), "3000000", form], capture_output=True, text=True)
-    assert out.returncode == 0, out.stdout[-2000:]
-    counts = dict(zip(out.stdout.split()[0::2], out.stdout.split()[1::2]))
-    assert int(counts["mismatches"]) == 0 and int(counts["decided"]) > 1_500_000
-
-
 def test_margins_absorb_an_approximate_reciprocal(tmp_path):
     """On the device 1/x in the deciding arithmetic is one MUFU.RCP (relative error 2^-23) and
     a*b+c is one FFMA; on the host they are exact quotient and fmaf. With the reciprocal pushed

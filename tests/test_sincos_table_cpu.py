@@ -1,5 +1,5 @@
-"""quasi_b200/csrc/sincos_table.hpp (the kernel's sin/cos with -DQUASI_SINCOS_LOOKUP=1, a
-build-time option) on the host: for every phi = 2*pi*r1 the shader's RNG can produce it must
+"""quasi_b200/csrc/sincos_table.hpp (the kernels' sin/cos, device_common.cuh:sincos_round_once)
+on the host: for every phi = 2*pi*r1 the shader's RNG can produce it must
 return the bits the oracle defines, (float)sin((double)phi) and (float)cos((double)phi)."""
 import subprocess
 import sys
