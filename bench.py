@@ -2,36 +2,45 @@
 """bench.py - the headline measurement: Mrays/s and ms/frame at 1080p, 64 spp.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload demo|demo4k|mesh] [--scaling strong|weak] [--reduce push|nccl]
 
 Workload (BASELINE.json configs[1]): the demo scene at 1920x1080, 64 samples per
 pixel, rendered headless through the unchanged plugin C ABI. One STEP is one
 whole frame: 64 Q_plugin_render calls (the first with camera_dirty set, so every
-step restarts accumulation and renders RNG frame indices 0..63), then, with
-N > 1 GPUs, one sum-reduce of the accumulation buffers to rank 0 and the 1/N
-scale. A ray is one closest-hit query (trace_scene,
-/root/reference/backends/metal/plugin.mm:199-212), counted on the device.
+step restarts accumulation and renders RNG frame indices 0..63). A ray is one
+closest-hit query (trace_scene, /root/reference/backends/metal/plugin.mm:199-212),
+counted on the device.
 
   value   rays per step / device time per step (CUDA events on the frame stream,
           max over ranks); nothing crosses PCIe inside the timed region.
   e2e     the same frames through the same C ABI, wall clock, including the
-          per-call parameter blocks going to the device and Q_plugin_readback_aov
-          bringing the four HDR layers (132.7 MB) back into host memory.
-  roofline    the dominant kernel (pathtrace_accumulate_kernel) against measured
-              HBM bandwidth with the algorithmic 128 B/pixel/call.
-              The kernel is FP32-issue-bound, not HBM-bound: see DESIGN.md.
+          per-call parameter blocks going to the device and the four HDR layers
+          (132.7 MB at 1080p) arriving in host memory: Q_plugin_readback_aov on one
+          GPU, the shared host frame of quasi_b200.multi_gpu.shard_exchange on several.
+  roofline    the dominant kernel (pathtrace_accumulate_kernel) against measured HBM
+              bandwidth with the algorithmic 128 B/pixel/launch, as the
+              contract asks; the kernel is bound by instruction issue, so `issue` holds
+              the figure that explains it: warp instructions per launch (ncu, only when
+              the loaded library's SASS is the build that was profiled) over the issue
+              slots the launch had (SMs x 4 schedulers x SM clock x kernel time).
+  parity  outside every timed region: a 320x180 frame rendered the same way (same shard
+          plan, same exchange) compared with the CPU oracle bit for bit.
   cpu_baseline / --impl reference
           the reference's own shader text compiled for the CPU (oracle/_ref),
           or the plain-C port when that is absent, on every host core.
 
-Multi-GPU (launched by torchrun, one rank per GPU): weak scaling. Rank r renders
-RNG frame indices r, r+N, r+2N, ... (64 per rank, 64*N spp in total).
+Multi-GPU (launched by torchrun, one rank per GPU): STRONG scaling by default: the same
+1080p x 64 spp frame, rank r of N rendering the 64/N RNG frame indices r, r+N, ... and one
+exchange per frame (sum over ranks in rank order, 1/N scale, frame into host memory).
+--scaling weak gives every rank 64 spp (64 N in total).
+--workload demo4k is BASELINE configs[3]: 3840x2160, 1024 spp in total.
 """
 from __future__ import annotations
 
 import argparse
-import ctypes as C
 import json
 import os
+import subprocess
 import sys
 import threading
 import time
@@ -40,10 +49,17 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
+sys.path.insert(0, str(ROOT / "tools"))
 
-WIDTH, HEIGHT, SPP = 1920, 1080, 64
-METRIC = "Mrays/s @1080p 64spp (demo scene, headless via plugin C ABI)"
-ALGORITHMIC_BYTES_PER_PIXEL_PER_CALL = 128  # 4 layers x (16 B read + 16 B write), SURVEY.md 8d
+WORKLOADS = {"demo": (1920, 1080, 64), "demo4k": (3840, 2160, 1024)}
+ALGORITHMIC_BYTES_PER_PIXEL_PER_LAUNCH = 128  # 4 layers x (16 B read + 16 B write), SURVEY.md 8d
+PARITY_SIZE = (320, 180)
+
+
+def metric_name(workload):
+    w, h, spp = WORKLOADS[workload]
+    return ("Mrays/s @1080p 64spp (demo scene, headless via plugin C ABI)" if workload == "demo" else
+            f"Mrays/s @{w}x{h} {spp}spp (demo scene, sample-sharded, headless via plugin C ABI)")
 
 
 def measured_peaks():
@@ -106,31 +122,32 @@ class clock_sampler(threading.Thread):
 
 # ---------------------------------------------------------------- CPU arm ----
 
-def cpu_arm(budget_s: float, steps: int, warmup: int):
+def cpu_arm(budget_s: float, steps: int, warmup: int, workload: str = "demo"):
     """Times the reference's CPU form of the path on all host cores.
 
-    Returns (mrays_per_s, ms_per_step, descriptor). Each step renders
-    `spp_step` of the 64 samples per pixel at the full 1920x1080 (frames
-    0..spp_step-1), sized so that warmup+steps fit in `budget_s`.
+    Returns (mrays_per_s, ms_per_step, descriptor). Each step renders `spp_step` of the frame's
+    samples per pixel at the full size (frames 0..spp_step-1), sized so that warmup+steps fit in
+    `budget_s`.
     """
     from oracle_lib import Oracle, Reference
 
+    width, height, spp = WORKLOADS[workload]
     oracle = Oracle()
     use_ref = Reference.available()
     impl = Reference() if use_ref else oracle
     cores = impl.cores()
-    u = oracle.scene(WIDTH, HEIGHT)
+    u = oracle.scene(width, height)
 
     def run(n_frames):
         t0 = time.perf_counter()
-        impl.render_frames(u, WIDTH, HEIGHT, n_frames)
+        impl.render_frames(u, width, height, n_frames)
         return time.perf_counter() - t0
 
     t1 = run(1)  # also pages the library in
     per_step_budget = budget_s / max(1, steps + warmup)
-    spp_step = int(max(1, min(SPP, per_step_budget // max(t1, 1e-3))))
+    spp_step = int(max(1, min(spp, per_step_budget // max(t1, 1e-3))))
     # ray count of exactly those frames, from the bit-identical C port, outside the timed region
-    _, rays = oracle.render_frames(u, WIDTH, HEIGHT, spp_step)
+    _, rays = oracle.render_frames(u, width, height, spp_step)
     for _ in range(warmup):
         run(spp_step)
     t = [run(spp_step) for _ in range(steps)]
@@ -139,11 +156,11 @@ def cpu_arm(budget_s: float, steps: int, warmup: int):
     desc = {
         "value": round(mrays, 3), "unit": "Mrays/s", "cores": cores,
         "kind": "reference" if use_ref else "port",
-        "sample": f"{spp_step} of {SPP} spp per step at {WIDTH}x{HEIGHT} (frames 0..{spp_step - 1}), "
+        "sample": f"{spp_step} of {spp} spp per step at {width}x{height} (frames 0..{spp_step - 1}), "
                   f"{steps} timed steps, {rays} rays per step; "
                   + ("reference shader text (oracle/_ref) compiled g++ -O2 -ffp-contract=off"
                      if use_ref else "plain-C port (oracle/quasi_oracle.c) gcc -O2 -ffp-contract=off"),
-        "ms_per_full_frame_extrapolated": round(total / steps * 1e3 * SPP / spp_step, 1),
+        "ms_per_full_frame_extrapolated": round(total / steps * 1e3 * spp / spp_step, 1),
     }
     return mrays, total / steps * 1e3, desc
 
@@ -152,13 +169,16 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return  # rank 0 alone runs the CPU arm
-    mrays, ms, desc = cpu_arm(budget_s=args.cpu_budget or 120.0, steps=args.steps, warmup=args.warmup)
+    workload = args.workload if args.workload in WORKLOADS else "demo"
+    width, height, spp = WORKLOADS[workload]
+    mrays, ms, desc = cpu_arm(budget_s=args.cpu_budget or 120.0, steps=args.steps, warmup=args.warmup, workload=workload)
     line = {
-        "impl": "reference", "metric": METRIC, "value": round(mrays, 3), "unit": "Mrays/s",
+        "impl": "reference", "metric": metric_name(workload), "value": round(mrays, 3), "unit": "Mrays/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "higher_is_better": True, "scaling": "strong" if args.gpus > 1 and args.scaling != "weak" else "weak",
+        "vs_baseline": None, "dtype": "f32",
         "data": "synthetic (procedural Cornell box, counter-based RNG)",
-        "config": {"workload": f"demo scene {WIDTH}x{HEIGHT}, {SPP} spp per frame, CPU, bounded sample per step"},
+        "config": {"workload": f"demo scene {width}x{height}, {spp} spp per frame, CPU, bounded sample per step"},
         "cpu_baseline": desc,
         "e2e": {"value": round(mrays, 3), "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -168,12 +188,98 @@ def run_reference(args):
 
 # ---------------------------------------------------------------- GPU arm ----
 
+def profiled_kernel(name_prefix: str):
+    """The ncu figures of a kernel from profiles/ncu_summary.json, but only if the library that is loaded now is,
+    instruction for instruction, the build they were captured on (tools/sass_fingerprint.py); else None."""
+    summary = ROOT / "profiles" / "ncu_summary.json"
+    if not summary.exists():
+        return None
+    try:
+        import sass_fingerprint
+
+        entry = json.loads(summary.read_text()).get(name_prefix)
+        if not entry or "sass_md5" not in entry:
+            return None
+        now = sass_fingerprint.fingerprints()
+        if now.get(entry["kernel"], {}).get("md5") != entry["sass_md5"]:
+            return None
+        return entry
+    except Exception:
+        return None
+
+
+def parity_check(args, dist, rank, world, local_rank, spp_rank):
+    """Outside every timed region: a 320x180 frame with this run's shard plan, against the CPU oracle."""
+    import numpy as np
+    from oracle_lib import Oracle, bits
+    from quasi_b200.headless import headless_host
+
+    w, h = PARITY_SIZE
+    samples = max(1, min(spp_rank, 8))
+    host = headless_host(w, h, device_ordinal=local_rank, shard_index=rank, shard_count=world, single_stream=True)
+
+    def render():
+        host.render_frame(camera_dirty=True)
+        for _ in range(samples - 1):
+            host.render_frame(camera_dirty=False)
+
+    out = {"size": f"{w}x{h}", "spp_per_gpu": samples}
+    oracle = Oracle() if rank == 0 else None
+    if world == 1:
+        render()
+        got = host.readback_aov()
+        want, rays = oracle.render_frames(oracle.scene(w, h), w, h, samples)
+        out["bit_exact"] = bool(all(np.array_equal(bits(g), bits(x)) for g, x in zip(got, want)))
+        out["rays_equal"] = bool(host.stats().rays == rays)
+    else:
+        from quasi_b200.multi_gpu import shard_exchange
+
+        want = None
+        if rank == 0:
+            u = oracle.scene(w, h)
+            shards = [oracle.render_frames(u, w, h, samples, frame_first=g, frame_stride=world)[0] for g in range(world)]
+            want = [oracle.combine_shards([s[l] for s in shards]) for l in range(4)]
+        for mode in ("push", "nccl"):
+            exchange = shard_exchange(host, dist, mode=mode)
+            exchange.begin_frame()
+            render()
+            exchange.combine()
+            got = exchange.result_numpy()
+            exchange.close()
+            if rank == 0:
+                if mode == "push":
+                    out["push_bit_exact"] = bool(all(np.array_equal(bits(g), bits(x)) for g, x in zip(got, want)))
+                else:
+                    out["nccl_max_abs"] = float(max(np.abs(g - x).max() for g, x in zip(got, want)))
+    host.close()
+    return out
+
+
+def cpp_host_leg(width, height, spp):
+    """The C++ headless host (quasi_b200/host, the delivery vehicle) on the same frame: wall time of a frame set
+    from the first Q_plugin_render to the four layers on the host, warm (median of sets 2..)."""
+    exe, lib = ROOT / "quasi_b200" / "bin" / "quasi_headless", ROOT / "quasi_b200" / "lib" / "libquasi_cuda.so"
+    if not exe.exists():
+        return None
+    try:
+        out = subprocess.run([str(exe), "--render", str(spp), "--repeat", "6", "--readback-each", "--width", str(width),
+                              "--height", str(height), "--json", "--out", "/tmp/quasi_bench_host.exr", str(lib)],
+                             capture_output=True, text=True, timeout=120)
+        line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
+        sets = sorted(json.loads(line)["set_ms"][1:])
+        return {"ms_per_frame_e2e": round(sets[len(sets) // 2], 3), "sets": len(sets) + 1,
+                "what": f"quasi_headless --render {spp} --repeat 6 --readback-each: wall time per {spp}-call frame set "
+                        "including the blocking AOV readback, first set (cold) left out"}
+    except Exception as e:  # the bench line must not depend on this leg
+        return {"error": str(e)[:200]}
+
+
 def run_ours(args):
     import torch
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; libquasi_cuda.so has no CPU fallback")
-    import quasi_b200
+    import quasi_b200  # noqa: F401
     from quasi_b200.headless import headless_host
 
     rank = int(os.environ.get("RANK", "0"))
@@ -182,6 +288,11 @@ def run_ours(args):
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    width, height, spp = WORKLOADS[args.workload]
+    strong = world > 1 and args.scaling != "weak"
+    if strong and spp % world != 0:
+        raise SystemExit(f"bench.py: {spp} spp do not split over {world} GPUs")
+    spp_rank = spp // world if strong else spp
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -189,27 +300,27 @@ def run_ours(args):
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    host = headless_host(WIDTH, HEIGHT, device_ordinal=local_rank, shard_index=rank, shard_count=world,
+    host = headless_host(width, height, device_ordinal=local_rank, shard_index=rank, shard_count=world,
                          single_stream=True)
     device = host.context.device
     stream = host.context.frame_stream()
-    n_px = WIDTH * HEIGHT
-    reducer = None
+    n_px = width * height
+    exchange = None
     if world > 1:
-        from quasi_b200.multi_gpu import shard_reducer
+        from quasi_b200.multi_gpu import shard_exchange
 
-        reducer = shard_reducer(host, dist, mode=args.reduce)
-        pinned = torch.empty(n_px * 16, dtype=torch.float32).pin_memory() if rank == 0 else None
-
-    def render_frame_set():
-        host.render_frame(camera_dirty=True)
-        for _ in range(SPP - 1):
-            host.render_frame(camera_dirty=False)
+        exchange = shard_exchange(host, dist, mode=args.reduce)
 
     def step():
-        render_frame_set()
-        if reducer is not None:
-            reducer.combine()  # one exchange per frame: sum over ranks, 1/N scale, result on rank 0
+        if exchange is not None:
+            exchange.begin_frame()
+        host.render_frame(camera_dirty=True)
+        for _ in range(spp_rank - 1):
+            host.render_frame(camera_dirty=False)
+        if exchange is not None:
+            exchange.combine()  # one exchange per frame: sum over ranks, 1/N scale, towards host memory
+        else:
+            host.plugin.fn("Q_cuda_plugin_flush")(host.plugin._handle, stream.cuda_stream)  # launch what was collected
 
     def barrier():
         torch.cuda.synchronize(device)
@@ -222,7 +333,7 @@ def run_ours(args):
         step()
     barrier()
     s0 = host.stats()
-    reducer_launches0 = reducer.launches if reducer else 0
+    exchange_launches0 = exchange.launches if exchange else 0
     sampler = clock_sampler(local_rank)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -236,21 +347,18 @@ def run_ours(args):
     s1 = host.stats()
     rays_local = s1.rays - s0.rays
     render_launches_local = s1.kernel_launches - s0.kernel_launches
-    launches_local = render_launches_local + (reducer.launches - reducer_launches0 if reducer else 0)
+    launches_local = render_launches_local + (exchange.launches - exchange_launches0 if exchange else 0)
 
     # ---- end to end through the public API with host buffers (e2e) ----
     def e2e_step():
         step()
         if world == 1:
-            rb = host.plugin.readback_aov()          # blocking D2H of the four layers
+            rb = host.plugin.readback_aov()          # blocking: the four layers in host memory
             assert rb.buffers[0].data, "readback returned no data"
             host.plugin.readback_aov_free(rb)
-        elif rank == 0:
-            from quasi_b200.multi_gpu import device_tensor
-
-            with torch.cuda.stream(stream):          # the combined layers, D2H into pinned memory
-                pinned.copy_(device_tensor(reducer.result_ptr, n_px * 16, device), non_blocking=True)
-            stream.synchronize()
+        else:
+            exchange.finish_frame()                  # blocking: rank 0 returns when every slice is in host memory
+            exchange.release_frame()
 
     for _ in range(min(args.warmup, 3)):
         e2e_step()
@@ -271,39 +379,63 @@ def run_ours(args):
     else:
         rays_total, launches = rays_local, launches_local
 
+    # ---- parity of this configuration against the oracle, outside every timed region ----
+    parity = None
+    if not args.no_parity:
+        parity = parity_check(args, dist, rank, world, local_rank, spp_rank)
+
     if rank == 0:
         ms_step = ms_total / args.steps
         rays_step = rays_total / args.steps
         value = rays_step / (ms_step * 1e-3) / 1e6
         e2e_value = rays_step / (e2e_s / args.steps) / 1e6
         peak, peak_src = measured_peaks()
-        # the step is back-to-back launches of the one kernel: SPP of them, or SPP / k under QUASI_CUDA_BATCH=k
         launches_per_step = max(1.0, render_launches_local / args.steps)
-        kernel_ms = ms_step / launches_per_step
-        achieved = ALGORITHMIC_BYTES_PER_PIXEL_PER_CALL * n_px / (kernel_ms * 1e-3) / 1e9
-        traffic, issue_util = None, None
-        summary = ROOT / "profiles" / "ncu_summary.json"
-        if summary.exists():
-            try:
-                k = json.loads(summary.read_text()).get("pathtrace_accumulate_kernel", {})
-                traffic, issue_util = k.get("dram_bytes_per_launch"), k.get("issue_slot_utilization")
-            except Exception:
-                traffic = None
-        param_bytes = int(launches_per_step) * (7856 + 80)  # sizeof(scene_params) + sizeof(frame_params) per launch
+        # the step of one GPU is back-to-back launches of the one kernel (one per frame when the plugin batches)
+        kernel_ms = ms_step / launches_per_step if world == 1 else None
+        roofline = None
+        if kernel_ms is not None:
+            achieved = ALGORITHMIC_BYTES_PER_PIXEL_PER_LAUNCH * n_px / (kernel_ms * 1e-3) / 1e9
+            batched = launches_per_step < spp_rank
+            prof = profiled_kernel("pathtrace_accumulate_kernel_batched" if batched else "pathtrace_accumulate_kernel")
+            issue = None
+            if prof and clocks.get("sm_mhz"):
+                per_launch = prof["warp_instructions_per_sample"] * (spp_rank / launches_per_step)
+                slots = 148 * 4 * clocks["sm_mhz"] * 1e6 * kernel_ms * 1e-3
+                issue = {"warp_inst_per_launch": int(per_launch), "frac": round(per_launch / slots, 4),
+                         "warp_inst_per_ray": round(per_launch * launches_per_step / rays_step, 2),
+                         "issue_slot_utilization_ncu": prof.get("issue_slot_utilization"),
+                         "threads_per_instruction_ncu": prof.get("threads_per_instruction"),
+                         "source": prof.get("source")}
+            roofline = {
+                "bound": "hbm", "kernel": "pathtrace_accumulate_kernel",
+                "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4),
+                "traffic": prof.get("dram_bytes_per_launch") if prof else None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": ALGORITHMIC_BYTES_PER_PIXEL_PER_LAUNCH * n_px,
+                "samples_per_launch": spp_rank / launches_per_step,
+                "kernel_ms": round(kernel_ms, 5),
+                "issue": issue,
+                "note": "the contract's HBM figure: 128 B/pixel per LAUNCH (history read + result written once however many "
+                        "samples the launch folds in, SURVEY.md 8d). The kernel is bound by instruction issue, not HBM "
+                        "(a 16-quad scan per ray): `issue` is the fraction of the launch's issue slots it fills; "
+                        "traffic / issue come from ncu and are null unless the loaded library is the profiled build",
+            }
+        param_bytes = int(launches_per_step) * (8624 + 80 + 144)  # scene, frame and batch parameter blocks per launch
         line = {
-            "metric": METRIC, "value": round(value, 2), "unit": "Mrays/s", "n_gpus": world,
+            "metric": metric_name(args.workload), "value": round(value, 2), "unit": "Mrays/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic (procedural Cornell box, counter-based RNG, no inputs to load)",
             "config": {
-                "workload": f"demo scene {WIDTH}x{HEIGHT}, {SPP} spp per GPU per frame "
-                            f"({SPP * world} spp total), 5 bounces, 4 AOV layers, plugin C ABI",
-                "spp_per_gpu": SPP, "spp_total": SPP * world, "render_calls_per_step": SPP,
+                "workload": f"demo scene {width}x{height}, {spp_rank * world} spp per frame"
+                            + (f" ({spp_rank} per GPU)" if world > 1 else "") + ", 5 bounces, 4 AOV layers, plugin C ABI",
+                "spp_per_gpu": spp_rank, "spp_total": spp_rank * world, "render_calls_per_step": spp_rank,
                 "launches_per_step": launches_per_step,
                 "parallelism": f"sample-sharded x{world}" + (
-                    f", 1 {args.reduce} combine/frame (sum over ranks, 1/N scale, result on rank 0)"
+                    f", 1 {args.reduce} exchange per frame (rank-ordered sum, 1/N scale, frame into host memory)"
                     if world > 1 else ""),
-                "l2": "no flush: each launch streams the 132.7 MB accumulation set, larger than the 126 MB L2",
+                "l2": "no flush: a frame streams the 132.7 MB accumulation set (265 MB at 4K x 4 layers), larger than the 126 MB L2",
                 "rays_per_step": rays_step,
             },
             "e2e": {"value": round(e2e_value, 2), "unit": "Mrays/s",
@@ -311,31 +443,30 @@ def run_ours(args):
                     "h2d_bytes_per_step": param_bytes, "d2h_bytes_per_step": n_px * 64},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {
-                "bound": "hbm", "kernel": "pathtrace_accumulate_kernel",
-                "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": ALGORITHMIC_BYTES_PER_PIXEL_PER_CALL * n_px,
-                "kernel_ms": round(kernel_ms, 5),
-                "issue_slot_utilization_ncu": issue_util,
-                "note": "instruction-issue-bound kernel (16-quad scan per ray, ~36 warp instructions per ray): the "
-                        "HBM fraction is low by design, the issue slots are the resource that is full "
-                        "(ncu, profiles/ncu_summary.json); see DESIGN.md section 4.1",
-            },
+            "roofline": roofline,
+            "parity": parity,
         }
+        if world > 1:
+            line["config"]["limiter"] = ("per frame: the slowest rank's render, then one local reduce kernel per rank and each "
+                                         "rank's slice crossing its own PCIe link" if args.reduce == "push" else
+                                         "per frame: the slowest rank's render, ncclReduce to rank 0, the scale pass and the "
+                                         "whole frame crossing rank 0's PCIe link")
         if world == 1 and not args.no_cpu:
-            _, _, desc = cpu_arm(budget_s=args.cpu_budget or 20.0, steps=1, warmup=0)
+            _, _, desc = cpu_arm(budget_s=args.cpu_budget or 20.0, steps=1, warmup=0, workload=args.workload)
             line["cpu_baseline"] = desc
-        print(json.dumps(line), flush=True)
 
-    if reducer is not None:
-        dist.barrier()
-        if rank != 0:
-            reducer.close()   # unmap peers before their owners free
-        dist.barrier()
-        if rank == 0:
-            reducer.close()
+    if exchange is not None:
+        exchange.close()
     host.close()
+
+    if rank == 0:
+        if world == 1 and args.workload == "demo" and not args.no_extra:
+            line["config"]["cpp_host"] = cpp_host_leg(width, height, spp)
+            try:
+                line["extra"] = {"mesh": mesh_measurement(steps=3, warmup=3, builder="sah", cpu=False)}
+            except Exception as e:
+                line["extra"] = {"mesh": {"error": str(e)[:200]}}
+        print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -343,21 +474,19 @@ def run_ours(args):
 
 # ------------------------------------------------- config 3 (not the headline) ----
 
-def run_mesh(args):
-    """BASELINE configs[2]: the 1 M-triangle terrain scene (SAH BVH, or LBVH built on the GPU with
-    --mesh-builder lbvh), 1920x1080, 16 spp, 4 bounces, one GPU. Same conventions as the headline:
-    a step is one 16-spp frame, `value` is device-timed, `e2e` includes the readback, the CPU
-    baseline is the mesh oracle on every host core on a bounded sample."""
+def mesh_measurement(steps, warmup, builder, cpu):
+    """BASELINE configs[2]: the 1 M-triangle terrain scene (SAH BVH, or LBVH built on the GPU), 1920x1080, 16 spp,
+    4 bounces, one GPU. Same conventions as the headline: a step is one 16-spp frame, `value` is device-timed,
+    `e2e` includes the readback, the CPU baseline is the mesh oracle on every host core on a bounded sample."""
     import torch
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; libquasi_cuda.so has no CPU fallback")
     from quasi_b200.headless import headless_host
 
+    width, height = 1920, 1080
     spp, bounces, grid = 16, 4, 707
-    host = headless_host(WIDTH, HEIGHT, single_stream=True,
+    host = headless_host(width, height, single_stream=True,
                          env={"QUASI_CUDA_SCENE": "mesh", "QUASI_CUDA_MESH_GRID": grid, "QUASI_CUDA_MESH_SEED": 1,
-                              "QUASI_CUDA_MAX_BOUNCES": bounces, "QUASI_CUDA_MESH_BUILDER": args.mesh_builder})
+                              "QUASI_CUDA_MAX_BOUNCES": bounces, "QUASI_CUDA_MESH_BUILDER": builder})
     stream = host.context.frame_stream()
 
     def step():
@@ -365,7 +494,7 @@ def run_mesh(args):
         for _ in range(spp - 1):
             host.render_frame(camera_dirty=False)
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step()
     torch.cuda.synchronize()
     s0 = host.stats()
@@ -373,16 +502,16 @@ def run_mesh(args):
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
     ev1.record(stream)
     torch.cuda.synchronize()
     clocks = sampler.stop()
-    ms_step = ev0.elapsed_time(ev1) / args.steps
+    ms_step = ev0.elapsed_time(ev1) / steps
     s1 = host.stats()
-    rays = (s1.rays - s0.rays) / args.steps
-    nodes = (s1.nodes_visited - s0.nodes_visited) / args.steps
-    tris = (s1.triangles_tested - s0.triangles_tested) / args.steps
+    rays = (s1.rays - s0.rays) / steps
+    nodes = (s1.nodes_visited - s0.nodes_visited) / steps
+    tris = (s1.triangles_tested - s0.triangles_tested) / steps
     launches = s1.kernel_launches - s0.kernel_launches
 
     def e2e_step():
@@ -391,42 +520,51 @@ def run_mesh(args):
         assert rb.buffers[0].data, "readback returned no data"
         host.plugin.readback_aov_free(rb)
 
-    for _ in range(min(args.warmup, 3)):
+    for _ in range(min(warmup, 3)):
         e2e_step()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         e2e_step()
-    e2e_s = (time.perf_counter() - t0) / args.steps
+    e2e_s = (time.perf_counter() - t0) / steps
     messages = [m for m in host.messages if "esh" in m]
     host.close()
 
-    peak, peak_src = measured_peaks()
     bytes_step = nodes * 32 + tris * 48  # nodes visited x 32 B + triangles tested x 48 B
+    prof = profiled_kernel("mesh_pathtrace_kernel")
+    issue = None
+    if prof and clocks.get("sm_mhz"):
+        per_launch = prof["warp_instructions_per_launch"]
+        slots = 148 * 4 * clocks["sm_mhz"] * 1e6 * (ms_step / spp) * 1e-3
+        issue = {"warp_inst_per_launch": int(per_launch), "frac": round(per_launch / slots, 4),
+                 "issue_slot_utilization_ncu": prof.get("issue_slot_utilization"),
+                 "threads_per_instruction_ncu": prof.get("threads_per_instruction"),
+                 "l1_hit_rate_ncu": prof.get("l1_hit_rate"), "l2_hit_rate_ncu": prof.get("l2_hit_rate"),
+                 "dram_bytes_per_launch_ncu": (prof.get("dram_bytes_read", 0) + prof.get("dram_bytes_write", 0)) or None}
     line = {
         "metric": "Mrays/s @1080p 16spp (1 M-triangle mesh scene, 4 bounces, headless via plugin C ABI)",
-        "value": round(rays / (ms_step * 1e-3) / 1e6, 2), "unit": "Mrays/s", "n_gpus": 1, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
+        "value": round(rays / (ms_step * 1e-3) / 1e6, 2), "unit": "Mrays/s", "n_gpus": 1, "steps": steps,
+        "warmup": warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32",
         "data": "synthetic (procedural terrain box from pcg_hash, no inputs to load)",
-        "config": {"workload": f"terrain mesh grid {grid} ({12 + 2 * grid * grid} triangles), {WIDTH}x{HEIGHT}, {spp} spp, "
-                               f"{bounces} bounces, BVH builder {args.mesh_builder}",
+        "config": {"workload": f"terrain mesh grid {grid} ({12 + 2 * grid * grid} triangles), {width}x{height}, {spp} spp, "
+                               f"{bounces} bounces, BVH builder {builder}",
                    "rays_per_step": rays, "nodes_per_ray": round(nodes / rays, 2),
                    "triangles_per_ray": round(tris / rays, 2), "plugin_messages": messages,
                    "l2": "no flush: the scene (20-37 MB of nodes, 96 MB of triangles and shading records) is meant "
                          "to be served by L2; the 132.7 MB accumulation set is streamed every launch"},
         "e2e": {"value": round(rays / e2e_s / 1e6, 2), "unit": "Mrays/s", "ms_per_step": round(e2e_s * 1e3, 4),
-                "h2d_bytes_per_step": spp * (320 + 80), "d2h_bytes_per_step": WIDTH * HEIGHT * 64},
+                "h2d_bytes_per_step": spp * (320 + 80), "d2h_bytes_per_step": width * height * 64},
         "gpu_launches": launches, "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "mesh_pathtrace_kernel",
-                     "achieved": round(bytes_step / (ms_step * 1e-3) / 1e9, 1), "peak": peak, "unit": "GB/s",
-                     "frac": round(bytes_step / (ms_step * 1e-3) / 1e9 / peak, 4), "traffic": None,
-                     "peak_source": peak_src, "algorithmic_bytes_per_launch": round(bytes_step / spp),
+        "roofline": {"bound": "issue", "kernel": "mesh_pathtrace_kernel", "issue": issue,
+                     "cache_served": {"achieved": round(bytes_step / (ms_step * 1e-3) / 1e9, 1), "unit": "GB/s",
+                                      "algorithmic_bytes_per_launch": round(bytes_step / spp),
+                                      "what": "nodes visited x 32 B + triangles tested x 48 B (SURVEY.md 8d), served by L1 and "
+                                              "L2, NOT HBM traffic: DRAM traffic is ~0.8 GB per launch (ncu)"},
                      "kernel_ms": round(ms_step / spp, 5),
-                     "note": "algorithmic bytes (nodes x 32 B + triangles x 48 B) are served by L1/L2, not HBM "
-                             "(DRAM traffic is ~0.8 GB per launch, profiles/ncu_summary.json): the kernel is "
-                             "bound by instruction issue at 14.6 of 32 lanes, see DESIGN.md section 4.3"},
+                     "note": "bound by instruction issue at low SIMD efficiency, then L1/L2 latency (DESIGN.md 4.3); no HBM "
+                             "fraction is quoted because the bytes above never reach HBM"},
     }
-    if not args.no_cpu:
+    if cpu:
         from oracle_lib import MeshOracle
 
         cw, ch, cframes = 960, 540, 4
@@ -439,7 +577,15 @@ def run_mesh(args):
             "value": round(st["rays"] / cpu_s / 1e6, 3), "unit": "Mrays/s", "cores": os.cpu_count(), "kind": "port",
             "sample": f"{cw}x{ch}, {cframes} spp of the same scene and BVH (oracle/quasi_oracle_mesh.c, gcc -O2 "
                       f"-ffp-contract=off, one thread per core), {st['rays']} rays in {cpu_s:.2f} s"}
-    print(json.dumps(line), flush=True)
+    return line
+
+
+def run_mesh(args):
+    import torch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; libquasi_cuda.so has no CPU fallback")
+    print(json.dumps(mesh_measurement(args.steps, args.warmup, args.mesh_builder, not args.no_cpu)), flush=True)
 
 
 def main():
@@ -448,13 +594,19 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--reduce", choices=["p2p", "p2p_host", "nccl"], default="nccl",
-                    help="multi-GPU combine: NCCL reduce + scale kernel (default: 0.25 ms per frame faster at 8 "
-                         "GPUs) or the fused peer-memory kernel (p2p: fixed summation order, bit-exact vs the oracle)")
+    ap.add_argument("--reduce", choices=["push", "nccl"], default="push",
+                    help="multi-GPU exchange: tiles pushed to the slice owners by the render kernel + one local reduce "
+                         "kernel per rank, frame into shared host memory (default; fixed summation order, bit-exact vs "
+                         "the oracle), or NCCL reduce to rank 0 + scale kernel + copy to the host")
+    ap.add_argument("--scaling", choices=["strong", "weak"], default="strong",
+                    help="N > 1: split the frame's samples over the GPUs (default) or give every GPU the whole 64")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the 320x180 comparison with the oracle")
+    ap.add_argument("--no-extra", action="store_true", help="skip the C++ host and mesh-scene legs of the default run")
     ap.add_argument("--cpu-budget", type=float, default=0.0, help="seconds of CPU work for the CPU legs")
-    ap.add_argument("--workload", choices=["demo", "mesh"], default="demo",
-                    help="demo = the headline (BASELINE configs[1]); mesh = configs[2], the 1 M-triangle scene, 1 GPU")
+    ap.add_argument("--workload", choices=["demo", "demo4k", "mesh"], default="demo",
+                    help="demo = the headline (BASELINE configs[1]); demo4k = configs[3], 4K x 1024 spp; "
+                         "mesh = configs[2], the 1 M-triangle scene, 1 GPU")
     ap.add_argument("--mesh-builder", choices=["sah", "lbvh"], default="sah")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -21,8 +21,8 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 LIB = ROOT / "quasi_b200" / "lib" / "libquasi_cuda.so"
 RECORD = ROOT / "profiles" / "verified_sass.json"
-# kernels that exist in the library but have not run on a GPU yet (QUASI_CUDA_BATCH forms)
-UNVERIFIED = re.compile(r"pathtrace_accumulate_kernel<.*, true, (true|false)>|mesh_pathtrace_kernel<(true|false), true>")
+# kernels that exist in the library but have not run on a GPU yet (none at the moment)
+UNVERIFIED = re.compile(r"^$")
 
 
 def fingerprints():
