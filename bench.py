@@ -71,7 +71,7 @@ def measured_peaks():
 
 
 class clock_sampler(threading.Thread):
-    """Samples SM clocks and throttle reasons of one GPU every 20 ms via NVML."""
+    """Samples SM clocks and throttle reasons of one GPU every 5 ms via NVML."""
 
     REASONS = {
         0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap",
@@ -107,7 +107,7 @@ class clock_sampler(threading.Thread):
                 self.power.append(self.nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
             except Exception:
                 pass
-            self._stop_evt.wait(0.02)
+            self._stop_evt.wait(0.005)
 
     def stop(self):
         self._stop_evt.set()
@@ -311,14 +311,16 @@ def run_ours(args):
 
         exchange = shard_exchange(host, dist, mode=args.reduce)
 
-    def step():
+    def step(to_host=False):
         if exchange is not None:
             exchange.begin_frame()
         host.render_frame(camera_dirty=True)
         for _ in range(spp_rank - 1):
             host.render_frame(camera_dirty=False)
         if exchange is not None:
-            exchange.combine()  # one exchange per frame: sum over ranks, 1/N scale, towards host memory
+            # one exchange per frame: sum over ranks in rank order, 1/N scale; the reduced slices stay on the GPUs
+            # in the device-timed loop and go to the shared host frame in the end-to-end loop
+            exchange.combine(to_host=to_host)
         else:
             host.plugin.fn("Q_cuda_plugin_flush")(host.plugin._handle, stream.cuda_stream)  # launch what was collected
 
@@ -351,7 +353,7 @@ def run_ours(args):
 
     # ---- end to end through the public API with host buffers (e2e) ----
     def e2e_step():
-        step()
+        step(to_host=True)
         if world == 1:
             rb = host.plugin.readback_aov()          # blocking: the four layers in host memory
             assert rb.buffers[0].data, "readback returned no data"

@@ -213,6 +213,8 @@ typedef struct Q_cuda_ipc_handle {
 Q_PLUGIN_EXPORT int Q_cuda_alloc(uint64_t bytes, void** out_device_ptr);
 Q_PLUGIN_EXPORT int Q_cuda_free(void* device_ptr);
 Q_PLUGIN_EXPORT int Q_cuda_memset_async(void* device_ptr, int value, uint64_t bytes, void* stream);
+/* cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, stream): device, peer-mapped or pinned host memory either side. */
+Q_PLUGIN_EXPORT int Q_cuda_memcpy_async(void* dst, const void* src, uint64_t bytes, void* stream);
 /* Export a Q_cuda_alloc'd buffer, or the plugin's contiguous layer block
  * (device_ptr[0] of Q_cuda_plugin_layers). */
 Q_PLUGIN_EXPORT int Q_cuda_ipc_export(void* device_ptr, Q_cuda_ipc_handle* out);

@@ -127,5 +127,5 @@ CUDA_EXTENSION_SYMBOLS = (  # quasi_cuda_backend.h
     "Q_cuda_combine_shards", "Q_cuda_alloc", "Q_cuda_free", "Q_cuda_ipc_export", "Q_cuda_ipc_open",
     "Q_cuda_ipc_close", "Q_cuda_probe_sincos", "Q_cuda_plugin_mesh_view", "Q_cuda_memset_async",
     "Q_cuda_plugin_set_export", "Q_cuda_plugin_flush", "Q_cuda_push_slices", "Q_cuda_reduce_slices_sync",
-    "Q_cuda_host_register", "Q_cuda_host_unregister",
+    "Q_cuda_host_register", "Q_cuda_host_unregister", "Q_cuda_memcpy_async",
 )

@@ -974,6 +974,11 @@ Q_PLUGIN_EXPORT int Q_cuda_memset_async(void* device_ptr, int value, uint64_t by
     return cudaMemsetAsync(device_ptr, value, bytes, static_cast<cudaStream_t>(stream)) == cudaSuccess ? 0 : -1;
 }
 
+Q_PLUGIN_EXPORT int Q_cuda_memcpy_async(void* dst, const void* src, uint64_t bytes, void* stream) {
+    if (!dst || !src) return -1;
+    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, static_cast<cudaStream_t>(stream)) == cudaSuccess ? 0 : -1;
+}
+
 Q_PLUGIN_EXPORT int Q_cuda_probe_sincos(const float* phi, float* sin_out, float* cos_out,
                                         uint64_t n, void* stream) {
     if (!phi || !sin_out || !cos_out) return -1;

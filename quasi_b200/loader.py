@@ -158,6 +158,7 @@ class loader:
                                                     C.c_uint32, C.c_uint64, C.c_float, C.c_void_p, C.c_void_p]),
             "Q_cuda_host_register": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]),
             "Q_cuda_host_unregister": (C.c_int, [C.c_void_p]),
+            "Q_cuda_memcpy_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
             "Q_cuda_memset_async": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p]),
             "Q_cuda_alloc": (C.c_int, [C.c_uint64, C.POINTER(C.c_void_p)]),
             "Q_cuda_free": (C.c_int, [C.c_void_p]),

@@ -136,8 +136,15 @@ class shard_exchange:
     """Combines the per-rank accumulation layers of one frame: begin_frame() before the frame's render
     calls, combine() after them (enqueue only), finish_frame() when the frame is wanted on the host."""
 
-    def __init__(self, host, dist, mode: str = "push"):
+    def __init__(self, host, dist, mode: str = "push", host_path: str | None = None):
+        """`host_path` (push mode): how a reduced slice reaches the shared host frame: "store", the reduce kernel
+        writes it there itself (zero-copy stores over PCIe), or "dma", the kernel writes device memory and a
+        copy engine moves the slice (the default: QUASI_EXCHANGE_HOST_PATH overrides)."""
+        import os
+
         import torch
+
+        self.host_path = host_path or os.environ.get("QUASI_EXCHANGE_HOST_PATH", "dma")
 
         if mode not in ("push", "nccl"):
             raise ValueError(mode)
@@ -199,6 +206,7 @@ class shard_exchange:
         # staging: two frames (parity) x `world` slots x `per` float4; flags: one block, zeroed before anyone sees it
         slot_bytes = self.per * 16
         self.staging = self._alloc(2 * self.world * slot_bytes)
+        self.device_slice = self._alloc(slot_bytes)  # combine(to_host=False): the reduced slice, kept on this GPU
         self.flags = self._alloc(256)
         if self.fn("Q_cuda_memset_async")(self.flags, 0, 256, self.stream.cuda_stream) != 0:
             raise RuntimeError("Q_cuda_memset_async(flags) failed")
@@ -234,8 +242,10 @@ class shard_exchange:
             rc = self.fn("Q_cuda_plugin_set_export")(self.handle, C.byref(self.tables[self.epoch & 1]))
             assert rc == 0
 
-    def combine(self):
-        """After the frame's last render call; enqueue only."""
+    def combine(self, to_host: bool = True):
+        """After the frame's last render call; enqueue only. `to_host` False: the reduced slice stays in this GPU's
+        memory (nothing crosses PCIe: what bench.py's device-timed figure wants); True: it goes to the shared
+        host frame, which finish_frame() then waits for."""
         if self.mode == "nccl":
             return self._combine_nccl()
         slot_bytes = self.per * 16
@@ -247,16 +257,21 @@ class shard_exchange:
                                                self.stream.cuda_stream)
             assert rc == 0
             self.launches += 1
-        if self._handed_out:
+        if to_host and self._handed_out:
             self.frame.wait_consumed(self._handed_out)  # the segment still holds a frame rank 0 is looking at
             self._handed_out = 0
         flags = (C.c_void_p * self.world)(*self.flag_ptrs)
         mine = self.staging + (self.epoch & 1) * self.world * slot_bytes
+        direct = to_host and self.host_path == "store"
+        out = self.frame_device_ptr + self.lo * 16 if direct else self.device_slice
         rc = self.fn("Q_cuda_reduce_slices_sync")(mine, self.per, flags, self.world, self.rank, self.epoch,
-                                                  self.hi - self.lo, 0.0, self.frame_device_ptr + self.lo * 16,
-                                                  self.stream.cuda_stream)
+                                                  self.hi - self.lo, 0.0, out, self.stream.cuda_stream)
         assert rc == 0
         self.launches += 1
+        if to_host and not direct and self.hi > self.lo:
+            rc = self.fn("Q_cuda_memcpy_async")(self.frame.address + self.lo * 16, self.device_slice,
+                                                (self.hi - self.lo) * 16, self.stream.cuda_stream)
+            assert rc == 0
 
     def _combine_nccl(self):
         torch, dist = self.torch, self.dist

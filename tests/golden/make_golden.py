@@ -104,6 +104,7 @@ def main() -> None:
         "512x512_acc3": (512, 512, 3, 0),
         "config2_1920x1080_f0": (1920, 1080, 1, 0),
         "config4_3840x2160_f1": (3840, 2160, 1, 1),  # seeds collide above 1920x1080
+        "config2_1920x1080_64spp": (1920, 1080, 64, 0),  # the headline frame at full size (about 20 s on 8 cores)
     }.items():
         u = ref.scene(w, h)
         layers = ref.render_frames(u, w, h, n, frame_first=first)

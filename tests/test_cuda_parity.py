@@ -145,9 +145,13 @@ def test_config4_4k_colliding_seeds_match_reference_checksum(torch_cuda, golden)
         assert sha(layer) == g[name], name
 
 
-def test_full_size_properties_1080p_64spp(torch_cuda):
-    """BASELINE config 2 at full size, through size-independent properties."""
+def test_full_size_properties_1080p_64spp(torch_cuda, golden):
+    """BASELINE config 2 at full size: the reference's own checksum of the finished frame (oracle/_ref, written
+    by tests/golden/make_golden.py), then size-independent properties."""
     got, stats = render(1920, 1080, 64)
+    g = golden.checksums["config2_1920x1080_64spp"]
+    for name, layer in zip(LAYERS, got):
+        assert sha(layer) == g[name], name
     beauty, albedo, normal, depth = got
     assert stats.frame_count == 64 and stats.paths == 64 * 1920 * 1080
     assert 64 * 1920 * 1080 <= stats.rays <= 5 * 64 * 1920 * 1080

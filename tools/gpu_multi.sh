@@ -1,9 +1,20 @@
-N=${1:-8}
-mkdir -p gpurun_out
-nvidia-smi topo -m > gpurun_out/topo.txt 2>&1
-timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 tests/multi_gpu_check.py 2>&1 | grep MULTI_GPU_CHECK | tee gpurun_out/multi_check_$N.log
-for mode in nccl p2p; do
-timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 10 --warmup 3 --reduce $mode 2> gpurun_out/bench_multi_$mode.err | tail -1 | tee gpurun_out/bench_gpus${N}_$mode.json | cut -c1-330
+# Under `gpurun --gpus N`: the multi-GPU parity check on N ranks, then bench.py --gpus N with both exchanges
+# (strong scaling on the 1080p x 64 spp frame; weak scaling; BASELINE config 4 at 4K).
+#   usage: bash tools/gpu_multi.sh N
+N=${1:-2}
+mkdir -p gpurun_out; log=gpurun_out/multi_$N.log; : > $log
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
+nvidia-smi topo -m > gpurun_out/topo_$N.txt 2>&1
+echo "== multi_gpu_check.py on $N ranks" | tee -a $log
+timeout 600 $TR --master-port 29533 tests/multi_gpu_check.py > gpurun_out/multi_check_$N.log 2>&1; grep -E "FAIL|MULTI_GPU_CHECK|Error|error" gpurun_out/multi_check_$N.log | head -20 | cut -c1-300 | tee -a $log
+i=0
+for opts in "--reduce push" "--reduce nccl" "--reduce push --scaling weak" "--reduce push --workload demo4k --steps 3"; do
+  i=$((i+1))
+  echo "== bench.py --gpus $N $opts" | tee -a $log
+  timeout 600 $TR --master-port $((29540+i)) bench.py --gpus $N --no-cpu $opts > gpurun_out/bench_multi_${N}_$i.json 2> gpurun_out/bench_multi_${N}_$i.err
+  tail -1 gpurun_out/bench_multi_${N}_$i.json | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('   value', d['value'], 'ms', d['ms_per_step'], '| e2e', d['e2e']['value'], 'ms', d['e2e']['ms_per_step'], '|', d['scaling'], '| parity', d.get('parity'))" 2>&1 | tail -1 | cut -c1-400 | tee -a $log
+  grep -E "Error|error|Traceback" gpurun_out/bench_multi_${N}_$i.err | head -5 | cut -c1-300 | tee -a $log
 done
-timeout 120 quasi_b200/bin/quasi_headless --render $((1024 / N)) --width 3840 --height 2160 --gpus $N --json --out /tmp/config4.exr quasi_b200/lib/libquasi_cuda.so > gpurun_out/config4_g$N.log 2>&1
-grep '^{' gpurun_out/config4_g$N.log | tail -1 | tee gpurun_out/config4_g$N.json
+echo "== bench.py (1 GPU, for the ratio)" | tee -a $log
+timeout 300 python bench.py --no-cpu --no-extra > gpurun_out/bench_multi_${N}_single.json 2>> gpurun_out/bench_multi_${N}_1.err
+tail -1 gpurun_out/bench_multi_${N}_single.json | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('   value', d['value'], 'ms', d['ms_per_step'], '| e2e', d['e2e']['value'], 'ms', d['e2e']['ms_per_step'], '| parity', d.get('parity'))" 2>&1 | tail -1 | cut -c1-300 | tee -a $log
