@@ -148,7 +148,7 @@ typedef struct Q_cuda_layers {
 #define Q_CUDA_MAX_EXPORT_SLICES 16u
 typedef struct Q_cuda_export_table {
     uint32_t struct_size;       /* sizeof(Q_cuda_export_table) */
-    uint32_t slices;            /* 1 .. Q_CUDA_MAX_EXPORT_SLICES */
+    uint32_t slices;            /* 1 .. Q_CUDA_MAX_EXPORT_SLICES; 0: export nothing (and keep the readback mirror off) */
     uint32_t float4_per_slice;  /* > 0 */
     uint32_t reserved;
     void* base[Q_CUDA_MAX_EXPORT_SLICES];

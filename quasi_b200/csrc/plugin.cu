@@ -465,10 +465,12 @@ void flush_pending(plugin_state* state, cudaStream_t stream = nullptr) {
         const uint64_t n_px = static_cast<uint64_t>(f.width) * f.height;
         if (state->external_export) {
             const Q_cuda_export_table& t = state->export_table;
-            launch.export_slices = t.slices;
-            launch.export_per = t.float4_per_slice;
-            launch.export_per_magic = static_cast<uint32_t>((uint64_t{1} << 32) / t.float4_per_slice);
-            for (uint32_t i = 0; i < t.slices; i++) launch.export_base[i] = t.base[i];
+            if (t.slices != 0) {  // (a table of no slices: nothing leaves the GPU during the launch)
+                launch.export_slices = t.slices;
+                launch.export_per = t.float4_per_slice;
+                launch.export_per_magic = static_cast<uint32_t>((uint64_t{1} << 32) / t.float4_per_slice);
+                for (uint32_t i = 0; i < t.slices; i++) launch.export_base[i] = t.base[i];
+            }
         } else if (state->mirror_enabled && n_px < (uint64_t{1} << 30)) {
             const size_t bytes = static_cast<size_t>(n_px) * 4 * sizeof(float);
             bool have = true;
@@ -869,8 +871,8 @@ Q_PLUGIN_EXPORT int Q_cuda_plugin_set_export(Q_plugin_handle* handle, const Q_cu
     auto* state = reinterpret_cast<plugin_state*>(handle);
     if (cudaSetDevice(state->device) != cudaSuccess) return -1;
     if (table != nullptr) {
-        if (table->struct_size < sizeof(Q_cuda_export_table) || table->slices == 0 ||
-            table->slices > Q_CUDA_MAX_EXPORT_SLICES || table->float4_per_slice == 0) {
+        if (table->struct_size < sizeof(Q_cuda_export_table) || table->slices > Q_CUDA_MAX_EXPORT_SLICES ||
+            (table->slices != 0 && table->float4_per_slice == 0)) {
             return -1;
         }
         for (uint32_t i = 0; i < table->slices; i++) {

@@ -5,7 +5,9 @@ import sys
 sys.path.insert(0, "."); sys.path.insert(0, "tests")
 from quasi_b200.headless import headless_host
 import numpy as np
-h = headless_host(97, 61, present=True); h.render(3); a = h.readback_aov(); print("quad", h.stats().rays); h.close()
+h = headless_host(97, 61, present=True); h.render(3); a = h.readback_aov(); print("quad, one launch per call + tonemap", h.stats().rays); h.close()
+h = headless_host(97, 61); h.render(7); a = h.readback_aov(); b = h.readback_aov(); print("quad, batched launch with the tile export", h.stats().rays, h.stats().kernel_launches); h.close()
+h = headless_host(61, 35, env={"QUASI_CUDA_BATCH": 3, "QUASI_CUDA_MIRROR": 0, "QUASI_CUDA_SCAN": "generic"}); h.render(7); a = h.readback_aov(); print("quad, generic scan, batches of 3", h.stats().rays); h.close()
 for builder in ("sah", "lbvh"):
     h = headless_host(80, 45, env={"QUASI_CUDA_SCENE": "mesh", "QUASI_CUDA_MESH_GRID": 40, "QUASI_CUDA_MESH_SEED": 1,
                                    "QUASI_CUDA_MAX_BOUNCES": 4, "QUASI_CUDA_MESH_BUILDER": builder})
