@@ -79,9 +79,6 @@ using namespace dev;
 #ifndef QUASI_MESH_RUN_EXIT
 #define QUASI_MESH_RUN_EXIT 4
 #endif
-#ifndef QUASI_MESH_POSTPONE
-#define QUASI_MESH_POSTPONE 0
-#endif
 
 constexpr int k_block_threads = 256;
 constexpr int k_blocks_per_sm = QUASI_MESH_BLOCKS_PER_SM;
@@ -89,11 +86,6 @@ constexpr int k_warps_per_block = k_block_threads / 32;
 constexpr int k_min_waiting = QUASI_MESH_MIN_WAITING;  ///< finished queries that trigger a service phase
 constexpr int k_leaf_batch = QUASI_MESH_LEAF_BATCH;    ///< lanes holding a leaf that trigger the triangle phase
 constexpr int k_run_exit = QUASI_MESH_RUN_EXIT;        ///< lanes leaving a descent run that end it
-/// A lane that reaches a leaf puts it aside and goes on descending; only at a second leaf (or with an empty
-/// stack) does it wait for the triangle phase, which then meets more holders and leaves the descent more lanes
-/// (speculative traversal, Aila & Laine 2009). The postponed leaf's hit is not known while the lane descends,
-/// so it prunes a little less; the result cannot change (boxes only prune what the ray provably misses).
-constexpr bool k_postpone = QUASI_MESH_POSTPONE != 0;
 constexpr size_t k_stack_bytes = static_cast<size_t>(k_mesh_stack_entries) * k_block_threads * 6;
 constexpr uint32_t k_miss = 0xffffffffu;
 constexpr uint32_t k_done = 0xffffffffu;  ///< node reference: the query has finished
@@ -243,7 +235,6 @@ mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_co
     uint32_t rng = 0, bounce = 0, pixel = 0;
     // query state
     uint32_t cur = k_done;
-    [[maybe_unused]] uint32_t held = 0;  // k_postpone: a leaf put aside (leaf references are never 0)
     mesh_hit best{1e30f, k_miss, 0u};
     v3 inv = make_v3(0.0f, 0.0f, 0.0f), oi = inv;
 
@@ -256,9 +247,8 @@ mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_co
         bool new_ray = false, fresh = false;
         v3 fu = make_v3(0.0f, 0.0f, 0.0f), fv = fu, fw = fu;  // scattering frame of a continuing path
         float uv_x = 0.0f, uv_y = 0.0f;                        // pixel centre of a new path
-        const bool finished = active && cur == k_done && (!k_postpone || held == 0u);
-        QUASI_EMU_PASS(0, finished)  // service: shading
-        if (finished) {
+        QUASI_EMU_PASS(0, active && cur == k_done)  // service: shading
+        if (active && cur == k_done) {
             // One bounce of path_trace (plugin.mm:232-273) around the finished query.
             const bool is_hit = best.prim != k_miss;
             v3 n = make_v3(0.0f, 0.0f, 0.0f), q_emission = n, q_albedo = n;
@@ -416,17 +406,20 @@ mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_co
             // low 3 bits of cur: 0 interior, 1..4 leaf with that many triangles, 6 k_pop, 7 k_done
             const bool descending = (cur & 7u) == 0u || cur == k_pop;
             const uint32_t m_descending = __ballot_sync(0xffffffffu, descending);
-            // lanes that cannot go on without the triangle phase
-            const bool at_leaf = (cur & 7u) - 1u < 4u;
-            const uint32_t m_leaf = __ballot_sync(0xffffffffu, k_postpone ? (at_leaf || (cur == k_done && held != 0u)) : at_leaf);
+            const uint32_t m_leaf = __ballot_sync(0xffffffffu, (cur & 7u) - 1u < 4u);
             const uint32_t m_tracing = m_descending | m_leaf;
             // enough finished queries to make shading worth issuing, or nothing to traverse
             if (m_tracing == 0u || __popc(m_active & ~m_tracing) >= k_min_waiting) break;
             QUASI_EMU_PASS(2, m_tracing != 0u)  // scheduler iterations
+#if defined(QUASI_HOST_EMULATION) && defined(QUASI_EMU_STATS)
+            if (!(m_descending != 0u && __popc(m_leaf) < k_leaf_batch)) {
+                for (uint32_t k = 0; k < 4u; k++) QUASI_EMU_PASS(4, (cur & 7u) - 1u < 4u && (cur & 7u) > k)  // triangle passes
+            }
+#endif
             if (m_descending != 0u && __popc(m_leaf) < k_leaf_batch) {
-                // Descent run: one level per iteration for every lane that is not waiting for the
-                // triangle phase, until k_run_exit of them have left the descent. The others sit
-                // this out; they are served once k_leaf_batch have gathered.
+                // Descent run: one level per iteration for every lane that is not holding a
+                // leaf, until k_run_exit of them have reached a leaf or finished. Leaf
+                // holders sit this out; they are served once k_leaf_batch have gathered.
                 const int keep = max(__popc(m_descending) - k_run_exit, 0);
                 do {
                     QUASI_EMU_PASS(3, (cur & 7u) == 0u || cur == k_pop)  // descent passes
@@ -440,40 +433,8 @@ mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_co
                             interior_step(nodes, stack, inv, oi, best.t, cur);
                         }
                     }
-                    if constexpr (k_postpone) {
-                        if ((cur & 7u) - 1u < 4u && held == 0u) {  // a first leaf: put it aside, go on
-                            held = cur;
-                            cur = stack.after_node();
-                        }
-                    }
                 } while (__popc(__ballot_sync(0xffffffffu, (cur & 7u) == 0u || cur == k_pop)) > keep);
-            } else if constexpr (k_postpone) {
-                // Triangle phase: every lane that has a leaf aside tests it (also lanes still descending),
-                // then a lane standing at a second leaf puts that one aside and is served by the next pass.
-                if (held == 0u && at_leaf) {  // (with no lane descending a first leaf can still be in `cur`)
-                    held = cur;
-                    cur = stack.after_node();
-                }
-                while (__any_sync(0xffffffffu, held != 0u)) {
-                    QUASI_EMU_PASS(4, held != 0u)  // triangle passes
-                    if (held != 0u) {
-                        const uint32_t first = held >> 3, count = held & 7u;
-                        for (uint32_t k = 0; k < count; k++) {
-                            const uint32_t slot = first + k;
-                            intersect(__ldg(scene.tri_v0 + slot), __ldg(scene.tri_e1 + slot), __ldg(scene.tri_e2 + slot),
-                                      slot, ro, rd, best);
-                        }
-                        tris_tested += count;
-                        held = 0u;
-                        if ((cur & 7u) - 1u < 4u) {
-                            held = cur;
-                            cur = stack.after_node();
-                        }
-                    }
-                }
-            } else {
-                QUASI_EMU_PASS(4, at_leaf)  // triangle passes
-                if (at_leaf) {
+            } else if ((cur & 7u) - 1u < 4u) {
                 const uint32_t first = cur >> 3, count = cur & 7u;
                 for (uint32_t k = 0; k < count; k++) {
                     const uint32_t slot = first + k;
@@ -482,7 +443,6 @@ mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_co
                 }
                 tris_tested += count;
                 cur = stack.after_node();
-                }
             }
         }
     }
