@@ -18,8 +18,8 @@ counted on the device.
           (132.7 MB at 1080p) arriving in host memory: Q_plugin_readback_aov on one
           GPU, the shared host frame of quasi_b200.multi_gpu.shard_exchange on several.
   roofline    the dominant kernel (pathtrace_accumulate_kernel) against measured HBM
-              bandwidth with the algorithmic 128 B/pixel/launch, as the
-              contract asks; the kernel is bound by instruction issue, so `issue` holds
+              bandwidth with the algorithmic 128 B/pixel per render call x the
+              calls a launch processes, as the contract asks; the kernel is bound by instruction issue, so `issue` holds
               the figure that explains it: warp instructions per launch (ncu, only when
               the loaded library's SASS is the build that was profiled) over the issue
               slots the launch had (SMs x 4 schedulers x SM clock x kernel time).
@@ -52,7 +52,7 @@ sys.path.insert(0, str(ROOT / "tests"))
 sys.path.insert(0, str(ROOT / "tools"))
 
 WORKLOADS = {"demo": (1920, 1080, 64), "demo4k": (3840, 2160, 1024)}
-ALGORITHMIC_BYTES_PER_PIXEL_PER_LAUNCH = 128  # 4 layers x (16 B read + 16 B write), SURVEY.md 8d
+ALGORITHMIC_BYTES_PER_PIXEL_PER_CALL = 128  # 4 layers x (16 B read + 16 B write) per Q_plugin_render call, SURVEY.md 8d
 PARITY_SIZE = (320, 180)
 
 
@@ -397,7 +397,11 @@ def run_ours(args):
         kernel_ms = ms_step / launches_per_step if world == 1 else None
         roofline = None
         if kernel_ms is not None:
-            achieved = ALGORITHMIC_BYTES_PER_PIXEL_PER_LAUNCH * n_px / (kernel_ms * 1e-3) / 1e9
+            # SURVEY.md 8d's unit is one Q_plugin_render call (one sample per pixel: 128 B/px); a launch processes
+            # samples_per_launch of them (64 when the plugin batches, 1 otherwise)
+            samples_per_launch = spp_rank / launches_per_step
+            algorithmic = ALGORITHMIC_BYTES_PER_PIXEL_PER_CALL * n_px * samples_per_launch
+            achieved = algorithmic / (kernel_ms * 1e-3) / 1e9
             batched = launches_per_step < spp_rank
             prof = profiled_kernel("pathtrace_accumulate_kernel_batched" if batched else "pathtrace_accumulate_kernel")
             issue = None
@@ -414,13 +418,14 @@ def run_ours(args):
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4),
                 "traffic": prof.get("dram_bytes_per_launch") if prof else None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": ALGORITHMIC_BYTES_PER_PIXEL_PER_LAUNCH * n_px,
-                "samples_per_launch": spp_rank / launches_per_step,
+                "algorithmic_bytes_per_launch": int(algorithmic),
+                "samples_per_launch": samples_per_launch,
                 "kernel_ms": round(kernel_ms, 5),
                 "issue": issue,
-                "note": "the contract's HBM figure: 128 B/pixel per LAUNCH (history read + result written once however many "
-                        "samples the launch folds in, SURVEY.md 8d). The kernel is bound by instruction issue, not HBM "
-                        "(a 16-quad scan per ray): `issue` is the fraction of the launch's issue slots it fills; "
+                "note": "the contract's HBM figure: SURVEY.md 8d's 128 B/pixel per render call x the calls one launch "
+                        "processes. `traffic` (ncu, DRAM bytes of one launch) is far below it for a batched launch because "
+                        "a pixel's history stays in L2 between its samples. The kernel is bound by instruction issue, not "
+                        "HBM (a 16-quad scan per ray): `issue` is the fraction of the launch's issue slots it fills; "
                         "traffic / issue come from ncu and are null unless the loaded library is the profiled build",
             }
         param_bytes = int(launches_per_step) * (8624 + 80 + 144)  # scene, frame and batch parameter blocks per launch

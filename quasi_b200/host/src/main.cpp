@@ -358,6 +358,22 @@ int main(int argc, char* argv[]) {
         }
         workers.push_back(std::move(w));
     }
+    // With several GPUs the frame is combined on GPU 0 from the layers themselves; nobody reads a single GPU's
+    // frame back, so its readback mirror (the batched launches' export into pinned host memory) stays off.
+    // (After a hot reload the new instance has its mirror on again until the next run: a cost, not an error.)
+    auto disable_mirrors = [&] {
+        if (workers.size() < 2) return;
+        using set_export_fn = int (*)(Q_plugin_handle*, const Q_cuda_export_table*);
+        for (auto& w : workers) {
+            auto set_export = w->manager->extension<set_export_fn>("Q_cuda_plugin_set_export");
+            auto* plugin = w->manager->plugin();
+            if (!set_export || !plugin) continue;
+            Q_cuda_export_table none{};
+            none.struct_size = sizeof none;
+            (void)set_export(plugin->native_handle(), &none);
+        }
+    };
+    disable_mirrors();
     if (auto info = workers[0]->manager->info()) {
         std::printf("Loaded plugin: %s v%u.%u.%u\n", info->name, info->version.major, info->version.minor,
                     info->version.patch);

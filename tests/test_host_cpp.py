@@ -216,3 +216,25 @@ def test_backend_under_the_references_own_loader_and_manager(oracle, tmp_path):
     want, _ = oracle.render_frames(oracle.scene(w, h), w, h, n)
     for name, g, wv in zip(LAYERS, got, want):
         assert np.array_equal(g.view(np.uint32), wv.view(np.uint32)), name
+
+
+@pytest.mark.gpu
+def test_headless_host_repeats_a_frame_set_and_reports_its_wall_time(host_built, oracle, tmp_path):
+    """--repeat R --readback-each: R frame sets, each restarted at sample 0 and each ending with the blocking AOV
+    readback (what bench.py quotes as config.cpp_host); the EXR saved at the end is the last set's frame."""
+    import json
+
+    import quasi_b200
+
+    w, h, n = 96, 54, 5
+    out = tmp_path / "repeat.exr"
+    run = subprocess.run([str(BIN / "quasi_headless"), "--render", str(n), "--repeat", "3", "--readback-each", "--width", str(w),
+                          "--height", str(h), "--out", str(out), "--json", str(quasi_b200.PLUGIN_PATH)],
+                         capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0, run.stdout[-2000:] + run.stderr[-2000:]
+    stats = json.loads([l for l in run.stdout.splitlines() if l.startswith("{")][-1])
+    assert stats["frames"] == 3 * n and len(stats["set_ms"]) == 3 and all(ms > 0 for ms in stats["set_ms"])
+    want, _ = oracle.render_frames(oracle.scene(w, h), w, h, n)
+    got, _ = read_exr(out)
+    assert np.array_equal(got["depth.Z"].view(np.uint32), want[3][..., 0].view(np.uint32))
+    assert np.array_equal(got["R"], want[0][..., 0].astype(np.float16))

@@ -4,7 +4,7 @@ World size 2, no GPU: each rank renders its shard of frame indices with the CPU
 oracle (standing in for its GPU), then the ranks run the same combine protocol
 bench.py uses (quasi_b200.multi_gpu.reduce_mean_to_root). Checks the shard plan
 (union of samples == the single-GPU sample set), the combine against the
-oracle's rank-ordered mean, and the slice partition of the fused p2p kernel.
+oracle's rank-ordered mean, and the slice partition of the push exchange.
 """
 import os
 import sys
