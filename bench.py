@@ -239,16 +239,16 @@ def parity_check(args, dist, rank, world, local_rank, spp_rank):
             u = oracle.scene(w, h)
             shards = [oracle.render_frames(u, w, h, samples, frame_first=g, frame_stride=world)[0] for g in range(world)]
             want = [oracle.combine_shards([s[l] for s in shards]) for l in range(4)]
-        for mode in ("push", "nccl"):
+        for mode in ("push", "fused", "nccl"):
             exchange = shard_exchange(host, dist, mode=mode)
-            exchange.begin_frame()
+            exchange.begin_frame(render_calls=samples)
             render()
             exchange.combine()
             got = exchange.result_numpy()
             exchange.close()
             if rank == 0:
-                if mode == "push":
-                    out["push_bit_exact"] = bool(all(np.array_equal(bits(g), bits(x)) for g, x in zip(got, want)))
+                if mode != "nccl":
+                    out[mode + "_bit_exact"] = bool(all(np.array_equal(bits(g), bits(x)) for g, x in zip(got, want)))
                 else:
                     out["nccl_max_abs"] = float(max(np.abs(g - x).max() for g, x in zip(got, want)))
     host.close()
@@ -313,7 +313,7 @@ def run_ours(args):
 
     def step(to_host=False):
         if exchange is not None:
-            exchange.begin_frame()
+            exchange.begin_frame(to_host=to_host, render_calls=spp_rank)
         host.render_frame(camera_dirty=True)
         for _ in range(spp_rank - 1):
             host.render_frame(camera_dirty=False)
@@ -456,6 +456,9 @@ def run_ours(args):
         if world > 1:
             line["config"]["limiter"] = ("per frame: the slowest rank's render, then one local reduce kernel per rank and each "
                                          "rank's slice crossing its own PCIe link" if args.reduce == "push" else
+                                         "per frame: the slowest rank's render, whose tiles are reduced and sent to the host "
+                                         "by the render kernels themselves as their last copy arrives; then a device-side "
+                                         "barrier" if args.reduce == "fused" else
                                          "per frame: the slowest rank's render, ncclReduce to rank 0, the scale pass and the "
                                          "whole frame crossing rank 0's PCIe link")
         if world == 1 and not args.no_cpu:
@@ -601,7 +604,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--reduce", choices=["push", "nccl"], default="push",
+    ap.add_argument("--reduce", choices=["push", "fused", "nccl"], default="push",
                     help="multi-GPU exchange: tiles pushed to the slice owners by the render kernel + one local reduce "
                          "kernel per rank, frame into shared host memory (default; fixed summation order, bit-exact vs "
                          "the oracle), or NCCL reduce to rank 0 + scale kernel + copy to the host")

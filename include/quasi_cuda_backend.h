@@ -160,6 +160,41 @@ typedef struct Q_cuda_export_table {
  * malformed table. The memory behind base[] must stay valid until the launches have completed. */
 Q_PLUGIN_EXPORT int Q_cuda_plugin_set_export(Q_plugin_handle* handle, const Q_cuda_export_table* table);
 
+/* The export with the reduce fused in (multi-GPU, G ranks). The layer block is cut into G slices along rows of
+ * 8x4 tiles: slice s is the float4 [slice_lo[s], slice_lo[s + 1]) with every slice_lo[s] = (layer * height +
+ * 4 * tile_row) * width, slice_lo[G] = 4 * width * height, so that the 32 pixels of a tile in one layer (a unit)
+ * have one owner. Rank s owns slice s: a staging area of G slots of `slot_stride` float4 (slot g receives rank
+ * g's copy of the slice) and 4 * tiles arrival counters (uint32, [layer * tiles + tile], zeroed ONCE; tiles =
+ * ceil(width / 8) * ceil(height / 4)), both mapped by every rank (Q_cuda_ipc_open). A batched launch stores every
+ * finished tile into its slot at the owners, then adds one to the units' counters; the launch whose arrival is the
+ * G-th for a unit, on whichever GPU, loads the G copies, sums them in rank order, scales by 1/G and stores
+ * float4 i of the unit to out[s] + (i - slice_lo[s]), s being the unit's slice (out[s]: the place of slice s in
+ * pinned host memory every rank has mapped, or in its owner's device memory): the exchange and the frame's way
+ * to the host are part of the render. Every rank must make the same render calls per frame, and
+ * a buffer (staging + counters) may be used again only when every rank's launches of the frame before have
+ * completed (Q_cuda_reduce_slices_sync with n_float4 = 0 is that barrier; two buffers alternate in
+ * quasi_b200/multi_gpu.py). A frame whose last launch is a single sample exports nothing (Q_cuda_plugin_flush
+ * returns 0): such a frame goes through Q_cuda_push_slices + Q_cuda_reduce_slices_sync on every rank. */
+typedef struct Q_cuda_reduce_table {
+    uint32_t struct_size; /* sizeof(Q_cuda_reduce_table) */
+    uint32_t ranks;       /* G, 2 .. Q_CUDA_MAX_EXPORT_SLICES */
+    uint32_t rank;        /* this rank: its slot */
+    uint32_t slot_stride; /* float4 between two slots of a staging area, >= the longest slice */
+    uint32_t slice_lo[Q_CUDA_MAX_EXPORT_SLICES + 1];
+    uint32_t render_calls; /* render calls the frame will make after this set: only the launch that holds the last of
+                            * them exports and reduces (a frame of several launches: one arrival per rank and unit);
+                            * 0: every launch does (one launch per frame) */
+    void* staging[Q_CUDA_MAX_EXPORT_SLICES];      /* [s]: slot 0 of rank s's staging area for this frame */
+    uint32_t* counters[Q_CUDA_MAX_EXPORT_SLICES]; /* [s]: rank s's counters for this frame's buffer */
+    void* out[Q_CUDA_MAX_EXPORT_SLICES];          /* [s]: where float4 slice_lo[s] of the finished frame goes */
+} Q_cuda_reduce_table;
+
+/* Sets (table != NULL) or clears the fused export + reduce for the launches that follow; replaces a table set
+ * with Q_cuda_plugin_set_export and vice versa. Returns 0, or -1 for a malformed table. A table whose slices do
+ * not fit the viewport of a launch (not the four layers, or a slice that starts inside a row of tiles) is not
+ * used by that launch, which then exports nothing (Q_cuda_plugin_flush returns 0). */
+Q_PLUGIN_EXPORT int Q_cuda_plugin_set_reduce(Q_plugin_handle* handle, const Q_cuda_reduce_table* table);
+
 /* Launches the render calls the plugin has collected (QUASI_CUDA_BATCH) on `stream` (NULL: the
  * plugin's own queue) without waiting for them. A host that keeps the device pointers of
  * Q_cuda_plugin_layers across frames calls this before it reads the layers on the device; every
@@ -234,6 +269,10 @@ Q_PLUGIN_EXPORT int Q_cuda_ipc_close(void* device_ptr);
 /* block[i] -> table->base[i / P][i % P] for i < n_float4, enqueued on `stream`. */
 Q_PLUGIN_EXPORT int Q_cuda_push_slices(const float* block, uint64_t n_float4, const Q_cuda_export_table* table,
                                        void* stream);
+
+/* The same into this rank's slots of a Q_cuda_reduce_table (the slices cut along rows of tiles). */
+Q_PLUGIN_EXPORT int Q_cuda_push_slices_reduce(const float* block, uint64_t n_float4, const Q_cuda_reduce_table* table,
+                                              void* stream);
 
 /* One launch, enqueue only. Device-side flags replace host barriers: the kernel stores `epoch` into
  * flags[g][rank] of every rank g (its frame, and everything it pushed, is complete: the launch follows the

@@ -106,6 +106,14 @@ class Q_cuda_export_table(C.Structure):  # quasi_cuda_backend.h
                 ("reserved", C.c_uint32), ("base", C.c_void_p * Q_CUDA_MAX_EXPORT_SLICES)]
 
 
+class Q_cuda_reduce_table(C.Structure):  # quasi_cuda_backend.h
+    _fields_ = [("struct_size", C.c_uint32), ("ranks", C.c_uint32), ("rank", C.c_uint32), ("slot_stride", C.c_uint32),
+                ("slice_lo", C.c_uint32 * (Q_CUDA_MAX_EXPORT_SLICES + 1)), ("render_calls", C.c_uint32),
+                ("staging", C.c_void_p * Q_CUDA_MAX_EXPORT_SLICES),
+                ("counters", C.c_void_p * Q_CUDA_MAX_EXPORT_SLICES),
+                ("out", C.c_void_p * Q_CUDA_MAX_EXPORT_SLICES)]
+
+
 # Sizes on x86-64 Linux (probed from the reference headers).
 assert C.sizeof(Q_plugin_context) == 40
 assert C.sizeof(Q_render_frame) == 72
@@ -127,5 +135,6 @@ CUDA_EXTENSION_SYMBOLS = (  # quasi_cuda_backend.h
     "Q_cuda_combine_shards", "Q_cuda_alloc", "Q_cuda_free", "Q_cuda_ipc_export", "Q_cuda_ipc_open",
     "Q_cuda_ipc_close", "Q_cuda_probe_sincos", "Q_cuda_plugin_mesh_view", "Q_cuda_memset_async",
     "Q_cuda_plugin_set_export", "Q_cuda_plugin_flush", "Q_cuda_push_slices", "Q_cuda_reduce_slices_sync",
-    "Q_cuda_host_register", "Q_cuda_host_unregister", "Q_cuda_memcpy_async",
+    "Q_cuda_host_register", "Q_cuda_host_unregister", "Q_cuda_memcpy_async", "Q_cuda_plugin_set_reduce",
+    "Q_cuda_push_slices_reduce",
 )

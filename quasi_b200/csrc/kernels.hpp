@@ -94,10 +94,10 @@ cudaError_t launch_combine_shards(const float* const* shards, uint32_t n_shards,
 /// Words in a rank's flag block for launch_reduce_slices_sync: arrive[16] (the rest is spare).
 inline constexpr uint32_t k_sync_words = 2 * k_max_shards + 1;
 
-/// @brief The layer block slice by slice to base[i / float4_per_slice] + i % float4_per_slice (the addressing
-/// of batch_params' export), for a frame whose last launch exported nothing.
-cudaError_t launch_push_slices(const float* block, uint64_t n_float4, void* const* base, uint32_t slices,
-                               uint32_t float4_per_slice, cudaStream_t stream);
+/// @brief The layer block slice by slice: float4 i of slice s (slice_lo[s] <= i < slice_lo[s + 1]) to
+/// base[s] + (i - slice_lo[s]) (the addressing of batch_params' export), for a frame whose last launch exported nothing.
+cudaError_t launch_push_slices(const float* block, uint64_t n_float4, void* const* base, const uint32_t* slice_lo,
+                               uint32_t slices, cudaStream_t stream);
 
 /// @brief The owner's half of the multi-GPU exchange (post.cu:reduce_slices_sync_kernel): waits on device-side
 /// flags until all `n_shards` ranks have completed the frame `epoch`, then out[i] = (sum over g in rank order

@@ -207,6 +207,23 @@ constexpr int k_block_threads = QUASI_QUAD_BLOCK_THREADS;
 constexpr int k_blocks_per_sm = QUASI_QUAD_BLOCKS_PER_SM;
 constexpr int k_warps_per_block = k_block_threads / 32;
 
+/// System-scope arrival counter on memory that may belong to another GPU (relaxed; the fences around it order).
+__device__ __forceinline__ unsigned int atomic_add_system(unsigned int* p, unsigned int v) {
+#if defined(QUASI_HOST_EMULATION)
+    return std::atomic_ref<unsigned int>(*p).fetch_add(v);
+#else
+    return atomicAdd_system(p, v);
+#endif
+}
+/// A float4 another GPU may have written a moment ago: not from this SM's L1.
+__device__ __forceinline__ float4 load_uncached(const float4* p) {
+#if defined(QUASI_HOST_EMULATION)
+    return *p;
+#else
+    return __ldcv(p);
+#endif
+}
+
 // ------------------------------------------------------------------------------------------------
 // Path state lives in per-warp queues in shared memory; every warp iteration is ONE kind of work
 // for 32 paths.
@@ -255,7 +272,7 @@ constexpr uint32_t k_tile_slots = 16;      // Batch: tiles a warp may hold at on
 constexpr uint32_t k_queue_words = k_bq_fields * k_bq + 2 * k_pq + 2 * k_tile_slots;  // per warp
 constexpr size_t k_wavefront_smem = static_cast<size_t>(k_warps_per_block) * k_queue_words * sizeof(uint32_t);
 
-template <int NQ, class Layout, bool Batch = false>
+template <int NQ, class Layout, bool Batch = false, bool Reduce = false>
 __global__ void __launch_bounds__(k_block_threads, k_blocks_per_sm)
 pathtrace_accumulate_kernel(const __grid_constant__ scene_params scene, const __grid_constant__ frame_params frame,
                            const __grid_constant__ batch_params launch, float4* __restrict__ beauty,
@@ -537,19 +554,68 @@ pathtrace_accumulate_kernel(const __grid_constant__ scene_params scene, const __
                         tile_y++;
                     }
                     const uint32_t px = tile_x * 8u + (lane & 7u), py = tile_y * 4u + (lane >> 3);
-                    if (px < frame.width && py < frame.height) {
-                        const uint32_t pixel = py * frame.width + px;
-                        const float4* const layers[4] = {beauty, albedo, normal, depth};
+                    const bool inside = px < frame.width && py < frame.height;
+                    const uint32_t pixel = py * frame.width + px;
+                    const float4* const layers[4] = {beauty, albedo, normal, depth};
+                    auto slice_of = [&launch](uint32_t i) {  // slice_lo[s] <= i < slice_lo[s + 1]
+                        uint32_t at = 0;
+                        while (at + 1u < launch.export_slices && i >= launch.slice_lo[at + 1u]) at++;
+                        return at;
+                    };
+                    if (inside) {
 #pragma unroll
                         for (uint32_t l = 0; l < 4u; l++) {
                             const uint32_t i = l * n_px + pixel;
-                            uint32_t slice = __umulhi(i, launch.export_per_magic);
-                            uint32_t within = i - slice * launch.export_per;
-                            if (within >= launch.export_per) {
-                                within -= launch.export_per;
-                                slice++;
+                            const uint32_t slice = slice_of(i);
+                            static_cast<float4*>(launch.export_base[slice])[i - launch.slice_lo[slice]] = layers[l][pixel];
+                        }
+                    }
+                    if constexpr (Reduce) {
+                        // Fused reduce (batch_params): the four units of this tile have been stored at their owners;
+                        // lanes 0..3 report the arrival of layer `lane` (fence, then the counter: the barrier before
+                        // them makes the fence cover every lane's stores), and where this warp's arrival is the G-th,
+                        // it sums the unit's G copies in rank order and stores the finished unit.
+                        __syncwarp();
+                        const uint32_t first_pixel = tile_y * 4u * frame.width + tile_x * 8u;  // always inside the image
+                        uint32_t unit_slice = 0, arrivals = 0;
+                        if (lane < 4u) {
+                            __threadfence_system();
+                            unit_slice = slice_of(lane * n_px + first_pixel);
+                            arrivals = atomic_add_system(launch.reduce_counters[unit_slice] + lane * n_tiles + done_tile, 1u) + 1u;
+                            if (arrivals % launch.reduce_ranks == 0u) __threadfence_system();  // the other ranks' copies are visible from here on
+                        }
+                        uint32_t m_last = __ballot_sync(0xffffffffu, lane < 4u && arrivals % launch.reduce_ranks == 0u);
+                        while (m_last != 0u) {
+                            const uint32_t l = static_cast<uint32_t>(__ffs(static_cast<int>(m_last))) - 1u;
+                            m_last &= m_last - 1u;
+                            const uint32_t slice = __shfl_sync(0xffffffffu, unit_slice, static_cast<int>(l));
+                            if (inside) {
+                                const uint32_t within = l * n_px + pixel - launch.slice_lo[slice];
+                                const float4* copy = static_cast<const float4*>(launch.reduce_staging[slice]) + within;
+                                float4 sum = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                                for (uint32_t g0 = 0; g0 < launch.reduce_ranks; g0 += 4u) {  // four round trips in flight
+                                    float4 v[4];
+#pragma unroll
+                                    for (uint32_t j = 0; j < 4u; j++) {
+                                        if (g0 + j < launch.reduce_ranks) v[j] = load_uncached(copy + static_cast<size_t>(g0 + j) * launch.reduce_slot_stride);
+                                    }
+#pragma unroll
+                                    for (uint32_t j = 0; j < 4u; j++) {
+                                        if (g0 + j < launch.reduce_ranks) {
+                                            if (g0 + j == 0u) {
+                                                sum = v[0];  // (not 0 + v: -0 stays -0, as in the oracle's combine)
+                                            } else {
+                                                sum.x = sum.x + v[j].x;
+                                                sum.y = sum.y + v[j].y;
+                                                sum.z = sum.z + v[j].z;
+                                                sum.w = sum.w + v[j].w;
+                                            }
+                                        }
+                                    }
+                                }
+                                const float k = launch.reduce_scale;
+                                static_cast<float4*>(launch.reduce_out[slice])[within] = make_float4(sum.x * k, sum.y * k, sum.z * k, sum.w * k);
                             }
-                            static_cast<float4*>(launch.export_base[slice])[within] = layers[l][pixel];
                         }
                     }
                 }
@@ -599,21 +665,25 @@ cudaError_t launch_pathtrace_accumulate(const scene_params& scene, const frame_p
     auto* n = reinterpret_cast<float4*>(layers[2]);
     auto* d = reinterpret_cast<float4*>(layers[3]);
     const bool batched = frame.batch_samples > 1u;
+    const bool reduce = batched && launch.reduce_ranks > 1u;  // (the fused multi-GPU reduce is an instantiation of its own)
     auto run = [&](auto kernel) {
         kernel<<<blocks, k_block_threads, k_wavefront_smem, stream>>>(scene, frame, launch, b, a, n, d, ray_counter,
                                                                      tile_counters);
         return cudaGetLastError();
     };
     if (!generic_scan && cornell_layout::matches(scene)) {
-        return batched ? run(pathtrace_accumulate_kernel<16, cornell_layout, true>)
-                       : run(pathtrace_accumulate_kernel<16, cornell_layout, false>);
+        return reduce    ? run(pathtrace_accumulate_kernel<16, cornell_layout, true, true>)
+               : batched ? run(pathtrace_accumulate_kernel<16, cornell_layout, true>)
+                         : run(pathtrace_accumulate_kernel<16, cornell_layout, false>);
     }
     if (!generic_scan && cornell_quads_layout::matches(scene)) {
-        return batched ? run(pathtrace_accumulate_kernel<16, cornell_quads_layout, true>)
-                       : run(pathtrace_accumulate_kernel<16, cornell_quads_layout, false>);
+        return reduce    ? run(pathtrace_accumulate_kernel<16, cornell_quads_layout, true, true>)
+               : batched ? run(pathtrace_accumulate_kernel<16, cornell_quads_layout, true>)
+                         : run(pathtrace_accumulate_kernel<16, cornell_quads_layout, false>);
     }
-    return batched ? run(pathtrace_accumulate_kernel<32, dynamic_layout, true>)
-                   : run(pathtrace_accumulate_kernel<32, dynamic_layout, false>);
+    return reduce    ? run(pathtrace_accumulate_kernel<32, dynamic_layout, true, true>)
+           : batched ? run(pathtrace_accumulate_kernel<32, dynamic_layout, true>)
+                     : run(pathtrace_accumulate_kernel<32, dynamic_layout, false>);
 }
 
 }  // namespace Q::cuda

@@ -139,6 +139,9 @@ struct plugin_state {
     // block to the GPU that owns it (peer memory) instead; takes the place of the mirror while set.
     bool external_export = false;
     Q_cuda_export_table export_table{};
+    bool external_reduce = false;  ///< Q_cuda_plugin_set_reduce: the export with the multi-GPU reduce fused in
+    Q_cuda_reduce_table reduce_table{};
+    uint32_t reduce_calls_seen = 0;  ///< render calls since Q_cuda_plugin_set_reduce (reduce_table.render_calls)
     bool last_launch_exported = false;  ///< the most recent launch sent every tile of the layers to the export target
     uint32_t pending = 0;              ///< render calls collected and not yet launched
     uint32_t pending_first_sample = 0; ///< frame_count of the first of them
@@ -441,6 +444,17 @@ void drop_mirror(plugin_state* state) {
 /// call may no longer exist (a host may create one per frame). Either way it is ordered after the previous launch.
 /// If the launch cannot be made, the collected calls are taken back (frame_count and the path statistic), so that
 /// the samples that follow carry the weights of what is really in the layers.
+/// Whether a fused-reduce table (Q_cuda_plugin_set_reduce) was cut for this viewport: the slices cover the four
+/// layers and each starts on a row of tiles of one layer, so that a tile's 32 pixels in a layer have one owner.
+bool reduce_table_fits(const Q_cuda_reduce_table& t, uint32_t width, uint32_t height) {
+    if (width == 0 || height == 0 || t.slice_lo[t.ranks] != 4ull * width * height) return false;
+    for (uint32_t i = 0; i < t.ranks; i++) {
+        const uint32_t lo = t.slice_lo[i];
+        if (lo % width != 0 || ((lo / width) % height) % 4 != 0) return false;
+    }
+    return true;
+}
+
 void flush_pending(plugin_state* state, cudaStream_t stream = nullptr) {
     if (state->pending == 0) return;
     const Q_render_frame& f = state->pending_frame;
@@ -463,15 +477,34 @@ void flush_pending(plugin_state* state, cudaStream_t stream = nullptr) {
     bool mirrored = false;
     if (collected > 1u) {
         const uint64_t n_px = static_cast<uint64_t>(f.width) * f.height;
-        if (state->external_export) {
+        const uint32_t total = static_cast<uint32_t>(4 * n_px);
+        if (state->external_reduce && state->reduce_calls_seen < state->reduce_table.render_calls) {
+            // not the frame's last launch: its tiles are not final, nothing is exported and nothing arrives
+        } else if (state->external_reduce && n_px < (uint64_t{1} << 30) && reduce_table_fits(state->reduce_table, f.width, f.height)) {
+            const Q_cuda_reduce_table& t = state->reduce_table;
+            launch.export_slices = t.ranks;
+            launch.reduce_ranks = t.ranks;
+            launch.reduce_slot_stride = t.slot_stride;
+            launch.reduce_scale = 1.0f / static_cast<float>(t.ranks);
+            for (uint32_t i = 0; i <= t.ranks; i++) launch.slice_lo[i] = t.slice_lo[i];
+            for (uint32_t i = 0; i < t.ranks; i++) {
+                launch.reduce_staging[i] = t.staging[i];
+                launch.reduce_counters[i] = t.counters[i];
+                launch.reduce_out[i] = t.out[i];
+                launch.export_base[i] = static_cast<float4*>(t.staging[i]) + static_cast<size_t>(t.rank) * t.slot_stride;
+            }
+        } else if (state->external_export && n_px < (uint64_t{1} << 30)) {
             const Q_cuda_export_table& t = state->export_table;
             if (t.slices != 0) {  // (a table of no slices: nothing leaves the GPU during the launch)
                 launch.export_slices = t.slices;
-                launch.export_per = t.float4_per_slice;
-                launch.export_per_magic = static_cast<uint32_t>((uint64_t{1} << 32) / t.float4_per_slice);
-                for (uint32_t i = 0; i < t.slices; i++) launch.export_base[i] = t.base[i];
+                for (uint32_t i = 0; i < t.slices; i++) {
+                    launch.export_base[i] = t.base[i];
+                    const uint64_t lo = static_cast<uint64_t>(i) * t.float4_per_slice;
+                    launch.slice_lo[i] = lo < total ? static_cast<uint32_t>(lo) : total;
+                }
+                launch.slice_lo[t.slices] = total;
             }
-        } else if (state->mirror_enabled && n_px < (uint64_t{1} << 30)) {
+        } else if (state->mirror_enabled && !state->external_export && !state->external_reduce && n_px < (uint64_t{1} << 30)) {
             const size_t bytes = static_cast<size_t>(n_px) * 4 * sizeof(float);
             bool have = true;
             for (int i = 0; i < Q_AOV_COUNT && have; i++) {
@@ -481,9 +514,11 @@ void flush_pending(plugin_state* state, cudaStream_t stream = nullptr) {
             }
             if (have) {  // one slice per layer
                 launch.export_slices = Q_AOV_COUNT;
-                launch.export_per = static_cast<uint32_t>(n_px);
-                launch.export_per_magic = static_cast<uint32_t>((uint64_t{1} << 32) / n_px);
-                for (int i = 0; i < Q_AOV_COUNT; i++) launch.export_base[i] = state->mirror[i];
+                for (int i = 0; i < Q_AOV_COUNT; i++) {
+                    launch.export_base[i] = state->mirror[i];
+                    launch.slice_lo[i] = static_cast<uint32_t>(i * n_px);
+                }
+                launch.slice_lo[Q_AOV_COUNT] = total;
                 mirrored = true;
             }
         }
@@ -526,6 +561,7 @@ void render_batched(plugin_state* state, const Q_render_frame* frame) {
     }
     state->pending_frame.command_buffer = frame->command_buffer;
     state->pending++;
+    state->reduce_calls_seen++;
     state->paths += static_cast<uint64_t>(frame->width) * frame->height;
     state->frame_count++;
     if (state->pending >= state->batch) flush_pending(state, stream);
@@ -881,7 +917,38 @@ Q_PLUGIN_EXPORT int Q_cuda_plugin_set_export(Q_plugin_handle* handle, const Q_cu
     }
     flush_pending(state);  // what has been collected goes where it was meant to go
     state->external_export = table != nullptr;
-    if (table != nullptr) state->export_table = *table;
+    if (table != nullptr) {
+        state->export_table = *table;
+        state->external_reduce = false;
+    }
+    state->mirror_valid = false;
+    return 0;
+}
+
+Q_PLUGIN_EXPORT int Q_cuda_plugin_set_reduce(Q_plugin_handle* handle, const Q_cuda_reduce_table* table) {
+    if (!handle) return -1;
+    auto* state = reinterpret_cast<plugin_state*>(handle);
+    if (cudaSetDevice(state->device) != cudaSuccess) return -1;
+    if (table != nullptr) {
+        if (table->struct_size < sizeof(Q_cuda_reduce_table) || table->ranks < 2 || table->ranks > Q_CUDA_MAX_EXPORT_SLICES ||
+            table->rank >= table->ranks || table->slice_lo[0] != 0) {
+            return -1;
+        }
+        for (uint32_t i = 0; i < table->ranks; i++) {
+            const uint32_t lo = table->slice_lo[i], hi = table->slice_lo[i + 1];
+            if (table->staging[i] == nullptr || table->counters[i] == nullptr || table->out[i] == nullptr || hi < lo ||
+                hi - lo > table->slot_stride) {
+                return -1;
+            }
+        }
+    }
+    flush_pending(state);  // what has been collected goes where it was meant to go
+    state->external_reduce = table != nullptr;
+    state->reduce_calls_seen = 0;
+    if (table != nullptr) {
+        state->reduce_table = *table;
+        state->external_export = false;
+    }
     state->mirror_valid = false;
     return 0;
 }
@@ -934,8 +1001,31 @@ Q_PLUGIN_EXPORT int Q_cuda_combine_shards(const float* const* shards, uint32_t n
 
 Q_PLUGIN_EXPORT int Q_cuda_push_slices(const float* block, uint64_t n_float4, const Q_cuda_export_table* table,
                                        void* stream) {
-    if (!block || !table || table->struct_size < sizeof(Q_cuda_export_table)) return -1;
-    return Q::cuda::launch_push_slices(block, n_float4, table->base, table->slices, table->float4_per_slice,
+    if (!block || !table || table->struct_size < sizeof(Q_cuda_export_table) || table->slices == 0 ||
+        table->slices > Q_CUDA_MAX_EXPORT_SLICES || table->float4_per_slice == 0 || n_float4 >= (uint64_t{1} << 32)) {
+        return -1;
+    }
+    uint32_t slice_lo[Q_CUDA_MAX_EXPORT_SLICES + 1];
+    for (uint32_t i = 0; i <= table->slices; i++) {
+        const uint64_t lo = static_cast<uint64_t>(i) * table->float4_per_slice;
+        slice_lo[i] = lo < n_float4 && i < table->slices ? static_cast<uint32_t>(lo) : static_cast<uint32_t>(n_float4);
+    }
+    return Q::cuda::launch_push_slices(block, n_float4, table->base, slice_lo, table->slices,
+                                       static_cast<cudaStream_t>(stream)) == cudaSuccess ? 0 : -1;
+}
+
+Q_PLUGIN_EXPORT int Q_cuda_push_slices_reduce(const float* block, uint64_t n_float4, const Q_cuda_reduce_table* table,
+                                              void* stream) {
+    if (!block || !table || table->struct_size < sizeof(Q_cuda_reduce_table) || table->ranks < 2 ||
+        table->ranks > Q_CUDA_MAX_EXPORT_SLICES || table->rank >= table->ranks) {
+        return -1;
+    }
+    void* base[Q_CUDA_MAX_EXPORT_SLICES];
+    for (uint32_t i = 0; i < table->ranks; i++) {
+        if (table->staging[i] == nullptr) return -1;
+        base[i] = static_cast<float4*>(table->staging[i]) + static_cast<size_t>(table->rank) * table->slot_stride;
+    }
+    return Q::cuda::launch_push_slices(block, n_float4, base, table->slice_lo, table->ranks,
                                        static_cast<cudaStream_t>(stream)) == cudaSuccess ? 0 : -1;
 }
 

@@ -171,24 +171,21 @@ __device__ __forceinline__ void wait_epoch(const uint32_t* p, uint32_t epoch) {
 
 struct export_list {
     float4* base[k_max_export_slices];
+    uint32_t slice_lo[k_max_export_slices + 1];
+    uint32_t slices;
 };
 
 /// The layer block of this GPU, slice by slice, to where batch_params' export would have sent it
 /// (scene_params.hpp): for frames whose last launch was not a batched one (a launch of one sample
 /// exports nothing). Reads HBM once, writes over NVLink (or PCIe) with 16-byte stores.
 __global__ void __launch_bounds__(k_threads)
-push_slices_kernel(const float4* __restrict__ block, const __grid_constant__ export_list to, uint32_t per,
-                   uint32_t per_magic, uint64_t n) {
+push_slices_kernel(const float4* __restrict__ block, const __grid_constant__ export_list to, uint64_t n) {
     const uint64_t stride = static_cast<uint64_t>(gridDim.x) * k_threads;
     for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * k_threads + threadIdx.x; i < n; i += stride) {
         const uint32_t index = static_cast<uint32_t>(i);
-        uint32_t slice = __umulhi(index, per_magic);
-        uint32_t within = index - slice * per;
-        if (within >= per) {
-            within -= per;
-            slice++;
-        }
-        to.base[slice][within] = ld_stream(block + i);
+        uint32_t slice = 0;
+        while (slice + 1u < to.slices && index >= to.slice_lo[slice + 1u]) slice++;
+        to.base[slice][index - to.slice_lo[slice]] = ld_stream(block + i);
     }
 }
 
@@ -277,21 +274,22 @@ cudaError_t launch_combine_shards(const float* const* shards, uint32_t n_shards,
 
 namespace Q::cuda {
 
-cudaError_t launch_push_slices(const float* block, uint64_t n_float4, void* const* base, uint32_t slices,
-                               uint32_t float4_per_slice, cudaStream_t stream) {
-    if (slices == 0 || slices > k_max_export_slices || float4_per_slice == 0 || n_float4 >= (uint64_t{1} << 32) ||
-        n_float4 > static_cast<uint64_t>(slices) * float4_per_slice) {
+cudaError_t launch_push_slices(const float* block, uint64_t n_float4, void* const* base, const uint32_t* slice_lo,
+                               uint32_t slices, cudaStream_t stream) {
+    if (slices == 0 || slices > k_max_export_slices || n_float4 >= (uint64_t{1} << 32) || slice_lo[0] != 0 ||
+        slice_lo[slices] < n_float4) {
         return cudaErrorInvalidValue;
     }
     if (n_float4 == 0) return cudaSuccess;
     export_list to{};
+    to.slices = slices;
     for (uint32_t g = 0; g < slices; g++) {
-        if (base[g] == nullptr) return cudaErrorInvalidValue;
+        if (base[g] == nullptr || slice_lo[g + 1] < slice_lo[g]) return cudaErrorInvalidValue;
         to.base[g] = static_cast<float4*>(base[g]);
+        to.slice_lo[g] = slice_lo[g];
     }
-    push_slices_kernel<<<grid_for(n_float4), k_threads, 0, stream>>>(
-        reinterpret_cast<const float4*>(block), to, float4_per_slice,
-        static_cast<uint32_t>((uint64_t{1} << 32) / float4_per_slice), n_float4);
+    to.slice_lo[slices] = slice_lo[slices];
+    push_slices_kernel<<<grid_for(n_float4), k_threads, 0, stream>>>(reinterpret_cast<const float4*>(block), to, n_float4);
     return cudaGetLastError();
 }
 

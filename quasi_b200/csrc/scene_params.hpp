@@ -170,15 +170,29 @@ struct alignas(16) frame_params {
 /// time: into pinned host memory (the frame is on the host when the launch ends: plugin.cu, readback) or
 /// into other GPUs' memory over NVLink (multi-GPU: each rank pushes every slice of its layers to the
 /// slice's owner while it renders). The block of 4 * width * height float4 is cut into `export_slices`
-/// slices of `export_per` float4 (the last one shorter); float4 i goes to
-/// export_base[i / export_per] + (i % export_per). 0 slices: nothing is exported.
+/// slices, slice s being the float4 [slice_lo[s], slice_lo[s + 1]); float4 i of slice s goes to
+/// export_base[s] + (i - slice_lo[s]). 0 slices: nothing is exported.
+///
+/// Fused reduce (`reduce_ranks` = G > 1; multi-GPU): export_base[s] is this rank's slot in the staging area of
+/// the GPU that owns slice s, and the slices are cut along rows of tiles, so that the 32 pixels of a tile in one
+/// layer (a unit) have one owner. After storing a unit a warp adds one to the unit's arrival counter at the owner
+/// (system-scope atomic on peer memory, after a system-scope fence); the warp whose arrival is the G-th, on
+/// whichever GPU it runs, loads the G staged copies of the unit, sums them IN RANK ORDER, scales by 1/G and stores
+/// the unit of the finished frame to reduce_out[s] + (i - slice_lo[s]) (s the unit's slice: pinned host memory
+/// every GPU has mapped, or the owner's device memory). The reduce and the frame's way to the host are then part
+/// of the render as well: what is left after the last rank's launch is its last tiles. The counters are never reset: a unit of one staging buffer receives exactly G arrivals per
+/// frame that uses the buffer, so the G-th is the one that makes the count a multiple of G.
 inline constexpr uint32_t k_max_export_slices = 16;
 struct alignas(16) batch_params {
     void* export_base[k_max_export_slices];
+    uint32_t slice_lo[k_max_export_slices + 1];
     uint32_t export_slices;
-    uint32_t export_per;
-    uint32_t export_per_magic;  ///< floor(2^32 / export_per)
-    uint32_t reserved;
+    uint32_t reduce_ranks;         ///< G; 0 or 1: no fused reduce
+    uint32_t reduce_slot_stride;   ///< float4 between the slots of two ranks in a staging area
+    float reduce_scale;            ///< 1 / G
+    void* reduce_staging[k_max_export_slices];             ///< slice s: slot 0 of its owner's staging area
+    unsigned int* reduce_counters[k_max_export_slices];    ///< slice s: its owner's arrival counters, [layer * n_tiles + tile]
+    void* reduce_out[k_max_export_slices];                 ///< slice s: where float4 slice_lo[s] of the finished frame goes
 };
 
 /// The scene as the host describes it: the same 12+8 floats per quad the Metal

@@ -152,6 +152,8 @@ class loader:
             "Q_cuda_combine_shards": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint32, C.c_uint64,
                                                 C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
             "Q_cuda_plugin_set_export": (C.c_int, [C.c_void_p, C.POINTER(abi.Q_cuda_export_table)]),
+            "Q_cuda_plugin_set_reduce": (C.c_int, [C.c_void_p, C.POINTER(abi.Q_cuda_reduce_table)]),
+            "Q_cuda_push_slices_reduce": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(abi.Q_cuda_reduce_table), C.c_void_p]),
             "Q_cuda_plugin_flush": (C.c_int, [C.c_void_p, C.c_void_p]),
             "Q_cuda_push_slices": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(abi.Q_cuda_export_table), C.c_void_p]),
             "Q_cuda_reduce_slices_sync": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p), C.c_uint32, C.c_uint32,

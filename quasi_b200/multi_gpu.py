@@ -21,6 +21,15 @@ means) * (1/N). Two implementations of that exchange:
         instead of through rank 0's. No host barrier, no staging copy, no NCCL, and unlike
         NCCL's ring/tree the summation order is fixed: the result is bit-identical to the
         oracle's rank-ordered combine.
+  fused the whole exchange inside the render kernel (Q_cuda_plugin_set_reduce). Slices are cut along rows of
+        8x4 tiles, so that a tile's 32 pixels in one layer (a unit) have one owner. A warp that has stored a
+        finished tile at the owners adds one to the units' arrival counters there (system-scope atomics over
+        NVLink); the warp whose arrival is the N-th for a unit, on whichever GPU it runs, loads the N staged
+        copies, sums them in rank order, scales and stores the unit into the shared host frame. The reduce and
+        the frame's way to the host overlap the render of every rank; what follows the render is only a
+        device-side barrier (so that a staging buffer is not reused while a peer still reads it). Bit-identical
+        to the oracle's combine like `push`. A frame whose last launch is a single sample falls back to
+        push + reduce with the same buffers.
   nccl  torch.distributed.reduce(SUM) of a copy of the block to rank 0 on the frame
         stream, the 1/N scale kernel on rank 0, then rank 0 copies the frame to the
         host. The baseline.
@@ -46,6 +55,19 @@ def slice_bounds(total: int, world: int, rank: int):
     per = (total + world - 1) // world
     lo = min(total, rank * per)
     return lo, min(total, lo + per)
+
+
+def tile_row_slices(width: int, height: int, world: int):
+    """slice_lo[0..world] of the fused exchange: the 4-layer block (float4 index = (layer * height + y) * width + x)
+    cut into `world` slices along rows of 8x4 tiles, as even as that allows (4 * ceil(height / 4) rows of tiles
+    over the four layers; slice s starts at row ceil(s * rows / world))."""
+    tiles_y = (height + 3) // 4
+    rows = 4 * tiles_y
+    lo = []
+    for s in range(world + 1):
+        row = -(-s * rows // world)
+        lo.append(4 * width * height if s == world else ((row // tiles_y) * height + (row % tiles_y) * 4) * width)
+    return lo
 
 
 def reduce_mean_to_root(tensor, dist, world: int, dst: int = 0):
@@ -146,7 +168,7 @@ class shard_exchange:
 
         self.host_path = host_path or os.environ.get("QUASI_EXCHANGE_HOST_PATH", "dma")
 
-        if mode not in ("push", "nccl"):
+        if mode not in ("push", "fused", "nccl"):
             raise ValueError(mode)
         self.torch, self.host, self.dist, self.mode = torch, host, dist, mode
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
@@ -166,6 +188,8 @@ class shard_exchange:
         self.frame = None
         if mode == "push":
             self._setup_push()
+        elif mode == "fused":
+            self._setup_fused()
         else:
             self._setup_nccl()
 
@@ -234,11 +258,67 @@ class shard_exchange:
             raise RuntimeError("Q_cuda_host_register(frame) failed")
         self.frame_device_ptr = dev.value
 
+    def _setup_fused(self):
+        w, h = self.host.context.width, self.host.context.height
+        self.slice_lo = tile_row_slices(w, h, self.world)
+        self.lo, self.hi = self.slice_lo[self.rank], self.slice_lo[self.rank + 1]
+        self.per = max(1, max(b - a for a, b in zip(self.slice_lo, self.slice_lo[1:])))  # slot stride, float4
+        slot_bytes = self.per * 16
+        n_tiles = ((w + 7) // 8) * ((h + 3) // 4)
+        counter_bytes = 4 * n_tiles * 4
+        self.staging = self._alloc(2 * self.world * slot_bytes)
+        self.counters = self._alloc(2 * counter_bytes)
+        self.device_slice = self._alloc(slot_bytes)  # begin_frame(to_host=False): the finished slice stays on its owner
+        self.flags = self._alloc(256)
+        for ptr, n in ((self.flags, 256), (self.counters, 2 * counter_bytes)):
+            if self.fn("Q_cuda_memset_async")(ptr, 0, n, self.stream.cuda_stream) != 0:
+                raise RuntimeError("Q_cuda_memset_async failed")
+        self.stream.synchronize()
+        gathered = [None] * self.world
+        self.dist.all_gather_object(gathered, tuple(self._export(p) for p in (self.staging, self.counters, self.flags,
+                                                                              self.device_slice)))
+        mapped = []
+        for g, handles in enumerate(gathered):
+            own = (self.staging, self.counters, self.flags, self.device_slice)
+            mapped.append(own if g == self.rank else tuple(self._open(x) for x in handles))
+        self.staging_ptrs = [m[0] for m in mapped]
+        self.flag_ptrs = [m[2] for m in mapped]
+        self.frame = host_frame(self.dist, self.total_float4 * 4)
+        dev = C.c_void_p()
+        if self.fn("Q_cuda_host_register")(self.frame.address, self.frame.data_bytes, C.byref(dev)) != 0:
+            raise RuntimeError("Q_cuda_host_register(frame) failed")
+        self.frame_device_ptr = dev.value
+        self.reduce_tables = {}
+        for parity in range(2):
+            for to_host in (False, True):
+                t = abi.Q_cuda_reduce_table()
+                t.struct_size = C.sizeof(abi.Q_cuda_reduce_table)
+                t.ranks, t.rank, t.slot_stride = self.world, self.rank, self.per
+                for s in range(self.world + 1):
+                    t.slice_lo[s] = self.slice_lo[s]
+                for s in range(self.world):
+                    t.staging[s] = mapped[s][0] + parity * self.world * slot_bytes
+                    t.counters[s] = mapped[s][1] + parity * counter_bytes
+                    t.out[s] = self.frame_device_ptr + self.slice_lo[s] * 16 if to_host else mapped[s][3]
+                self.reduce_tables[parity, to_host] = t
+
     # ---- per frame ----
-    def begin_frame(self):
-        """Before the frame's first render call: from here on the batched launches push their tiles."""
+    def begin_frame(self, to_host: bool = True, render_calls: int = 0):
+        """Before the frame's first render call: from here on the batched launches push their tiles. Fused mode,
+        where the frame leaves during the render: `to_host`, whether the finished frame goes to the shared host
+        frame or stays on the GPUs, slice by slice (see combine); `render_calls`, how many render calls the frame
+        will make on every rank (needed when they may not fit one batched launch: only the last launch exports)."""
         self.epoch += 1
-        if self.mode == "push":
+        if self.mode == "fused":
+            self._to_host = to_host
+            if to_host and self._handed_out:
+                self.frame.wait_consumed(self._handed_out)  # the segment still holds a frame rank 0 is looking at
+                self._handed_out = 0
+            table = self.reduce_tables[self.epoch & 1, to_host]
+            table.render_calls = render_calls
+            rc = self.fn("Q_cuda_plugin_set_reduce")(self.handle, C.byref(table))
+            assert rc == 0
+        elif self.mode == "push":
             rc = self.fn("Q_cuda_plugin_set_export")(self.handle, C.byref(self.tables[self.epoch & 1]))
             assert rc == 0
         elif self.epoch == 1:
@@ -256,6 +336,8 @@ class shard_exchange:
         host frame, which finish_frame() then waits for."""
         if self.mode == "nccl":
             return self._combine_nccl()
+        if self.mode == "fused":
+            return self._combine_fused()
         slot_bytes = self.per * 16
         exported = self.fn("Q_cuda_plugin_flush")(self.handle, self.stream.cuda_stream)
         assert exported >= 0
@@ -280,6 +362,30 @@ class shard_exchange:
             rc = self.fn("Q_cuda_memcpy_async")(self.frame.address + self.lo * 16, self.device_slice,
                                                 (self.hi - self.lo) * 16, self.stream.cuda_stream)
             assert rc == 0
+
+    def _combine_fused(self):
+        """The frame was reduced, and sent where it is wanted, by the render launches themselves; what is enqueued here
+        is the device-side barrier between frames (Q_cuda_reduce_slices_sync over no elements: arrive, wait for every
+        rank), which keeps frame e + 2 out of the staging buffer and counters of frame e while a peer's launch of
+        frame e may still read them. A frame whose last launch exported nothing (a single sample) goes the `push`
+        way instead, with the same staging buffer: Q_cuda_push_slices_reduce, then the reduce proper."""
+        table = self.reduce_tables[self.epoch & 1, self._to_host]
+        exported = self.fn("Q_cuda_plugin_flush")(self.handle, self.stream.cuda_stream)
+        assert exported >= 0
+        flags = (C.c_void_p * self.world)(*self.flag_ptrs)
+        mine = self.staging + (self.epoch & 1) * self.world * self.per * 16
+        n = 0
+        if exported == 0:
+            rc = self.fn("Q_cuda_push_slices_reduce")(self._layer_block(), self.total_float4, C.byref(table),
+                                                      self.stream.cuda_stream)
+            assert rc == 0
+            self.launches += 1
+            n = self.hi - self.lo
+        out = self.frame_device_ptr + self.lo * 16 if self._to_host else self.device_slice
+        rc = self.fn("Q_cuda_reduce_slices_sync")(mine, self.per, flags, self.world, self.rank, self.epoch, n, 0.0, out,
+                                                  self.stream.cuda_stream)
+        assert rc == 0
+        self.launches += 1
 
     def _combine_nccl(self):
         torch, dist = self.torch, self.dist
@@ -315,7 +421,7 @@ class shard_exchange:
 
     def release_frame(self):
         """Rank 0 is done with what finish_frame returned."""
-        if self.mode == "push" and self.rank == 0:
+        if self.mode in ("push", "fused") and self.rank == 0:
             self.frame.consumed(self.epoch)
 
     def result_numpy(self):
@@ -330,14 +436,17 @@ class shard_exchange:
 
     def close(self):
         self.fn("Q_cuda_plugin_set_export")(self.handle, None)
-        if self.mode == "push":
+        if self.mode == "fused":
+            self.fn("Q_cuda_plugin_set_reduce")(self.handle, None)
+        peer = self.mode in ("push", "fused")
+        if peer:
             self.stream.synchronize()
             self.fn("Q_cuda_host_unregister")(self.frame.address)
             self.dist.barrier()  # nobody still pushes into, or waits on, memory that is about to go
         for p in self._opened:
             self.fn("Q_cuda_ipc_close")(p)
         self._opened = []
-        if self.mode == "push":
+        if peer:
             self.dist.barrier()
         for p in self._own:
             self.fn("Q_cuda_free")(p)

@@ -156,6 +156,7 @@ inline T __ldg(const T* p) { return *p; }
 template <class T>
 inline T __ldcg(const T* p) { return *p; }
 inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 inline void __threadfence_block() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 inline unsigned atomicAdd(unsigned* p, unsigned v) { return std::atomic_ref<unsigned>(*p).fetch_add(v); }
 inline unsigned atomicSub(unsigned* p, unsigned v) { return std::atomic_ref<unsigned>(*p).fetch_sub(v); }

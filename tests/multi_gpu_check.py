@@ -7,7 +7,8 @@
 Each rank renders its sample shard through the plugin C ABI; the shards are combined by the
 push exchange (quasi_b200/multi_gpu.py: tiles pushed to the slice owners by the batched render
 kernel, one local reduce kernel per rank, the frame landing in host memory shared by all ranks)
-and by NCCL. Rank 0 checks: every shard bit-exact against the oracle; the push result bit-exact
+by the fused exchange (the reduce inside the render kernel: arrival counters at the owners, the last
+arrival sums) and by NCCL. Rank 0 checks: every shard bit-exact against the oracle; the push result bit-exact
 against the oracle's rank-ordered combine, with batched launches (export fused into the render),
 with one launch per sample (Q_cuda_push_slices after the fact), and over back-to-back frames of
 different length with no host synchronisation in between; the NCCL result within float tolerance,
@@ -96,6 +97,23 @@ def main():
         check(f"push, {label}, one-sample frame", exchange.result_numpy(), 1)
         exchange.close()
 
+        # the exchange fused into the render kernel: staged tiles counted at their owners, the last arrival reduces
+        exchange = shard_exchange(host, dist, mode="fused")
+        exchange.begin_frame(render_calls=5)
+        render(host, 5)
+        exchange.combine()
+        check(f"fused, {label}", exchange.result_numpy(), 5)
+        for samples in (3, 7, 2, 5):  # back to back: the device-side barrier alone keeps a buffer from early reuse
+            exchange.begin_frame(to_host=samples == 5, render_calls=samples)
+            render(host, samples)
+            exchange.combine()
+        check(f"fused, {label}, after four unsynchronised frames", exchange.result_numpy(), 5)
+        exchange.begin_frame(render_calls=1)
+        render(host, 1)  # nothing is exported by a single-sample launch: push + reduce with the same buffers
+        exchange.combine()
+        check(f"fused, {label}, one-sample frame", exchange.result_numpy(), 1)
+        exchange.close()
+
         exchange = shard_exchange(host, dist, mode="nccl")
         exchange.begin_frame()
         render(host, 5)
@@ -106,6 +124,24 @@ def main():
             failures.append(f"nccl, {label}: rank {rank}'s own layers changed under the combine")
         exchange.close()
         host.close()
+
+    # a frame of several launches (5 calls, 2 per launch, then 1): only the launch with the frame's last call may
+    # export; here that is a single-sample launch, so the frame falls back to push + reduce. And 6 calls, 3 per
+    # launch: the second launch alone exports and reduces.
+    host = headless_host(w, h, device_ordinal=local, shard_index=rank, shard_count=world, single_stream=True,
+                         env={"QUASI_CUDA_BATCH": 2})
+    exchange = shard_exchange(host, dist, mode="fused")
+    for samples in (5, 2, 5):
+        exchange.begin_frame(render_calls=samples)
+        render(host, samples)
+        exchange.combine()
+    check("fused, frames of several launches (batch 2)", exchange.result_numpy(), 5)
+    exchange.begin_frame(render_calls=2)
+    render(host, 2)
+    exchange.combine()
+    check("fused, batch 2, a frame of one launch after them", exchange.result_numpy(), 2)
+    exchange.close()
+    host.close()
 
     all_failures = [None] * world
     dist.all_gather_object(all_failures, failures)

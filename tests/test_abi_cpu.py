@@ -30,7 +30,7 @@ def declared_symbols(header: Path):
 def test_library_exports_every_declared_symbol(library):
     names = declared_symbols(ROOT / "include/quasi_plugin_abi.h") + declared_symbols(
         ROOT / "include/quasi_cuda_backend.h")
-    assert len(names) == 30 and set(abi.REQUIRED_SYMBOLS + abi.OPTIONAL_SYMBOLS) <= set(names)
+    assert len(names) == 32 and set(abi.REQUIRED_SYMBOLS + abi.OPTIONAL_SYMBOLS) <= set(names)
     for n in names:
         assert library.has_symbol(n), n
 
@@ -115,6 +115,9 @@ int main(void) {
     offsetof(Q_cuda_persistent_state, frame_count), offsetof(Q_cuda_persistent_state, device_ordinal));
   printf("%zu %zu %zu %zu\n", offsetof(Q_render_frame, camera), offsetof(Q_render_frame, camera_dirty),
     offsetof(Q_plugin_context, gpu), offsetof(Q_plugin_context, request_shutdown));
+  printf("%zu %zu %zu %zu %zu %zu\n", sizeof(Q_cuda_export_table), offsetof(Q_cuda_export_table, base),
+    sizeof(Q_cuda_reduce_table), offsetof(Q_cuda_reduce_table, staging), offsetof(Q_cuda_reduce_table, counters),
+    offsetof(Q_cuda_reduce_table, out));
   return 0; }''')
     exe = tmp_path / "layout"
     subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", f"-I{ROOT / 'include'}", str(src), "-o", str(exe)], check=True)
@@ -126,8 +129,11 @@ int main(void) {
     assert sizes[:6] == [40, 72, 32, 40, 24, 96]  # SURVEY.md 8b, probed from the reference headers
     P = abi.Q_cuda_persistent_state
     assert [int(x) for x in out[10:14]] == [C.sizeof(P), P.layers.offset, P.frame_count.offset, P.device_ordinal.offset]
-    assert [int(x) for x in out[14:]] == [abi.Q_render_frame.camera.offset, abi.Q_render_frame.camera_dirty.offset,
-                                          abi.Q_plugin_context.gpu.offset, abi.Q_plugin_context.request_shutdown.offset]
+    assert [int(x) for x in out[14:18]] == [abi.Q_render_frame.camera.offset, abi.Q_render_frame.camera_dirty.offset,
+                                            abi.Q_plugin_context.gpu.offset, abi.Q_plugin_context.request_shutdown.offset]
+    E, R = abi.Q_cuda_export_table, abi.Q_cuda_reduce_table  # the multi-GPU tables of quasi_cuda_backend.h
+    assert [int(x) for x in out[18:]] == [C.sizeof(E), E.base.offset, C.sizeof(R), R.staging.offset, R.counters.offset,
+                                          R.out.offset]
 
 
 @pytest.mark.skipif(not Path("/root/reference/src").exists(), reason="reference tree not present")

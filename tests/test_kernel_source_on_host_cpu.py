@@ -86,3 +86,30 @@ def test_mesh_kernel_source_renders_the_mesh_oracle_image(tmp_path):
                 assert bad == 0, f"{name}: {bad} pixels differ (grid {grid}, wide {wide})"
             words = run.stdout.split()
             assert int(words[words.index("rays") + 1]) == stats["rays"]
+
+
+def test_kernel_source_fused_reduce_is_the_oracles_combine(tmp_path, oracle):
+    """The multi-GPU form on one host: G shards rendered one after the other, each batched launch storing its
+    tiles into the owners' staging slots and counting arrivals; the launch that brings a unit's G-th arrival
+    sums the copies in rank order (batch_params' fused reduce). The finished frame must be the oracle's
+    rank-ordered combine of the G shard images, bit for bit, on ragged sizes and with slices that end inside
+    a layer."""
+    exe = build(tmp_path, [])
+    for width, height, samples, ranks in ((64, 36, 3, 2), (61, 35, 2, 3), (33, 17, 4, 8), (97, 61, 2, 5)):
+        out = tmp_path / "frame.bin"
+        run = subprocess.run([str(exe), str(width), str(height), str(samples), str(samples), "quads", str(out), str(ranks)],
+                             capture_output=True, text=True, timeout=600)
+        assert run.returncode == 0, run.stdout + run.stderr
+        u = oracle.scene(width, height)
+        shards, rays = [], 0
+        for g in range(ranks):
+            layers, n = oracle.render_frames(u, width, height, samples, frame_first=g, frame_stride=ranks)
+            shards.append(layers)
+            rays += n
+        got = np.fromfile(out, dtype=np.float32).reshape(4, height, width, 4)
+        for l, name in enumerate(LAYERS):
+            want = oracle.combine_shards([s[l] for s in shards])
+            bad = int((bits(got[l]) != bits(want)).any(axis=-1).sum())
+            assert bad == 0, f"{name}: {bad} pixels differ ({width}x{height}, {samples} samples, {ranks} ranks)"
+        words = run.stdout.split()
+        assert int(words[words.index("rays") + 1]) == rays
