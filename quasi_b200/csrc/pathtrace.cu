@@ -207,12 +207,28 @@ constexpr int k_block_threads = QUASI_QUAD_BLOCK_THREADS;
 constexpr int k_blocks_per_sm = QUASI_QUAD_BLOCKS_PER_SM;
 constexpr int k_warps_per_block = k_block_threads / 32;
 
-/// System-scope arrival counter on memory that may belong to another GPU (relaxed; the fences around it order).
-__device__ __forceinline__ unsigned int atomic_add_system(unsigned int* p, unsigned int v) {
+/// System-scope arrival counter on memory that may belong to another GPU, with release semantics: everything this
+/// thread wrote, and everything it has observed (the other lanes' stores, through the __syncwarp before), is
+/// visible to whoever reads the new count. atom.release and not __threadfence_system() + atomicAdd_system: the
+/// fence is MEMBAR.SC.SYS followed by CCTL.IVALL, an invalidation of the SM's whole L1 per finished tile, which
+/// cost the render 4 % on two GPUs (the tiles' own accumulators live there between samples); the release atomic
+/// is MEMBAR.ALL.SYS + ATOMG and leaves the L1 alone.
+__device__ __forceinline__ unsigned int arrive_release_system(unsigned int* p) {
 #if defined(QUASI_HOST_EMULATION)
-    return std::atomic_ref<unsigned int>(*p).fetch_add(v);
+    return std::atomic_ref<unsigned int>(*p).fetch_add(1u, std::memory_order_release);
 #else
-    return atomicAdd_system(p, v);
+    unsigned int before;
+    asm volatile("atom.add.release.sys.global.u32 %0, [%1], 1;" : "=r"(before) : "l"(p) : "memory");
+    return before;
+#endif
+}
+/// The other half, executed only by the thread whose arrival was the last: what the earlier arrivals released is
+/// visible to the loads that follow.
+__device__ __forceinline__ void acquire_fence_system() {
+#if defined(QUASI_HOST_EMULATION)
+    std::atomic_thread_fence(std::memory_order_acquire);
+#else
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
 #endif
 }
 /// A float4 another GPU may have written a moment ago: not from this SM's L1.
@@ -572,19 +588,19 @@ pathtrace_accumulate_kernel(const __grid_constant__ scene_params scene, const __
                     }
                     if constexpr (Reduce) {
                         // Fused reduce (batch_params): the four units of this tile have been stored at their owners;
-                        // lanes 0..3 report the arrival of layer `lane` (fence, then the counter: the barrier before
-                        // them makes the fence cover every lane's stores), and where this warp's arrival is the G-th,
+                        // lanes 0..3 report the arrival of layer `lane` (a release on the counter: the barrier before
+                        // it makes the release cover every lane's stores), and where this warp's arrival is the G-th,
                         // it sums the unit's G copies in rank order and stores the finished unit.
                         __syncwarp();
                         const uint32_t first_pixel = tile_y * 4u * frame.width + tile_x * 8u;  // always inside the image
                         uint32_t unit_slice = 0, arrivals = 0;
                         if (lane < 4u) {
-                            __threadfence_system();
                             unit_slice = slice_of(lane * n_px + first_pixel);
-                            arrivals = atomic_add_system(launch.reduce_counters[unit_slice] + lane * n_tiles + done_tile, 1u) + 1u;
-                            if (arrivals % launch.reduce_ranks == 0u) __threadfence_system();  // the other ranks' copies are visible from here on
+                            arrivals = arrive_release_system(launch.reduce_counters[unit_slice] + lane * n_tiles + done_tile) + 1u;
+                            if (arrivals % launch.reduce_ranks == 0u) acquire_fence_system();  // the other ranks' copies are visible from here on
                         }
                         uint32_t m_last = __ballot_sync(0xffffffffu, lane < 4u && arrivals % launch.reduce_ranks == 0u);
+                        if (m_last != 0u) __syncwarp();  // every lane's loads below come after the fence of the lane that arrived
                         while (m_last != 0u) {
                             const uint32_t l = static_cast<uint32_t>(__ffs(static_cast<int>(m_last))) - 1u;
                             m_last &= m_last - 1u;
