@@ -44,11 +44,20 @@ cudaError_t launch_pathtrace_accumulate(const scene_params& scene, const frame_p
                                         unsigned int* tile_counters, int sm_count, cudaStream_t stream,
                                         bool generic_scan = false);
 
+/// A range of device memory whose lines a launch asks the L2 to keep (cudaAccessPropertyPersisting, launch attribute
+/// cudaLaunchAttributeAccessPolicyWindow): the BVH nodes, which every ray reads twenty times, next to layers that are
+/// streamed through once per launch. bytes == 0: no window.
+struct l2_window {
+    const void* base = nullptr;
+    size_t bytes = 0;
+    float hit_ratio = 1.0f;
+};
+
 /// @brief The mesh-scene form of launch_pathtrace_accumulate (BASELINE config 3).
 /// @param counters Device array of 3: rays, BVH nodes visited (box tests), triangles tested.
 cudaError_t launch_mesh_pathtrace(const mesh_params& scene, const frame_params& frame, float* const layers[4],
                                   unsigned long long* counters, unsigned int* tile_counters, int sm_count,
-                                  cudaStream_t stream);
+                                  cudaStream_t stream, const l2_window& keep = {});
 
 /// Triangles in ORIGINAL order on the device: what build_lbvh reads.
 struct lbvh_input {

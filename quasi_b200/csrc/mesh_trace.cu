@@ -130,6 +130,22 @@ struct lane_stack {
     __device__ __forceinline__ uint32_t after_node() const { return sp > 0 ? k_pop : k_done; }
 };
 
+#ifndef QUASI_MESH_STREAM_LAYERS
+#define QUASI_MESH_STREAM_LAYERS 0
+#endif
+/// accumulate_pixel (device_common.cuh) on a layer this launch touches exactly once per pixel: with
+/// QUASI_MESH_STREAM_LAYERS the history is read and the result written with the evict-first hints (ld/st.global.cs),
+/// so that the 266 MB of layer traffic per launch do not push the nodes and triangles out of the L2.
+__device__ __forceinline__ void accumulate_once(float4* __restrict__ layer, size_t idx, float4 sample, bool first,
+                                                float weight) {
+#if QUASI_MESH_STREAM_LAYERS && !defined(QUASI_HOST_EMULATION)
+    if (!first) sample = mix4(__ldcs(layer + idx), sample, weight);
+    __stcs(layer + idx, sample);
+#else
+    accumulate_pixel(layer, idx, sample, first, weight);
+#endif
+}
+
 using slab::box_hit;  // slab_test.hpp: the pruning arithmetic, shared with the host check
 
 /// 1/x for the slab test (slab_test.hpp).
@@ -278,11 +294,11 @@ mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_co
                     first_t = best.t;
                 }
                 const float nd = fminf(fmaxf((first_t - 1.0f) / 4.0f, 0.0f), 1.0f);
-                accumulate_pixel(albedo, pixel, make_float4(a.x, a.y, a.z, 1.0f), first_sample,
+                accumulate_once(albedo, pixel, make_float4(a.x, a.y, a.z, 1.0f), first_sample,
                                  weight);
-                accumulate_pixel(normal, pixel, make_float4(nn.x, nn.y, nn.z, 1.0f), first_sample,
+                accumulate_once(normal, pixel, make_float4(nn.x, nn.y, nn.z, 1.0f), first_sample,
                                  weight);
-                accumulate_pixel(depth, pixel, make_float4(nd, nd, nd, 1.0f), first_sample,
+                accumulate_once(depth, pixel, make_float4(nd, nd, nd, 1.0f), first_sample,
                                  weight);
             }
 
@@ -310,7 +326,7 @@ mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_co
                 ro = point + n * 0.001f;
                 new_ray = true;  // the direction is drawn below, together with the new paths' camera rays
             } else {
-                accumulate_pixel(beauty, pixel, make_float4(color.x, color.y, color.z, 1.0f),
+                accumulate_once(beauty, pixel, make_float4(color.x, color.y, color.z, 1.0f),
                                  first_sample, weight);
                 active = false;
             }
@@ -463,7 +479,7 @@ mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_co
 #if !defined(QUASI_HOST_EMULATION)  // tests/cuda_emulation has its own launcher
 cudaError_t launch_mesh_pathtrace(const mesh_params& scene, const frame_params& frame, float* const layers[4],
                                   unsigned long long* counters, unsigned int* tile_counters, int sm_count,
-                                  cudaStream_t stream) {
+                                  cudaStream_t stream, const l2_window& keep) {
     const uint32_t n_tiles = ((frame.width + 7u) / 8u) * ((frame.height + 3u) / 4u);
     uint32_t blocks = static_cast<uint32_t>(sm_count) * k_blocks_per_sm;
     const uint32_t needed = (n_tiles + k_warps_per_block - 1u) / k_warps_per_block;
@@ -478,10 +494,25 @@ cudaError_t launch_mesh_pathtrace(const mesh_params& scene, const frame_params& 
     for (cudaError_t e : attr) {
         if (e != cudaSuccess) return e;
     }
-    kernel<<<blocks, k_block_threads, k_stack_bytes, stream>>>(
-        scene, frame, reinterpret_cast<float4*>(layers[0]), reinterpret_cast<float4*>(layers[1]),
-        reinterpret_cast<float4*>(layers[2]), reinterpret_cast<float4*>(layers[3]), counters, tile_counters);
-    return cudaGetLastError();
+    cudaLaunchConfig_t config{};
+    config.gridDim = dim3(blocks);
+    config.blockDim = dim3(k_block_threads);
+    config.dynamicSmemBytes = k_stack_bytes;
+    config.stream = stream;
+    cudaLaunchAttribute attribute{};
+    if (keep.bytes != 0) {
+        attribute.id = cudaLaunchAttributeAccessPolicyWindow;
+        attribute.val.accessPolicyWindow.base_ptr = const_cast<void*>(keep.base);
+        attribute.val.accessPolicyWindow.num_bytes = keep.bytes;
+        attribute.val.accessPolicyWindow.hitRatio = keep.hit_ratio;
+        attribute.val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attribute.val.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+        config.attrs = &attribute;
+        config.numAttrs = 1;
+    }
+    return cudaLaunchKernelEx(&config, kernel, scene, frame, reinterpret_cast<float4*>(layers[0]),
+                              reinterpret_cast<float4*>(layers[1]), reinterpret_cast<float4*>(layers[2]),
+                              reinterpret_cast<float4*>(layers[3]), counters, tile_counters);
 }
 
 #endif  // !QUASI_HOST_EMULATION

@@ -608,26 +608,13 @@ pathtrace_accumulate_kernel(const __grid_constant__ scene_params scene, const __
                             if (inside) {
                                 const uint32_t within = l * n_px + pixel - launch.slice_lo[slice];
                                 const float4* copy = static_cast<const float4*>(launch.reduce_staging[slice]) + within;
-                                float4 sum = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                                for (uint32_t g0 = 0; g0 < launch.reduce_ranks; g0 += 4u) {  // four round trips in flight
-                                    float4 v[4];
-#pragma unroll
-                                    for (uint32_t j = 0; j < 4u; j++) {
-                                        if (g0 + j < launch.reduce_ranks) v[j] = load_uncached(copy + static_cast<size_t>(g0 + j) * launch.reduce_slot_stride);
-                                    }
-#pragma unroll
-                                    for (uint32_t j = 0; j < 4u; j++) {
-                                        if (g0 + j < launch.reduce_ranks) {
-                                            if (g0 + j == 0u) {
-                                                sum = v[0];  // (not 0 + v: -0 stays -0, as in the oracle's combine)
-                                            } else {
-                                                sum.x = sum.x + v[j].x;
-                                                sum.y = sum.y + v[j].y;
-                                                sum.z = sum.z + v[j].z;
-                                                sum.w = sum.w + v[j].w;
-                                            }
-                                        }
-                                    }
+                                float4 sum = load_uncached(copy);
+                                for (uint32_t g = 1; g < launch.reduce_ranks; g++) {
+                                    const float4 v = load_uncached(copy + static_cast<size_t>(g) * launch.reduce_slot_stride);
+                                    sum.x = sum.x + v.x;
+                                    sum.y = sum.y + v.y;
+                                    sum.z = sum.z + v.z;
+                                    sum.w = sum.w + v.w;
                                 }
                                 const float k = launch.reduce_scale;
                                 static_cast<float4*>(launch.reduce_out[slice])[within] = make_float4(sum.x * k, sum.y * k, sum.z * k, sum.w * k);

@@ -15,6 +15,7 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -107,6 +108,7 @@ struct plugin_state {
     bool use_mesh = false;
     Q::cuda::mesh::scene mesh;
     Q::cuda::mesh_params mesh_device{};
+    Q::cuda::l2_window mesh_keep{};  ///< QUASI_CUDA_MESH_L2_KEEP: the part of the mesh the launches ask the L2 to keep
     void* mesh_buffers[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  ///< [5]: the 4-wide tree, if asked for
     uint32_t wide_nodes = 0;
 
@@ -240,6 +242,10 @@ bool leave_layers_with_host(plugin_state* state) {
 }
 
 void free_mesh(plugin_state* state) {
+    if (state->mesh_keep.bytes != 0) {  // the lines the launches asked the L2 to keep are ordinary lines again
+        cudaCtxResetPersistingL2Cache();
+        state->mesh_keep = {};
+    }
     for (auto& b : state->mesh_buffers) {
         if (b) cudaFree(b);
         b = nullptr;
@@ -387,6 +393,28 @@ bool create_mesh(plugin_state* state, uint32_t grid, uint32_t seed, uint32_t max
         }
     }
     finish_mesh_params(state, max_bounces);
+    // QUASI_CUDA_MESH_L2_KEEP=<percent>: the launches ask the L2 to keep the BVH nodes (a persisting access window
+    // over the node array with that hit ratio), up to the share of the L2 the device lets be set aside.
+    if (const uint32_t percent = env_u32("QUASI_CUDA_MESH_L2_KEEP", 0, 0, 100); percent != 0) {
+        int most = 0, window = 0;
+        cudaDeviceGetAttribute(&most, cudaDevAttrMaxPersistingL2CacheSize, state->device);
+        cudaDeviceGetAttribute(&window, cudaDevAttrMaxAccessPolicyWindowSize, state->device);
+        const size_t node_bytes = static_cast<size_t>(state->mesh_device.n_nodes) * (state->mesh_device.wide ? 128u : 32u);
+        const size_t aside = std::min<size_t>(static_cast<size_t>(most), node_bytes);
+        if (aside != 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, aside) == cudaSuccess) {
+            state->mesh_keep.base = state->mesh_device.nodes;
+            state->mesh_keep.bytes = std::min<size_t>(node_bytes, static_cast<size_t>(window));
+            state->mesh_keep.hit_ratio = std::min(1.0f, static_cast<float>(aside) / static_cast<float>(state->mesh_keep.bytes)) *
+                                         static_cast<float>(percent) / 100.0f;
+            char msg[200];
+            std::snprintf(msg, sizeof msg, "Mesh nodes: %zu MB asked to stay in the L2 (set aside %zu of at most %d MB, hit ratio %.2f)",
+                          state->mesh_keep.bytes >> 20, aside >> 20, most >> 20, static_cast<double>(state->mesh_keep.hit_ratio));
+            log_msg(state, msg);
+        } else {
+            (void)cudaGetLastError();
+            log_msg(state, "QUASI_CUDA_MESH_L2_KEEP: this device sets no L2 aside");
+        }
+    }
     char buf[160];
     std::snprintf(buf, sizeof buf, "Mesh scene: %u triangles, %u BVH nodes, depth %u", state->mesh_device.n_triangles,
                   static_cast<uint32_t>(state->mesh.nodes.size()), state->mesh.depth);
@@ -745,8 +773,8 @@ Q_PLUGIN_EXPORT void Q_plugin_render(Q_plugin_handle* handle, Q_render_frame* fr
 
     auto* tile_counters = reinterpret_cast<unsigned int*>(state->ray_counter + 3);
     const cudaError_t launched =
-        state->use_mesh ? Q::cuda::launch_mesh_pathtrace(state->mesh_device, fp, state->layers,
-                                                         state->ray_counter, tile_counters, state->sm_count, stream)
+        state->use_mesh ? Q::cuda::launch_mesh_pathtrace(state->mesh_device, fp, state->layers, state->ray_counter,
+                                                         tile_counters, state->sm_count, stream, state->mesh_keep)
                         : Q::cuda::launch_pathtrace_accumulate(state->scene, fp, Q::cuda::batch_params{}, state->layers,
                                                                state->ray_counter, tile_counters, state->sm_count,
                                                                stream, state->generic_scan);

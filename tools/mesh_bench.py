@@ -32,6 +32,7 @@ def main():
                     help="BVH builder: binned SAH on the host (default) or LBVH on the GPU")
     ap.add_argument("--wide", type=int, default=0, help="1: the kernel walks the 4-wide tree (QUASI_CUDA_MESH_WIDE); 2: both forms, one after the other")
     ap.add_argument("--plugin", default=None, help="path of a libquasi_cuda.so build to measure")
+    ap.add_argument("--env", action="append", default=[], help="KEY=VALUE for the plugin's environment (repeatable)")
     args = ap.parse_args()
 
     import torch
@@ -53,7 +54,8 @@ def measure(args, torch, headless_host, quasi_b200, wide):
                          plugin_path=args.plugin or quasi_b200.PLUGIN_PATH,
                          env={"QUASI_CUDA_SCENE": "mesh", "QUASI_CUDA_MESH_GRID": args.grid,
                               "QUASI_CUDA_MESH_SEED": 1, "QUASI_CUDA_MAX_BOUNCES": args.bounces,
-                              "QUASI_CUDA_MESH_BUILDER": args.builder, "QUASI_CUDA_MESH_WIDE": wide})
+                              "QUASI_CUDA_MESH_BUILDER": args.builder, "QUASI_CUDA_MESH_WIDE": wide,
+                              **dict(kv.split("=", 1) for kv in args.env)})
     stream = host.context.frame_stream()
 
     def step():
