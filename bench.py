@@ -394,7 +394,10 @@ def run_ours(args):
         peak, peak_src = measured_peaks()
         launches_per_step = max(1.0, render_launches_local / args.steps)
         # the step of one GPU is back-to-back launches of the one kernel (one per frame when the plugin batches)
-        kernel_ms = ms_step / launches_per_step if world == 1 else None
+        # (several GPUs, fused exchange: a step is that launch plus a device-side barrier of a few microseconds, and
+        # the launch is the Reduce instantiation of the same kernel, whose tail per finished tile is not in the ncu
+        # capture: the ncu-only fields are left out)
+        kernel_ms = ms_step / launches_per_step if world == 1 or args.reduce == "fused" else None
         roofline = None
         if kernel_ms is not None:
             # SURVEY.md 8d's unit is one Q_plugin_render call (one sample per pixel: 128 B/px); a launch processes
@@ -410,14 +413,14 @@ def run_ours(args):
                 slots = 148 * 4 * clocks["sm_mhz"] * 1e6 * kernel_ms * 1e-3
                 issue = {"warp_inst_per_launch": int(per_launch), "frac": round(per_launch / slots, 4),
                          "warp_inst_per_ray": round(per_launch * launches_per_step / rays_step, 2),
-                         "issue_slot_utilization_ncu": prof.get("issue_slot_utilization"),
-                         "threads_per_instruction_ncu": prof.get("threads_per_instruction"),
+                         "issue_slot_utilization_ncu": prof.get("issue_slot_utilization") if world == 1 else None,
+                         "threads_per_instruction_ncu": prof.get("threads_per_instruction") if world == 1 else None,
                          "source": prof.get("source")}
             roofline = {
                 "bound": "hbm", "kernel": "pathtrace_accumulate_kernel",
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4),
-                "traffic": prof.get("dram_bytes_per_launch") if prof else None, "peak_source": peak_src,
+                "traffic": prof.get("dram_bytes_per_launch") if prof and world == 1 else None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": int(algorithmic),
                 "samples_per_launch": samples_per_launch,
                 "kernel_ms": round(kernel_ms, 5),
@@ -604,10 +607,11 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--reduce", choices=["push", "fused", "nccl"], default="push",
-                    help="multi-GPU exchange: tiles pushed to the slice owners by the render kernel + one local reduce "
-                         "kernel per rank, frame into shared host memory (default; fixed summation order, bit-exact vs "
-                         "the oracle), or NCCL reduce to rank 0 + scale kernel + copy to the host")
+    ap.add_argument("--reduce", choices=["push", "fused", "nccl"], default="fused",
+                    help="multi-GPU exchange: fused = inside the render kernel (tiles staged at the slice owners, counted, "
+                         "reduced in rank order by the last arrival and stored into the shared host frame; the default); "
+                         "push = tiles pushed by the render kernel + one local reduce kernel per rank (both bit-exact vs "
+                         "the oracle); nccl = NCCL reduce to rank 0 + scale kernel + copy to the host")
     ap.add_argument("--scaling", choices=["strong", "weak"], default="strong",
                     help="N > 1: split the frame's samples over the GPUs (default) or give every GPU the whole 64")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
