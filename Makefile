@@ -17,8 +17,8 @@ NVCCFLAGS := $(ARCH) -O3 -std=c++20 -lineinfo $(NVCC_NUMERICS) --cudart shared \
              -Xcompiler $(HOST_FLAGS) -Iinclude -Iquasi_b200/csrc
 
 CSRC := quasi_b200/csrc
-PLUGIN_SRCS := $(CSRC)/plugin.cu $(CSRC)/pathtrace.cu $(CSRC)/mesh_trace.cu $(CSRC)/lbvh_build.cu $(CSRC)/post.cu
-PLUGIN_HDRS := $(CSRC)/kernels.hpp $(CSRC)/scene_params.hpp $(CSRC)/scan_decide.hpp $(CSRC)/slab_test.hpp $(CSRC)/wide_bvh.hpp $(CSRC)/sincos_table.hpp $(CSRC)/sincos_table_data.inc $(CSRC)/sincos_table_constants.inc $(CSRC)/device_common.cuh $(CSRC)/mesh_scene.hpp include/quasi_plugin_abi.h \
+PLUGIN_SRCS := $(CSRC)/plugin.cu $(CSRC)/pathtrace.cu $(CSRC)/mesh_trace.cu $(CSRC)/mesh_wavefront.cu $(CSRC)/lbvh_build.cu $(CSRC)/post.cu
+PLUGIN_HDRS := $(CSRC)/mesh_traverse.cuh $(CSRC)/quantized_bvh.hpp $(CSRC)/kernels.hpp $(CSRC)/scene_params.hpp $(CSRC)/scan_decide.hpp $(CSRC)/slab_test.hpp $(CSRC)/wide_bvh.hpp $(CSRC)/sincos_table.hpp $(CSRC)/sincos_table_data.inc $(CSRC)/sincos_table_constants.inc $(CSRC)/device_common.cuh $(CSRC)/mesh_scene.hpp include/quasi_plugin_abi.h \
                include/quasi_cuda_backend.h
 PLUGIN_SO := quasi_b200/lib/libquasi_cuda.so
 

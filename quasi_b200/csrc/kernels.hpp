@@ -27,6 +27,9 @@ struct alignas(16) mesh_params {
     uint32_t max_bounces;
     uint32_t wide;          ///< 1: `nodes` is the 4-wide tree and n_nodes counts its nodes
     float materials[k_mesh_materials * 8];  ///< per material: albedo.xyz, 0, emission.xyz, 0
+    const uint4* pairs;     ///< quantized_bvh.hpp: 2 uint4 per pair of children; null: the float tree only
+    float grid_origin[3];   ///< of the quantized boxes
+    float grid_step[3];
 };
 
 /// @brief frame.batch_samples new samples per pixel (one by default), folded into the four accumulated
@@ -58,6 +61,32 @@ struct l2_window {
 cudaError_t launch_mesh_pathtrace(const mesh_params& scene, const frame_params& frame, float* const layers[4],
                                   unsigned long long* counters, unsigned int* tile_counters, int sm_count,
                                   cudaStream_t stream, const l2_window& keep = {});
+
+/// Device memory of the wavefront form of the mesh scene (mesh_wavefront.cu), sized for `capacity` paths (pixels x
+/// samples of a batch): two ray queues, the hits of the queue being traced, the results of every path.
+inline constexpr uint32_t k_mesh_wave_counters = 72;  ///< one per wave (bounce), + 1; QUASI_CUDA_MAX_BOUNCES <= 64
+struct mesh_wave_buffers {
+    float4* origin[2];        ///< queue 0 / 1, by position: {ray origin, path (pixel + sample * pixels; bit 31: it has a
+                              ///< colour entry; all ones: no ray here) as bits}
+    float4* direction[2];     ///< {unit direction, RNG state as bits}
+    float4* throughput[2];    ///< {throughput, -}: written for waves >= 1 (a camera ray's is 1)
+    float4* colour[2];        ///< {colour gathered so far, -}
+    float2* hit;              ///< by position in the queue being traced: {t, slot in leaf order as bits (all ones: none)}
+    float4* out_beauty;       ///< by path: {beauty, 1}
+    float4* out_albedo_depth; ///< by path: {albedo, depth AOV value}
+    float4* out_normal;       ///< by path: {normal AOV, 1}
+    uint32_t* counts;         ///< [k_mesh_wave_counters] rays of wave w (in queue w & 1), then as many queue heads
+    uint64_t capacity;        ///< entries of a queue (every lane of every 8x4 tile, times the samples of a batch)
+};
+/// Bytes of device memory per path behind a mesh_wave_buffers.
+size_t mesh_wave_bytes_per_path();
+
+/// @brief frame.batch_samples samples per pixel of the mesh scene as waves of rays (mesh_wavefront.cu), folded into
+/// the four layers in place, in sample order. Enqueue only; 2 * max_bounces + 2 launches.
+/// @param launches if not null: receives the number of kernels launched.
+cudaError_t launch_mesh_wavefront(const mesh_params& scene, const frame_params& frame, const mesh_wave_buffers& q,
+                                  float* const layers[4], unsigned long long* counters, int sm_count, cudaStream_t stream,
+                                  uint32_t* launches = nullptr);
 
 /// Triangles in ORIGINAL order on the device: what build_lbvh reads.
 struct lbvh_input {

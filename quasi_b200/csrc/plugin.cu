@@ -9,6 +9,7 @@
 
 #include "kernels.hpp"
 #include "mesh_scene.hpp"
+#include "quantized_bvh.hpp"
 #include "wide_bvh.hpp"
 
 #include <quasi_cuda_backend.h>
@@ -108,8 +109,11 @@ struct plugin_state {
     bool use_mesh = false;
     Q::cuda::mesh::scene mesh;
     Q::cuda::mesh_params mesh_device{};
+    bool mesh_wavefront = false;     ///< headless calls of the mesh scene are collected and traced as waves (mesh_wavefront.cu)
+    void* wave_block = nullptr;      ///< the one allocation behind `wave`
+    Q::cuda::mesh_wave_buffers wave{};
     Q::cuda::l2_window mesh_keep{};  ///< QUASI_CUDA_MESH_L2_KEEP: the part of the mesh the launches ask the L2 to keep
-    void* mesh_buffers[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  ///< [5]: the 4-wide tree, if asked for
+    void* mesh_buffers[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  ///< [5]: the 4-wide tree, if asked for; [6]: the quantized pairs
     uint32_t wide_nodes = 0;
 
     float* layers[Q_AOV_COUNT] = {nullptr, nullptr, nullptr, nullptr};
@@ -241,7 +245,47 @@ bool leave_layers_with_host(plugin_state* state) {
     return true;
 }
 
+void free_wave(plugin_state* state) {
+    if (state->wave_block) cudaFree(state->wave_block);
+    state->wave_block = nullptr;
+    state->wave = {};
+}
+
+/// Device memory for `paths` paths in flight as waves; keeps what is there if it is large enough.
+bool ensure_wave(plugin_state* state, uint64_t paths) {
+    if (state->wave_block && state->wave.capacity >= paths) return true;
+    free_wave(state);
+    const size_t counter_bytes = 2 * Q::cuda::k_mesh_wave_counters * sizeof(uint32_t);
+    const size_t bytes = static_cast<size_t>(paths) * Q::cuda::mesh_wave_bytes_per_path() + 256 + counter_bytes;
+    if (cudaMalloc(&state->wave_block, bytes) != cudaSuccess) {
+        (void)cudaGetLastError();
+        state->wave_block = nullptr;
+        return false;
+    }
+    auto* at = static_cast<float4*>(state->wave_block);
+    auto take = [&at, paths]() {
+        float4* p = at;
+        at += paths;
+        return p;
+    };
+    Q::cuda::mesh_wave_buffers& w = state->wave;
+    for (int i = 0; i < 2; i++) {
+        w.origin[i] = take();
+        w.direction[i] = take();
+        w.throughput[i] = take();
+        w.colour[i] = take();
+    }
+    w.out_beauty = take();
+    w.out_albedo_depth = take();
+    w.out_normal = take();
+    w.hit = reinterpret_cast<float2*>(at);
+    w.counts = reinterpret_cast<uint32_t*>(w.hit + paths);
+    w.capacity = paths;
+    return true;
+}
+
 void free_mesh(plugin_state* state) {
+    free_wave(state);
     if (state->mesh_keep.bytes != 0) {  // the lines the launches asked the L2 to keep are ordinary lines again
         cudaCtxResetPersistingL2Cache();
         state->mesh_keep = {};
@@ -393,6 +437,25 @@ bool create_mesh(plugin_state* state, uint32_t grid, uint32_t seed, uint32_t max
         }
     }
     finish_mesh_params(state, max_bounces);
+    // The binary tree once more with both children of a node in one 32-byte sector (quantized_bvh.hpp), for the
+    // wavefront trace kernel; QUASI_CUDA_MESH_QUANT=0 keeps it on the float tree.
+    if (state->mesh_wavefront && state->mesh_device.wide == 0 && env_u32("QUASI_CUDA_MESH_QUANT", 1, 0, 1) != 0) {
+        const mesh::quantized_tree grid = mesh::quantize_pairs(state->mesh);
+        const size_t bytes = grid.pairs.size() * sizeof(uint32_t);
+        if (bytes == 0) {
+            log_msg(state, "mesh BVH is not numbered in pairs: the trace kernel walks the float tree");
+        } else if (!check(state, cudaMalloc(&state->mesh_buffers[6], bytes), "cudaMalloc(quantized pairs)") ||
+                   !check(state, cudaMemcpy(state->mesh_buffers[6], grid.pairs.data(), bytes, cudaMemcpyHostToDevice),
+                          "upload(quantized pairs)")) {
+            return false;
+        } else {
+            state->mesh_device.pairs = static_cast<const uint4*>(state->mesh_buffers[6]);
+            for (int a = 0; a < 3; a++) {
+                state->mesh_device.grid_origin[a] = grid.origin[a];
+                state->mesh_device.grid_step[a] = grid.step[a];
+            }
+        }
+    }
     // QUASI_CUDA_MESH_L2_KEEP=<percent>: the launches ask the L2 to keep the BVH nodes (a persisting access window
     // over the node array with that hit ratio), up to the share of the L2 the device lets be set aside.
     if (const uint32_t percent = env_u32("QUASI_CUDA_MESH_L2_KEEP", 0, 0, 100); percent != 0) {
@@ -501,6 +564,38 @@ void flush_pending(plugin_state* state, cudaStream_t stream = nullptr) {
                            state->pending_first_sample, fp);
     fp.batch_samples = collected;
     fp.frame_stride = state->shard_count;
+    if (state->use_mesh) {
+        // The mesh scene: the collected calls as waves of rays (mesh_wavefront.cu); without the memory for that,
+        // one launch of the one-kernel form per call, exactly what Q_plugin_render would have made.
+        order_after_render(state, stream);
+        const uint64_t n_px = static_cast<uint64_t>(f.width) * f.height;
+        cudaError_t launched = cudaSuccess;
+        const uint64_t entries = static_cast<uint64_t>((f.width + 7u) / 8u) * ((f.height + 3u) / 4u) * 32u * collected;
+        if (n_px * collected < (uint64_t{1} << 31) && ensure_wave(state, entries)) {
+            uint32_t made = 0;
+            launched = Q::cuda::launch_mesh_wavefront(state->mesh_device, fp, state->wave, state->layers, state->ray_counter,
+                                                      state->sm_count, stream, &made);
+            state->kernel_launches += made;
+        } else {
+            auto* tile_counters = reinterpret_cast<unsigned int*>(state->ray_counter + 3);
+            for (uint32_t s = 0; s < collected && launched == cudaSuccess; s++) {
+                frame_params one;
+                Q::cuda::prepare_frame(f.camera.position, f.camera.target, f.camera.up, f.camera.fov, f.width, f.height,
+                                       frame_index + s * state->shard_count, state->pending_first_sample + s, one);
+                launched = Q::cuda::launch_mesh_pathtrace(state->mesh_device, one, state->layers, state->ray_counter,
+                                                          tile_counters, state->sm_count, stream, state->mesh_keep);
+                state->kernel_launches++;
+            }
+        }
+        if (!check(state, launched, "mesh pathtrace (batch)")) {
+            take_back();
+            return;
+        }
+        state->last_launch_exported = false;
+        cudaEventRecord(state->last_render, stream);
+        state->render_pending = true;
+        return;
+    }
     Q::cuda::batch_params launch{};
     bool mirrored = false;
     if (collected > 1u) {
@@ -663,7 +758,10 @@ Q_PLUGIN_EXPORT Q_plugin_handle* Q_plugin_create(Q_plugin_context* ctx) {
         const char* scene_name = std::getenv("QUASI_CUDA_SCENE");
         if (scene_name && std::strcmp(scene_name, "mesh") == 0) {
             state->use_mesh = true;
-            state->batch = 1;  // the mesh kernel takes one sample per launch (a batched form was 0.7 % slower)
+            // QUASI_CUDA_MESH_WAVEFRONT=0: one launch of the one-kernel path tracer per call (mesh_trace.cu); default:
+            // headless calls are collected, QUASI_CUDA_MESH_BATCH at a time, and traced as waves (mesh_wavefront.cu)
+            state->mesh_wavefront = env_u32("QUASI_CUDA_MESH_WAVEFRONT", 1, 0, 1) != 0;
+            state->batch = state->mesh_wavefront ? env_u32("QUASI_CUDA_MESH_BATCH", 16, 1, 64) : 1;
             ok = create_mesh(state, env_u32("QUASI_CUDA_MESH_GRID", 707, 1, 4000),
                              env_u32("QUASI_CUDA_MESH_SEED", 1, 0, 65535), bounces);
         }
@@ -739,7 +837,7 @@ Q_PLUGIN_EXPORT void Q_plugin_render(Q_plugin_handle* handle, Q_render_frame* fr
 
     if (cudaSetDevice(state->device) != cudaSuccess) return;
 
-    if (state->batch > 1 && !(drawable && drawable->pixels) && frame->width < 65536u &&
+    if ((state->batch > 1 || state->mesh_wavefront) && !(drawable && drawable->pixels) && frame->width < 65536u &&
         frame->height < 65536u) {  // the batched kernel keeps a lane's pixel as two 16-bit coordinates
         render_batched(state, frame);
         return;

@@ -11,16 +11,16 @@ from oracle_lib import MeshOracle, bits
 pytestmark = pytest.mark.gpu
 
 
-def mesh_host(width, height, grid, bounces=4, seed=1, builder="sah", wide=0):
+def mesh_host(width, height, grid, bounces=4, seed=1, builder="sah", wide=0, **env):
     from quasi_b200.headless import headless_host
 
     return headless_host(width, height, env={"QUASI_CUDA_SCENE": "mesh", "QUASI_CUDA_MESH_GRID": grid,
                                              "QUASI_CUDA_MESH_SEED": seed, "QUASI_CUDA_MAX_BOUNCES": bounces,
-                                             "QUASI_CUDA_MESH_BUILDER": builder, "QUASI_CUDA_MESH_WIDE": wide})
+                                             "QUASI_CUDA_MESH_BUILDER": builder, "QUASI_CUDA_MESH_WIDE": wide, **env})
 
 
-def render(width, height, frames, grid, bounces=4, builder="sah", wide=0):
-    h = mesh_host(width, height, grid, bounces, builder=builder, wide=wide)
+def render(width, height, frames, grid, bounces=4, builder="sah", wide=0, **env):
+    h = mesh_host(width, height, grid, bounces, builder=builder, wide=wide, **env)
     h.render(frames)
     layers = h.readback_aov()
     stats = h.stats()
@@ -46,6 +46,34 @@ def test_small_meshes_vs_oracle_and_brute_force(grid, size, frames):
         brute, _ = m.render_frames(w, h, frames, max_bounces=4, use_bvh=False)
         assert_bit_exact(got, brute)
     assert stats.nodes_visited > 0 and stats.triangles_tested > 0
+
+
+@pytest.mark.parametrize("env", [{"QUASI_CUDA_MESH_WAVEFRONT": 0}, {"QUASI_CUDA_MESH_BATCH": 1},
+                                 {"QUASI_CUDA_MESH_BATCH": 2}, {"QUASI_CUDA_MESH_BATCH": 5},
+                                 {"QUASI_CUDA_MESH_BATCH": 3, "QUASI_CUDA_MESH_WIDE": 1},
+                                 {"QUASI_CUDA_MESH_BATCH": 4, "QUASI_CUDA_MAX_BOUNCES": 7}])
+def test_both_forms_and_every_batch_length_render_the_oracle_image(env):
+    """The one-kernel path tracer (QUASI_CUDA_MESH_WAVEFRONT=0: mesh_trace.cu, one launch per call) and the wavefront
+    form (mesh_wavefront.cu) with batches that divide the frame's calls and batches that do not, on a ragged
+    image: the same bits as the oracle, the same number of rays."""
+    grid, w, h, frames = 24, 157, 83, 5
+    bounces = int(env.get("QUASI_CUDA_MAX_BOUNCES", 4))
+    host = mesh_host(w, h, grid, **env)
+    host.render(frames)
+    got, stats = host.readback_aov(), host.stats()
+    want, st = MeshOracle(grid).render_frames(w, h, frames, max_bounces=bounces, use_bvh=True)
+    assert_bit_exact(got, want)
+    assert stats.rays == st["rays"] and stats.paths == frames * w * h
+    # accumulation goes on across a readback (a batch cut short by it) and restarts with camera_dirty
+    host.render_frame(camera_dirty=False)
+    host.render_frame(camera_dirty=False)
+    more, _ = MeshOracle(grid).render_frames(w, h, frames + 2, max_bounces=bounces, use_bvh=True)
+    assert_bit_exact(host.readback_aov(), more)
+    host.render_frame(camera_dirty=True)
+    host.render_frame(camera_dirty=False)
+    again, _ = MeshOracle(grid).render_frames(w, h, 2, max_bounces=bounces, use_bvh=True)
+    assert_bit_exact(host.readback_aov(), again)
+    host.close()
 
 
 def test_plugin_built_bvh_equals_oracle_bvh():

@@ -88,6 +88,26 @@ def test_mesh_kernel_source_renders_the_mesh_oracle_image(tmp_path):
             assert int(words[words.index("rays") + 1]) == stats["rays"]
 
 
+def test_mesh_wavefront_source_renders_the_mesh_oracle_image(tmp_path):
+    """mesh_wavefront.cu (ray generation, the trace kernel that refills its lanes from a queue, shade with its
+    compaction, resolve in sample order) in the launch sequence of launch_mesh_wavefront: batches that divide the
+    frame count and batches that do not, both tree forms, a ragged image."""
+    exe = build(tmp_path, [], harness="run_mesh_wave")
+    for grid, width, height, frames, wide, batch in ((3, 64, 36, 2, 0, 2), (24, 80, 45, 2, 0, 1), (3, 61, 35, 5, 0, 3),
+                                                     (24, 48, 27, 4, 1, 4), (24, 33, 17, 3, 0, 16)):
+        want, stats = MeshOracle(grid).render_frames(width, height, frames, max_bounces=4, use_bvh=True)
+        out = tmp_path / "layers.bin"
+        run = subprocess.run([str(exe), str(grid), str(width), str(height), str(frames), str(wide), str(out), str(batch)],
+                             capture_output=True, text=True, timeout=900)
+        assert run.returncode == 0, run.stdout + run.stderr
+        got = np.fromfile(out, dtype=np.float32).reshape(4, height, width, 4)
+        for name, g, w in zip(LAYERS, got, want):
+            bad = int((bits(g) != bits(w)).any(axis=-1).sum())
+            assert bad == 0, f"{name}: {bad} pixels differ (grid {grid}, wide {wide}, batch {batch})"
+        words = run.stdout.split()
+        assert int(words[words.index("rays") + 1]) == stats["rays"]
+
+
 def test_kernel_source_fused_reduce_is_the_oracles_combine(tmp_path, oracle):
     """The multi-GPU form on one host: G shards rendered one after the other, each batched launch storing its
     tiles into the owners' staging slots and counting arrivals; the launch that brings a unit's G-th arrival
