@@ -48,7 +48,7 @@ namespace {
 #define QUASI_WAVE_LEAF_BATCH 8
 #endif
 #ifndef QUASI_WAVE_RUN_EXIT
-#define QUASI_WAVE_RUN_EXIT 4
+#define QUASI_WAVE_RUN_EXIT 12
 #endif
 #ifndef QUASI_WAVE_CHUNK
 #define QUASI_WAVE_CHUNK 128
@@ -161,6 +161,7 @@ mesh_wave_trace_kernel(const __grid_constant__ mesh_params scene, const float4* 
     uint32_t cur = k_done;
     mesh_hit best{1e30f, k_miss, 0u};
     v3 ro = make_v3(0.0f, 0.0f, 0.0f), rd = make_v3(0.0f, 0.0f, -1.0f), inv = ro, oi = ro;
+    [[maybe_unused]] uint32_t near_x = 0, near_y = 0, near_z = 0;  // Quant: quant_ray's selectors
     uint32_t chunk_next = 0, chunk_end = 0;  // warp-uniform: the rays this warp has reserved and not yet handed out
     bool dry = false;                        // warp-uniform: the queue head has passed the last ray
     uint32_t rays = 0, nodes_visited = 0, tris_tested = 0;
@@ -230,6 +231,7 @@ mesh_wave_trace_kernel(const __grid_constant__ mesh_params scene, const float4* 
                         const slab::quant_ray r = slab::make_quant_ray(scene.grid_origin, scene.grid_step, inv, oi);
                         inv = r.a;
                         oi = r.b;
+                        near_x = r.near_x, near_y = r.near_y, near_z = r.near_z;
                     }
                 }
             }
@@ -250,11 +252,6 @@ mesh_wave_trace_kernel(const __grid_constant__ mesh_params scene, const float4* 
             // nothing to walk, or enough lanes without a query while the queue still has rays for them
             if (m_tracing == 0u || (!source_empty && 32 - __popc(m_tracing) >= k_refill)) break;
             QUASI_WAVE_PASS(2, m_tracing != 0u)
-#if defined(QUASI_HOST_EMULATION) && defined(QUASI_EMU_STATS)
-            if (!(m_descending != 0u && __popc(m_leaf) < k_wave_leaf_batch)) {
-                for (uint32_t k = 0; k < 4u; k++) QUASI_WAVE_PASS(4, (cur & 7u) - 1u < 4u && (cur & 7u) > k)
-            }
-#endif
             if (m_descending != 0u && __popc(m_leaf) < k_wave_leaf_batch) {
                 const int keep = max(__popc(m_descending) - k_wave_run_exit, 0);
                 do {
@@ -266,22 +263,27 @@ mesh_wave_trace_kernel(const __grid_constant__ mesh_params scene, const float4* 
                             wide_step(nodes, stack, inv, oi, best.t, cur);
                         } else if constexpr (Quant) {
                             nodes_visited += 2u;
-                            interior_step_quantized(scene.pairs, stack, slab::quant_ray{inv, oi}, best.t, cur);
+                            interior_step_quantized(scene.pairs, stack, slab::quant_ray{inv, oi, near_x, near_y, near_z}, best.t, cur);
                         } else {
                             nodes_visited += 2u;
                             interior_step(nodes, stack, inv, oi, best.t, cur);
                         }
                     }
                 } while (__popc(__ballot_sync(0xffffffffu, (cur & 7u) == 0u || cur == k_pop)) > keep);
-            } else if ((cur & 7u) - 1u < 4u) {
-                const uint32_t first = cur >> 3, n = cur & 7u;
-                for (uint32_t k = 0; k < n; k++) {
-                    const uint32_t slot = first + k;
-                    intersect(__ldg(scene.tri_v0 + slot), __ldg(scene.tri_e1 + slot), __ldg(scene.tri_e2 + slot), slot, ro,
-                              rd, best);
+            } else {
+#if defined(QUASI_HOST_EMULATION) && defined(QUASI_EMU_STATS)
+                for (uint32_t k = 0; k < 4u; k++) QUASI_WAVE_PASS(4, (cur & 7u) - 1u < 4u && (cur & 7u) > k)
+#endif
+                if ((cur & 7u) - 1u < 4u) {
+                    const uint32_t first = cur >> 3, n = cur & 7u;
+                    for (uint32_t k = 0; k < n; k++) {
+                        const uint32_t slot = first + k;
+                        intersect(__ldg(scene.tri_v0 + slot), __ldg(scene.tri_e1 + slot), __ldg(scene.tri_e2 + slot), slot, ro,
+                                  rd, best);
+                    }
+                    tris_tested += n;
+                    cur = stack.after_node();
                 }
-                tris_tested += n;
-                cur = stack.after_node();
             }
         }
     }

@@ -14,8 +14,8 @@
 /// The slab test only decides which subtrees are NOT visited (slab_test.hpp), so a larger box cannot change a hit:
 /// the image stays the oracle's bit for bit.
 ///
-/// A pair is 8 words: {Llo.x | Llo.y << 16, Llo.z | Lhi.x << 16, Lhi.y | Lhi.z << 16, Rlo.x | Rlo.y << 16,
-/// Rlo.z | Rhi.x << 16, Rhi.y | Rhi.z << 16, reference of L, reference of R} (references as in the float tree:
+/// A pair is 8 words: {Llo.x | Lhi.x << 16, Llo.y | Lhi.y << 16, Llo.z | Lhi.z << 16, Rlo.x | Rhi.x << 16,
+/// Rlo.y | Rhi.y << 16, Rlo.z | Rhi.z << 16, reference of L, reference of R} (references as in the float tree:
 /// left_first << 3 | count). No integer-to-float conversion on the way to the slab test: a 16-bit index q is put
 /// into the mantissa of 2^23 (one PRMT), which is the float 8388608 + q, and the plane's distance along the ray is
 /// one FFMA with per-ray constants, t = (8388608 + q) * a + b, a = scale / dir, b = (grid origin - ray origin) / dir
@@ -47,11 +47,17 @@ QUASI_SCAN_FN float fused(float a, float b, float c) {
 #endif
 }
 
-/// Per-ray constants of the quantized slab test.
+/// Per-ray constants of the quantized slab test. `near`: for each axis the PRMT selector that takes, from a word
+/// {lower bound | upper bound << 16}, the bound the ray meets first (the lower one where the direction is positive)
+/// and puts it into the mantissa of 2^23; `near ^ k_other_half` takes the other bound. The order of the two plane
+/// distances of an axis is known from the sign of `a` (a fused multiply-add is monotonic in the index), so the slab
+/// test needs no minimum and maximum per axis: seven instructions less per box than box_hit, same values.
 struct quant_ray {
     v3 a;  ///< grid step / direction
     v3 b;  ///< (grid origin - ray origin) / direction - 8388608 * a
+    uint32_t near_x, near_y, near_z;
 };
+inline constexpr uint32_t k_low_half = 0x7610u, k_high_half = 0x7632u, k_other_half = 0x0022u;
 
 /// `inv` = reciprocal(dir), `oi` = origin * inv, as for box_hit.
 QUASI_SCAN_FN quant_ray make_quant_ray(const float grid_origin[3], const float grid_step[3], v3 inv, v3 oi) {
@@ -60,38 +66,31 @@ QUASI_SCAN_FN quant_ray make_quant_ray(const float grid_origin[3], const float g
     r.b = {fused(-8388608.0f, r.a.x, fused(grid_origin[0], inv.x, -oi.x)),
            fused(-8388608.0f, r.a.y, fused(grid_origin[1], inv.y, -oi.y)),
            fused(-8388608.0f, r.a.z, fused(grid_origin[2], inv.z, -oi.z))};
+    r.near_x = r.a.x < 0.0f ? k_high_half : k_low_half;
+    r.near_y = r.a.y < 0.0f ? k_high_half : k_low_half;
+    r.near_z = r.a.z < 0.0f ? k_high_half : k_low_half;
     return r;
 }
 
-/// The float 8388608 + (low / high half of w).
-QUASI_SCAN_FN float grid_float_lo(uint32_t w) {
+/// The float 8388608 + (the half of w that `selector` names).
+QUASI_SCAN_FN float grid_float(uint32_t w, uint32_t selector) {
 #if defined(__CUDA_ARCH__)
-    return __uint_as_float(__byte_perm(w, 0x4b000000u, 0x7610u));
+    return __uint_as_float(__byte_perm(w, 0x4b000000u, selector));
 #else
-    const uint32_t bits = 0x4b000000u | (w & 0xffffu);
-    float f;
-    std::memcpy(&f, &bits, 4);
-    return f;
-#endif
-}
-QUASI_SCAN_FN float grid_float_hi(uint32_t w) {
-#if defined(__CUDA_ARCH__)
-    return __uint_as_float(__byte_perm(w, 0x4b000000u, 0x7632u));
-#else
-    const uint32_t bits = 0x4b000000u | (w >> 16);
+    const uint32_t bits = 0x4b000000u | (selector == k_low_half ? (w & 0xffffu) : (w >> 16));
     float f;
     std::memcpy(&f, &bits, 4);
     return f;
 #endif
 }
 
-/// box_hit (slab_test.hpp) for a box given as three words {lo.x | lo.y << 16, lo.z | hi.x << 16, hi.y | hi.z << 16}.
-QUASI_SCAN_FN bool box_hit_quantized(uint32_t w0, uint32_t w1, uint32_t w2, const quant_ray& r, float closest, float& t_near) {
-    const float t0x = fused(grid_float_lo(w0), r.a.x, r.b.x), t1x = fused(grid_float_hi(w1), r.a.x, r.b.x);
-    const float t0y = fused(grid_float_hi(w0), r.a.y, r.b.y), t1y = fused(grid_float_lo(w2), r.a.y, r.b.y);
-    const float t0z = fused(grid_float_lo(w1), r.a.z, r.b.z), t1z = fused(grid_float_hi(w2), r.a.z, r.b.z);
-    const float tn = std::fmax(std::fmax(std::fmin(t0x, t1x), std::fmin(t0y, t1y)), std::fmax(std::fmin(t0z, t1z), 0.0f));
-    const float tf = std::fmin(std::fmin(std::fmax(t0x, t1x), std::fmax(t0y, t1y)), std::fmin(std::fmax(t0z, t1z), closest));
+/// box_hit (slab_test.hpp) for a box given as three words {lo.x | hi.x << 16, lo.y | hi.y << 16, lo.z | hi.z << 16}.
+QUASI_SCAN_FN bool box_hit_quantized(uint32_t wx, uint32_t wy, uint32_t wz, const quant_ray& r, float closest, float& t_near) {
+    const float nx = fused(grid_float(wx, r.near_x), r.a.x, r.b.x), fx = fused(grid_float(wx, r.near_x ^ k_other_half), r.a.x, r.b.x);
+    const float ny = fused(grid_float(wy, r.near_y), r.a.y, r.b.y), fy = fused(grid_float(wy, r.near_y ^ k_other_half), r.a.y, r.b.y);
+    const float nz = fused(grid_float(wz, r.near_z), r.a.z, r.b.z), fz = fused(grid_float(wz, r.near_z ^ k_other_half), r.a.z, r.b.z);
+    const float tn = std::fmax(std::fmax(nx, ny), std::fmax(nz, 0.0f));
+    const float tf = std::fmin(std::fmin(fx, fy), std::fmin(fz, closest));
     t_near = tn;
     return tn <= tf;
 }
@@ -152,9 +151,7 @@ inline quantized_tree quantize_pairs(const scene& s) {
             const node& nd = s.nodes[2 * static_cast<size_t>(p) + 1 + c];
             const uint32_t lo[3] = {index(nd.bmin[0], 0, false), index(nd.bmin[1], 1, false), index(nd.bmin[2], 2, false)};
             const uint32_t hi[3] = {index(nd.bmax[0], 0, true), index(nd.bmax[1], 1, true), index(nd.bmax[2], 2, true)};
-            w[3 * c + 0] = lo[0] | (lo[1] << 16);
-            w[3 * c + 1] = lo[2] | (hi[0] << 16);
-            w[3 * c + 2] = hi[1] | (hi[2] << 16);
+            for (int a = 0; a < 3; a++) w[3 * c + a] = lo[a] | (hi[a] << 16);
             w[6 + c] = (nd.left_first << 3) | nd.count;
         }
     }
