@@ -543,16 +543,26 @@ def mesh_measurement(steps, warmup, builder, cpu):
     host.close()
 
     bytes_step = nodes * 32 + tris * 48  # nodes visited x 32 B + triangles tested x 48 B
-    prof = profiled_kernel("mesh_pathtrace_kernel")
+    # The frame is 2 * bounces + 2 launches (mesh_wavefront.cu); the trace kernel's four launches are 84 % of it under
+    # ncu (profiles/ncu_summary.json), and that share of this run's frame time is what its issue slots are counted over.
+    prof = profiled_kernel("mesh_wave_trace_kernel")
     issue = None
+    trace_ms = None
     if prof and clocks.get("sm_mhz"):
-        per_launch = prof["warp_instructions_per_launch"]
-        slots = 148 * 4 * clocks["sm_mhz"] * 1e6 * (ms_step / spp) * 1e-3
-        issue = {"warp_inst_per_launch": int(per_launch), "frac": round(per_launch / slots, 4),
+        share = prof["time_ms_under_ncu_per_frame"] / prof["frame_ms_under_ncu_all_kernels"]
+        trace_ms = ms_step * share
+        per_frame = prof["warp_instructions_per_frame"]
+        slots = 148 * 4 * clocks["sm_mhz"] * 1e6 * trace_ms * 1e-3
+        issue = {"warp_inst_per_frame": int(per_frame), "frac": round(per_frame / slots, 4),
+                 "warp_inst_per_ray": round(per_frame / rays, 2),
+                 "kernel_share_of_frame_ncu": round(share, 4),
                  "issue_slot_utilization_ncu": prof.get("issue_slot_utilization"),
                  "threads_per_instruction_ncu": prof.get("threads_per_instruction"),
+                 "threads_per_instruction_per_wave_ncu": prof.get("threads_per_instruction_per_wave"),
                  "l1_hit_rate_ncu": prof.get("l1_hit_rate"), "l2_hit_rate_ncu": prof.get("l2_hit_rate"),
-                 "dram_bytes_per_launch_ncu": (prof.get("dram_bytes_read", 0) + prof.get("dram_bytes_write", 0)) or None}
+                 "l1_data_pipe_utilization_per_wave_ncu": prof.get("l1_data_pipe_utilization_per_wave"),
+                 "dram_bytes_per_frame_ncu": (prof.get("dram_bytes_read", 0) + prof.get("dram_bytes_write", 0)) or None,
+                 "source": prof.get("source")}
     line = {
         "metric": "Mrays/s @1080p 16spp (1 M-triangle mesh scene, 4 bounces, headless via plugin C ABI)",
         "value": round(rays / (ms_step * 1e-3) / 1e6, 2), "unit": "Mrays/s", "n_gpus": 1, "steps": steps,
@@ -563,19 +573,23 @@ def mesh_measurement(steps, warmup, builder, cpu):
                                f"{bounces} bounces, BVH builder {builder}",
                    "rays_per_step": rays, "nodes_per_ray": round(nodes / rays, 2),
                    "triangles_per_ray": round(tris / rays, 2), "plugin_messages": messages,
-                   "l2": "no flush: the scene (20-37 MB of nodes, 96 MB of triangles and shading records) is meant "
-                         "to be served by L2; the 132.7 MB accumulation set is streamed every launch"},
+                   "l2": "no flush: the scene (19 MB of quantized nodes, 96 MB of triangles and shading records) is meant "
+                         "to be served by L2; the ray queues of a 16-sample batch (GBs) are streamed through it"},
         "e2e": {"value": round(rays / e2e_s / 1e6, 2), "unit": "Mrays/s", "ms_per_step": round(e2e_s * 1e3, 4),
                 "h2d_bytes_per_step": spp * (320 + 80), "d2h_bytes_per_step": width * height * 64},
         "gpu_launches": launches, "clocks": clocks,
-        "roofline": {"bound": "issue", "kernel": "mesh_pathtrace_kernel", "issue": issue,
+        "roofline": {"bound": "issue", "kernel": "mesh_wave_trace_kernel", "issue": issue,
                      "cache_served": {"achieved": round(bytes_step / (ms_step * 1e-3) / 1e9, 1), "unit": "GB/s",
-                                      "algorithmic_bytes_per_launch": round(bytes_step / spp),
-                                      "what": "nodes visited x 32 B + triangles tested x 48 B (SURVEY.md 8d), served by L1 and "
-                                              "L2, NOT HBM traffic: DRAM traffic is ~0.8 GB per launch (ncu)"},
-                     "kernel_ms": round(ms_step / spp, 5),
-                     "note": "bound by instruction issue at low SIMD efficiency, then L1/L2 latency (DESIGN.md 4.3); no HBM "
-                             "fraction is quoted because the bytes above never reach HBM"},
+                                      "algorithmic_bytes_per_frame": round(bytes_step),
+                                      "what": "nodes visited x 32 B + triangles tested x 48 B (SURVEY.md 8d's unit; the "
+                                              "quantized tree reads 16 B per node), served by L1 and L2, NOT HBM traffic"},
+                     "kernel_ms_per_frame": round(trace_ms, 4) if trace_ms else None,
+                     "launches_per_frame": launches / steps,
+                     "note": "config 3 is a wavefront: ray generation, then per bounce a persistent trace kernel and a "
+                             "streaming shade kernel, then the resolve (accumulate) pass. The trace kernel is bound by "
+                             "instruction issue at 17 to 23 of 32 lanes (DESIGN.md 4.3); the shade and resolve kernels "
+                             "stream the ray queues at HBM speed. No HBM fraction is quoted for the trace kernel because "
+                             "the bytes above are served by L1/L2"},
     }
     if cpu:
         from oracle_lib import MeshOracle

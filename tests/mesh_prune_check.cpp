@@ -12,8 +12,11 @@
 // binary one (wide_bvh.hpp: collapse_wide and wide_visit, the code the kernel compiles), after
 // a structural check of that tree: every leaf slot reachable exactly once, every child box
 // the box of a node of the binary tree, the stack bound it reports never exceeded.
-//   usage: mesh_prune_check [grid] [rays] [wide [stack limit]]   -> prints counts, exit code 1 on any mismatch
+// With "quant" the rays go through the binary tree in its quantized form (quantized_bvh.hpp), after a check that every
+// quantized box holds its float box with half a grid step to spare and carries the tree's references.
+//   usage: mesh_prune_check [grid] [rays] [wide [stack limit] | quant]   -> prints counts, exit code 1 on any mismatch
 #include "mesh_scene.hpp"
+#include "quantized_bvh.hpp"
 #include "slab_test.hpp"
 #include "wide_bvh.hpp"
 
@@ -64,12 +67,21 @@ hit brute_force(const mesh::scene& s, v3 o, v3 d) {
 
 /// The traversal of mesh_trace.cu in one thread: near child first, far child deferred with its
 /// entry distance (kept at the precision of the kernel's stack: upper 16 bits), culled on pop.
-hit through_the_tree(const mesh::scene& s, v3 o, v3 d, uint64_t& boxes) {
+/// With `grid` (mode "quant") the children are tested in their quantized form (quantized_bvh.hpp: the pairs, the
+/// per-ray constants and box_hit_quantized as the wavefront trace kernel compiles them); the root stays a float box.
+hit through_the_tree(const mesh::scene& s, v3 o, v3 d, uint64_t& boxes, const mesh::quantized_tree* grid = nullptr) {
     hit best;
     const v3 inv{slab::reciprocal(d.x), slab::reciprocal(d.y), slab::reciprocal(d.z)};
     const v3 oi{o.x * inv.x, o.y * inv.y, o.z * inv.z};
+    slab::quant_ray qr{};
+    if (grid) qr = slab::make_quant_ray(grid->origin, grid->step, inv, oi);
     auto box = [&](const mesh::node& n, float& tn) {
         boxes++;
+        const size_t index = static_cast<size_t>(&n - s.nodes.data());
+        if (grid && index != 0) {
+            const uint32_t* w = &grid->pairs[(index - 1) / 2 * mesh::k_pair_words + 3 * ((index - 1) % 2)];
+            return slab::box_hit_quantized(w[0], w[1], w[2], qr, best.t, tn);
+        }
         return slab::box_hit(f4{n.bmin[0], n.bmin[1], n.bmin[2], 0.0f}, f4{n.bmax[0], n.bmax[1], n.bmax[2], 0.0f}, inv, oi,
                              best.t, tn);
     };
@@ -257,6 +269,7 @@ int main(int argc, char** argv) {
     const uint32_t grid = argc > 1 ? static_cast<uint32_t>(std::atoi(argv[1])) : 40u;
     const long rays = argc > 2 ? std::atol(argv[2]) : 200000;
     const bool wide = argc > 3 && std::strcmp(argv[3], "wide") == 0;
+    const bool quant = argc > 3 && std::strcmp(argv[3], "quant") == 0;
     mesh::scene s;
     mesh::generate_triangles(grid, 1, s);
     mesh::build_bvh(s);
@@ -272,6 +285,26 @@ int main(int argc, char** argv) {
                     "structure violations %ld\n",
                     w.node_count, s.nodes.size(), s.nodes.size() / 2, static_cast<double>(w.children) / w.node_count, w.depth,
                     s.depth, w.stack_need, structure);
+    }
+
+    mesh::quantized_tree lattice;
+    if (quant) {
+        lattice = mesh::quantize_pairs(s);
+        // every quantized box holds the float box it stands for, with room, and the references are the tree's
+        long outside = lattice.pairs.empty() ? 1 : 0;
+        for (size_t i = 1; i < s.nodes.size() && !lattice.pairs.empty(); i++) {
+            const uint32_t* w = &lattice.pairs[(i - 1) / 2 * mesh::k_pair_words];
+            const uint32_t* b = w + 3 * ((i - 1) % 2);
+            for (int a = 0; a < 3; a++) {
+                const double lo = lattice.origin[a] + static_cast<double>(b[a] & 0xffffu) * lattice.step[a];
+                const double hi = lattice.origin[a] + static_cast<double>(b[a] >> 16) * lattice.step[a];
+                if (!(lo <= s.nodes[i].bmin[a] - 0.5 * lattice.step[a]) || !(hi >= s.nodes[i].bmax[a] + 0.5 * lattice.step[a])) outside++;
+            }
+            if (w[6 + (i - 1) % 2] != ((s.nodes[i].left_first << 3) | s.nodes[i].count)) outside++;
+        }
+        structure += outside;
+        std::printf("quantized tree: %u pairs, grid step %.3g %.3g %.3g, structure violations %ld\n", lattice.pair_count,
+                    lattice.step[0], lattice.step[1], lattice.step[2], outside);
     }
 
     std::mt19937 rng(11);
@@ -316,7 +349,8 @@ int main(int argc, char** argv) {
         if (!(len > 0.0f)) continue;
         d = {d.x / len, d.y / len, d.z / len};
         const hit want = brute_force(s, o, d);
-        const hit got = wide ? through_the_wide_tree(s, w, o, d, boxes, visits, high_water) : through_the_tree(s, o, d, boxes);
+        const hit got = wide ? through_the_wide_tree(s, w, o, d, boxes, visits, high_water)
+                             : through_the_tree(s, o, d, boxes, quant ? &lattice : nullptr);
         hits += want.prim != 0xffffffffu;
         if (got.prim != want.prim || got.t != want.t) {
             if (mismatches < 10) {

@@ -42,3 +42,17 @@ def test_wide_tree_is_the_binary_tree_regrouped_and_finds_the_brute_force_hit(tm
         visits = float(words[words.index("visits_per_ray") + 1])
         assert deepest <= bound <= int(limit)
         assert visits < most_visits
+
+
+@pytest.mark.parametrize("flags", [(), ("-DQUASI_SCAN_CHECK_PERTURB",)], ids=["exact-reciprocal", "reciprocal-2ulp-off"])
+def test_quantized_tree_holds_the_float_tree_and_finds_the_brute_force_hit(tmp_path, flags):
+    """quantized_bvh.hpp as the wavefront trace kernel compiles it: 16-bit boxes on a grid, plane distances by one
+    fused multiply-add from the index in the mantissa of 2^23, near and far plane chosen by the ray's sign."""
+    exe = tmp_path / "mesh_prune_check"
+    subprocess.run(["g++", "-std=c++20", "-O2", "-ffp-contract=off", "-Wall", "-Wextra", "-pthread", *flags,
+                    f"-I{ROOT / 'quasi_b200' / 'csrc'}", str(ROOT / "tests" / "mesh_prune_check.cpp"), "-o", str(exe)],
+                   check=True)
+    for grid in ("32", "3"):
+        out = subprocess.run([str(exe), grid, "80000", "quant"], capture_output=True, text=True)
+        assert out.returncode == 0, out.stdout[-2000:]
+        assert "structure violations 0" in out.stdout and "mismatches 0" in out.stdout
