@@ -284,6 +284,132 @@ std::vector<float> combine_on_root(std::vector<std::unique_ptr<gpu_worker>>& wor
     return host;
 }
 
+/// The sample-shard exchange of one frame as part of the render (quasi_cuda_backend.h: Q_cuda_plugin_set_reduce),
+/// for several GPUs driven by this process: the layer block is cut into G slices along rows of 8x4 tiles, GPU s owns
+/// slice s (a staging area of G slots and an arrival counter per tile and layer, in its own memory, reached by the
+/// others through peer access), and the batched render kernels store every finished tile at its owners, count its
+/// arrivals and, where an arrival is the G-th, sum the G copies in rank order and store the finished tile into
+/// `frame`, pinned host memory every GPU has mapped. When the last GPU's last launch ends, the frame is on the host:
+/// no combine pass, no copy. One frame per set-up (--repeat uses combine_on_root).
+struct fused_exchange {
+    std::vector<int> devices;
+    std::vector<void*> staging, counters;
+    float* frame = nullptr;
+    uint64_t frame_floats = 0;
+    bool active = false;
+
+    /// slice_lo[0..G] (quasi_b200/multi_gpu.py:tile_row_slices): 4 * ceil(h / 4) rows of tiles over the four layers,
+    /// slice s starts at row ceil(s * rows / G).
+    static std::vector<uint32_t> slices(uint32_t w, uint32_t h, uint32_t ranks) {
+        const uint32_t tiles_y = (h + 3u) / 4u, rows = 4u * tiles_y;
+        std::vector<uint32_t> lo(ranks + 1u);
+        for (uint32_t s = 0; s <= ranks; s++) {
+            const uint32_t row = (s * rows + ranks - 1u) / ranks;
+            lo[s] = s == ranks ? 4u * w * h : ((row / tiles_y) * h + (row % tiles_y) * 4u) * w;
+        }
+        return lo;
+    }
+
+    bool setup(std::vector<std::unique_ptr<gpu_worker>>& workers, uint32_t w, uint32_t h, uint32_t render_calls) {
+        using set_reduce_fn = int (*)(Q_plugin_handle*, const Q_cuda_reduce_table*);
+        const uint32_t ranks = static_cast<uint32_t>(workers.size());
+        if (ranks < 2 || ranks > Q_CUDA_MAX_EXPORT_SLICES || w == 0 || h == 0) return false;
+        for (auto& wk : workers) devices.push_back(wk->context.device_ordinal());
+        for (int a : devices) {
+            if (cudaSetDevice(a) != cudaSuccess) return false;
+            for (int b : devices) {
+                if (a == b) continue;
+                const cudaError_t e = cudaDeviceEnablePeerAccess(b, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                    (void)cudaGetLastError();
+                    return false;
+                }
+                (void)cudaGetLastError();
+            }
+        }
+        const std::vector<uint32_t> lo = slices(w, h, ranks);
+        uint32_t stride = 1;
+        for (uint32_t s = 0; s < ranks; s++) stride = std::max(stride, lo[s + 1] - lo[s]);
+        const size_t n_tiles = static_cast<size_t>((w + 7u) / 8u) * ((h + 3u) / 4u);
+        frame_floats = static_cast<uint64_t>(w) * h * 16u;
+        if (cudaHostAlloc(reinterpret_cast<void**>(&frame), frame_floats * sizeof(float),
+                          cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
+            (void)cudaGetLastError();
+            frame = nullptr;
+            return false;
+        }
+        for (int d : devices) {
+            void *st = nullptr, *ct = nullptr;
+            if (cudaSetDevice(d) != cudaSuccess || cudaMalloc(&st, static_cast<size_t>(ranks) * stride * 16u) != cudaSuccess ||
+                cudaMalloc(&ct, 4u * n_tiles * sizeof(uint32_t)) != cudaSuccess ||
+                cudaMemset(ct, 0, 4u * n_tiles * sizeof(uint32_t)) != cudaSuccess) {
+                (void)cudaGetLastError();
+                if (st) cudaFree(st);
+                if (ct) cudaFree(ct);
+                return false;
+            }
+            staging.push_back(st);
+            counters.push_back(ct);
+        }
+        for (uint32_t g = 0; g < ranks; g++) {
+            auto set_reduce = workers[g]->manager->extension<set_reduce_fn>("Q_cuda_plugin_set_reduce");
+            auto* plugin = workers[g]->manager->plugin();
+            if (!set_reduce || !plugin) return false;
+            Q_cuda_reduce_table t{};
+            t.struct_size = sizeof t;
+            t.ranks = ranks;
+            t.rank = g;
+            t.slot_stride = stride;
+            t.render_calls = render_calls;
+            for (uint32_t s = 0; s <= ranks; s++) t.slice_lo[s] = lo[s];
+            for (uint32_t s = 0; s < ranks; s++) {
+                t.staging[s] = staging[s];
+                t.counters[s] = static_cast<uint32_t*>(counters[s]);
+                t.out[s] = frame + static_cast<size_t>(lo[s]) * 4u;
+            }
+            if (set_reduce(plugin->native_handle(), &t) != 0) return false;
+        }
+        active = true;
+        return true;
+    }
+
+    /// After the frame's render calls: launches what the plugins still hold; true if every GPU's last launch carried
+    /// the exchange, i.e. `frame` is the finished frame once the GPUs are idle (they are waited for here).
+    bool finish(std::vector<std::unique_ptr<gpu_worker>>& workers) {
+        using flush_fn = int (*)(Q_plugin_handle*, void*);
+        bool all = active;
+        for (auto& wk : workers) {
+            auto flush = wk->manager->extension<flush_fn>("Q_cuda_plugin_flush");
+            auto* plugin = wk->manager->plugin();
+            if (!flush || !plugin || flush(plugin->native_handle(), wk->context.queue()) != 1) all = false;
+        }
+        for (int d : devices) {
+            cudaSetDevice(d);
+            cudaDeviceSynchronize();
+        }
+        return all;
+    }
+
+    void release(std::vector<std::unique_ptr<gpu_worker>>& workers) {
+        using set_reduce_fn = int (*)(Q_plugin_handle*, const Q_cuda_reduce_table*);
+        for (auto& wk : workers) {
+            auto set_reduce = wk->manager->extension<set_reduce_fn>("Q_cuda_plugin_set_reduce");
+            if (auto* plugin = wk->manager->plugin(); set_reduce && plugin) (void)set_reduce(plugin->native_handle(), nullptr);
+        }
+        for (size_t i = 0; i < staging.size(); i++) {
+            cudaSetDevice(devices[i]);
+            cudaDeviceSynchronize();
+            cudaFree(staging[i]);
+            cudaFree(counters[i]);
+        }
+        staging.clear();
+        counters.clear();
+        if (frame) cudaFreeHost(frame);
+        frame = nullptr;
+        active = false;
+    }
+};
+
 }  // namespace
 
 int main(int argc, char* argv[]) {
@@ -374,6 +500,19 @@ int main(int argc, char* argv[]) {
         }
     };
     disable_mirrors();
+    // One frame on several GPUs: the exchange rides inside the render (fused_exchange); QUASI_HOST_EXCHANGE=pull keeps
+    // the combine pass on GPU 0 after the render, which is also what any failure to set the fused form up falls back to.
+    fused_exchange exchange;
+    const char* exchange_mode = std::getenv("QUASI_HOST_EXCHANGE");
+    if (workers.size() > 1 && opt.render_frames > 0 && opt.repeat == 1 && !opt.watch && !opt.present &&
+        !(exchange_mode && std::strcmp(exchange_mode, "pull") == 0)) {
+        if (exchange.setup(workers, opt.width, opt.height, static_cast<uint32_t>(opt.render_frames))) {
+            std::printf("[Host] Shard exchange fused into the render kernels (%zu GPUs)\n", workers.size());
+        } else {
+            exchange.release(workers);
+            disable_mirrors();
+        }
+    }
     if (auto info = workers[0]->manager->info()) {
         std::printf("Loaded plugin: %s v%u.%u.%u\n", info->name, info->version.major, info->version.minor,
                     info->version.patch);
@@ -397,7 +536,6 @@ int main(int argc, char* argv[]) {
         return std::all_of(workers.begin(), workers.end(), [](const auto& w) { return w->finished; });
     };
     while (!all_finished()) scheduler.tick();
-    const double elapsed_s = std::chrono::duration<double>(clock_type::now() - start).count();
 
     // Statistics (Mrays/s needs the backend's ray counter; the reference has none).
     uint64_t rays = 0, paths = 0, frames = 0, launches = 0;
@@ -410,6 +548,8 @@ int main(int argc, char* argv[]) {
         }
         frames += w->frames;
     }
+    // (taken after the statistics: asking for them launches the render calls a plugin still holds and waits for them)
+    const double elapsed_s = std::chrono::duration<double>(clock_type::now() - start).count();
     std::printf("[Host] %llu frames, %llu paths, %llu rays in %.3f s: %.1f Mrays/s, %.3f ms/frame\n",
                 static_cast<unsigned long long>(frames), static_cast<unsigned long long>(paths),
                 static_cast<unsigned long long>(rays), elapsed_s, static_cast<double>(rays) / elapsed_s / 1e6,
@@ -452,9 +592,19 @@ int main(int argc, char* argv[]) {
                 std::printf("[Host] Plugin does not support HDR readback\n");
             }
         } else {
-            std::printf("[Host] Combining %zu sample shards on GPU %d...\n", workers.size(),
-                        workers[0]->context.device_ordinal());
-            std::vector<float> host = combine_on_root(workers, opt.width, opt.height);
+            std::vector<float> host;
+            if (exchange.active && exchange.finish(workers)) {
+                std::printf("[Host] Frame of %zu sample shards reduced inside the render kernels\n", workers.size());
+                host.assign(exchange.frame, exchange.frame + exchange.frame_floats);
+            } else {
+                if (exchange.active) {  // e.g. a last launch of a single sample: nothing was exported
+                    exchange.release(workers);
+                    disable_mirrors();
+                }
+                std::printf("[Host] Combining %zu sample shards on GPU %d...\n", workers.size(),
+                            workers[0]->context.device_ordinal());
+                host = combine_on_root(workers, opt.width, opt.height);
+            }
             if (host.empty()) {
                 std::fprintf(stderr, "[Host] Shard combine failed\n");
                 exit_code = EXIT_FAILURE;
@@ -497,6 +647,7 @@ int main(int argc, char* argv[]) {
     }
 
     std::printf("Shutting down...\n");
+    exchange.release(workers);
     workers.clear();  // managers destroy their plugins before the contexts go away
     return exit_code;
 }

@@ -118,6 +118,37 @@ def test_headless_host_renders_the_oracle_image_to_exr(host_built, oracle, tmp_p
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["fused", "pull"])
+def test_headless_host_on_several_gpus_writes_the_oracles_combined_frame(host_built, oracle, tmp_path, mode):
+    """--gpus G in one process: GPU g renders the RNG frame indices g, g + G, ...; the frame written to the EXR is the
+    oracle's rank-ordered combine of the shard images, with the exchange inside the render kernels (the default:
+    fused_exchange in host/src/main.cpp, Q_cuda_plugin_set_reduce over peer access) and with the combine pass on GPU 0
+    that it falls back to (QUASI_HOST_EXCHANGE=pull)."""
+    import torch
+
+    import quasi_b200
+
+    gpus = min(torch.cuda.device_count(), 4)
+    if gpus < 2:
+        pytest.skip("needs >= 2 GPUs")
+    w, h, n = 200, 113, 5
+    out = tmp_path / "frame.exr"
+    run = subprocess.run([str(BIN / "quasi_headless"), "--render", str(n), "--gpus", str(gpus), "--width", str(w),
+                          "--height", str(h), "--out", str(out), str(quasi_b200.PLUGIN_PATH)],
+                         capture_output=True, text=True, timeout=300, env={**os.environ, "QUASI_HOST_EXCHANGE": mode})
+    assert run.returncode == 0, run.stdout[-2000:] + run.stderr[-2000:]
+    assert ("reduced inside the render kernels" in run.stdout) == (mode == "fused"), run.stdout[-2000:]
+    u = oracle.scene(w, h)
+    shards = [oracle.render_frames(u, w, h, n, frame_first=g, frame_stride=gpus)[0] for g in range(gpus)]
+    want = [oracle.combine_shards([s[l] for s in shards]) for l in range(4)]
+    got, _ = read_exr(out)
+    for k, ch in enumerate("RGBA"):
+        assert np.array_equal(got[ch], want[0][..., k].astype(np.float16)), ch
+    assert np.array_equal(got["depth.Z"].view(np.uint32), want[3][..., 0].view(np.uint32))
+    assert np.array_equal(got["normal.Y"], want[2][..., 1].astype(np.float16))
+
+
+@pytest.mark.gpu
 def test_headless_host_hot_reload_continuity(host_built, tmp_path):
     """BASELINE configs[4]: progressive 1 spp/frame with the backend replaced mid-run.
     Accumulation restarts at sample 0 after a reload, as in the reference (state
