@@ -11,7 +11,13 @@ h = headless_host(61, 35, env={"QUASI_CUDA_BATCH": 3, "QUASI_CUDA_MIRROR": 0, "Q
 for builder in ("sah", "lbvh"):
     h = headless_host(80, 45, env={"QUASI_CUDA_SCENE": "mesh", "QUASI_CUDA_MESH_GRID": 40, "QUASI_CUDA_MESH_SEED": 1,
                                    "QUASI_CUDA_MAX_BOUNCES": 4, "QUASI_CUDA_MESH_BUILDER": builder})
-    h.render(2); a = h.readback_aov(); print("mesh", builder, h.stats().rays); h.close()
+    h.render(2); a = h.readback_aov(); print("mesh, wavefront form (quantized tree)", builder, h.stats().rays); h.close()
+h = headless_host(77, 45, env={"QUASI_CUDA_SCENE": "mesh", "QUASI_CUDA_MESH_GRID": 40, "QUASI_CUDA_MESH_SEED": 1, "QUASI_CUDA_MAX_BOUNCES": 4,
+                               "QUASI_CUDA_MESH_BATCH": 2, "QUASI_CUDA_MESH_QUANT": 0})
+h.render(5); a = h.readback_aov(); print("mesh, wavefront form, float tree, ragged image, batches of 2", h.stats().rays); h.close()
+h = headless_host(80, 45, env={"QUASI_CUDA_SCENE": "mesh", "QUASI_CUDA_MESH_GRID": 40, "QUASI_CUDA_MESH_SEED": 1, "QUASI_CUDA_MAX_BOUNCES": 4,
+                               "QUASI_CUDA_MESH_WAVEFRONT": 0})
+h.render(2); a = h.readback_aov(); print("mesh, one-kernel form", h.stats().rays); h.close()
 h = headless_host(64, 36, keep_accumulation=True); h.render(2); h.reload(); h.render(2); print("persist", h.stats().frame_count); h.close()
 PY
 for tool in memcheck racecheck initcheck synccheck; do
