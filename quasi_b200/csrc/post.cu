@@ -77,8 +77,11 @@ __device__ __noinline__ unsigned tonemap_channel_precise(float c) {
 /// The same 8-bit value, cheaply: three MUFU operations give 255 * (c / (c + 1))^(1/2.2) to within
 /// 6e-4 (rcp 2^-23, lg2 2^-22 absolute on an exponent of at most 22 where the result is not yet
 /// zero, ex2 2^-22), which rounds to the same integer as the literal form unless it lies within
-/// 2e-3 of a rounding boundary; those channels (0.4 %), and anything not finite, take the literal
-/// form. Rounding and conversion are done by the adder (y + 2^23 is y rounded to nearest even, its
+/// 7e-4 of a rounding boundary (6e-4, the literal form's own 6e-5 and the product's 1.5e-5); those
+/// channels (0.14 %), and anything not finite, take the literal form. The width of that band is what
+/// the pass costs: the literal form is ~150 instructions for the whole warp whenever ONE lane needs it,
+/// and with a band of 2e-3 (0.4 % of the channels, 12 % of the warp-level calls) the pass ran at 0.65
+/// of HBM bandwidth at 4K, with 1e-3 at 0.77, with 7e-4 at 0.79 (profiles/r2b_tonemap_band.log). Rounding and conversion are done by the adder (y + 2^23 is y rounded to nearest even, its
 /// low mantissa bits are the integer): F2I and FRND share the MUFU pipe, which is what bounds this
 /// pass once powf is gone (ncu, round 2: powf for every channel ran at 0.24 of HBM bandwidth, the
 /// MUFU form with floorf and F2I at 0.43 with the XU pipe 71 % busy).
@@ -87,7 +90,7 @@ __device__ __forceinline__ unsigned tonemap_channel(float c) {
     const float y = mufu_ex2(mufu_lg2(r) * (1.0f / 2.2f)) * 255.0f;
     const float rounded = y + 8388608.0f;
     const float off = y - (rounded - 8388608.0f);  // in [-1/2, 1/2]
-    if (!(fabsf(off) <= 0.5f - 2e-3f)) return tonemap_channel_precise(c);  // near a boundary, or NaN
+    if (!(fabsf(off) <= 0.5f - 7e-4f)) return tonemap_channel_precise(c);  // near a boundary, or NaN
     return __float_as_uint(rounded) & 0xffu;
 }
 
