@@ -78,3 +78,31 @@ def test_slice_partition_is_exact():
             assert spans[0][0] == 0 and spans[-1][1] == total
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             assert all(hi >= lo for lo, hi in spans)
+
+
+def test_tile_row_slices_give_every_tile_of_a_layer_one_owner():
+    """The fused exchange's cut (multi_gpu.py:tile_row_slices, the same formula in host/src/main.cpp and in the
+    emulator harness): the slices cover the four layers exactly, are as even as rows of tiles allow, and every
+    boundary falls on a row of 8x4 tiles of one layer, so the 32 pixels of a tile in a layer never straddle two
+    owners (the kernel counts arrivals per tile and layer at ONE owner)."""
+    sys.path.insert(0, str(ROOT))
+    from quasi_b200.multi_gpu import tile_row_slices
+
+    for w, h in ((1920, 1080), (3840, 2160), (320, 180), (61, 35), (33, 17), (8, 4), (1, 1)):
+        for world in (2, 3, 4, 5, 8, 16):
+            lo = tile_row_slices(w, h, world)
+            assert len(lo) == world + 1 and lo[0] == 0 and lo[-1] == 4 * w * h
+            assert all(a <= b for a, b in zip(lo, lo[1:]))
+            tiles_y = (h + 3) // 4
+            for x in lo[:-1]:
+                assert x % w == 0 and ((x // w) % h) % 4 == 0           # starts a row of tiles of one layer
+            sizes = [b - a for a, b in zip(lo, lo[1:])]
+            rows = [-(-(s + 1) * 4 * tiles_y // world) - (-(-s * 4 * tiles_y // world)) for s in range(world)]
+            assert max(rows) - min(rows) <= 1                          # rows of tiles per slice: as even as it gets
+            # every unit (tile, layer) lies inside one slice
+            for layer in range(4):
+                for ty in range(tiles_y):
+                    first = (layer * h + ty * 4) * w
+                    last = (layer * h + min(h, ty * 4 + 4)) * w - 1
+                    owner = max(s for s in range(world) if lo[s] <= first)
+                    assert last < lo[owner + 1] or sizes[owner] == 0, (w, h, world, layer, ty)
