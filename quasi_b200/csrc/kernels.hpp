@@ -8,6 +8,7 @@
 #include <cuda_runtime_api.h>
 
 #include <cstdint>
+#include <functional>
 
 namespace Q::cuda {
 
@@ -82,11 +83,13 @@ struct mesh_wave_buffers {
 size_t mesh_wave_bytes_per_path();
 
 /// @brief frame.batch_samples samples per pixel of the mesh scene as waves of rays (mesh_wavefront.cu), folded into
-/// the four layers in place, in sample order. Enqueue only; 2 * max_bounces + 2 launches.
+/// the four layers in place, in sample order. Enqueue only; 2 * max_bounces + 3 launches.
 /// @param launches if not null: receives the number of kernels launched.
+/// @param first_hit_layers_enqueued if set: called once the kernel that leaves albedo, normal and depth final has been
+///        enqueued on `stream` (after the first shade pass; the beauty layer is final when the last launch ends).
 cudaError_t launch_mesh_wavefront(const mesh_params& scene, const frame_params& frame, const mesh_wave_buffers& q,
                                   float* const layers[4], unsigned long long* counters, int sm_count, cudaStream_t stream,
-                                  uint32_t* launches = nullptr);
+                                  uint32_t* launches = nullptr, const std::function<void()>& first_hit_layers_enqueued = {});
 
 /// Triangles in ORIGINAL order on the device: what build_lbvh reads.
 struct lbvh_input {

@@ -19,7 +19,7 @@
 ///                             the other queue (one atomic per warp), finished ones store their colour;
 ///   mesh_wave_resolve_kernel  accumulate (plugin.mm:313-330): the k samples of a pixel folded into the four layers
 ///                             in sample order, layers read and written once per batch instead of once per sample.
-/// All rays of wave b are at bounce b, so a frame of k samples is 2 * max_bounces + 2 launches however large k is:
+/// All rays of wave b are at bounce b, so a frame of k samples is 2 * max_bounces + 3 launches however large k is:
 /// the plugin collects the headless render calls of a frame (QUASI_CUDA_MESH_BATCH, default 16) as it does for the
 /// demo scene. Every draw of a path's RNG stream happens in the order of the shader, every sample is folded with
 /// the weight of its own call: the image is the oracle's bit for bit, as with the one-kernel form (which stays for
@@ -439,7 +439,10 @@ mesh_wave_shade_kernel(const __grid_constant__ mesh_params scene, const __grid_c
     }
 }
 
-/// accumulate (plugin.mm:313-330) for the `samples` samples of the batch, in sample order, in place.
+/// accumulate (plugin.mm:313-330) for the `samples` samples of the batch, in sample order, in place. `Beauty`: the
+/// beauty layer, when every path has ended; otherwise the three first-hit layers (albedo, normal, depth), which are
+/// complete after the first shade pass, so that they can leave for the host while the later waves are traced.
+template <bool Beauty>
 __global__ void __launch_bounds__(k_block_threads)
 mesh_wave_resolve_kernel(const __grid_constant__ frame_params frame, const __grid_constant__ mesh_wave_buffers q,
                          uint32_t samples, float4* __restrict__ beauty, float4* __restrict__ albedo,
@@ -450,31 +453,40 @@ mesh_wave_resolve_kernel(const __grid_constant__ frame_params frame, const __gri
         const bool fresh = frame.sample_index == 0u;  // history before the first sample is defined as zero
         float4 b = make_float4(0.0f, 0.0f, 0.0f, 0.0f), a = b, n = b, d = b;
         if (!fresh) {
-            b = load_once(beauty + pixel);
-            a = load_once(albedo + pixel);
-            n = load_once(normal + pixel);
-            d = load_once(depth + pixel);
+            if constexpr (Beauty) {
+                b = load_once(beauty + pixel);
+            } else {
+                a = load_once(albedo + pixel);
+                n = load_once(normal + pixel);
+                d = load_once(depth + pixel);
+            }
         }
         for (uint32_t s = 0; s < samples; s++) {
             const size_t path = static_cast<size_t>(s) * n_px + pixel;
-            const float4 sb = load_once(q.out_beauty + path), sa = load_once(q.out_albedo_depth + path),
-                         sn = load_once(q.out_normal + path);
             const uint32_t sample_index = frame.sample_index + s;
-            const float4 va = make_float4(sa.x, sa.y, sa.z, 1.0f), vd = make_float4(sa.w, sa.w, sa.w, 1.0f);
-            if (sample_index == 0u) {
-                b = sb, a = va, n = sn, d = vd;
+            const float weight = 1.0f / static_cast<float>(sample_index + 1u);
+            if constexpr (Beauty) {
+                const float4 sb = load_once(q.out_beauty + path);
+                b = sample_index == 0u ? sb : mix4(b, sb, weight);
             } else {
-                const float weight = 1.0f / static_cast<float>(sample_index + 1u);
-                b = mix4(b, sb, weight);
-                a = mix4(a, va, weight);
-                n = mix4(n, sn, weight);
-                d = mix4(d, vd, weight);
+                const float4 sa = load_once(q.out_albedo_depth + path), sn = load_once(q.out_normal + path);
+                const float4 va = make_float4(sa.x, sa.y, sa.z, 1.0f), vd = make_float4(sa.w, sa.w, sa.w, 1.0f);
+                if (sample_index == 0u) {
+                    a = va, n = sn, d = vd;
+                } else {
+                    a = mix4(a, va, weight);
+                    n = mix4(n, sn, weight);
+                    d = mix4(d, vd, weight);
+                }
             }
         }
-        store_once(beauty + pixel, b);
-        store_once(albedo + pixel, a);
-        store_once(normal + pixel, n);
-        store_once(depth + pixel, d);
+        if constexpr (Beauty) {
+            store_once(beauty + pixel, b);
+        } else {
+            store_once(albedo + pixel, a);
+            store_once(normal + pixel, n);
+            store_once(depth + pixel, d);
+        }
     }
 }
 
@@ -486,7 +498,7 @@ size_t mesh_wave_bytes_per_path() { return 2 * 4 * sizeof(float4) + sizeof(float
 
 cudaError_t launch_mesh_wavefront(const mesh_params& scene, const frame_params& frame, const mesh_wave_buffers& q,
                                   float* const layers[4], unsigned long long* counters, int sm_count, cudaStream_t stream,
-                                  uint32_t* launches) {
+                                  uint32_t* launches, const std::function<void()>& first_hit_layers_enqueued) {
     const uint32_t samples = frame.batch_samples > 1u ? frame.batch_samples : 1u;
     const uint64_t n_px = static_cast<uint64_t>(frame.width) * frame.height;
     if (n_px == 0) return cudaSuccess;
@@ -512,6 +524,10 @@ cudaError_t launch_mesh_wavefront(const mesh_params& scene, const frame_params& 
     mesh_wave_raygen_kernel<<<static_cast<uint32_t>(raygen_needed < streaming_blocks ? raygen_needed : streaming_blocks),
                               k_block_threads, 0, stream>>>(frame, q, samples);
     uint32_t made = 1;
+    const uint64_t resolve_needed = (n_px + k_block_threads - 1u) / k_block_threads;
+    const uint32_t resolve_blocks = static_cast<uint32_t>(resolve_needed < streaming_blocks ? resolve_needed : streaming_blocks);
+    float4* const l[4] = {reinterpret_cast<float4*>(layers[0]), reinterpret_cast<float4*>(layers[1]),
+                          reinterpret_cast<float4*>(layers[2]), reinterpret_cast<float4*>(layers[3])};
     const uint32_t trace_blocks = static_cast<uint32_t>(sm_count) * k_wave_blocks_per_sm;
     for (uint32_t wave = 0; wave < scene.max_bounces; wave++) {
         const uint32_t in = wave & 1u;
@@ -523,13 +539,13 @@ cudaError_t launch_mesh_wavefront(const mesh_params& scene, const frame_params& 
                                                                         q.counts + k_mesh_wave_counters + wave, counters);
         mesh_wave_shade_kernel<<<streaming_blocks, k_block_threads, 0, stream>>>(scene, q, wave);
         made += 2;
+        if (wave == 0u) {  // albedo, normal and depth are first-hit values: final from here on
+            mesh_wave_resolve_kernel<false><<<resolve_blocks, k_block_threads, 0, stream>>>(frame, q, samples, l[0], l[1], l[2], l[3]);
+            made += 1;
+            if (first_hit_layers_enqueued) first_hit_layers_enqueued();
+        }
     }
-    const uint64_t resolve_needed = (n_px + k_block_threads - 1u) / k_block_threads;
-    mesh_wave_resolve_kernel<<<static_cast<uint32_t>(resolve_needed < streaming_blocks ? resolve_needed : streaming_blocks),
-                               k_block_threads, 0, stream>>>(frame, q, samples, reinterpret_cast<float4*>(layers[0]),
-                                                             reinterpret_cast<float4*>(layers[1]),
-                                                             reinterpret_cast<float4*>(layers[2]),
-                                                             reinterpret_cast<float4*>(layers[3]));
+    mesh_wave_resolve_kernel<true><<<resolve_blocks, k_block_threads, 0, stream>>>(frame, q, samples, l[0], l[1], l[2], l[3]);
     made += 1;
     if (launches) *launches = made;
     return cudaGetLastError();

@@ -140,6 +140,12 @@ struct plugin_state {
     // on the host: the 64 B/px device-to-host transfer is spread over the launch instead of following it.
     bool mirror_enabled = false;
     bool mirror_valid = false;         ///< the buffers hold what the layers hold
+    // Mesh scene (wavefront form): the mirror is filled by copies on a stream of its own, the three first-hit layers
+    // while the later waves are still being traced, the beauty layer after the last launch; `mirror_copied` follows
+    // the last of them, and a readback that uses the mirror waits for it as well as for the render.
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t layers_ready = nullptr, mirror_copied = nullptr;
+    bool mirror_by_copy = false;
     float* mirror[Q_AOV_COUNT] = {nullptr, nullptr, nullptr, nullptr};
     // Q_cuda_plugin_set_export: a multi-GPU host has the batched launches push every slice of the layer
     // block to the GPU that owns it (peer memory) instead; takes the place of the mirror while set.
@@ -172,6 +178,7 @@ bool check(const plugin_state* state, cudaError_t err, const char* what) {
 }
 
 void free_layers(plugin_state* state) {
+    if (state->copy_stream) cudaStreamSynchronize(state->copy_stream);  // the mirror copies read the layers
     if (state->layers[0]) cudaFree(state->layers[0]);
     for (auto& l : state->layers) l = nullptr;
 }
@@ -516,10 +523,14 @@ Q_aov_buffer download_layer(plugin_state* state, int layer) {
 /// Orders `stream` after the most recent render without blocking the host.
 void order_after_render(plugin_state* state, cudaStream_t stream) {
     if (state->render_pending) cudaStreamWaitEvent(stream, state->last_render, 0);
+    // (mesh scene: what follows may write the layers that the last batch's mirror copies read)
+    if (state->mirror_by_copy && state->mirror_copied) cudaStreamWaitEvent(stream, state->mirror_copied, 0);
 }
 
 
 void drop_mirror(plugin_state* state) {
+    if (state->copy_stream) cudaStreamSynchronize(state->copy_stream);  // nothing is still being copied into them
+    state->mirror_by_copy = false;
     for (auto& m : state->mirror) {
         if (m) g_pool.release(m);
         m = nullptr;
@@ -535,6 +546,23 @@ void drop_mirror(plugin_state* state) {
 /// call may no longer exist (a host may create one per frame). Either way it is ordered after the previous launch.
 /// If the launch cannot be made, the collected calls are taken back (frame_count and the path statistic), so that
 /// the samples that follow carry the weights of what is really in the layers.
+/// The stream and events behind the mesh scene's mirror copies, made on first use.
+bool mirror_copies_ready(plugin_state* state) {
+    if (state->copy_stream) return true;
+    if (cudaStreamCreateWithFlags(&state->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&state->layers_ready, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&state->mirror_copied, cudaEventDisableTiming) != cudaSuccess) {
+        (void)cudaGetLastError();
+        if (state->copy_stream) cudaStreamDestroy(state->copy_stream);
+        if (state->layers_ready) cudaEventDestroy(state->layers_ready);
+        if (state->mirror_copied) cudaEventDestroy(state->mirror_copied);
+        state->copy_stream = nullptr;
+        state->layers_ready = state->mirror_copied = nullptr;
+        return false;
+    }
+    return true;
+}
+
 /// Whether a fused-reduce table (Q_cuda_plugin_set_reduce) was cut for this viewport: the slices cover the four
 /// layers and each starts on a row of tiles of one layer, so that a tile's 32 pixels in a layer have one owner.
 bool reduce_table_fits(const Q_cuda_reduce_table& t, uint32_t width, uint32_t height) {
@@ -571,11 +599,39 @@ void flush_pending(plugin_state* state, cudaStream_t stream = nullptr) {
         const uint64_t n_px = static_cast<uint64_t>(f.width) * f.height;
         cudaError_t launched = cudaSuccess;
         const uint64_t entries = static_cast<uint64_t>((f.width + 7u) / 8u) * ((f.height + 3u) / 4u) * 32u * collected;
+        bool mirrored = false;
         if (n_px * collected < (uint64_t{1} << 31) && ensure_wave(state, entries)) {
+            // The readback mirror (QUASI_CUDA_MIRROR), the wavefront's way: a copy engine takes albedo, normal and depth
+            // to pinned host memory as soon as the first shade pass has made them final, under the waves that
+            // follow, and the beauty layer after the last launch; neither copy is on the render's stream.
+            const size_t layer_bytes = static_cast<size_t>(n_px) * 4 * sizeof(float);
+            bool mirror = state->mirror_enabled && !state->external_export && !state->external_reduce && mirror_copies_ready(state);
+            for (int i = 0; i < Q_AOV_COUNT && mirror; i++) {
+                if (!state->mirror[i]) state->mirror[i] = g_pool.acquire(layer_bytes);
+                mirror = state->mirror[i] != nullptr;
+            }
+            auto copy_first_hit_layers = [&] {
+                bool ok = cudaEventRecord(state->layers_ready, stream) == cudaSuccess &&
+                          cudaStreamWaitEvent(state->copy_stream, state->layers_ready, 0) == cudaSuccess;
+                for (int i = 1; i < Q_AOV_COUNT && ok; i++) {
+                    ok = cudaMemcpyAsync(state->mirror[i], state->layers[i], layer_bytes, cudaMemcpyDeviceToHost,
+                                         state->copy_stream) == cudaSuccess;
+                }
+                mirror = ok;
+            };
             uint32_t made = 0;
             launched = Q::cuda::launch_mesh_wavefront(state->mesh_device, fp, state->wave, state->layers, state->ray_counter,
-                                                      state->sm_count, stream, &made);
+                                                      state->sm_count, stream, &made,
+                                                      mirror ? std::function<void()>(copy_first_hit_layers) : std::function<void()>());
             state->kernel_launches += made;
+            if (launched == cudaSuccess && mirror) {
+                mirrored = cudaEventRecord(state->layers_ready, stream) == cudaSuccess &&
+                           cudaStreamWaitEvent(state->copy_stream, state->layers_ready, 0) == cudaSuccess &&
+                           cudaMemcpyAsync(state->mirror[0], state->layers[0], layer_bytes, cudaMemcpyDeviceToHost,
+                                           state->copy_stream) == cudaSuccess &&
+                           cudaEventRecord(state->mirror_copied, state->copy_stream) == cudaSuccess;
+                if (!mirrored) (void)cudaGetLastError();
+            }
         } else {
             auto* tile_counters = reinterpret_cast<unsigned int*>(state->ray_counter + 3);
             for (uint32_t s = 0; s < collected && launched == cudaSuccess; s++) {
@@ -592,6 +648,8 @@ void flush_pending(plugin_state* state, cudaStream_t stream = nullptr) {
             return;
         }
         state->last_launch_exported = false;
+        state->mirror_valid = mirrored;
+        state->mirror_by_copy = mirrored;
         cudaEventRecord(state->last_render, stream);
         state->render_pending = true;
         return;
@@ -805,6 +863,9 @@ Q_PLUGIN_EXPORT void Q_plugin_destroy(Q_plugin_handle* handle) {
     free_mesh(state);
     if (!leave_layers_with_host(state)) free_layers(state);
     drop_mirror(state);
+    if (state->copy_stream) cudaStreamDestroy(state->copy_stream);
+    if (state->layers_ready) cudaEventDestroy(state->layers_ready);
+    if (state->mirror_copied) cudaEventDestroy(state->mirror_copied);
     if (state->ray_counter) cudaFree(state->ray_counter);
     if (state->last_render) cudaEventDestroy(state->last_render);
     delete state;
@@ -906,7 +967,8 @@ Q_PLUGIN_EXPORT Q_readback_result Q_plugin_readback(Q_plugin_handle* handle) {
     flush_pending(state);
 
     if (state->mirror_valid && state->render_pending &&
-        check(state, cudaEventSynchronize(state->last_render), "readback sync (mirror)")) {
+        check(state, cudaEventSynchronize(state->last_render), "readback sync (mirror)") &&
+        (!state->mirror_by_copy || check(state, cudaEventSynchronize(state->mirror_copied), "readback sync (mirror copies)"))) {
         // the batched launch has put the frame into pinned host buffers itself: hand the beauty layer over
         result.data = state->mirror[Q_AOV_BEAUTY];
         result.width = state->last_width;
@@ -950,7 +1012,8 @@ Q_PLUGIN_EXPORT Q_readback_aov_result Q_plugin_readback_aov(Q_plugin_handle* han
 
     if (state->mirror_valid) {
         // the batched launch has put the frame into pinned host buffers itself: wait for it, hand them over
-            if (state->render_pending && check(state, cudaEventSynchronize(state->last_render), "readback sync (mirror)")) {
+        if (state->render_pending && check(state, cudaEventSynchronize(state->last_render), "readback sync (mirror)") &&
+            (!state->mirror_by_copy || check(state, cudaEventSynchronize(state->mirror_copied), "readback sync (mirror copies)"))) {
             for (int i = 0; i < Q_AOV_COUNT; i++) {
                 result.buffers[i] = Q_aov_buffer{state->mirror[i], state->last_width, state->last_height, 4};
                 state->mirror[i] = nullptr;  // the caller's now; the next batch gets fresh ones

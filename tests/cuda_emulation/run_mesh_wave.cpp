@@ -100,9 +100,13 @@ int main(int argc, char** argv) {
             wide ? run(mesh_wave_trace_kernel<true, false>)
                  : (quant ? run(mesh_wave_trace_kernel<false, true>) : run(mesh_wave_trace_kernel<false, false>));
             emu::launch(mesh_wave_shade_kernel, 3u, k_block_threads, 1u, scene, q, wave);
+            if (wave == 0u) {  // the first-hit layers, as soon as they are final
+                emu::launch(mesh_wave_resolve_kernel<false>, 2u, k_block_threads, 1u, frame, q, samples, layers[0].data(),
+                            layers[1].data(), layers[2].data(), layers[3].data());
+            }
         }
-        emu::launch(mesh_wave_resolve_kernel, 2u, k_block_threads, 1u, frame, q, samples, layers[0].data(), layers[1].data(),
-                    layers[2].data(), layers[3].data());
+        emu::launch(mesh_wave_resolve_kernel<true>, 2u, k_block_threads, 1u, frame, q, samples, layers[0].data(),
+                    layers[1].data(), layers[2].data(), layers[3].data());
     }
     FILE* out = std::fopen(argv[6], "wb");
     if (!out) return 5;
