@@ -164,7 +164,7 @@ Q_PLUGIN_EXPORT int Q_cuda_plugin_set_export(Q_plugin_handle* handle, const Q_cu
  * 8x4 tiles: slice s is the float4 [slice_lo[s], slice_lo[s + 1]) with every slice_lo[s] = (layer * height +
  * 4 * tile_row) * width, slice_lo[G] = 4 * width * height, so that the 32 pixels of a tile in one layer (a unit)
  * have one owner. Rank s owns slice s: a staging area of G slots of `slot_stride` float4 (slot g receives rank
- * g's copy of the slice) and 4 * tiles arrival counters (uint32, [layer * tiles + tile], zeroed ONCE; tiles =
+ * g's copy of the slice) and 4 * tiles arrival counters (uint32, [layer * tiles + tile], zeroed before the first frame: the launch that completes a unit zeroes its counter again; tiles =
  * ceil(width / 8) * ceil(height / 4)), both mapped by every rank (Q_cuda_ipc_open). A batched launch stores every
  * finished tile into its slot at the owners, then adds one to the units' counters; the launch whose arrival is the
  * G-th for a unit, on whichever GPU, loads the G copies, sums them in rank order, scales by 1/G and stores

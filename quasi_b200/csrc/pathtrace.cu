@@ -598,10 +598,14 @@ pathtrace_accumulate_kernel(const __grid_constant__ scene_params scene, const __
                         uint32_t unit_slice = 0, arrivals = 0;
                         if (lane < 4u) {
                             unit_slice = slice_of(lane * n_px + first_pixel);
-                            arrivals = arrive_release_system(launch.reduce_counters[unit_slice] + lane * n_tiles + done_tile) + 1u;
-                            if (arrivals % launch.reduce_ranks == 0u) acquire_fence_system();  // the other ranks' copies are visible from here on
+                            unsigned int* const counter = launch.reduce_counters[unit_slice] + lane * n_tiles + done_tile;
+                            arrivals = arrive_release_system(counter) + 1u;
+                            if (arrivals == launch.reduce_ranks) {
+                                acquire_fence_system();  // the other ranks' copies are visible from here on
+                                *counter = 0u;           // nobody else touches it before the buffer's next frame
+                            }
                         }
-                        uint32_t m_last = __ballot_sync(0xffffffffu, lane < 4u && arrivals % launch.reduce_ranks == 0u);
+                        uint32_t m_last = __ballot_sync(0xffffffffu, lane < 4u && arrivals == launch.reduce_ranks);
                         if (m_last != 0u) __syncwarp();  // every lane's loads below come after the fence of the lane that arrived
                         while (m_last != 0u) {
                             const uint32_t l = static_cast<uint32_t>(__ffs(static_cast<int>(m_last))) - 1u;

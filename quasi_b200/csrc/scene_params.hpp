@@ -180,8 +180,9 @@ struct alignas(16) frame_params {
 /// whichever GPU it runs, loads the G staged copies of the unit, sums them IN RANK ORDER, scales by 1/G and stores
 /// the unit of the finished frame to reduce_out[s] + (i - slice_lo[s]) (s the unit's slice: pinned host memory
 /// every GPU has mapped, or the owner's device memory). The reduce and the frame's way to the host are then part
-/// of the render as well: what is left after the last rank's launch is its last tiles. The counters are never reset: a unit of one staging buffer receives exactly G arrivals per
-/// frame that uses the buffer, so the G-th is the one that makes the count a multiple of G.
+/// of the render as well: what is left after the last rank's launch is its last tiles. A unit of one staging buffer
+/// receives exactly G arrivals per frame that uses the buffer; the G-th puts the counter back to zero (nobody else
+/// touches it before the buffer's next frame, which the device-side barrier between frames keeps away).
 inline constexpr uint32_t k_max_export_slices = 16;
 struct alignas(16) batch_params {
     void* export_base[k_max_export_slices];

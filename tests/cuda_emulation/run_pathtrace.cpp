@@ -58,7 +58,7 @@ int main(int argc, char** argv) {
         }
         std::vector<std::vector<float4>> staging(ranks, std::vector<float4>(static_cast<size_t>(ranks) * longest,
                                                                              make_float4(-7.0f, -7.0f, -7.0f, -7.0f)));
-        std::vector<std::vector<unsigned int>> counters(ranks, std::vector<unsigned int>(4u * n_tiles, ranks * 5u));  // not zero: a multiple of G
+        std::vector<std::vector<unsigned int>> counters(ranks, std::vector<unsigned int>(4u * n_tiles, 0u));
         std::vector<float4> finished(4u * n, make_float4(-1.0f, -1.0f, -1.0f, -1.0f));
         launch.export_slices = launch.reduce_ranks = ranks;
         launch.reduce_slot_stride = longest;
@@ -85,6 +85,11 @@ int main(int argc, char** argv) {
         if (!out) return 5;
         std::fwrite(finished.data(), sizeof(float4), finished.size(), out);
         std::fclose(out);
+        for (const auto& c : counters) {  // every unit has been completed, and its counter put back
+            for (unsigned int v : c) {
+                if (v != 0u) return 9;
+            }
+        }
         std::printf("rays %llu launches %u\n", rays, ranks);
         return 0;
     }
