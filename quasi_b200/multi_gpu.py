@@ -5,9 +5,9 @@ scene (/root/reference/backends/metal/plugin.mm:295), so GPU r of N renders the
 RNG frame indices r, r+N, r+2N, ... for every pixel into its own full-frame
 layers (the plugin does this itself from Q_cuda_device_desc.shard_index/count).
 The only exchange is the combine: result = (sum over ranks of the per-rank
-means) * (1/N). Two implementations of that exchange:
+means) * (1/N). Three implementations of that exchange:
 
-  push  (default) reduce-scatter by peer stores, fused into the render. The contiguous
+  push  reduce-scatter by peer stores, fused into the render. The contiguous
         4-layer block is cut into N slices; rank s owns slice s and a staging area of N
         slots (CUDA IPC, mapped by every rank). A rank's batched render kernel sends every
         8x4 tile that has received its last sample to the owners of its four layers' slices
@@ -21,11 +21,11 @@ means) * (1/N). Two implementations of that exchange:
         instead of through rank 0's. No host barrier, no staging copy, no NCCL, and unlike
         NCCL's ring/tree the summation order is fixed: the result is bit-identical to the
         oracle's rank-ordered combine.
-  fused the whole exchange inside the render kernel (Q_cuda_plugin_set_reduce). Slices are cut along rows of
+  fused (default) the whole exchange inside the render kernel (Q_cuda_plugin_set_reduce). Slices are cut along rows of
         8x4 tiles, so that a tile's 32 pixels in one layer (a unit) have one owner. A warp that has stored a
         finished tile at the owners adds one to the units' arrival counters there (system-scope atomics over
         NVLink); the warp whose arrival is the N-th for a unit, on whichever GPU it runs, loads the N staged
-        copies, sums them in rank order, scales and stores the unit into the shared host frame. The reduce and
+        copies, sums them in rank order, scales, stores the unit into the shared host frame and puts the counter back. The reduce and
         the frame's way to the host overlap the render of every rank; what follows the render is only a
         device-side barrier (so that a staging buffer is not reused while a peer still reads it). Bit-identical
         to the oracle's combine like `push`. A frame whose last launch is a single sample falls back to
@@ -158,7 +158,7 @@ class shard_exchange:
     """Combines the per-rank accumulation layers of one frame: begin_frame() before the frame's render
     calls, combine() after them (enqueue only), finish_frame() when the frame is wanted on the host."""
 
-    def __init__(self, host, dist, mode: str = "push", host_path: str | None = None):
+    def __init__(self, host, dist, mode: str = "fused", host_path: str | None = None):
         """`host_path` (push mode): how a reduced slice reaches the shared host frame: "store", the reduce kernel
         writes it there itself (zero-copy stores over PCIe), or "dma", the kernel writes device memory and a
         copy engine moves the slice (the default: QUASI_EXCHANGE_HOST_PATH overrides)."""
