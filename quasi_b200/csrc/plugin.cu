@@ -110,6 +110,7 @@ struct plugin_state {
     Q::cuda::mesh::scene mesh;
     Q::cuda::mesh_params mesh_device{};
     bool mesh_wavefront = false;     ///< headless calls of the mesh scene are collected and traced as waves (mesh_wavefront.cu)
+    uint32_t mesh_wave_min = 4;      ///< fewer collected calls than this go through the one-kernel form, one launch each
     void* wave_block = nullptr;      ///< the one allocation behind `wave`
     Q::cuda::mesh_wave_buffers wave{};
     Q::cuda::l2_window mesh_keep{};  ///< QUASI_CUDA_MESH_L2_KEEP: the part of the mesh the launches ask the L2 to keep
@@ -600,7 +601,9 @@ void flush_pending(plugin_state* state, cudaStream_t stream = nullptr) {
         cudaError_t launched = cudaSuccess;
         const uint64_t entries = static_cast<uint64_t>((f.width + 7u) / 8u) * ((f.height + 3u) / 4u) * 32u * collected;
         bool mirrored = false;
-        if (n_px * collected < (uint64_t{1} << 31) && ensure_wave(state, entries)) {
+        // (a wave has a ramp and a tail of its own, and a batch is 2 * bounces + 3 launches: measured per 16 samples at
+        // 1080p, batches of 1 take 37 ms, of 4 26.1 ms, of 16 16.9 ms, the one-kernel form 26.3 ms)
+        if (collected >= state->mesh_wave_min && n_px * collected < (uint64_t{1} << 31) && ensure_wave(state, entries)) {
             // The readback mirror (QUASI_CUDA_MIRROR), the wavefront's way: a copy engine takes albedo, normal and depth
             // to pinned host memory as soon as the first shade pass has made them final, under the waves that
             // follow, and the beauty layer after the last launch; neither copy is on the render's stream.
@@ -820,6 +823,7 @@ Q_PLUGIN_EXPORT Q_plugin_handle* Q_plugin_create(Q_plugin_context* ctx) {
             // headless calls are collected, QUASI_CUDA_MESH_BATCH at a time, and traced as waves (mesh_wavefront.cu)
             state->mesh_wavefront = env_u32("QUASI_CUDA_MESH_WAVEFRONT", 1, 0, 1) != 0;
             state->batch = state->mesh_wavefront ? env_u32("QUASI_CUDA_MESH_BATCH", 16, 1, 64) : 1;
+            state->mesh_wave_min = env_u32("QUASI_CUDA_MESH_WAVEFRONT_MIN", 4, 1, 64);
             ok = create_mesh(state, env_u32("QUASI_CUDA_MESH_GRID", 707, 1, 4000),
                              env_u32("QUASI_CUDA_MESH_SEED", 1, 0, 65535), bounces);
         }

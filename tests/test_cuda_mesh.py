@@ -16,7 +16,9 @@ def mesh_host(width, height, grid, bounces=4, seed=1, builder="sah", wide=0, **e
 
     return headless_host(width, height, env={"QUASI_CUDA_SCENE": "mesh", "QUASI_CUDA_MESH_GRID": grid,
                                              "QUASI_CUDA_MESH_SEED": seed, "QUASI_CUDA_MAX_BOUNCES": bounces,
-                                             "QUASI_CUDA_MESH_BUILDER": builder, "QUASI_CUDA_MESH_WIDE": wide, **env})
+                                             "QUASI_CUDA_MESH_BUILDER": builder, "QUASI_CUDA_MESH_WIDE": wide,
+                                             # (these tests render two to five calls: as waves, however few they are)
+                                             "QUASI_CUDA_MESH_WAVEFRONT_MIN": 1, **env})
 
 
 def render(width, height, frames, grid, bounces=4, builder="sah", wide=0, **env):
@@ -49,6 +51,7 @@ def test_small_meshes_vs_oracle_and_brute_force(grid, size, frames):
 
 
 @pytest.mark.parametrize("env", [{"QUASI_CUDA_MESH_WAVEFRONT": 0}, {"QUASI_CUDA_MESH_BATCH": 1},
+                                 {"QUASI_CUDA_MESH_WAVEFRONT_MIN": 4},  # the default: 5 calls as waves, then 2 and 2 one by one
                                  {"QUASI_CUDA_MESH_BATCH": 2}, {"QUASI_CUDA_MESH_BATCH": 5},
                                  {"QUASI_CUDA_MESH_BATCH": 3, "QUASI_CUDA_MESH_WIDE": 1},
                                  {"QUASI_CUDA_MESH_BATCH": 4, "QUASI_CUDA_MAX_BOUNCES": 7}])
