@@ -21,7 +21,7 @@ struct alignas(16) mesh_params {
     const float4* nodes;    ///< 2 float4 per node: {min.xyz, left_first} {max.xyz, count}; wide: 8 per node (wide_bvh.hpp)
     const float4* tri_v0;   ///< leaf order: {v0.xyz, material}
     const float4* tri_e1;   ///< leaf order: {e1.xyz, original index}
-    const float4* tri_e2;   ///< leaf order: {e2.xyz, 0}
+    const float4* tri_e2;   ///< leaf order: {e2.xyz, slot | material << k_mesh_slot_bits as bits}
     const float4* tri_shade;  ///< leaf order, 3 per triangle: mesh_scene.hpp:shading_record
     uint32_t n_nodes;
     uint32_t n_triangles;
@@ -65,6 +65,7 @@ cudaError_t launch_mesh_pathtrace(const mesh_params& scene, const frame_params& 
 
 /// Device memory of the wavefront form of the mesh scene (mesh_wavefront.cu), sized for `capacity` paths (pixels x
 /// samples of a batch): two ray queues, the hits of the queue being traced, the results of every path.
+inline constexpr uint32_t k_mesh_slot_bits = 28;  ///< tri_e2[slot].w = slot | material << 28: what a hit is recorded as (mesh_scene.hpp:k_slot_bits)
 inline constexpr uint32_t k_mesh_wave_counters = 72;  ///< one per wave (bounce), + 1; QUASI_CUDA_MAX_BOUNCES <= 64
 struct mesh_wave_buffers {
     float4* origin[2];        ///< queue 0 / 1, by position: {ray origin, path (pixel + sample * pixels; bit 31: it has a

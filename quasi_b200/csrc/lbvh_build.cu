@@ -310,7 +310,9 @@ gather_kernel(const uint32_t* __restrict__ leaf_order, const float4* __restrict_
     float4 edge = e1[t];
     edge.w = __uint_as_float(t);  // original index: the tie rule of the closest hit
     out_e1[k] = edge;
-    out_e2[k] = e2[t];
+    float4 other = e2[t];
+    other.w = __uint_as_float(k | (__float_as_uint(v0[t].w) << k_mesh_slot_bits));  // what a hit is recorded as (mesh_scene.hpp)
+    out_e2[k] = other;
     for (int r = 0; r < 3; r++) out_shade[3u * k + r] = shade[3u * t + r];
 }
 

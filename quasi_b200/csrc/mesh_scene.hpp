@@ -65,6 +65,7 @@ struct material {
 };
 
 inline constexpr uint32_t k_material_count = 5;
+inline constexpr uint32_t k_slot_bits = 28;  ///< a recorded hit: slot in leaf order | material << k_slot_bits (fewer than 2^28 triangles, 8 materials)
 inline constexpr uint32_t k_sah_bins = 16;
 inline constexpr uint32_t k_leaf_max = 2;
 /// Triangles whose box area exceeds this fraction of the scene's are split off at the root.
@@ -505,7 +506,9 @@ inline void pack_for_device(const scene& s, std::vector<float4_t>& nodes, std::v
         const triangle& t = s.triangles[original];
         tri_v0[slot] = {t.v0[0], t.v0[1], t.v0[2], bits_to_float(t.material)};
         tri_e1[slot] = {t.e1[0], t.e1[1], t.e1[2], bits_to_float(original)};
-        tri_e2[slot] = {t.e2[0], t.e2[1], t.e2[2], 0.0f};
+        // what a hit is recorded as: the slot, with the material in the top four bits (k_slot_bits), so that shading
+        // a hit needs the shading record only
+        tri_e2[slot] = {t.e2[0], t.e2[1], t.e2[2], bits_to_float(static_cast<uint32_t>(slot) | (t.material << k_slot_bits))};
         shading_record(t, &tri_shade[slot * 3]);
     }
 }

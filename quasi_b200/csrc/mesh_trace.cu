@@ -154,9 +154,9 @@ mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_co
             v3 n = make_v3(0.0f, 0.0f, 0.0f), q_emission = n, q_albedo = n;
             bool is_light = false;
             if (is_hit) {
-                const float4* rec = scene.tri_shade + 3u * static_cast<size_t>(best.slot);
+                const float4* rec = scene.tri_shade + 3u * static_cast<size_t>(best.slot & ((1u << mesh::k_slot_bits) - 1u));
                 const float4 s0 = __ldg(rec), s1 = __ldg(rec + 1), s2 = __ldg(rec + 2);
-                const float* m = s_material + __float_as_uint(__ldg(scene.tri_v0 + best.slot).w) * 8u;
+                const float* m = s_material + (best.slot >> mesh::k_slot_bits) * 8u;
                 q_albedo = load_v3(m);
                 q_emission = load_v3(m + 4);
                 is_light = fmaxf(q_emission.x, fmaxf(q_emission.y, q_emission.z)) > 0.1f;
@@ -338,8 +338,7 @@ mesh_pathtrace_kernel(const __grid_constant__ mesh_params scene, const __grid_co
                 const uint32_t first = cur >> 3, count = cur & 7u;
                 for (uint32_t k = 0; k < count; k++) {
                     const uint32_t slot = first + k;
-                    intersect(__ldg(scene.tri_v0 + slot), __ldg(scene.tri_e1 + slot), __ldg(scene.tri_e2 + slot),
-                              slot, ro, rd, best);
+                    intersect(__ldg(scene.tri_v0 + slot), __ldg(scene.tri_e1 + slot), __ldg(scene.tri_e2 + slot), ro, rd, best);
                 }
                 tris_tested += count;
                 cur = stack.after_node();

@@ -24,7 +24,7 @@ constexpr uint32_t k_pop = 0xfffffffeu;   ///< node reference: take the next ent
 struct mesh_hit {
     float t;
     uint32_t prim;  ///< original triangle index, k_miss = none
-    uint32_t slot;  ///< position in leaf order (where its float4s are)
+    uint32_t slot;  ///< position in leaf order (where its float4s are), material in the top four bits
 };
 
 /// Per-lane traversal stack, all of it in shared memory: node references as
@@ -69,8 +69,7 @@ __device__ __forceinline__ float slab_reciprocal(float x) { return slab::recipro
 /// oracle/quasi_oracle_mesh.c:qm_intersect, evaluated without branches: every
 /// lane computes u, v and t and the early returns become one predicate. Values
 /// computed past a failed test are never used (NaN and infinity compare false).
-__device__ __forceinline__ void intersect(float4 v0m, float4 e1p, float4 e2_, uint32_t slot, v3 o, v3 d,
-                                          mesh_hit& best) {
+__device__ __forceinline__ void intersect(float4 v0m, float4 e1p, float4 e2_, v3 o, v3 d, mesh_hit& best) {
     const v3 e1 = make_v3(e1p.x, e1p.y, e1p.z), e2 = make_v3(e2_.x, e2_.y, e2_.z);
     const v3 pvec = cross(d, e2);
     const float det = dot(e1, pvec);
@@ -90,7 +89,7 @@ __device__ __forceinline__ void intersect(float4 v0m, float4 e1p, float4 e2_, ui
     const bool ok = !reject;
     best.t = ok ? t : best.t;
     best.prim = ok ? prim : best.prim;
-    best.slot = ok ? slot : best.slot;
+    best.slot = ok ? __float_as_uint(e2_.w) : best.slot;  // slot | material << k_slot_bits (mesh_scene.hpp)
 }
 
 /// Node references are {left_first << 3 | count}: count 0 = interior, 1..4 = leaf.

@@ -278,8 +278,7 @@ mesh_wave_trace_kernel(const __grid_constant__ mesh_params scene, const float4* 
                     const uint32_t first = cur >> 3, n = cur & 7u;
                     for (uint32_t k = 0; k < n; k++) {
                         const uint32_t slot = first + k;
-                        intersect(__ldg(scene.tri_v0 + slot), __ldg(scene.tri_e1 + slot), __ldg(scene.tri_e2 + slot), slot, ro,
-                                  rd, best);
+                        intersect(__ldg(scene.tri_v0 + slot), __ldg(scene.tri_e1 + slot), __ldg(scene.tri_e2 + slot), ro, rd, best);
                     }
                     tris_tested += n;
                     cur = stack.after_node();
@@ -347,15 +346,16 @@ mesh_wave_shade_kernel(const __grid_constant__ mesh_params scene, const __grid_c
                 path &= ~k_has_colour;
             }
             const float best_t = h.x;
-            const uint32_t slot = __float_as_uint(h.y);
+            const uint32_t recorded = __float_as_uint(h.y);  // slot | material << k_slot_bits, or all ones
+            const uint32_t slot = recorded & ((1u << mesh::k_slot_bits) - 1u);
 
-            const bool is_hit = slot != k_miss;
+            const bool is_hit = recorded != k_miss;
             v3 n = make_v3(0.0f, 0.0f, 0.0f), q_emission = n, q_albedo = n, fu = n, fv = n, fw = n;
             bool is_light = false;
             if (is_hit) {
                 const float4* rec = scene.tri_shade + 3u * static_cast<size_t>(slot);
                 const float4 s0 = __ldg(rec), s1 = __ldg(rec + 1), s2 = __ldg(rec + 2);
-                const float* m = s_material + __float_as_uint(__ldg(scene.tri_v0 + slot).w) * 8u;
+                const float* m = s_material + (recorded >> mesh::k_slot_bits) * 8u;
                 q_albedo = load_v3(m);
                 q_emission = load_v3(m + 4);
                 is_light = fmaxf(q_emission.x, fmaxf(q_emission.y, q_emission.z)) > 0.1f;

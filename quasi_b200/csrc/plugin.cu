@@ -26,6 +26,8 @@
 
 namespace {
 
+static_assert(Q::cuda::k_mesh_slot_bits == Q::cuda::mesh::k_slot_bits, "one definition of a recorded hit");
+
 using Q::cuda::frame_params;
 using Q::cuda::scene_params;
 
